@@ -1,0 +1,585 @@
+// dtx_api.cu -- the C ABI (include/detex_b200.h) over the kernels.
+//
+// Host-side responsibilities only: packing subspaces into 16-vector basis blocks, laying
+// out the K segments, sizing / growing device buffers, building the work-item list and
+// launching K0 -> K1 -> K3 on the context's stream.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/detex_b200.h"
+#include "dtx_kernels.cuh"
+
+using namespace dtx;
+
+namespace dtx {
+void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int row_begin, int row_end,
+                     double* d_cc, int* d_lag, double* d_sub, int num_sms, cudaStream_t st);
+}
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
+        if (e != cudaSuccess) {
+            want = n;
+            e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct BasisSet {
+    BasisLayout lay{};
+    int R = 0;
+    std::vector<int> rank_off;
+    bool has_thr = false;
+    DevBuf<double> d_U;
+    DevBuf<int> d_rank_off, d_slot_row;
+    DevBuf<BlockInfo> d_binfo;
+    DevBuf<uint8_t> d_Aimg;
+    DevBuf<float> d_thr;
+    DevBuf<unsigned long long> d_hist;
+    DevBuf<double> d_fas;
+    void release() {
+        d_U.release(); d_rank_off.release(); d_slot_row.release(); d_binfo.release();
+        d_Aimg.release(); d_thr.release(); d_hist.release(); d_fas.release();
+    }
+};
+
+}  // namespace
+
+struct dtx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 0;
+    std::string err;
+    std::map<int, BasisSet> sets;
+
+    // current batch
+    int nchunks = 0;
+    int dtype = DTX_F64;
+    std::vector<long long> raw_off;  // element offsets in raw buffer
+    std::vector<long long> rawL;
+    const void* d_raw = nullptr;     // points into raw_own or caller memory
+    DevBuf<uint8_t> raw_own;
+
+    // last run
+    int run_set = -1;
+    int run_S = 0;
+    bool ran = false;
+    bool have_ds64 = false;
+    std::vector<ChunkDesc> h_chunks;
+    DevBuf<ChunkDesc> d_chunks;
+    DevBuf<int2> d_items;
+    DevBuf<__half> d_xsplit;
+    DevBuf<float> d_mu, d_invE, d_DS, d_scale, d_rowmax;
+    DevBuf<double> d_DS64, d_sum;
+    DevBuf<unsigned> d_maxbits;
+    DevBuf<int> d_rowflags, d_ncand;
+    DevBuf<Candidate> d_cand;
+    int cand_cap = 1 << 20;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool k1_timed = false;
+};
+
+namespace {
+
+int fail(dtx_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define DTX_CUDA(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            char buf_[512];                                                                \
+            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call,                   \
+                     cudaGetErrorString(e_), __FILE__, __LINE__);                          \
+            return fail(ctx, DTX_ERR_CUDA, buf_);                                          \
+        }                                                                                  \
+    } while (0)
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+extern "C" {
+
+int dtx_version(void) { return 100; }
+
+int dtx_create(int device, void* stream, dtx_ctx** out) {
+    if (!out) return DTX_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return DTX_ERR_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DTX_ERR_CUDA;
+    if (prop.major != 10) return DTX_ERR_DEVICE;  // sm_100a only, no fallback
+    if (cudaSetDevice(device) != cudaSuccess) return DTX_ERR_CUDA;
+    dtx_ctx* ctx = new dtx_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return DTX_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    *out = ctx;
+    return DTX_OK;
+}
+
+void dtx_destroy(dtx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->sets) kv.second.release();
+    ctx->raw_own.release(); ctx->d_chunks.release(); ctx->d_items.release(); ctx->d_xsplit.release();
+    ctx->d_mu.release(); ctx->d_invE.release(); ctx->d_DS.release(); ctx->d_scale.release();
+    ctx->d_rowmax.release(); ctx->d_DS64.release(); ctx->d_sum.release(); ctx->d_maxbits.release();
+    ctx->d_rowflags.release(); ctx->d_ncand.release(); ctx->d_cand.release();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* dtx_last_error(const dtx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int dtx_sync(dtx_ctx* ctx) {
+    if (!ctx) return DTX_ERR_ARG;
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DTX_OK;
+}
+
+int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank_off, int S, int n,
+                  int Nc, const double* thresholds) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (!U || !rank_off || S < 1 || Nc < 1 || n < Nc || n % Nc != 0)
+        return fail(ctx, DTX_ERR_ARG, "dtx_set_bases: bad shape (need S>=1, n % Nc == 0)");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    const int R = rank_off[S];
+    for (int s = 0; s < S; ++s) {
+        const int r = rank_off[s + 1] - rank_off[s];
+        if (r < 1 || r > VEC_PER_BLOCK)
+            return fail(ctx, DTX_ERR_ARG, "dtx_set_bases: subspace rank must be in 1..16");
+    }
+    BasisSet& bs = ctx->sets[set_id];
+    BasisLayout& lay = bs.lay;
+    lay = BasisLayout{};
+    lay.Nc = Nc;
+    lay.n = n;
+    lay.ns = n / Nc;
+    lay.S = S;
+    bs.R = R;
+    bs.rank_off.assign(rank_off, rank_off + S + 1);
+
+    // K segments: per channel, taps 0 .. ns+7 (8 phases) rounded to 64, split at MAX_SEG_TAPS
+    const int Kc = round_up(lay.ns + 7, CHUNK_TAPS);
+    int nseg = 0, chunk0 = 0;
+    for (int c = 0; c < Nc; ++c)
+        for (int t0 = 0; t0 < Kc; t0 += MAX_SEG_TAPS) {
+            if (nseg >= MAX_SEGS) return fail(ctx, DTX_ERR_ARG, "dtx_set_bases: template too long");
+            Seg& sg = lay.seg[nseg++];
+            sg.chan = c;
+            sg.tap0 = t0;
+            sg.ntaps = std::min(MAX_SEG_TAPS, Kc - t0);
+            sg.chunk0 = chunk0;
+            chunk0 += sg.ntaps / CHUNK_TAPS;
+        }
+    lay.nseg = nseg;
+    lay.nchunks = chunk0;
+
+    // pack subspaces into blocks of 16 vector slots, first-fit decreasing by rank
+    std::vector<int> order(S);
+    for (int s = 0; s < S; ++s) order[s] = s;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return (rank_off[a + 1] - rank_off[a]) > (rank_off[b + 1] - rank_off[b]);
+    });
+    std::vector<int> used;                    // slots used per block
+    std::vector<std::vector<int>> members;    // subspaces per block
+    for (int s : order) {
+        const int r = rank_off[s + 1] - rank_off[s];
+        int b = -1;
+        for (size_t i = 0; i < used.size(); ++i)
+            if (used[i] + r <= VEC_PER_BLOCK) { b = static_cast<int>(i); break; }
+        if (b < 0) { used.push_back(0); members.emplace_back(); b = static_cast<int>(used.size()) - 1; }
+        used[b] += r;
+        members[b].push_back(s);
+    }
+    lay.nblocks = static_cast<int>(used.size());
+    std::vector<int> slot_row(static_cast<size_t>(lay.nblocks) * VEC_PER_BLOCK, -1);
+    std::vector<BlockInfo> binfo(static_cast<size_t>(lay.nblocks) * VEC_PER_BLOCK);
+    double umax = 0.0;
+    for (long long i = 0; i < static_cast<long long>(R) * n; ++i) umax = std::max(umax, std::fabs(U[i]));
+    int eu = 0;
+    if (umax > 0 && std::isfinite(umax)) eu = 13 - std::ilogb(umax);  // max|U| * 2^eu in [2^13, 2^14)
+    lay.u_exp = eu;
+    lay.u_inv_scale = std::ldexp(1.0f, -eu);
+    for (int b = 0; b < lay.nblocks; ++b) {
+        int slot = 0, maxrank = 1;
+        for (int s : members[b]) maxrank = std::max(maxrank, rank_off[s + 1] - rank_off[s]);
+        for (int i = 0; i < VEC_PER_BLOCK; ++i) {
+            BlockInfo& bi = binfo[static_cast<size_t>(b) * VEC_PER_BLOCK + i];
+            bi.sumU = 0.f; bi.out_row = -1; bi.nrows = 0; bi.maxrank = maxrank;
+        }
+        for (int s : members[b]) {
+            const int r = rank_off[s + 1] - rank_off[s];
+            for (int k = 0; k < r; ++k, ++slot) {
+                const int row = rank_off[s] + k;
+                slot_row[static_cast<size_t>(b) * VEC_PER_BLOCK + slot] = row;
+                BlockInfo& bi = binfo[static_cast<size_t>(b) * VEC_PER_BLOCK + slot];
+                long double su = 0;
+                for (int j = 0; j < n; ++j) su += U[static_cast<long long>(row) * n + j];
+                bi.sumU = static_cast<float>(su);
+                bi.out_row = s;
+                bi.nrows = (k == 0) ? r : 0;
+            }
+        }
+    }
+    DTX_CUDA(bs.d_U.reserve(static_cast<size_t>(R) * n));
+    DTX_CUDA(bs.d_rank_off.reserve(S + 1));
+    DTX_CUDA(bs.d_slot_row.reserve(slot_row.size()));
+    DTX_CUDA(bs.d_binfo.reserve(binfo.size()));
+    DTX_CUDA(bs.d_thr.reserve(S));
+    DTX_CUDA(bs.d_hist.reserve(static_cast<size_t>(S) * HIST_BINS));
+    DTX_CUDA(bs.d_fas.reserve(static_cast<size_t>(S) * 5));
+    const size_t img_bytes = static_cast<size_t>(lay.nblocks) * lay.nchunks * 32768;
+    DTX_CUDA(bs.d_Aimg.reserve(img_bytes));
+    // synchronous copies: the caller's arrays need not outlive this call
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    DTX_CUDA(cudaMemcpy(bs.d_U.p, U, sizeof(double) * R * n, cudaMemcpyHostToDevice));
+    DTX_CUDA(cudaMemcpy(bs.d_rank_off.p, rank_off, sizeof(int) * (S + 1), cudaMemcpyHostToDevice));
+    DTX_CUDA(cudaMemcpy(bs.d_slot_row.p, slot_row.data(), sizeof(int) * slot_row.size(), cudaMemcpyHostToDevice));
+    DTX_CUDA(cudaMemcpy(bs.d_binfo.p, binfo.data(), sizeof(BlockInfo) * binfo.size(), cudaMemcpyHostToDevice));
+    std::vector<float> thr(S, INFINITY);
+    bs.has_thr = thresholds != nullptr;
+    if (thresholds) for (int s = 0; s < S; ++s) thr[s] = static_cast<float>(thresholds[s]);
+    DTX_CUDA(cudaMemcpy(bs.d_thr.p, thr.data(), sizeof(float) * S, cudaMemcpyHostToDevice));
+    DTX_CUDA(cudaMemset(bs.d_hist.p, 0, sizeof(unsigned long long) * S * HIST_BINS));
+    DTX_CUDA(cudaMemset(bs.d_fas.p, 0, sizeof(double) * S * 5));
+    launch_basis_image(bs.d_U.p, bs.d_slot_row.p, lay, bs.d_Aimg.p, ctx->stream);
+    DTX_CUDA(cudaGetLastError());
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DTX_OK;
+}
+
+static int set_chunk_table(dtx_ctx* ctx, int nchunks, const int64_t* L, const int64_t* offs, int dtype) {
+    if (nchunks < 1 || !L) return fail(ctx, DTX_ERR_ARG, "need nchunks >= 1");
+    if (dtype != DTX_F64 && dtype != DTX_F32) return fail(ctx, DTX_ERR_ARG, "dtype must be DTX_F64 or DTX_F32");
+    ctx->nchunks = nchunks;
+    ctx->dtype = dtype;
+    ctx->raw_off.resize(nchunks);
+    ctx->rawL.resize(nchunks);
+    long long off = 0;
+    for (int i = 0; i < nchunks; ++i) {
+        if (L[i] < 1 || L[i] > (1LL << 30)) return fail(ctx, DTX_ERR_ARG, "chunk length out of range");
+        ctx->rawL[i] = L[i];
+        ctx->raw_off[i] = offs ? offs[i] : off;
+        off += (L[i] + 1) & ~1LL;  // keep chunks 16 B aligned for both dtypes
+    }
+    ctx->ran = false;
+    return DTX_OK;
+}
+
+int dtx_load_chunks(dtx_ctx* ctx, int nchunks, const void* const* host_ptrs, const int64_t* L, int dtype) {
+    if (!ctx || !host_ptrs) return DTX_ERR_ARG;
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    int rc = set_chunk_table(ctx, nchunks, L, nullptr, dtype);
+    if (rc) return rc;
+    const size_t esz = dtype == DTX_F32 ? 4 : 8;
+    const long long total = ctx->raw_off.back() + ((ctx->rawL.back() + 1) & ~1LL);
+    // the previous batch may still be in flight on the stream: order the overwrite behind it
+    DTX_CUDA(ctx->raw_own.reserve(static_cast<size_t>(total) * esz));
+    for (int i = 0; i < nchunks; ++i)
+        DTX_CUDA(cudaMemcpyAsync(ctx->raw_own.p + ctx->raw_off[i] * esz, host_ptrs[i],
+                                 static_cast<size_t>(L[i]) * esz, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->d_raw = ctx->raw_own.p;
+    return DTX_OK;
+}
+
+int dtx_attach_device_chunks(dtx_ctx* ctx, int nchunks, const void* dev_base, const int64_t* elem_offsets,
+                             const int64_t* L, int dtype) {
+    if (!ctx || !dev_base || !elem_offsets) return DTX_ERR_ARG;
+    int rc = set_chunk_table(ctx, nchunks, L, elem_offsets, dtype);
+    if (rc) return rc;
+    ctx->d_raw = dev_base;
+    return DTX_OK;
+}
+
+int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_lo, double hist_hi,
+                   int lta_window, int want_fas, int keep_ds64) {
+    if (!ctx) return DTX_ERR_ARG;
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    auto it = ctx->sets.find(set_id);
+    if (it == ctx->sets.end()) return fail(ctx, DTX_ERR_STATE, "dtx_detect_run: unknown basis set");
+    if (ctx->nchunks < 1 || !ctx->d_raw) return fail(ctx, DTX_ERR_STATE, "dtx_detect_run: no chunks loaded");
+    if (engine != DTX_ENGINE_TCGEN05 && engine != DTX_ENGINE_FP64) return fail(ctx, DTX_ERR_ARG, "bad engine");
+    if (kblk == 0) kblk = 1;
+    if (kblk < 1 || kblk > 64) return fail(ctx, DTX_ERR_ARG, "kblk out of range");
+    BasisSet& bs = it->second;
+    const BasisLayout& lay = bs.lay;
+    const int Nc = lay.Nc, n = lay.n, ns = lay.ns, S = lay.S;
+    const int Kc = round_up(ns + 7, CHUNK_TAPS);
+    const int nchunks = ctx->nchunks;
+
+    ctx->h_chunks.resize(nchunks);
+    long long sig = 0, nrm = 0, ds = 0;
+    int max_Lpad = 0, max_ntiles = 0, maxT = 0;
+    long long nitems = 0;
+    for (int i = 0; i < nchunks; ++i) {
+        ChunkDesc& cd = ctx->h_chunks[i];
+        const long long L = ctx->rawL[i] / Nc * Nc;
+        if (L <= n) return fail(ctx, DTX_ERR_SHORT_CHUNK, "chunk not longer than the template (detect.py:262)");
+        cd.raw_off = ctx->raw_off[i];
+        cd.L = static_cast<int>(L);
+        cd.Ls = static_cast<int>(L / Nc);
+        cd.T = cd.Ls - ns + 1;
+        if (cd.T < 10) return fail(ctx, DTX_ERR_SHORT_CHUNK, "fewer than 10 lags (detect.py:270)");
+        cd.ntiles = (cd.T + TILE_T - 1) / TILE_T;
+        cd.Tpad = cd.ntiles * TILE_T;
+        cd.Lpad = round_up(cd.Tpad + Kc, 64);
+        cd.sig_off = sig; cd.norm_off = nrm; cd.ds_off = ds;
+        cd.pad0 = cd.pad1 = 0;
+        sig += 2LL * Nc * cd.Lpad;
+        nrm += cd.Tpad;
+        ds += static_cast<long long>(S) * cd.Tpad;
+        max_Lpad = std::max(max_Lpad, cd.Lpad);
+        max_ntiles = std::max(max_ntiles, cd.ntiles);
+        maxT = std::max(maxT, cd.T);
+        nitems += cd.ntiles;
+    }
+    std::vector<int2> items;
+    items.reserve(nitems);
+    for (int i = 0; i < nchunks; ++i)
+        for (int t = 0; t < ctx->h_chunks[i].ntiles; ++t) items.push_back(make_int2(i, t));
+
+    DTX_CUDA(ctx->d_chunks.reserve(nchunks));
+    DTX_CUDA(ctx->d_items.reserve(items.size()));
+    DTX_CUDA(ctx->d_xsplit.reserve(sig));
+    DTX_CUDA(ctx->d_mu.reserve(nrm));
+    DTX_CUDA(ctx->d_invE.reserve(nrm));
+    DTX_CUDA(ctx->d_DS.reserve(ds));
+    if (keep_ds64) DTX_CUDA(ctx->d_DS64.reserve(ds));
+    DTX_CUDA(ctx->d_scale.reserve(nchunks));
+    DTX_CUDA(ctx->d_sum.reserve(nchunks));
+    DTX_CUDA(ctx->d_maxbits.reserve(nchunks));
+    DTX_CUDA(ctx->d_rowmax.reserve(static_cast<size_t>(nchunks) * S));
+    DTX_CUDA(ctx->d_rowflags.reserve(static_cast<size_t>(nchunks) * S));
+    DTX_CUDA(ctx->d_ncand.reserve(1));
+    DTX_CUDA(ctx->d_cand.reserve(ctx->cand_cap));
+    cudaStream_t st = ctx->stream;
+    DTX_CUDA(cudaMemcpyAsync(ctx->d_chunks.p, ctx->h_chunks.data(), sizeof(ChunkDesc) * nchunks,
+                             cudaMemcpyHostToDevice, st));
+    DTX_CUDA(cudaMemcpyAsync(ctx->d_items.p, items.data(), sizeof(int2) * items.size(),
+                             cudaMemcpyHostToDevice, st));
+    DTX_CUDA(cudaMemsetAsync(ctx->d_ncand.p, 0, sizeof(int), st));
+
+    const int f32 = ctx->dtype == DTX_F32;
+    launch_k0(ctx->d_raw, f32, ctx->d_chunks.p, nchunks, Nc, n, max_Lpad, max_ntiles, ctx->d_sum.p,
+              ctx->d_maxbits.p, ctx->d_scale.p, ctx->d_xsplit.p, ctx->d_mu.p, ctx->d_invE.p, st);
+    DTX_CUDA(cudaGetLastError());
+    ctx->have_ds64 = false;
+    ctx->k1_timed = false;
+    if (engine == DTX_ENGINE_TCGEN05) {
+        K1Args a;
+        a.Aimg = bs.d_Aimg.p; a.xsplit = ctx->d_xsplit.p; a.mu = ctx->d_mu.p; a.invE = ctx->d_invE.p;
+        a.chunk_scale = ctx->d_scale.p; a.chunks = ctx->d_chunks.p; a.items = ctx->d_items.p;
+        a.binfo = bs.d_binfo.p; a.DS = ctx->d_DS.p; a.nitems = static_cast<int>(items.size());
+        a.kblk = kblk; a.num_sms = ctx->num_sms;
+        DTX_CUDA(cudaEventRecord(ctx->ev0, st));
+        launch_k1(a, lay, st);
+        DTX_CUDA(cudaEventRecord(ctx->ev1, st));
+        ctx->k1_timed = true;
+        DTX_CUDA(cudaGetLastError());
+        if (keep_ds64) {
+            launch_direct(ctx->d_raw, f32, ctx->d_chunks.p, nchunks, bs.d_U.p, bs.d_rank_off.p, S, n, Nc,
+                          maxT, ctx->d_sum.p, nullptr, ctx->d_DS64.p, st);
+            ctx->have_ds64 = true;
+        }
+    } else {
+        launch_direct(ctx->d_raw, f32, ctx->d_chunks.p, nchunks, bs.d_U.p, bs.d_rank_off.p, S, n, Nc, maxT,
+                      ctx->d_sum.p, ctx->d_DS.p, keep_ds64 ? ctx->d_DS64.p : nullptr, st);
+        ctx->have_ds64 = keep_ds64 != 0;
+    }
+    DTX_CUDA(cudaGetLastError());
+    launch_k3(ctx->d_DS.p, ctx->d_chunks.p, nchunks, S, bs.d_thr.p, ctx->d_rowmax.p, ctx->d_rowflags.p,
+              bs.d_hist.p, hist_lo, hist_hi, ctx->d_cand.p, ctx->cand_cap, ctx->d_ncand.p,
+              want_fas ? bs.d_fas.p : nullptr, st);
+    DTX_CUDA(cudaGetLastError());
+    if (bs.has_thr && lta_window > 0) {
+        launch_lta(ctx->d_DS.p, ctx->d_chunks.p, S, ctx->d_rowflags.p, ctx->d_cand.p, ctx->d_ncand.p,
+                   ctx->cand_cap, lta_window, st);
+        DTX_CUDA(cudaGetLastError());
+    }
+    ctx->run_set = set_id;
+    ctx->run_S = S;
+    ctx->ran = true;
+    return DTX_OK;
+}
+
+int dtx_num_lags(dtx_ctx* ctx, int chunk, int64_t* T) {
+    if (!ctx || !T) return DTX_ERR_ARG;
+    if (!ctx->ran || chunk < 0 || chunk >= ctx->nchunks) return fail(ctx, DTX_ERR_STATE, "no run / bad chunk");
+    *T = ctx->h_chunks[chunk].T;
+    return DTX_OK;
+}
+
+int dtx_get_ds(dtx_ctx* ctx, int chunk, int subspace, float* out, int64_t count) {
+    if (!ctx || !out) return DTX_ERR_ARG;
+    if (!ctx->ran || chunk < 0 || chunk >= ctx->nchunks || subspace < 0 || subspace >= ctx->run_S)
+        return fail(ctx, DTX_ERR_STATE, "dtx_get_ds: no run / bad index");
+    const ChunkDesc& cd = ctx->h_chunks[chunk];
+    if (count < cd.T) return fail(ctx, DTX_ERR_CAPACITY, "dtx_get_ds: buffer smaller than T");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    DTX_CUDA(cudaMemcpyAsync(out, ctx->d_DS.p + cd.ds_off + static_cast<long long>(subspace) * cd.Tpad,
+                             sizeof(float) * cd.T, cudaMemcpyDeviceToHost, ctx->stream));
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DTX_OK;
+}
+
+int dtx_get_ds64(dtx_ctx* ctx, int chunk, int subspace, double* out, int64_t count) {
+    if (!ctx || !out) return DTX_ERR_ARG;
+    if (!ctx->ran || !ctx->have_ds64 || chunk < 0 || chunk >= ctx->nchunks || subspace < 0 ||
+        subspace >= ctx->run_S)
+        return fail(ctx, DTX_ERR_STATE, "dtx_get_ds64: run with keep_ds64 first");
+    const ChunkDesc& cd = ctx->h_chunks[chunk];
+    if (count < cd.T) return fail(ctx, DTX_ERR_CAPACITY, "dtx_get_ds64: buffer smaller than T");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    DTX_CUDA(cudaMemcpyAsync(out, ctx->d_DS64.p + cd.ds_off + static_cast<long long>(subspace) * cd.Tpad,
+                             sizeof(double) * cd.T, cudaMemcpyDeviceToHost, ctx->stream));
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DTX_OK;
+}
+
+int dtx_get_rowstats(dtx_ctx* ctx, float* maxds, int32_t* flags, int64_t count) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (!ctx->ran) return fail(ctx, DTX_ERR_STATE, "dtx_get_rowstats: no run");
+    const int64_t rows = static_cast<int64_t>(ctx->nchunks) * ctx->run_S;
+    if (count < rows) return fail(ctx, DTX_ERR_CAPACITY, "dtx_get_rowstats: buffer too small");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    if (maxds) DTX_CUDA(cudaMemcpyAsync(maxds, ctx->d_rowmax.p, sizeof(float) * rows, cudaMemcpyDeviceToHost, ctx->stream));
+    if (flags) DTX_CUDA(cudaMemcpyAsync(flags, ctx->d_rowflags.p, sizeof(int) * rows, cudaMemcpyDeviceToHost, ctx->stream));
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DTX_OK;
+}
+
+int dtx_get_hist(dtx_ctx* ctx, int set_id, uint64_t* hist, int64_t count, int reset) {
+    if (!ctx) return DTX_ERR_ARG;
+    auto it = ctx->sets.find(set_id);
+    if (it == ctx->sets.end()) return fail(ctx, DTX_ERR_STATE, "dtx_get_hist: unknown basis set");
+    BasisSet& bs = it->second;
+    const int64_t nel = static_cast<int64_t>(bs.lay.S) * HIST_BINS;
+    if (hist && count < nel) return fail(ctx, DTX_ERR_CAPACITY, "dtx_get_hist: buffer too small");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    if (hist) DTX_CUDA(cudaMemcpyAsync(hist, bs.d_hist.p, sizeof(uint64_t) * nel, cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) DTX_CUDA(cudaMemsetAsync(bs.d_hist.p, 0, sizeof(uint64_t) * nel, ctx->stream));
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DTX_OK;
+}
+
+int dtx_get_fas(dtx_ctx* ctx, int set_id, double* fas, int64_t count, int reset) {
+    if (!ctx) return DTX_ERR_ARG;
+    auto it = ctx->sets.find(set_id);
+    if (it == ctx->sets.end()) return fail(ctx, DTX_ERR_STATE, "dtx_get_fas: unknown basis set");
+    BasisSet& bs = it->second;
+    const int64_t nel = static_cast<int64_t>(bs.lay.S) * 5;
+    if (fas && count < nel) return fail(ctx, DTX_ERR_CAPACITY, "dtx_get_fas: buffer too small");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    if (fas) DTX_CUDA(cudaMemcpyAsync(fas, bs.d_fas.p, sizeof(double) * nel, cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) DTX_CUDA(cudaMemsetAsync(bs.d_fas.p, 0, sizeof(double) * nel, ctx->stream));
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DTX_OK;
+}
+
+int dtx_get_candidates(dtx_ctx* ctx, dtx_cand* out, int64_t cap, int64_t* n) {
+    if (!ctx || !n) return DTX_ERR_ARG;
+    if (!ctx->ran) return fail(ctx, DTX_ERR_STATE, "dtx_get_candidates: no run");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    int nc = 0;
+    DTX_CUDA(cudaMemcpyAsync(&nc, ctx->d_ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n = nc;
+    int64_t ncopy = std::min<int64_t>(std::min<int64_t>(nc, ctx->cand_cap), cap);
+    if (out && ncopy > 0) {
+        static_assert(sizeof(dtx_cand) == sizeof(Candidate), "candidate layout");
+        DTX_CUDA(cudaMemcpyAsync(out, ctx->d_cand.p, sizeof(Candidate) * ncopy, cudaMemcpyDeviceToHost, ctx->stream));
+        DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (nc > ctx->cand_cap || nc > cap) return fail(ctx, DTX_ERR_CAPACITY, "candidate list truncated");
+    return DTX_OK;
+}
+
+int dtx_last_k1_ms(dtx_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return DTX_ERR_ARG;
+    if (!ctx->ran || !ctx->k1_timed) return fail(ctx, DTX_ERR_STATE, "no tcgen05 run to time");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    DTX_CUDA(cudaEventSynchronize(ctx->ev1));
+    DTX_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return DTX_OK;
+}
+
+int dtx_ccx(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int row_begin, int row_end,
+            int engine, double* cc, int32_t* lag, double* subsamp) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (!X || !cc || !lag || !subsamp) return fail(ctx, DTX_ERR_ARG, "dtx_ccx: null pointer");
+    if (N < 2 || Nc < 1 || n % Nc != 0 || n / Nc < 4)
+        return fail(ctx, DTX_ERR_ARG, "dtx_ccx: lengths not equal / not a multiple of Nc (construct.py:430-436)");
+    if (row_begin < 0 || row_end > N || row_begin >= row_end) return fail(ctx, DTX_ERR_ARG, "dtx_ccx: bad row range");
+    if (dtype != DTX_F64 && dtype != DTX_F32) return fail(ctx, DTX_ERR_ARG, "dtx_ccx: bad dtype");
+    (void)engine;  // both engines currently run the float64 kernel
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    const size_t esz = dtype == DTX_F32 ? 4 : 8;
+    const size_t rows = static_cast<size_t>(row_end - row_begin);
+    DevBuf<uint8_t> dX;
+    DevBuf<double> dcc, dsub;
+    DevBuf<int> dlag;
+    DTX_CUDA(dX.reserve(static_cast<size_t>(N) * n * esz));
+    DTX_CUDA(dcc.reserve(rows * N));
+    DTX_CUDA(dsub.reserve(rows * N));
+    DTX_CUDA(dlag.reserve(rows * N));
+    cudaStream_t st = ctx->stream;
+    DTX_CUDA(cudaMemcpyAsync(dX.p, X, static_cast<size_t>(N) * n * esz, cudaMemcpyHostToDevice, st));
+    DTX_CUDA(cudaMemsetAsync(dcc.p, 0, rows * N * sizeof(double), st));
+    DTX_CUDA(cudaMemsetAsync(dsub.p, 0, rows * N * sizeof(double), st));
+    DTX_CUDA(cudaMemsetAsync(dlag.p, 0, rows * N * sizeof(int), st));
+    launch_ccx_fp64(dX.p, dtype == DTX_F32, N, n, Nc, row_begin, row_end, dcc.p, dlag.p, dsub.p,
+                    ctx->num_sms, st);
+    DTX_CUDA(cudaGetLastError());
+    DTX_CUDA(cudaMemcpyAsync(cc, dcc.p, rows * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaMemcpyAsync(lag, dlag.p, rows * N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaMemcpyAsync(subsamp, dsub.p, rows * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaStreamSynchronize(st));
+    dX.release(); dcc.release(); dsub.release(); dlag.release();
+    return DTX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// dtx_kernels.cuh -- device-side data structures and kernel launchers of detex_b200.
+//
+// Data layout in HBM (one "batch" = the chunks of one dtx_run_* call):
+//   raw      : the caller's multiplexed chunks, f64 or f32, back to back
+//   xsplit   : per chunk [Nc][2][Lpad] fp16 -- de-multiplexed, centred, power-of-two
+//              scaled signal split into hi + lo halves (x*2^ex ~= hi + lo), zero padded
+//   mu/invE  : per chunk [Tpad] fp32 -- window mean and ((n-1)/n)/||w - mean||^2
+//   DS       : per chunk [S][Tpad] fp32 -- detection statistic, row per subspace
+//   Aimg     : per basis set [nblocks][nchunks][2][16 KB] fp16 -- the 8 phase-shifted
+//              copies of 16 basis vectors per block, pre-tiled in the exact
+//              shared-memory image the MMA descriptor reads (see k1_project.cu)
+#pragma once
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace dtx {
+
+constexpr int TILE_T = 2048;        // output lags per K1 tile (256 q-rows x 8 phases)
+constexpr int CHUNK_TAPS = 64;      // taps per A stage
+constexpr int VEC_PER_BLOCK = 16;   // basis vectors per K1 basis block (x 8 phases = 128 rows)
+constexpr int MAX_SEG_TAPS = 3072;  // taps per K segment (bounded by the smem signal span)
+constexpr int MAX_SEGS = 48;
+constexpr int HIST_BINS = 400;
+
+struct ChunkDesc {
+    long long raw_off;   // element offset of the chunk in the raw buffer
+    long long sig_off;   // fp16-element offset in xsplit
+    long long norm_off;  // element offset in mu / invE
+    long long ds_off;    // element offset in DS
+    int L;               // multiplexed samples used (multiple of Nc)
+    int Ls;              // samples per channel
+    int T;               // number of output lags  = Ls - ns + 1
+    int ntiles;          // ceil(T / TILE_T)
+    int Lpad;            // padded per-channel length of the split arrays
+    int Tpad;            // ntiles * TILE_T
+    int pad0, pad1;
+};
+
+struct Seg {
+    int chan;    // channel index
+    int tap0;    // first (phase-extended) tap of the segment
+    int ntaps;   // multiple of CHUNK_TAPS, <= MAX_SEG_TAPS
+    int chunk0;  // index of the segment's first 64-tap chunk inside a block image
+};
+
+struct BlockInfo {   // one per (basis block, vector slot)
+    float sumU;      // sum of the basis vector's entries (true units)
+    int out_row;     // DS row of the subspace this vector belongs to, -1 = padding
+    int nrows;       // rank of the subspace if this slot is its first vector, else 0
+    int maxrank;     // largest rank in the block (same value in all 16 slots)
+};
+
+struct BasisLayout {
+    int Nc, ns, n;            // channels, taps per channel, multiplexed length
+    int nseg;                 // K segments
+    int nchunks;              // 64-tap chunks per block image
+    int nblocks;              // basis blocks
+    int S;                    // subspaces (DS rows)
+    float u_inv_scale;        // 2^-eu
+    int u_exp;                // eu
+    Seg seg[MAX_SEGS];
+};
+
+// ------------------------------------------------------------------ launchers
+// k0_prep.cu
+void launch_k0(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nchunks, int Nc, int n,
+               int max_Lpad, int max_ntiles, double* d_sum, unsigned* d_maxbits, float* d_scale,
+               __half* d_xsplit, float* d_mu, float* d_invE, cudaStream_t st);
+
+// basis image (k1_project.cu)
+void launch_basis_image(const double* d_U, const int* d_slot_row, const BasisLayout& lay,
+                        uint8_t* d_Aimg, cudaStream_t st);
+
+// k1_project.cu : tcgen05 Hankel projection + normalisation -> DS
+struct K1Args {
+    const uint8_t* Aimg;
+    const __half* xsplit;
+    const float* mu;
+    const float* invE;
+    const float* chunk_scale;
+    const ChunkDesc* chunks;
+    const int2* items;
+    const BlockInfo* binfo;
+    float* DS;
+    int nitems;
+    int kblk;      // 64-tap chunks accumulated in TMEM between drains
+    int num_sms;
+};
+void launch_k1(const K1Args& a, const BasisLayout& lay, cudaStream_t st);
+int k1_smem_bytes();
+
+// k_direct.cu : float64 CUDA-core evaluation of the closed form (validation / small jobs)
+void launch_direct(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nchunks,
+                   const double* d_U, const int* d_rank_off, int S, int n, int Nc, int maxT,
+                   const double* d_sum, float* d_DS, double* d_DS64, cudaStream_t st);
+
+// k3_post.cu : per (chunk, subspace) row -> max, histogram, candidates
+struct Candidate {
+    int row;     // chunk * S + subspace
+    int t;       // lag index
+    float ds;    // detection statistic
+    float lta;   // centred |DS| mean over the LTA window (filled by launch_lta)
+};
+void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, const float* d_thr,
+               float* d_rowmax, int* d_rowflags, unsigned long long* d_hist, double hist_lo,
+               double hist_hi, Candidate* d_cand, int cand_cap, int* d_ncand,
+               double* d_fas /*[S][4] or null*/, cudaStream_t st);
+void launch_lta(const float* DS, const ChunkDesc* d_chunks, int S, const int* d_rowflags,
+                Candidate* d_cand, const int* d_ncand, int cand_cap, int W, cudaStream_t st);
+
+}  // namespace dtx

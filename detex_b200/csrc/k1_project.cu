@@ -1,0 +1,353 @@
+// k1_project.cu -- K1+K2: the subspace projection as a Hankel-tiled tcgen05 GEMM with the
+// detection-statistic normalisation fused into its epilogue.
+//
+// Replaces, for ALL subspaces of a station at once, the per-subspace FFT correlation
+//   m1 = ssFD * MPconFD ; if1 = real(ifft(m1))[:, n-1:L] - av_norm ; sum(if1^2)/b ; [::Nc]
+// of `_SSDetex._MPXDS` (reference detex/detect.py:559-578) == `fas._MPXSSCorr`
+// (detex/fas.py:120-134).
+//
+// Math (per channel c, de-multiplexed; exact because only channel-aligned lags are kept):
+//   P[k,t]  = sum_c sum_j U_c[k,j] x_c[t+j]
+//   DS[s,t] = ((n-1)/n) sum_{k in s} (P[k,t] - mu[t] sumU[k])^2 / (S2[t] - S1[t]^2/n)
+//
+// GEMM mapping.  fp16 elements are 2 B, a UMMA core-matrix row is 16 B = 8 elements, so the
+// output lag is split t = t0 + 8q + p.  For phase p the basis is shifted instead of the data:
+//   P[k, t0+8q+p] = sum_j' u_k[j'-p] x[t0 + 8q + j']
+//   D[(k,p), q]   = sum_j' A[(k,p), j'] B[q, j'],  A[(k,p),j'] = u_k[j'-p],  B[q,j'] = x[t0+8q+j']
+// * A (M = 128 rows = 16 basis vectors x 8 phases) is a plain matrix: pre-built once per
+//   basis set in HBM in the exact no-swizzle K-major smem image (Aimg) and streamed through a
+//   4-stage ring with 32 KB bulk copies (UBLKCP); it is L2-resident across the 148 CTAs.
+// * B (N = 256 rows) is a HANKEL matrix and is never materialised: row q starts 8 elements
+//   = 16 B after row q-1, which is exactly the row pitch inside a core matrix.  A K-major
+//   no-swizzle descriptor with LBO = 16 B (next K core matrix) and SBO = 128 B (next 8 rows)
+//   makes the tensor core read overlapping core matrices straight out of the 1-D signal
+//   span held in smem (verified on hardware: profiles/r01_hankel_probe.log).
+// * fp32-equivalent precision from fp16 tensor cores: both operands are split hi+lo (22 bits)
+//   and three MMAs are issued per K step (hi*hi, hi*lo, lo*hi).
+// * The tensor core TRUNCATES when it accumulates into fp32 TMEM (measured bias ~ -1e-7 per
+//   MMA relative to the running sum), so K is accumulated in TMEM only over `kblk` 64-tap
+//   chunks; 8 drain warps pull each partial sum out of TMEM (double-buffered accumulators)
+//   and add it to register accumulators with round-to-nearest.
+//
+// One persistent CTA per SM; work item = (chunk, tile of 2048 lags); inner loop over the
+// basis blocks so all CTAs stream the same A block from L2 at about the same time.
+#include "dtx_kernels.cuh"
+#include "tc_common.cuh"
+
+namespace dtx {
+namespace {
+
+constexpr int NQ = 256;
+constexpr int STAGES = 4;
+constexpr int STAGE_BYTES = 32768;                      // A_hi tile | A_lo tile (16 KB each)
+constexpr int TILE_BYTES = 16384;
+constexpr int SIG_HALFS = TILE_T + MAX_SEG_TAPS;        // per hi or lo span
+constexpr int SIG_BUF_BYTES = 2 * SIG_HALFS * 2;        // hi + lo
+constexpr int NORM_BUF_BYTES = 2 * TILE_T * 4;          // mu + invE
+constexpr int NTHREADS = 384;                           // warps 0-3: producer, MMA, 2 idle; warps 4-11: drain
+constexpr int FIRST_DRAIN_WARP = 4;
+constexpr int REGS_CTRL = 56, REGS_DRAIN = 224;        // setmaxnreg budgets (128*56 + 256*224 = 64512)
+constexpr int NDRAIN_WARPS = 8;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * SIG_BUF_BYTES + 2 * NORM_BUF_BYTES;
+
+struct K1Params {
+    K1Args a;
+    int nblocks, nchunks, nseg;
+    float u_inv_scale;
+    Seg seg[MAX_SEGS];
+};
+
+// A tile image, no-swizzle K-major: 16 row groups x 8 k-cores x (8 rows x 16 B)
+//   byte(r, jj) = (r/8)*1024 + (jj/8)*128 + (r%8)*16 + (jj%8)*2
+constexpr uint32_t A_LBO = 128, A_SBO = 1024;
+// Hankel view of the 1-D signal
+constexpr uint32_t B_LBO = 16, B_SBO = 128;
+
+struct Ring {
+    int idx = 0;
+    uint32_t phase = 0;
+    int n;
+    __device__ explicit Ring(int n_) : n(n_) {}
+    __device__ void advance() {
+        if (++idx == n) {
+            idx = 0;
+            phase ^= 1;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) k1_kernel(const __grid_constant__ K1Params P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sStage = smem;
+    uint8_t* sSig = smem + STAGES * STAGE_BYTES;
+    uint8_t* sNorm = sSig + 2 * SIG_BUF_BYTES;
+    __shared__ uint64_t full[STAGES], empty[STAGES];
+    __shared__ uint64_t sigfull[2], sigempty[2], accfull[2], accempty[2], normfull[2], normempty[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&sigfull[s], 1);
+            mbar_init(&sigempty[s], 1);
+            mbar_init(&accfull[s], 1);
+            mbar_init(&accempty[s], NDRAIN_WARPS);
+            mbar_init(&normfull[s], 1);
+            mbar_init(&normempty[s], NDRAIN_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(&tmem_base_s, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int kblk = P.a.kblk;
+
+    if (warp < FIRST_DRAIN_WARP) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
+      if (warp == 0) {
+        // =============================================================== producer
+        if (lane == 0) {
+            Ring st(STAGES), sg(2), nm(2);
+            for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
+                const int2 it = P.a.items[item];
+                const ChunkDesc cd = P.a.chunks[it.x];
+                // window mean / inverse energy of this tile
+                mbar_wait(&normempty[nm.idx], nm.phase ^ 1);
+                mbar_arrive_expect_tx(&normfull[nm.idx], NORM_BUF_BYTES);
+                bulk_g2s(sNorm + nm.idx * NORM_BUF_BYTES,
+                         P.a.mu + cd.norm_off + static_cast<long long>(it.y) * TILE_T, TILE_T * 4,
+                         &normfull[nm.idx]);
+                bulk_g2s(sNorm + nm.idx * NORM_BUF_BYTES + TILE_T * 4,
+                         P.a.invE + cd.norm_off + static_cast<long long>(it.y) * TILE_T, TILE_T * 4,
+                         &normfull[nm.idx]);
+                nm.advance();
+                const __half* sig0 = P.a.xsplit + cd.sig_off + static_cast<long long>(it.y) * TILE_T;
+                for (int b = 0; b < P.nblocks; ++b) {
+                    const uint8_t* ablk =
+                        P.a.Aimg + static_cast<size_t>(b) * P.nchunks * STAGE_BYTES;
+                    for (int g = 0; g < P.nseg; ++g) {
+                        const Seg sgm = P.seg[g];
+                        const uint32_t bytes = (TILE_T + sgm.ntaps) * 2;
+                        mbar_wait(&sigempty[sg.idx], sg.phase ^ 1);
+                        mbar_arrive_expect_tx(&sigfull[sg.idx], 2 * bytes);
+                        const __half* src =
+                            sig0 + static_cast<long long>(sgm.chan * 2) * cd.Lpad + sgm.tap0;
+                        bulk_g2s(sSig + sg.idx * SIG_BUF_BYTES, src, bytes, &sigfull[sg.idx]);
+                        bulk_g2s(sSig + sg.idx * SIG_BUF_BYTES + SIG_HALFS * 2, src + cd.Lpad, bytes,
+                                 &sigfull[sg.idx]);
+                        sg.advance();
+                        const int nck = sgm.ntaps / CHUNK_TAPS;
+                        for (int kc = 0; kc < nck; ++kc) {
+                            mbar_wait(&empty[st.idx], st.phase ^ 1);
+                            mbar_arrive_expect_tx(&full[st.idx], STAGE_BYTES);
+                            bulk_g2s(sStage + st.idx * STAGE_BYTES,
+                                     ablk + static_cast<size_t>(sgm.chunk0 + kc) * STAGE_BYTES,
+                                     STAGE_BYTES, &full[st.idx]);
+                            st.advance();
+                        }
+                    }
+                }
+            }
+        }
+      } else if (warp == 1) {
+        // ============================================================= MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = idesc_f16_f32(128, NQ);
+            const uint64_t a_base = smem_desc_kmajor_noswz(0, A_LBO, A_SBO);
+            const uint64_t b_base = smem_desc_kmajor_noswz(0, B_LBO, B_SBO);
+            const uint32_t stage0 = smem_u32(sStage), sig0 = smem_u32(sSig);
+            Ring st(STAGES), sg(2), ac(2);
+            for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
+                for (int b = 0; b < P.nblocks; ++b) {
+                    int cib = 0, done = 0;
+                    for (int g = 0; g < P.nseg; ++g) {
+                        const int nck = P.seg[g].ntaps / CHUNK_TAPS;
+                        mbar_wait(&sigfull[sg.idx], sg.phase);
+                        tc_fence_after();
+                        const uint32_t sh = sig0 + sg.idx * SIG_BUF_BYTES;
+                        const uint32_t sl = sh + SIG_HALFS * 2;
+                        for (int kc = 0; kc < nck; ++kc) {
+                            mbar_wait(&full[st.idx], st.phase);
+                            if (cib == 0) mbar_wait(&accempty[ac.idx], ac.phase ^ 1);
+                            tc_fence_after();
+                            const uint32_t d = tmem + ac.idx * NQ;
+                            const uint32_t ah = stage0 + st.idx * STAGE_BYTES;
+                            const uint32_t al = ah + TILE_BYTES;
+                            const uint32_t bo = kc * (CHUNK_TAPS * 2);
+#pragma unroll
+                            for (int kk = 0; kk < CHUNK_TAPS / 16; ++kk) {
+                                const uint64_t dah = a_base | ((ah + kk * 256) >> 4);
+                                const uint64_t dal = a_base | ((al + kk * 256) >> 4);
+                                const uint64_t dbh = b_base | ((sh + bo + kk * 32) >> 4);
+                                const uint64_t dbl = b_base | ((sl + bo + kk * 32) >> 4);
+                                umma_f16(d, dah, dbh, idesc, (cib | kk) ? 1u : 0u);
+                                umma_f16(d, dah, dbl, idesc, 1u);
+                                umma_f16(d, dal, dbh, idesc, 1u);
+                            }
+                            umma_commit(&empty[st.idx]);
+                            st.advance();
+                            ++cib;
+                            ++done;
+                            if (cib == kblk || done == P.nchunks) {
+                                umma_commit(&accfull[ac.idx]);
+                                ac.advance();
+                                cib = 0;
+                            }
+                        }
+                        umma_commit(&sigempty[sg.idx]);
+                        sg.advance();
+                    }
+                }
+            }
+        }
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_DRAIN));
+        // ================================================== drain + epilogue warps
+        const int dw = warp - FIRST_DRAIN_WARP;  // 0..7
+        const int lq = warp & 3;            // TMEM lane quarter this warp may read
+        const int colhalf = dw >> 2;        // which 128 of the 256 accumulator columns
+        const int p = 2 * lq + (lane & 1);  // phase of this thread's row
+        const int kl = lane >> 1;           // basis-vector slot of this thread's row
+        const uint32_t taddr0 = tmem + (static_cast<uint32_t>(lq * 32) << 16) + colhalf * 128;
+        const int ndrains = (P.nchunks + kblk - 1) / kblk;
+        Ring ac(2), nm(2);
+        float sums[128];
+        for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
+            const int2 it = P.a.items[item];
+            const ChunkDesc cd = P.a.chunks[it.x];
+            const float sc = P.a.chunk_scale[it.x] * P.u_inv_scale;
+            const float* smu = reinterpret_cast<const float*>(sNorm + nm.idx * NORM_BUF_BYTES);
+            const float* sie = smu + TILE_T;
+            for (int b = 0; b < P.nblocks; ++b) {
+#pragma unroll
+                for (int i = 0; i < 128; ++i) sums[i] = 0.f;
+                for (int dr = 0; dr < ndrains; ++dr) {
+                    mbar_wait(&accfull[ac.idx], ac.phase);
+                    tc_fence_after();
+                    const uint32_t ta = taddr0 + ac.idx * NQ;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t v[32];
+                        tmem_ld_x32(ta + i * 32, v);
+                        tmem_wait_ld();
+                        if (i == 3) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&accempty[ac.idx]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sums[i * 32 + j] += __uint_as_float(v[j]);
+                    }
+                    ac.advance();
+                }
+                // ------------------------------------------------ K2 epilogue
+                if (b == 0) mbar_wait(&normfull[nm.idx], nm.phase);
+                const BlockInfo bi = P.a.binfo[b * VEC_PER_BLOCK + kl];
+                const bool head = bi.nrows > 0 && bi.out_row >= 0;
+                float* dsrow = P.a.DS + cd.ds_off +
+                               static_cast<long long>(head ? bi.out_row : 0) * cd.Tpad +
+                               static_cast<long long>(it.y) * TILE_T;
+                const int maxrank = bi.maxrank;
+#pragma unroll
+                for (int i = 0; i < 128; ++i) {
+                    const int tl = 8 * (128 * colhalf + i) + p;
+                    const float c = fmaf(sums[i], sc, -smu[tl] * bi.sumU);
+                    const float v = c * c;
+                    float tot = v;
+                    for (int d = 1; d < maxrank; ++d) {
+                        const float o = __shfl_down_sync(0xffffffffu, v, 2 * d);
+                        if (d < bi.nrows) tot += o;
+                    }
+                    if (head) dsrow[tl] = tot * sie[tl];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&normempty[nm.idx]);
+            nm.advance();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------- basis image
+// One thread per 16-byte unit (8 taps of one row of one hi/lo tile).
+__global__ void __launch_bounds__(256)
+basis_image_kernel(const double* __restrict__ U, const int* __restrict__ slot_row,
+                   const __grid_constant__ BasisLayout lay, uint8_t* __restrict__ Aimg) {
+    const long long units_per_tile = 128 * 8;
+    const long long total = static_cast<long long>(lay.nblocks) * lay.nchunks * 2 * units_per_tile;
+    const long long gid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (gid >= total) return;
+    long long r_ = gid;
+    const int unit = static_cast<int>(r_ % units_per_tile);
+    r_ /= units_per_tile;
+    const int hl = static_cast<int>(r_ % 2);
+    r_ /= 2;
+    const int chunk = static_cast<int>(r_ % lay.nchunks);
+    const int b = static_cast<int>(r_ / lay.nchunks);
+    // unit -> (row group, k-core, row in group) in image order
+    const int rin = unit % 8, kc = (unit / 8) % 8, rg = unit / 64;
+    const int r = rg * 8 + rin;
+    const int w = r / 32, kslot = (r % 32) / 2, e = r & 1, ph = 2 * w + e;
+    // find the segment of this chunk
+    int g = 0;
+    while (g + 1 < lay.nseg && lay.seg[g + 1].chunk0 <= chunk) ++g;
+    const Seg sg = lay.seg[g];
+    const int tap_base = sg.tap0 + (chunk - sg.chunk0) * CHUNK_TAPS + kc * 8;
+    const int row = slot_row[b * VEC_PER_BLOCK + kslot];
+    __align__(16) __half out[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        const int j = tap_base + jj - ph;
+        float v = 0.f;
+        if (row >= 0 && j >= 0 && j < lay.ns)
+            v = static_cast<float>(
+                ldexp(U[static_cast<long long>(row) * lay.n + static_cast<long long>(j) * lay.Nc + sg.chan],
+                      lay.u_exp));
+        const __half hi = __float2half_rn(v);
+        out[jj] = hl == 0 ? hi : __float2half_rn(v - __half2float(hi));
+    }
+    uint8_t* dst = Aimg + (static_cast<size_t>(b) * lay.nchunks + chunk) * STAGE_BYTES +
+                   static_cast<size_t>(hl) * TILE_BYTES + rg * 1024 + kc * 128 + rin * 16;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(out);
+}
+
+}  // namespace
+
+int k1_smem_bytes() { return SMEM_BYTES; }
+
+void launch_basis_image(const double* d_U, const int* d_slot_row, const BasisLayout& lay,
+                        uint8_t* d_Aimg, cudaStream_t st) {
+    const long long total = static_cast<long long>(lay.nblocks) * lay.nchunks * 2 * 128 * 8;
+    const int grid = static_cast<int>((total + 255) / 256);
+    basis_image_kernel<<<grid, 256, 0, st>>>(d_U, d_slot_row, lay, d_Aimg);
+}
+
+void launch_k1(const K1Args& a, const BasisLayout& lay, cudaStream_t st) {
+    cudaFuncSetAttribute(k1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    K1Params P;
+    P.a = a;
+    P.nblocks = lay.nblocks;
+    P.nchunks = lay.nchunks;
+    P.nseg = lay.nseg;
+    P.u_inv_scale = lay.u_inv_scale;
+    for (int i = 0; i < lay.nseg; ++i) P.seg[i] = lay.seg[i];
+    int grid = a.nitems < a.num_sms ? a.nitems : a.num_sms;
+    if (grid < 1) return;
+    k1_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+}
+
+}  // namespace dtx

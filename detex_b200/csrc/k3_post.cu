@@ -1,0 +1,200 @@
+// k3_post.cu -- K3 / K5: per (chunk, subspace) row of the detection statistic ->
+//   MaxDS with the reference's inf-zeroing rule   (detex/detect.py:275-281)
+//   400-bin histogram                             (detect.py:178-181; fas.py:79)
+//   compacted candidates DS >= threshold          (first stage of _CreateCoeffArray, :410)
+//   FAS sufficient statistics N, sum x, sum x^2, sum log x, sum log1p(-x)  (fas.py:81-84,
+//     the quantities scipy.stats.beta.fit(floc=0, fscale=1) and beta.nnlf reduce to)
+// plus the centred LTA mean of |DS| at each candidate (detect.py:501-524).
+//
+// HBM-bound: each row is streamed twice (second pass hits L2 for rows up to ~1.5 MB).
+// One CTA per row, 128-bit loads, shared-memory privatised histogram.
+#include "dtx_kernels.cuh"
+
+namespace dtx {
+namespace {
+
+__device__ __forceinline__ float warp_max(float v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// np.histogram(x, bins=np.linspace(lo, hi, 401)): bin i holds edges[i] <= x < edges[i+1],
+// last bin closed; edges[i] = lo + i*step (float64), edges[400] = hi exactly.
+__device__ __forceinline__ int hist_bin(float xf, double lo, double hi, double step) {
+    const double x = static_cast<double>(xf);
+    if (!(x >= lo) || !(x <= hi)) return -1;
+    int i = static_cast<int>((x - lo) / step);
+    if (i > HIST_BINS - 1) i = HIST_BINS - 1;
+    while (i > 0 && x < lo + i * step) --i;
+    while (i < HIST_BINS - 1 && x >= lo + (i + 1) * step) ++i;
+    return i;
+}
+
+constexpr int K3_THREADS = 256;
+
+__global__ void __launch_bounds__(K3_THREADS)
+k3_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, int S,
+          const float* __restrict__ thr, float* __restrict__ rowmax, int* __restrict__ rowflags,
+          unsigned long long* __restrict__ hist, double hlo, double hhi,
+          Candidate* __restrict__ cand, int cand_cap, int* __restrict__ ncand,
+          double* __restrict__ fas) {
+    const ChunkDesc cd = chunks[blockIdx.y];
+    const int s = blockIdx.x;
+    const int row = blockIdx.y * S + s;
+    const float* x = DS + cd.ds_off + static_cast<long long>(s) * cd.Tpad;
+    const int T = cd.T;
+    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    __shared__ int sh_hist[HIST_BINS];
+    __shared__ float sh_f[8][2];
+    __shared__ int sh_i[8][2];
+    __shared__ double sh_d[8][4];
+    __shared__ float b_maxfin;
+    __shared__ int b_nan, b_inf, b_posinf;
+
+    // ---- pass 1: max / nan / inf
+    float mfin = -INFINITY;
+    int nnan = 0, ninf = 0, npinf = 0;
+    const int T4 = T & ~3;
+    for (int i = tid * 4; i < T4; i += K3_THREADS * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(x + i);
+        const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (isnan(a[k])) nnan = 1;
+            else if (isinf(a[k])) { ninf = 1; if (a[k] > 0) npinf = 1; }
+            else mfin = fmaxf(mfin, a[k]);
+        }
+    }
+    for (int i = T4 + tid; i < T; i += K3_THREADS) {
+        const float a = x[i];
+        if (isnan(a)) nnan = 1;
+        else if (isinf(a)) { ninf = 1; if (a > 0) npinf = 1; }
+        else mfin = fmaxf(mfin, a);
+    }
+    mfin = warp_max(mfin);
+    nnan = __any_sync(0xffffffffu, nnan);
+    ninf = __any_sync(0xffffffffu, ninf);
+    npinf = __any_sync(0xffffffffu, npinf);
+    if (l == 0) { sh_f[w][0] = mfin; sh_i[w][0] = nnan | (ninf << 1) | (npinf << 2); }
+    for (int i = tid; i < HIST_BINS; i += K3_THREADS) sh_hist[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        float m = -INFINITY; int f = 0;
+        for (int i = 0; i < 8; ++i) { m = fmaxf(m, sh_f[i][0]); f |= sh_i[i][0]; }
+        b_maxfin = m; b_nan = f & 1; b_inf = (f >> 1) & 1; b_posinf = (f >> 2) & 1;
+    }
+    __syncthreads();
+    const bool has_nan = b_nan != 0;
+    // reference: MaxDS = ssd.max(); if MaxDS > 1.1: ssd[isinf(ssd)] = 0; MaxDS = ssd.max()
+    const float max_all = b_posinf ? INFINITY : b_maxfin;
+    const bool zero_inf = !has_nan && (max_all > 1.1f) && b_inf;
+    float eff_max = max_all;
+    if (zero_inf) eff_max = fmaxf(b_maxfin, 0.f);
+    if (has_nan) eff_max = nanf("");
+    if (tid == 0) {
+        rowmax[row] = eff_max;
+        rowflags[row] = (has_nan ? 1 : 0) | (zero_inf ? 2 : 0);
+    }
+    if (has_nan) return;  // np.histogram raises -> chunk's histogram skipped; NaN max never triggers
+
+    // ---- pass 2: histogram, candidates, FAS sums
+    const double step = (hhi - hlo) / HIST_BINS;
+    const float th = thr ? thr[s] : INFINITY;
+    const bool trig = eff_max > th;  // _evalTrigCon: strict >
+    double f1 = 0, f2 = 0, f3 = 0, f4 = 0;
+    for (int i = tid; i < T; i += K3_THREADS) {
+        float a = x[i];
+        if (zero_inf && isinf(a)) a = 0.f;
+        const int b = hist_bin(a, hlo, hhi, step);
+        if (b >= 0) atomicAdd(&sh_hist[b], 1);
+        if (trig && a >= th) {
+            const int k = atomicAdd(ncand, 1);
+            if (k < cand_cap) {
+                Candidate c; c.row = row; c.t = i; c.ds = a; c.lta = 0.f;
+                cand[k] = c;
+            }
+        }
+        if (fas) {
+            const double d = static_cast<double>(a);
+            f1 += d; f2 += d * d;
+            f3 += static_cast<double>(logf(a));
+            f4 += static_cast<double>(log1pf(-a));
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < HIST_BINS; i += K3_THREADS) {
+        const int c = sh_hist[i];
+        if (c) atomicAdd(&hist[static_cast<long long>(s) * HIST_BINS + i], static_cast<unsigned long long>(c));
+    }
+    if (fas) {
+        f1 = warp_sum(f1); f2 = warp_sum(f2); f3 = warp_sum(f3); f4 = warp_sum(f4);
+        if (l == 0) { sh_d[w][0] = f1; sh_d[w][1] = f2; sh_d[w][2] = f3; sh_d[w][3] = f4; }
+        __syncthreads();
+        if (tid < 4) {
+            double t = 0;
+            for (int i = 0; i < 8; ++i) t += sh_d[i][tid];
+            atomicAdd(&fas[s * 5 + 1 + tid], t);
+        }
+        if (tid == 4) atomicAdd(&fas[s * 5], static_cast<double>(T));
+    }
+}
+
+// One warp per candidate: centred rolling mean of |DS| with pandas' window placement and
+// _replaceNanWithMean's edge rule (detect.py:517-524).
+__global__ void __launch_bounds__(256)
+lta_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, int S,
+           const int* __restrict__ rowflags, Candidate* __restrict__ cand,
+           const int* __restrict__ ncand, int cand_cap, int W) {
+    const int n = min(*ncand, cand_cap);
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+    if (wid >= n) return;
+    Candidate c = cand[wid];
+    const ChunkDesc cd = chunks[c.row / S];
+    const float* x = DS + cd.ds_off + static_cast<long long>(c.row % S) * cd.Tpad;
+    const bool zero_inf = (rowflags[c.row] & 2) != 0;
+    const int T = cd.T;
+    float out = nanf("");
+    if (T >= W) {
+        const int off = (W - 1) / 2;
+        const int first = W - 1 - off, last = T - 1 - off;  // valid centres
+        int i = c.t;
+        if (i < first) i = (first + 1 <= last) ? first + 1 : first;
+        if (i > last) i = last;
+        const int a0 = i - (W - 1) + off;
+        double acc = 0;
+        for (int j = l; j < W; j += 32) {
+            float v = x[a0 + j];
+            if (zero_inf && isinf(v)) v = 0.f;
+            acc += fabs(static_cast<double>(v));
+        }
+        acc = warp_sum(acc);
+        out = static_cast<float>(acc / W);
+    }
+    if (l == 0) cand[wid].lta = out;
+}
+
+}  // namespace
+
+void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, const float* d_thr,
+               float* d_rowmax, int* d_rowflags, unsigned long long* d_hist, double hist_lo,
+               double hist_hi, Candidate* d_cand, int cand_cap, int* d_ncand, double* d_fas,
+               cudaStream_t st) {
+    const dim3 grid(S, nchunks);
+    k3_kernel<<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist,
+                                           hist_lo, hist_hi,
+                                           d_cand, cand_cap, d_ncand, d_fas);
+}
+
+void launch_lta(const float* DS, const ChunkDesc* d_chunks, int S, const int* d_rowflags,
+                Candidate* d_cand, const int* d_ncand, int cand_cap, int W, cudaStream_t st) {
+    // grid sized for the capacity; warps beyond *ncand exit immediately
+    const int warps = cand_cap;
+    const int grid = (warps * 32 + 255) / 256;
+    lta_kernel<<<grid, 256, 0, st>>>(DS, d_chunks, S, d_rowflags, d_cand, d_ncand, cand_cap, W);
+}
+
+}  // namespace dtx

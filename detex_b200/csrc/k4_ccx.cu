@@ -1,0 +1,262 @@
+// k4_ccx.cu -- K4: pairwise maximum normalised cross-correlation of multiplexed event
+// waveforms; replaces construct._makeDFcclags / _CCX2 / _subSamp
+// (reference detex/construct.py:369-466).
+//
+// Closed form (checked against the reference to 1e-16): with ns = n/Nc,
+// trunc = n//(2Nc) - 1, for m = 0 .. nl-1 (nl = 2ns-1-2trunc) and per-channel shift
+// kappa = m + trunc + 1 - ns,
+//   res[m] = ( sum_c sum_j x1_c[j] x2_c[j+kappa]  -  sum(x1) a_c[m] ) / ( n b_c[m] std(x1) )
+// where x2 is zero outside [0, ns) and a, b are mean and population std of the zero-padded
+// length-n window of x2.  Then nanmax / nanargmax, the |res|>1 zeroing rule, the cosine-fit
+// sub-sample shift, lag = (argmax + 1 + trunc) Nc - n.
+//
+// This first engine evaluates the correlations in float64 on the FP64 pipe (register
+// window over 4 lags per thread, de-interleaved smem so the sliding read is conflict
+// free).  The per-event window statistics are computed once per event by ccx_stats.
+#include "dtx_kernels.cuh"
+
+namespace dtx {
+namespace {
+
+constexpr int CT = 256;          // threads
+constexpr int LT = 4 * CT;       // lags per tile (4 per thread)
+constexpr int JT = 256;          // taps per tile
+constexpr int X2ROW = (JT + LT) / 4 + 2;
+
+template <typename T>
+__global__ void __launch_bounds__(CT)
+ccx_stats(const T* __restrict__ X, int N, int n, int Nc, int trunc, int nl,
+          double* __restrict__ wa, double* __restrict__ wb, double* __restrict__ evsum,
+          double* __restrict__ evstd) {
+    extern __shared__ double sm[];  // P1[Nc][ns+1], P2[Nc][ns+1]
+    const int ev = blockIdx.x;
+    const int ns = n / Nc;
+    const T* x = X + static_cast<long long>(ev) * n;
+    double* P1 = sm;
+    double* P2 = sm + static_cast<size_t>(Nc) * (ns + 1);
+    if (threadIdx.x < Nc) {
+        const int c = threadIdx.x;
+        double s1 = 0, s2 = 0;
+        P1[c * (ns + 1)] = 0;
+        P2[c * (ns + 1)] = 0;
+        for (int i = 0; i < ns; ++i) {
+            const double v = static_cast<double>(x[static_cast<long long>(i) * Nc + c]);
+            s1 += v;
+            s2 += v * v;
+            P1[c * (ns + 1) + i + 1] = s1;
+            P2[c * (ns + 1) + i + 1] = s2;
+        }
+    }
+    __syncthreads();
+    const double nn = static_cast<double>(n);
+    if (threadIdx.x == 0) {
+        double s1 = 0, s2 = 0;
+        for (int c = 0; c < Nc; ++c) {
+            s1 += P1[c * (ns + 1) + ns];
+            s2 += P2[c * (ns + 1) + ns];
+        }
+        const double mean = s1 / nn;
+        double var = 0;  // np.std: two-pass population variance
+        for (int i = 0; i < n; ++i) {
+            const double d = static_cast<double>(x[i]) - mean;
+            var += d * d;
+        }
+        evsum[ev] = s1;
+        evstd[ev] = sqrt(var / nn);
+        (void)s2;
+    }
+    for (int m = threadIdx.x; m < nl; m += CT) {
+        const int kappa = m + trunc + 1 - ns;
+        const int lo = max(0, kappa), hi = min(ns, ns + kappa);
+        double s1 = 0, s2 = 0;
+        if (hi > lo)
+            for (int c = 0; c < Nc; ++c) {
+                s1 += P1[c * (ns + 1) + hi] - P1[c * (ns + 1) + lo];
+                s2 += P2[c * (ns + 1) + hi] - P2[c * (ns + 1) + lo];
+            }
+        const double a = s1 / nn;
+        double var = s2 / nn - a * a;
+        if (var < 0) var = 0;
+        wa[static_cast<long long>(ev) * nl + m] = a;
+        wb[static_cast<long long>(ev) * nl + m] = sqrt(var);
+    }
+}
+
+struct MaxLoc {
+    double mx, mn;
+    int imx;
+    int cnt;
+};
+
+__device__ __forceinline__ void ml_merge(MaxLoc& a, const MaxLoc& b) {
+    if (b.cnt) {
+        if (!a.cnt || b.mx > a.mx || (b.mx == a.mx && b.imx < a.imx)) {
+            a.mx = b.mx;
+            a.imx = b.imx;
+        }
+        if (!a.cnt || b.mn < a.mn) a.mn = b.mn;
+        a.cnt += b.cnt;
+    }
+}
+
+__device__ MaxLoc block_maxloc(const double* res, int nl, MaxLoc* sh) {
+    MaxLoc m{0, 0, 0, 0};
+    for (int i = threadIdx.x; i < nl; i += CT) {
+        const double v = res[i];
+        if (!isnan(v)) {
+            MaxLoc o{v, v, i, 1};
+            ml_merge(m, o);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        MaxLoc t;
+        t.mx = __shfl_xor_sync(0xffffffffu, m.mx, o);
+        t.mn = __shfl_xor_sync(0xffffffffu, m.mn, o);
+        t.imx = __shfl_xor_sync(0xffffffffu, m.imx, o);
+        t.cnt = __shfl_xor_sync(0xffffffffu, m.cnt, o);
+        ml_merge(m, t);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    MaxLoc r = sh[0];
+    for (int i = 1; i < CT / 32; ++i) ml_merge(r, sh[i]);
+    __syncthreads();
+    return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CT)
+ccx_kernel(const T* __restrict__ X, int N, int n, int Nc, int trunc, int nl, int row_begin,
+           const double* __restrict__ wa, const double* __restrict__ wb,
+           const double* __restrict__ evsum, const double* __restrict__ evstd,
+           double* __restrict__ cc, int* __restrict__ lag, double* __restrict__ sub) {
+    extern __shared__ double res[];  // [nl]
+    __shared__ double x1t[JT];
+    __shared__ double x2t[4][X2ROW];
+    __shared__ MaxLoc shml[CT / 32];
+    const int b = row_begin + blockIdx.y;
+    const int ns = n / Nc;
+    const int tid = threadIdx.x;
+    const T* x1 = X + static_cast<long long>(b) * n;
+    const double nn = static_cast<double>(n);
+    const double sum1 = evsum[b], std1 = evstd[b];
+    for (int c = b + 1 + blockIdx.x; c < N; c += gridDim.x) {
+        const T* x2 = X + static_cast<long long>(c) * n;
+        for (int m0 = 0; m0 < nl; m0 += LT) {
+            double acc[4] = {0, 0, 0, 0};
+            const int kappa0 = m0 + trunc + 1 - ns;  // shift of lag m0
+            for (int ch = 0; ch < Nc; ++ch)
+                for (int j0 = 0; j0 < ns; j0 += JT) {
+                    __syncthreads();
+                    for (int i = tid; i < JT; i += CT) {
+                        const int j = j0 + i;
+                        x1t[i] = j < ns ? static_cast<double>(x1[static_cast<long long>(j) * Nc + ch]) : 0.0;
+                    }
+                    for (int i = tid; i < JT + LT; i += CT) {
+                        const int j = j0 + kappa0 + i;
+                        const double v =
+                            (j >= 0 && j < ns) ? static_cast<double>(x2[static_cast<long long>(j) * Nc + ch]) : 0.0;
+                        x2t[i & 3][i >> 2] = v;
+                    }
+                    __syncthreads();
+                    // thread owns lags m0 + 4*tid + {0,1,2,3}: window w[q] = x2t[jj + 4*tid + q]
+                    double w0 = x2t[0][tid], w1 = x2t[1][tid], w2 = x2t[2][tid];
+#pragma unroll 4
+                    for (int jj = 0; jj < JT; ++jj) {
+                        const int e = jj + 3;
+                        const double w3 = x2t[e & 3][(e >> 2) + tid];
+                        const double a = x1t[jj];
+                        acc[0] = fma(a, w0, acc[0]);
+                        acc[1] = fma(a, w1, acc[1]);
+                        acc[2] = fma(a, w2, acc[2]);
+                        acc[3] = fma(a, w3, acc[3]);
+                        w0 = w1; w1 = w2; w2 = w3;
+                    }
+                }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int m = m0 + 4 * tid + q;
+                if (m < nl) {
+                    const double a = wa[static_cast<long long>(c) * nl + m];
+                    const double sb = wb[static_cast<long long>(c) * nl + m];
+                    res[m] = (acc[q] - sum1 * a) / (nn * sb * std1);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- _CCX2 tail (construct.py:453-466)
+        MaxLoc ml = block_maxloc(res, nl, shml);
+        double maxcc = 0.0, ss = 0.0;
+        int lg = 0;
+        if (ml.cnt > 0) {
+            if (ml.mx > 1.0 || ml.mn < -1.0) {
+                for (int i = tid; i < nl; i += CT) {
+                    const double v = res[i];
+                    if (v > 1.0 || v < -1.0) res[i] = 0.0;
+                }
+                __syncthreads();
+                ml = block_maxloc(res, nl, shml);
+            }
+            maxcc = ml.mx;
+            const int ind = ml.imx;
+            lg = (ind + 1 + trunc) * Nc - n;
+            if (ind == 0 || ind == nl - 1) {
+                ss = 0.0;
+            } else {
+                const double cb4 = res[ind - 1], caf = res[ind + 1], cn = res[ind];
+                const double alpha = acos((cb4 + caf) / (2 * cn));
+                const double alsi = sin(alpha);
+                const double tau = -(atan((cb4 - caf) / (2 * cn * alsi)) / alpha);
+                ss = (fabs(tau) > 0.5) ? static_cast<double>(ind) : tau;  // reference quirk, :418-421
+            }
+        }
+        if (tid == 0) {
+            const long long o = static_cast<long long>(blockIdx.y) * N + c;
+            cc[o] = maxcc;
+            lag[o] = lg;
+            sub[o] = ss;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int row_begin, int row_end,
+                     double* d_cc, int* d_lag, double* d_sub, int num_sms, cudaStream_t st) {
+    const int ns = n / Nc;
+    const int trunc = n / (2 * Nc) - 1;
+    const int nl = 2 * ns - 1 - 2 * trunc;
+    double *wa = nullptr, *wb = nullptr, *es = nullptr, *ed = nullptr;
+    cudaMallocAsync(reinterpret_cast<void**>(&wa), sizeof(double) * N * nl, st);
+    cudaMallocAsync(reinterpret_cast<void**>(&wb), sizeof(double) * N * nl, st);
+    cudaMallocAsync(reinterpret_cast<void**>(&es), sizeof(double) * N, st);
+    cudaMallocAsync(reinterpret_cast<void**>(&ed), sizeof(double) * N, st);
+    const size_t sm_stats = sizeof(double) * 2 * Nc * (ns + 1);
+    const size_t sm_res = sizeof(double) * nl;
+    const int rows = row_end - row_begin;
+    int gx = (2 * num_sms + rows - 1) / rows;
+    if (gx < 1) gx = 1;
+    if (gx > N) gx = N;
+    const dim3 grid(gx, rows);
+    if (dtype_f32) {
+        cudaFuncSetAttribute(ccx_stats<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_stats));
+        cudaFuncSetAttribute(ccx_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_res));
+        ccx_stats<float><<<N, CT, sm_stats, st>>>(static_cast<const float*>(d_X), N, n, Nc, trunc, nl, wa, wb, es, ed);
+        ccx_kernel<float><<<grid, CT, sm_res, st>>>(static_cast<const float*>(d_X), N, n, Nc, trunc, nl, row_begin,
+                                                    wa, wb, es, ed, d_cc, d_lag, d_sub);
+    } else {
+        cudaFuncSetAttribute(ccx_stats<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_stats));
+        cudaFuncSetAttribute(ccx_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_res));
+        ccx_stats<double><<<N, CT, sm_stats, st>>>(static_cast<const double*>(d_X), N, n, Nc, trunc, nl, wa, wb, es, ed);
+        ccx_kernel<double><<<grid, CT, sm_res, st>>>(static_cast<const double*>(d_X), N, n, Nc, trunc, nl, row_begin,
+                                                     wa, wb, es, ed, d_cc, d_lag, d_sub);
+    }
+    cudaFreeAsync(wa, st);
+    cudaFreeAsync(wb, st);
+    cudaFreeAsync(es, st);
+    cudaFreeAsync(ed, st);
+}
+
+}  // namespace dtx

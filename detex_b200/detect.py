@@ -1,0 +1,253 @@
+"""detect.py -- host-side mirror of the reference's detection hot path
+(`detex/detect.py`, class `_SSDetex`) on top of the CUDA engine.
+
+Same names, argument meaning, return objects and error behaviour as the reference's
+private callables, so a Detex maintainer can swap them in:
+
+  _MPXDS(MPcon, reqlen, ssTD, ssFD, Nc, MPconFD)     detect.py:559-578
+  getRA(...)                                          detect.py:220-296 (array part)
+  _CreateCoeffArray(...)                              detect.py:390-445
+  _downPlayArrayAroundMax / _evalTrigCon              detect.py:545-557 / 526-543
+  corDat(...)                                         detect.py:137-218 (chunk loop)
+
+All arithmetic on the path (projection, window energy, normalisation, max, histogram,
+threshold compaction, LTA) runs in the CUDA library.  The greedy pick over the compacted
+candidates is the reference's sequential loop, executed on the sparse list.
+There is no CPU fallback: without the extension / an sm_100 GPU these raise.
+"""
+import logging
+
+import numpy as np
+import pandas as pd
+
+from .engine import DtxError, Engine, ShortChunk
+
+log = logging.getLogger("detex_b200")
+
+CORDF_COLS = ['SSdetect', 'STALTA', 'TimeStamp', 'SampRate', 'MaxDS', 'MaxSTALTA', 'Nc', 'File']
+SAR_COLS = ['DS', 'DS_STALTA', 'STMP', 'Name', 'Sta', 'MSTAMPmin', 'MSTAMPmax', 'Mag', 'SNR',
+            'ProEnMag']
+HIST_BINS = np.linspace(0, 1, num=401)  # detect.py:80
+
+_default_engine = None
+
+
+def default_engine():
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(0)
+    return _default_engine
+
+
+def _MPXDS(MPcon, reqlen, ssTD, ssFD, Nc, MPconFD=None, engine=None, kernel="tcgen05"):
+    """Drop-in for `_SSDetex._MPXDS` (detect.py:559-578): detection statistic of ONE
+    subspace on ONE multiplexed chunk.  `reqlen`, `ssFD`, `MPconFD` (the FFT operands) are
+    accepted for signature compatibility and ignored.  Returns float64 ndarray of length
+    (len(MPcon) - n)//Nc + 1."""
+    eng = engine or default_engine()
+    U = np.atleast_2d(np.asarray(ssTD, dtype=np.float64))
+    eng.set_bases(-1, [U], int(Nc))
+    eng.load_chunks([np.asarray(MPcon)])
+    eng.detect_run(-1, engine=kernel)
+    return eng.get_ds(0, 0).astype(np.float64)
+
+
+def _downPlayArrayAroundMax(index, length, sr, buff=20):
+    """Index range zeroed around a pick (detect.py:545-557), as (lo, hi) half-open."""
+    if index < buff * sr + 1:
+        return 0, int(index + buff * sr)
+    elif index > length - buff * sr:
+        return int(index - sr * buff), length
+    else:
+        return int(index - sr * buff), int(sr * buff + index)
+
+
+def greedy_pick(t, ds, length, sr, buff=20):
+    """The `while Ceval.max() >= threshold` loop (detect.py:410-421) on the compacted
+    candidate list (t ascending lag indices, ds their values, all >= threshold).
+    Returns the positions (into t) of the picks in pick order."""
+    t = np.asarray(t)
+    ds = np.asarray(ds)
+    alive = np.ones(len(t), dtype=bool)
+    order = np.lexsort((t, -ds))  # value descending, first occurrence on ties (argmax rule)
+    picks = []
+    for k in order:
+        if not alive[k]:
+            continue
+        picks.append(k)
+        lo, hi = _downPlayArrayAroundMax(int(t[k]), length, sr, buff)
+        i0, i1 = np.searchsorted(t, lo, side="left"), np.searchsorted(t, hi, side="left")
+        alive[i0:i1] = False
+    return picks
+
+
+def _evalTrigCon(maxDS, threshold):
+    """detect.py:526-543, trigCon == 0."""
+    return bool(maxDS > threshold)
+
+
+class SSDetex(object):
+    """Batched detector for the subspaces (or singles) of one station.
+
+    Mirrors the state `_SSDetex._corDat` builds with `_loadMPSubSpace` (detect.py:149-150):
+    ssTD {name: U}, thresholds {name: float}, offsets {name: [..]}.
+    """
+
+    def __init__(self, ssTD, threshold, offsets, Nc, sta="", engine=None, set_id=0,
+                 triggerLTATime=5, triggerSTATime=0, fillZeros=False, calcHist=True,
+                 kernel="tcgen05", kblk=0):
+        self.names = sorted(ssTD.keys())
+        if not self.names:
+            raise ValueError("no subspaces")
+        self.ssTD = {k: np.atleast_2d(np.asarray(ssTD[k], dtype=np.float64)) for k in self.names}
+        self.threshold = dict(threshold)
+        self.offsets = dict(offsets)
+        self.Nc = int(Nc)
+        self.sta = sta
+        self.engine = engine or default_engine()
+        self.kernel = kernel
+        self.kblk = kblk
+        self.triggerLTATime = triggerLTATime
+        self.triggerSTATime = triggerSTATime
+        if triggerSTATime != 0:
+            # reference default is 0 (detex/subspace.py:1745-1761); the STA smoothing path is
+            # not on the GPU yet
+            raise NotImplementedError("triggerSTATime != 0 is not supported")
+        self.fillZeros = fillZeros
+        self.calcHist = calcHist
+        # group by basis length n: one basis set per distinct n (SampleTrims differ per subspace)
+        self.groups = {}
+        for name in self.names:
+            self.groups.setdefault(self.ssTD[name].shape[1], []).append(name)
+        self.set_ids = {}
+        for gi, (n, names) in enumerate(sorted(self.groups.items())):
+            sid = set_id * 1000 + gi
+            self.engine.set_bases(sid, [self.ssTD[k] for k in names], self.Nc,
+                                  thresholds=[self.threshold[k] for k in names])
+            self.set_ids[n] = sid
+        self.histdic = {na: np.zeros(len(HIST_BINS) - 1, dtype=np.int64) for na in self.names}
+
+    # ------------------------------------------------------------------ core
+    def run_chunks(self, chunks, sr, starts, keep_ds=False):
+        """Detection on a batch of multiplexed chunks.
+
+        Returns (ss_df rows as DataFrame with the reference's columns, per-chunk dicts
+        {name: MaxDS}, and optionally the dense DS arrays {(chunk, name): ndarray}).
+        Chunks the reference would skip (detect.py:262-274) are dropped with a warning."""
+        good = []
+        for i, c in enumerate(chunks):
+            L = len(c) // self.Nc * self.Nc
+            nmax = max(self.groups.keys())
+            if L <= nmax or (L - nmax) // self.Nc + 1 < 10:
+                log.warning("current data block on %s starting %s is shorter than template, skipping",
+                            self.sta, starts[i])
+                continue
+            good.append(i)
+        rows = []
+        maxds = [dict() for _ in chunks]
+        dense = {}
+        if not good:
+            return pd.DataFrame(columns=SAR_COLS), maxds, dense
+        eng = self.engine
+        eng.load_chunks([chunks[i] for i in good])
+        W = int(self.triggerLTATime * sr)
+        for n, names in sorted(self.groups.items()):
+            sid = self.set_ids[n]
+            eng.detect_run(sid, engine=self.kernel, kblk=self.kblk, hist_range=(0.0, 1.0),
+                           lta_window=0 if self.fillZeros else W)
+            mx, fl = eng.rowstats()
+            cand = eng.candidates()
+            S = len(names)
+            for gi, ci in enumerate(good):
+                T = eng.num_lags(gi)
+                for si, name in enumerate(names):
+                    maxds[ci][name] = float(mx[gi, si])
+                    if keep_ds:
+                        dense[(ci, name)] = eng.get_ds(gi, si).astype(np.float64)
+                    if not _evalTrigCon(mx[gi, si], self.threshold[name]):
+                        continue
+                    sel = cand[cand["row"] == gi * S + si]
+                    sel = sel[np.argsort(sel["t"], kind="stable")]
+                    picks = greedy_pick(sel["t"], sel["ds"], T, sr)
+                    if len(picks) > 4000:  # kill switch, detect.py:433-436
+                        raise Exception('over 4000 events found in single data block on %s for %s'
+                                        % (self.sta, name))
+                    minof, maxof = np.min(self.offsets[name]), np.max(self.offsets[name])
+                    for k in picks:
+                        coef = float(sel["ds"][k])
+                        times = float(sel["t"][k]) / sr + starts[ci]      # detect.py:413
+                        if self.fillZeros:
+                            sl = 0.0
+                        else:
+                            sl = abs(coef) / float(sel["lta"][k])         # STA == |DS|, detect.py:505-507
+                        rows.append([coef, sl, times, name, self.sta, times - maxof, times - minof,
+                                     np.nan, np.nan, np.nan])
+            if self.calcHist:
+                h = eng.hist(sid, reset=True)
+                for si, name in enumerate(names):
+                    self.histdic[name] = self.histdic[name] + h[si]
+        Sar = pd.DataFrame(rows, columns=SAR_COLS)
+        if len(Sar) and (Sar.DS > 1.05).any():  # detect.py:199-204
+            log.warning("DS values above 1 found in sar on %s, removing values above 1", self.sta)
+            Sar = Sar[Sar.DS <= 1.05].reset_index(drop=True)
+        return Sar, maxds, dense
+
+    def getRA(self, chunk, sr, start, File=None):
+        """CorDF of one chunk (array part of `_getRA`, detect.py:225-296): index = sorted
+        names, columns as the reference.  Returns None if the chunk must be skipped."""
+        from . import stalta
+        _, maxds, dense = self.run_chunks([chunk], sr, [start], keep_ds=True)
+        if not maxds[0]:
+            return None
+        CorDF = pd.DataFrame(index=self.names, columns=CORDF_COLS, dtype=object)
+        for name in self.names:
+            ds = dense[(0, name)]
+            CorDF.at[name, 'SSdetect'] = ds
+            CorDF.at[name, 'MaxDS'] = maxds[0][name]
+            CorDF.at[name, 'Nc'] = self.Nc
+            CorDF.at[name, 'SampRate'] = sr
+            CorDF.at[name, 'TimeStamp'] = start
+            CorDF.at[name, 'File'] = File
+            if not self.fillZeros:
+                sl = stalta.sta_lta_of_ds(ds, self.triggerLTATime * sr, self.triggerSTATime * sr)
+                CorDF.at[name, 'STALTA'] = sl
+                CorDF.at[name, 'MaxSTALTA'] = np.max(sl)
+        return CorDF
+
+    def corDat(self, chunks, sr, starts, batch=16):
+        """Chunk loop of `_corDat` (detect.py:157-212): returns (ss_df, histdic)."""
+        frames = []
+        for i in range(0, len(chunks), batch):
+            Sar, _, _ = self.run_chunks(chunks[i:i + batch], sr, starts[i:i + batch])
+            if len(Sar) > 300 * max(1, len(chunks[i:i + batch])):
+                log.warning("over 300 events found in single data block on %s", self.sta)
+            if len(Sar):
+                frames.append(Sar)
+        DF = pd.concat(frames, ignore_index=True) if frames else pd.DataFrame(columns=SAR_COLS)
+        return DF, self.histdic
+
+
+def _CreateCoeffArray(corSeries, name, threshold, sta, offsets, sr=None, start=None, buff=20):
+    """Mirror of `_SSDetex._CreateCoeffArray` (detect.py:390-445) for a CorDF row holding a
+    dense detection statistic (trigCon=0, estimateMags=False): greedy picks as a DataFrame
+    with the reference's columns.  Pure bookkeeping over an array the GPU produced."""
+    DS = np.asarray(corSeries.SSdetect)
+    sr = corSeries.SampRate if sr is None else sr
+    start = corSeries.TimeStamp if start is None else start
+    thr = threshold[name]
+    idx = np.nonzero(DS >= thr)[0]
+    picks = greedy_pick(idx, DS[idx], len(DS), sr, buff)
+    minof, maxof = np.min(offsets[name]), np.max(offsets[name])
+    rows = []
+    for k in picks:
+        i = int(idx[k])
+        times = float(i) / sr + start
+        try:
+            sl = float(corSeries.STALTA[i])
+        except TypeError:
+            sl = 0.0
+        rows.append([float(DS[i]), sl, times, name, sta, times - maxof, times - minof, np.nan, np.nan,
+                     np.nan])
+    if len(rows) > 4001:
+        raise Exception('over 4000 events found in single data block on %s for %s' % (sta, name))
+    return pd.DataFrame(rows, columns=SAR_COLS)

@@ -1,0 +1,170 @@
+"""engine.py -- thin object wrapper over the C ABI (one context = one GPU = one stream).
+
+Everything numerical happens in the CUDA library; this class only marshals NumPy arrays
+to pointers and maps status codes to exceptions the way the reference maps problems to
+`detex.log(level='error')` (raise) or to a skipped chunk (ShortChunk).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import CAND_DTYPE, DtxError, ENGINE_FP64, ENGINE_TCGEN05, HIST_BINS
+
+
+class ShortChunk(DtxError):
+    """Chunk not longer than the template / fewer than 10 lags (reference: skip the chunk,
+    detex/detect.py:262-274)."""
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine(object):
+    def __init__(self, device=0, stream=None):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        rc = self._L.dtx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise DtxError(rc, "dtx_create failed (needs an sm_100 GPU; there is no CPU fallback)")
+        self._h = h
+        self.device = device
+        self._S = {}
+        self._keep = None
+        self.nchunks = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dtx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc == 0:
+            return
+        msg = self._L.dtx_last_error(self._h).decode()
+        if rc == _lib.DTX_ERR_SHORT_CHUNK:
+            raise ShortChunk(rc, msg)
+        raise DtxError(rc, msg)
+
+    # ------------------------------------------------------------------ bases
+    def set_bases(self, set_id, bases, Nc, thresholds=None):
+        """bases: list of (r_i, n) float64 arrays (rows = basis vectors, multiplexed order)."""
+        bases = [np.atleast_2d(np.asarray(b, dtype=np.float64)) for b in bases]
+        n = bases[0].shape[1]
+        for b in bases:
+            if b.shape[1] != n:
+                raise DtxError(2, "all bases of a set must share the same length n")
+        U = np.ascontiguousarray(np.vstack(bases))
+        off = np.zeros(len(bases) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([b.shape[0] for b in bases])
+        thr = None
+        if thresholds is not None:
+            thr = np.ascontiguousarray(np.asarray(thresholds, dtype=np.float64))
+            assert thr.shape == (len(bases),)
+        self._check(self._L.dtx_set_bases(self._h, int(set_id), _ptr(U), _ptr(off), len(bases), int(n),
+                                          int(Nc), _ptr(thr) if thr is not None else None))
+        self._S[set_id] = len(bases)
+
+    # ----------------------------------------------------------------- chunks
+    def load_chunks(self, chunks):
+        """chunks: list of 1-D multiplexed arrays (float64 or float32), host memory."""
+        dt = np.float32 if all(np.asarray(c).dtype == np.float32 for c in chunks) else np.float64
+        arrs = [np.ascontiguousarray(np.asarray(c, dtype=dt)) for c in chunks]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        L = np.array([a.shape[0] for a in arrs], dtype=np.int64)
+        self._check(self._L.dtx_load_chunks(self._h, len(arrs), ptrs, _ptr(L),
+                                            _lib.DTX_F32 if dt == np.float32 else _lib.DTX_F64))
+        self._keep = arrs  # async H2D: keep the host arrays alive until the next sync
+        self.nchunks = len(arrs)
+
+    def attach_device_chunks(self, base_ptr, elem_offsets, lengths, f32=False):
+        off = np.ascontiguousarray(np.asarray(elem_offsets, dtype=np.int64))
+        L = np.ascontiguousarray(np.asarray(lengths, dtype=np.int64))
+        self._check(self._L.dtx_attach_device_chunks(self._h, len(L), C.c_void_p(int(base_ptr)), _ptr(off),
+                                                     _ptr(L), _lib.DTX_F32 if f32 else _lib.DTX_F64))
+        self.nchunks = len(L)
+
+    # -------------------------------------------------------------------- run
+    def detect_run(self, set_id, engine="tcgen05", kblk=0, hist_range=(0.0, 1.0), lta_window=0,
+                   want_fas=False, keep_ds64=False):
+        eng = ENGINE_TCGEN05 if engine == "tcgen05" else ENGINE_FP64
+        self._check(self._L.dtx_detect_run(self._h, int(set_id), eng, int(kblk), float(hist_range[0]),
+                                           float(hist_range[1]), int(lta_window), int(bool(want_fas)),
+                                           int(bool(keep_ds64))))
+        self._run_S = self._S[set_id]
+
+    def sync(self):
+        self._check(self._L.dtx_sync(self._h))
+
+    def num_lags(self, chunk):
+        T = C.c_int64()
+        self._check(self._L.dtx_num_lags(self._h, int(chunk), C.byref(T)))
+        return T.value
+
+    def get_ds(self, chunk, subspace):
+        out = np.empty(self.num_lags(chunk), dtype=np.float32)
+        self._check(self._L.dtx_get_ds(self._h, int(chunk), int(subspace), _ptr(out), out.size))
+        return out
+
+    def get_ds64(self, chunk, subspace):
+        out = np.empty(self.num_lags(chunk), dtype=np.float64)
+        self._check(self._L.dtx_get_ds64(self._h, int(chunk), int(subspace), _ptr(out), out.size))
+        return out
+
+    def rowstats(self):
+        n = self.nchunks * self._run_S
+        mx = np.empty(n, dtype=np.float32)
+        fl = np.empty(n, dtype=np.int32)
+        self._check(self._L.dtx_get_rowstats(self._h, _ptr(mx), _ptr(fl), n))
+        return mx.reshape(self.nchunks, self._run_S), fl.reshape(self.nchunks, self._run_S)
+
+    def hist(self, set_id, reset=False):
+        S = self._S[set_id]
+        h = np.empty(S * HIST_BINS, dtype=np.uint64)
+        self._check(self._L.dtx_get_hist(self._h, int(set_id), _ptr(h), h.size, int(reset)))
+        return h.reshape(S, HIST_BINS).astype(np.int64)
+
+    def fas(self, set_id, reset=False):
+        S = self._S[set_id]
+        f = np.empty(S * 5, dtype=np.float64)
+        self._check(self._L.dtx_get_fas(self._h, int(set_id), _ptr(f), f.size, int(reset)))
+        return f.reshape(S, 5)
+
+    def candidates(self, cap=1 << 20):
+        out = np.empty(cap, dtype=CAND_DTYPE)
+        n = C.c_int64()
+        rc = self._L.dtx_get_candidates(self._h, _ptr(out), cap, C.byref(n))
+        if rc == _lib.DTX_ERR_CAPACITY:
+            # mirrors the reference's kill switch for runaway trigger counts (detect.py:433-436)
+            raise DtxError(rc, "more than %d candidate lags above threshold" % cap)
+        self._check(rc)
+        return out[:n.value].copy()
+
+    def k1_ms(self):
+        ms = C.c_float()
+        self._check(self._L.dtx_last_k1_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    # -------------------------------------------------------------------- ccx
+    def ccx(self, X, Nc, row_begin=0, row_end=None, engine="fp64"):
+        X = np.asarray(X)
+        dt = np.float32 if X.dtype == np.float32 else np.float64
+        X = np.ascontiguousarray(X, dtype=dt)
+        N, n = X.shape
+        row_end = N if row_end is None else row_end
+        rows = row_end - row_begin
+        cc = np.zeros((rows, N), dtype=np.float64)
+        lag = np.zeros((rows, N), dtype=np.int32)
+        sub = np.zeros((rows, N), dtype=np.float64)
+        eng = ENGINE_TCGEN05 if engine == "tcgen05" else ENGINE_FP64
+        self._check(self._L.dtx_ccx(self._h, _ptr(X), _lib.DTX_F32 if dt == np.float32 else _lib.DTX_F64,
+                                    N, n, int(Nc), int(row_begin), int(row_end), eng, _ptr(cc), _ptr(lag),
+                                    _ptr(sub)))
+        return cc, lag, sub

@@ -1,0 +1,90 @@
+"""Seeded synthetic inputs with the shapes of BASELINE.json's configs.
+
+Host-side NumPy only; used by tests/, bench.py and __graft_entry__.smoke().  No network,
+no waveform files: the reference bundles none either.
+"""
+import numpy as np
+import scipy.signal
+
+
+def bandpassed_noise(rng, nsamp, sr=100.0, band=(1.0, 10.0), nchan=3):
+    """(nchan, nsamp) unit-variance Gaussian noise, zero-phase Butterworth band-passed --
+    the spectral shape `_applyFilter` (reference detex/construct.py:990-1030) leaves."""
+    x = rng.standard_normal((nchan, nsamp + 2000))
+    sos = scipy.signal.butter(2, band, btype="band", fs=sr, output="sos")
+    y = scipy.signal.sosfiltfilt(sos, x, axis=1)[:, 1000:1000 + nsamp]
+    return y / y.std(axis=1, keepdims=True)
+
+
+def multiplex(chans):
+    """construct.multiplex layout: [c0[0], c1[0], c2[0], c0[1], ...]."""
+    C = np.asarray(chans)
+    return np.ascontiguousarray(C.T).reshape(-1)
+
+
+def random_basis(rng, n, r, zero_mean=False):
+    """(r, n) orthonormal rows (QR of a Gaussian matrix), non-zero mean on purpose."""
+    q, _ = np.linalg.qr(rng.standard_normal((n, r)))
+    U = q.T.copy()
+    if zero_mean:
+        U -= U.mean(axis=1, keepdims=True)
+        q, _ = np.linalg.qr(U.T)
+        U = q.T.copy()
+    return U
+
+
+def wavelet_basis(rng, ns, Nc, r, sr=100.0):
+    """Basis whose span contains band-limited wavelets (so planted events score high)."""
+    n = ns * Nc
+    W = bandpassed_noise(rng, ns, sr=sr, nchan=Nc * r).reshape(r, Nc, ns)
+    taper = np.hanning(ns)
+    W = W * taper[None, None, :]
+    rows = np.array([multiplex(w) for w in W])
+    q, _ = np.linalg.qr(rows.T)
+    return q.T.copy().reshape(r, n)
+
+
+def plant(chunk_mux, template_mux, t, Nc, amp):
+    """Add amp * template at channel-aligned lag t of a multiplexed chunk (in place)."""
+    n = len(template_mux)
+    chunk_mux[t * Nc: t * Nc + n] += amp * template_mux
+    return chunk_mux
+
+
+def detection_case(seed, nchunks, Ls, ns, Nc, ranks, planted=0, sr=100.0, dtype=np.float64):
+    """Chunks + bases for a detection run.  ranks: list of subspace ranks."""
+    rng = np.random.default_rng(seed)
+    n = ns * Nc
+    bases = [random_basis(rng, n, r) if i % 2 else wavelet_basis(rng, ns, Nc, r, sr)
+             for i, r in enumerate(ranks)]
+    chunks = []
+    truth = []
+    for c in range(nchunks):
+        x = multiplex(bandpassed_noise(rng, Ls, sr=sr, nchan=Nc))
+        for _ in range(planted):
+            s = int(rng.integers(0, len(bases)))
+            t = int(rng.integers(0, Ls - ns))
+            coef = rng.standard_normal(bases[s].shape[0])
+            tem = coef @ bases[s]
+            amp = float(rng.uniform(3.0, 8.0)) * np.sqrt(n) / np.linalg.norm(tem)
+            plant(x, tem, t, Nc, amp)
+            truth.append((c, s, t))
+        chunks.append(x.astype(dtype))
+    return chunks, bases, truth
+
+
+def event_families(seed, nfam, per_fam, ns, Nc, sr=100.0, max_shift=100, noise=0.5):
+    """(nfam*per_fam, ns*Nc) multiplexed event waveforms: family wavelet shifted by a few
+    samples plus noise (config 3 shape: CC within family ~0.6-0.95)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for f in range(nfam):
+        base = bandpassed_noise(rng, ns + 2 * max_shift, sr=sr, nchan=Nc)
+        env = np.exp(-0.5 * ((np.arange(ns + 2 * max_shift) - (ns / 2 + max_shift)) / (ns / 6.0)) ** 2)
+        base = base * env[None, :]
+        for m in range(per_fam):
+            sh = int(rng.integers(-max_shift, max_shift + 1))
+            w = base[:, max_shift + sh: max_shift + sh + ns]
+            w = w + noise * w.std() * bandpassed_noise(rng, ns, sr=sr, nchan=Nc)
+            out.append(multiplex(w))
+    return np.array(out)

@@ -1,0 +1,125 @@
+/* detex_b200.h -- C ABI of the B200-native Detex hot path.
+ *
+ * Plain C, plain pointers and sizes, int status codes; no exceptions and no torch types
+ * cross this boundary.  The library is CUDA-only (sm_100a): dtx_create() fails on any
+ * other device and there is no CPU fallback.
+ *
+ * The reference (d-chambers/Detex, pure Python) has no FFI; the entry points below
+ * replace its private hot-path callables.  Each declaration cites the reference
+ * interface it stands in for (file:line under the reference tree).  INTEGRATION.md shows
+ * the ctypes binding a Detex maintainer would add.
+ *
+ * Threading: one host thread per context; all work of a context is issued on one CUDA
+ * stream (the caller's, if given to dtx_create).  Calls are asynchronous until a
+ * dtx_get_* / dtx_sync call.
+ */
+#ifndef DETEX_B200_H
+#define DETEX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dtx_ctx dtx_ctx;
+
+enum {
+    DTX_OK = 0,
+    DTX_ERR_CUDA = 1,        /* a CUDA call failed; see dtx_last_error */
+    DTX_ERR_ARG = 2,         /* invalid argument / shape (reference: detex.log(level='error') raises) */
+    DTX_ERR_DEVICE = 3,      /* not an sm_100 device */
+    DTX_ERR_SHORT_CHUNK = 4, /* chunk shorter than the template or < 10 lags (detect.py:262-274: skip) */
+    DTX_ERR_STATE = 5,       /* call order violated (no chunks loaded, unknown basis set, ...) */
+    DTX_ERR_CAPACITY = 6     /* caller-provided output too small */
+};
+
+enum { DTX_F64 = 0, DTX_F32 = 1 };
+
+/* engine selection for dtx_detect_run / dtx_ccx_run */
+enum {
+    DTX_ENGINE_TCGEN05 = 0, /* production: Hankel-tiled tcgen05 GEMM, split fp16 x3 */
+    DTX_ENGINE_FP64 = 1     /* validation: float64 CUDA-core closed form */
+};
+
+/* One candidate trigger: a lag whose statistic is >= the subspace threshold
+ * (the set `while Ceval.max() >= threshold` iterates over, detect.py:410). */
+typedef struct dtx_cand {
+    int32_t row;  /* chunk * S + subspace */
+    int32_t t;    /* lag index (sample of the chunk, channel-aligned) */
+    float ds;     /* detection statistic */
+    float lta;    /* centred rolling mean of |DS| over the LTA window at t (detect.py:501-524) */
+} dtx_cand;
+
+int dtx_version(void);
+
+/* Context ---------------------------------------------------------------------------- */
+/* `stream` is a cudaStream_t (or NULL for a private stream). */
+int dtx_create(int device, void* stream, dtx_ctx** out);
+void dtx_destroy(dtx_ctx* ctx);
+const char* dtx_last_error(const dtx_ctx* ctx);
+int dtx_sync(dtx_ctx* ctx);
+
+/* Basis upload -------------------------------------------------------------------------
+ * Replaces _SSDetex._loadMPSubSpace (detect.py:319-388) and fas._loadMPSubSpace /
+ * _loadMPSingles (fas.py:137-172): U holds the rows `row.SVD[k] for k in row.UsedSVDKeys`
+ * of S subspaces (or the unit-norm singleton templates) back to back, each of length n
+ * multiplexed samples (n % Nc == 0); subspace s owns rows rank_off[s]..rank_off[s+1]-1
+ * (rank <= 16).  thresholds[s] (may be NULL) is row.Threshold.  The library copies. */
+int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank_off, int S, int n,
+                  int Nc, const double* thresholds);
+
+/* Continuous data ----------------------------------------------------------------------
+ * Chunks are the multiplexed arrays `MPcon` produced by construct.multiplex
+ * (construct.py:928-987) inside _getRA (detect.py:241) / _getDSVect (fas.py:110).
+ * dtx_load_chunks copies host arrays to the device (the H2D leg of the end-to-end path);
+ * dtx_attach_device_chunks uses arrays already resident in HBM. L[i] is the multiplexed
+ * length; lengths are trimmed to a multiple of Nc at run time. */
+int dtx_load_chunks(dtx_ctx* ctx, int nchunks, const void* const* host_ptrs, const int64_t* L,
+                    int dtype);
+int dtx_attach_device_chunks(dtx_ctx* ctx, int nchunks, const void* dev_base,
+                             const int64_t* elem_offsets, const int64_t* L, int dtype);
+
+/* Detection statistic ------------------------------------------------------------------
+ * Replaces the `for ind,row in CorDF.iterrows(): _MPXDS(...)` loop of _SSDetex._getRA
+ * (detect.py:259-281) and fas._MPXSSCorr (fas.py:120-134) for every loaded chunk and every
+ * subspace of the set, then the per-row reductions of _corDat (detect.py:177-190):
+ * MaxDS with inf zeroing, np.histogram on linspace(hist_lo, hist_hi, 401) accumulated
+ * per subspace, candidate compaction against the thresholds, LTA of |DS| over
+ * `lta_window` samples at the candidates, and (want_fas) the beta-fit sufficient
+ * statistics of fas._initFAS (fas.py:74-84).
+ * kblk: 64-tap chunks accumulated in TMEM between drains (1, 2 or 4; 0 = default). */
+int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_lo, double hist_hi,
+                   int lta_window, int want_fas, int keep_ds64);
+
+/* Results (each call synchronises the stream) ------------------------------------------ */
+int dtx_num_lags(dtx_ctx* ctx, int chunk, int64_t* T);
+/* dense DS row (CorDF.SSdetect[name], detect.py:268) */
+int dtx_get_ds(dtx_ctx* ctx, int chunk, int subspace, float* out, int64_t count);
+int dtx_get_ds64(dtx_ctx* ctx, int chunk, int subspace, double* out, int64_t count);
+/* maxds[chunk*S+s] = CorDF.MaxDS (detect.py:275-281); flags bit0 = row has NaN, bit1 = infs zeroed */
+int dtx_get_rowstats(dtx_ctx* ctx, float* maxds, int32_t* flags, int64_t count);
+/* hist[s*400+b] accumulated over every run since the last reset (histdic, detect.py:146,181) */
+int dtx_get_hist(dtx_ctx* ctx, int set_id, uint64_t* hist, int64_t count, int reset);
+/* fas[s*5 + {0:N, 1:sum x, 2:sum x^2, 3:sum log x, 4:sum log1p(-x)}] */
+int dtx_get_fas(dtx_ctx* ctx, int set_id, double* fas, int64_t count, int reset);
+/* candidates of the last run; *n receives the number produced (may exceed cap: truncated) */
+int dtx_get_candidates(dtx_ctx* ctx, dtx_cand* out, int64_t cap, int64_t* n);
+
+/* Timing aid for bench.py: device milliseconds of the dominant kernel (K1) in the last
+ * dtx_detect_run, measured with CUDA events on the context's stream. */
+int dtx_last_k1_ms(dtx_ctx* ctx, float* ms);
+
+/* Pairwise CCX ---------------------------------------------------------------------------
+ * Replaces construct._makeDFcclags / _CCX2 / _subSamp (construct.py:369-466) for the N
+ * multiplexed event waveforms X[N][n] of one station: for every pair b < c in
+ * [row_begin, row_end) x (b, N) the maximum normalised cross-correlation, its lag in
+ * multiplexed samples and the cosine-fit sub-sample shift.  Outputs are dense row-major
+ * [(row_end-row_begin)][N] arrays (entries with c <= b untouched). */
+int dtx_ccx(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int row_begin, int row_end,
+            int engine, double* cc, int32_t* lag, double* subsamp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DETEX_B200_H */
