@@ -20,8 +20,8 @@ HIST_BINS = 400
 EXPORTS = [
     "dtx_version", "dtx_create", "dtx_destroy", "dtx_last_error", "dtx_sync", "dtx_set_bases",
     "dtx_load_chunks", "dtx_attach_device_chunks", "dtx_detect_run", "dtx_num_lags", "dtx_get_ds",
-    "dtx_get_ds64", "dtx_get_rowstats", "dtx_get_hist", "dtx_get_fas", "dtx_get_candidates",
-    "dtx_last_k1_ms", "dtx_ccx",
+    "dtx_get_ds64", "dtx_get_stalta", "dtx_get_rowstats", "dtx_get_hist", "dtx_get_fas", "dtx_get_candidates",
+    "dtx_last_k1_ms", "dtx_launch_count", "dtx_ccx",
 ]
 
 
@@ -62,11 +62,13 @@ def load():
     L.dtx_num_lags.argtypes = [p, C.c_int, C.POINTER(C.c_int64)]
     L.dtx_get_ds.argtypes = [p, C.c_int, C.c_int, p, C.c_int64]
     L.dtx_get_ds64.argtypes = [p, C.c_int, C.c_int, p, C.c_int64]
+    L.dtx_get_stalta.argtypes = [p, C.c_int, C.c_int, C.c_int, p, C.c_int64]
     L.dtx_get_rowstats.argtypes = [p, p, p, C.c_int64]
     L.dtx_get_hist.argtypes = [p, C.c_int, p, C.c_int64, C.c_int]
     L.dtx_get_fas.argtypes = [p, C.c_int, p, C.c_int64, C.c_int]
     L.dtx_get_candidates.argtypes = [p, p, C.c_int64, C.POINTER(C.c_int64)]
     L.dtx_last_k1_ms.argtypes = [p, C.POINTER(C.c_float)]
+    L.dtx_launch_count.argtypes = [p, C.POINTER(C.c_int64)]
     L.dtx_ccx.argtypes = [p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p, p, p]
     for name in EXPORTS:
         if name not in ("dtx_destroy", "dtx_last_error"):

@@ -101,6 +101,7 @@ struct dtx_ctx {
     int cand_cap = 1 << 20;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool k1_timed = false;
+    long long launches = 0;
 };
 
 namespace {
@@ -287,6 +288,7 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
     DTX_CUDA(cudaMemset(bs.d_hist.p, 0, sizeof(unsigned long long) * S * HIST_BINS));
     DTX_CUDA(cudaMemset(bs.d_fas.p, 0, sizeof(double) * S * 5));
     launch_basis_image(bs.d_U.p, bs.d_slot_row.p, lay, bs.d_Aimg.p, ctx->stream);
+    ctx->launches += 1;
     DTX_CUDA(cudaGetLastError());
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));
     return DTX_OK;
@@ -407,6 +409,7 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
     launch_k0(ctx->d_raw, f32, ctx->d_chunks.p, nchunks, Nc, n, max_Lpad, max_ntiles, ctx->d_sum.p,
               ctx->d_maxbits.p, ctx->d_scale.p, ctx->d_xsplit.p, ctx->d_mu.p, ctx->d_invE.p, st);
     DTX_CUDA(cudaGetLastError());
+    ctx->launches += 3;  // k0_stats, k0_split, k0_norm
     ctx->have_ds64 = false;
     ctx->k1_timed = false;
     if (engine == DTX_ENGINE_TCGEN05) {
@@ -419,6 +422,7 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
         launch_k1(a, lay, st);
         DTX_CUDA(cudaEventRecord(ctx->ev1, st));
         ctx->k1_timed = true;
+        ctx->launches += 1 + (keep_ds64 ? 1 : 0);
         DTX_CUDA(cudaGetLastError());
         if (keep_ds64) {
             launch_direct(ctx->d_raw, f32, ctx->d_chunks.p, nchunks, bs.d_U.p, bs.d_rank_off.p, S, n, Nc,
@@ -429,16 +433,19 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
         launch_direct(ctx->d_raw, f32, ctx->d_chunks.p, nchunks, bs.d_U.p, bs.d_rank_off.p, S, n, Nc, maxT,
                       ctx->d_sum.p, ctx->d_DS.p, keep_ds64 ? ctx->d_DS64.p : nullptr, st);
         ctx->have_ds64 = keep_ds64 != 0;
+        ctx->launches += 1;
     }
     DTX_CUDA(cudaGetLastError());
     launch_k3(ctx->d_DS.p, ctx->d_chunks.p, nchunks, S, bs.d_thr.p, ctx->d_rowmax.p, ctx->d_rowflags.p,
               bs.d_hist.p, hist_lo, hist_hi, ctx->d_cand.p, ctx->cand_cap, ctx->d_ncand.p,
               want_fas ? bs.d_fas.p : nullptr, st);
     DTX_CUDA(cudaGetLastError());
+    ctx->launches += 1;
     if (bs.has_thr && lta_window > 0) {
         launch_lta(ctx->d_DS.p, ctx->d_chunks.p, S, ctx->d_rowflags.p, ctx->d_cand.p, ctx->d_ncand.p,
                    ctx->cand_cap, lta_window, st);
         DTX_CUDA(cudaGetLastError());
+        ctx->launches += 1;
     }
     ctx->run_set = set_id;
     ctx->run_S = S;
@@ -477,6 +484,32 @@ int dtx_get_ds64(dtx_ctx* ctx, int chunk, int subspace, double* out, int64_t cou
     DTX_CUDA(cudaMemcpyAsync(out, ctx->d_DS64.p + cd.ds_off + static_cast<long long>(subspace) * cd.Tpad,
                              sizeof(double) * cd.T, cudaMemcpyDeviceToHost, ctx->stream));
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DTX_OK;
+}
+
+int dtx_get_stalta(dtx_ctx* ctx, int chunk, int subspace, int W, float* out, int64_t count) {
+    if (!ctx || !out) return DTX_ERR_ARG;
+    if (!ctx->ran || chunk < 0 || chunk >= ctx->nchunks || subspace < 0 || subspace >= ctx->run_S || W < 1)
+        return fail(ctx, DTX_ERR_STATE, "dtx_get_stalta: no run / bad index");
+    const ChunkDesc& cd = ctx->h_chunks[chunk];
+    if (count < cd.T) return fail(ctx, DTX_ERR_CAPACITY, "dtx_get_stalta: buffer smaller than T");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    if (cd.T < W) {
+        for (int i = 0; i < cd.T; ++i) out[i] = NAN;
+        return DTX_OK;
+    }
+    int flags = 0;
+    DTX_CUDA(cudaMemcpyAsync(&flags, ctx->d_rowflags.p + static_cast<long long>(chunk) * ctx->run_S + subspace,
+                             sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    DevBuf<float> tmp;
+    DTX_CUDA(tmp.reserve(cd.T));
+    launch_stalta_dense(ctx->d_DS.p + cd.ds_off + static_cast<long long>(subspace) * cd.Tpad, cd.T, W,
+                        (flags & 2) ? 1 : 0, tmp.p, ctx->stream);
+    DTX_CUDA(cudaGetLastError());
+    DTX_CUDA(cudaMemcpyAsync(out, tmp.p, sizeof(float) * cd.T, cudaMemcpyDeviceToHost, ctx->stream));
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    tmp.release();
     return DTX_OK;
 }
 
@@ -547,6 +580,12 @@ int dtx_last_k1_ms(dtx_ctx* ctx, float* ms) {
     return DTX_OK;
 }
 
+int dtx_launch_count(dtx_ctx* ctx, int64_t* n) {
+    if (!ctx || !n) return DTX_ERR_ARG;
+    *n = ctx->launches;
+    return DTX_OK;
+}
+
 int dtx_ccx(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int row_begin, int row_end,
             int engine, double* cc, int32_t* lag, double* subsamp) {
     if (!ctx) return DTX_ERR_ARG;
@@ -574,6 +613,7 @@ int dtx_ccx(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int ro
     launch_ccx_fp64(dX.p, dtype == DTX_F32, N, n, Nc, row_begin, row_end, dcc.p, dlag.p, dsub.p,
                     ctx->num_sms, st);
     DTX_CUDA(cudaGetLastError());
+    ctx->launches += 2;
     DTX_CUDA(cudaMemcpyAsync(cc, dcc.p, rows * N * sizeof(double), cudaMemcpyDeviceToHost, st));
     DTX_CUDA(cudaMemcpyAsync(lag, dlag.p, rows * N * sizeof(int), cudaMemcpyDeviceToHost, st));
     DTX_CUDA(cudaMemcpyAsync(subsamp, dsub.p, rows * N * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -109,4 +109,6 @@ void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, c
 void launch_lta(const float* DS, const ChunkDesc* d_chunks, int S, const int* d_rowflags,
                 Candidate* d_cand, const int* d_ncand, int cand_cap, int W, cudaStream_t st);
 
+void launch_stalta_dense(const float* row, int T, int W, int zero_inf, float* out, cudaStream_t st);
+
 }  // namespace dtx

@@ -177,6 +177,55 @@ lta_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, i
     if (l == 0) cand[wid].lta = out;
 }
 
+
+// Dense STA/LTA of one DS row (`_getStaLtaArray`, STA = 0 -> |DS|; detect.py:501-515):
+// out[i] = |DS[i]| / LTA[i_eff], LTA the centred rolling mean of |DS| over W samples with
+// the `_replaceNanWithMean` edge rule.  Only the CorDF.STALTA column needs it; the trigger
+// path uses lta_kernel on the sparse candidates.  One block per 1024 outputs, |DS| staged
+// in shared memory as a float64 prefix sum.
+constexpr int SL_TILE = 1024;
+__global__ void __launch_bounds__(256)
+stalta_dense_kernel(const float* __restrict__ x, int T, int W, int zero_inf, float* __restrict__ out) {
+    extern __shared__ double pre[];  // [SL_TILE + W + 1]
+    const int off = (W - 1) / 2;
+    const int first = W - 1 - off, last = T - 1 - off;
+    const int i0 = blockIdx.x * SL_TILE;
+    // centres needed by this tile after the edge rule: clamp(i) for i in [i0, i0+SL_TILE)
+    int clo = i0, chi = min(i0 + SL_TILE, T) - 1;
+    auto eff = [&](int i) {
+        if (i < first) return (first + 1 <= last) ? first + 1 : first;
+        if (i > last) return last;
+        return i;
+    };
+    // span of centres this tile can touch (eff(i) >= clamp(i); i < first maps to first+1)
+    const int cmin = min(max(clo, first), last);
+    int cmax = min(max(chi, first), last);
+    if (clo < first) cmax = max(cmax, min(first + 1, last));
+    const int a0 = cmin - (W - 1) + off;  // first sample needed
+    const int a1 = cmax + off;            // last sample needed
+    const int cnt = a1 - a0 + 1;
+    for (int j = threadIdx.x; j < cnt; j += 256) {
+        float v = x[a0 + j];
+        if (zero_inf && isinf(v)) v = 0.f;
+        pre[j + 1] = fabs(static_cast<double>(v));
+    }
+    if (threadIdx.x == 0) pre[0] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int j = 1; j <= cnt; ++j) pre[j] += pre[j - 1];
+    __syncthreads();
+    for (int k = threadIdx.x; k < SL_TILE; k += 256) {
+        const int i = i0 + k;
+        if (i >= T) break;
+        const int c = eff(i);
+        const int s0 = c - (W - 1) + off - a0;
+        const double lta = (pre[s0 + W] - pre[s0]) / W;
+        float v = x[i];
+        if (zero_inf && isinf(v)) v = 0.f;
+        out[i] = static_cast<float>(fabs(static_cast<double>(v)) / lta);
+    }
+}
+
 }  // namespace
 
 void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, const float* d_thr,
@@ -195,6 +244,14 @@ void launch_lta(const float* DS, const ChunkDesc* d_chunks, int S, const int* d_
     const int warps = cand_cap;
     const int grid = (warps * 32 + 255) / 256;
     lta_kernel<<<grid, 256, 0, st>>>(DS, d_chunks, S, d_rowflags, d_cand, d_ncand, cand_cap, W);
+}
+
+void launch_stalta_dense(const float* row, int T, int W, int zero_inf, float* out, cudaStream_t st) {
+    if (T < W) return;
+    const int grid = (T + SL_TILE - 1) / SL_TILE;
+    const size_t sm = sizeof(double) * (SL_TILE + 2 * W + 2);
+    cudaFuncSetAttribute(stalta_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+    stalta_dense_kernel<<<grid, 256, sm, st>>>(row, T, W, zero_inf, out);
 }
 
 }  // namespace dtx

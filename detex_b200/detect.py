@@ -195,23 +195,29 @@ class SSDetex(object):
     def getRA(self, chunk, sr, start, File=None):
         """CorDF of one chunk (array part of `_getRA`, detect.py:225-296): index = sorted
         names, columns as the reference.  Returns None if the chunk must be skipped."""
-        from . import stalta
-        _, maxds, dense = self.run_chunks([chunk], sr, [start], keep_ds=True)
-        if not maxds[0]:
+        L = len(chunk) // self.Nc * self.Nc
+        nmax = max(self.groups.keys())
+        if L <= nmax or (L - nmax) // self.Nc + 1 < 10:
             return None
+        eng = self.engine
+        eng.load_chunks([chunk])
         CorDF = pd.DataFrame(index=self.names, columns=CORDF_COLS, dtype=object)
-        for name in self.names:
-            ds = dense[(0, name)]
-            CorDF.at[name, 'SSdetect'] = ds
-            CorDF.at[name, 'MaxDS'] = maxds[0][name]
-            CorDF.at[name, 'Nc'] = self.Nc
-            CorDF.at[name, 'SampRate'] = sr
-            CorDF.at[name, 'TimeStamp'] = start
-            CorDF.at[name, 'File'] = File
-            if not self.fillZeros:
-                sl = stalta.sta_lta_of_ds(ds, self.triggerLTATime * sr, self.triggerSTATime * sr)
-                CorDF.at[name, 'STALTA'] = sl
-                CorDF.at[name, 'MaxSTALTA'] = np.max(sl)
+        W = int(self.triggerLTATime * sr)
+        for n, names in sorted(self.groups.items()):
+            eng.detect_run(self.set_ids[n], engine=self.kernel, kblk=self.kblk)
+            mx, _ = eng.rowstats()
+            eng.hist(self.set_ids[n], reset=True)  # getRA does not feed the station histogram
+            for si, name in enumerate(names):
+                CorDF.at[name, 'SSdetect'] = eng.get_ds(0, si).astype(np.float64)
+                CorDF.at[name, 'MaxDS'] = float(mx[0, si])
+                CorDF.at[name, 'Nc'] = self.Nc
+                CorDF.at[name, 'SampRate'] = sr
+                CorDF.at[name, 'TimeStamp'] = start
+                CorDF.at[name, 'File'] = File
+                if not self.fillZeros:
+                    sl = eng.get_stalta(0, si, W).astype(np.float64)
+                    CorDF.at[name, 'STALTA'] = sl
+                    CorDF.at[name, 'MaxSTALTA'] = np.max(sl)
         return CorDF
 
     def corDat(self, chunks, sr, starts, batch=16):

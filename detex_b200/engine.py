@@ -118,6 +118,11 @@ class Engine(object):
         self._check(self._L.dtx_get_ds64(self._h, int(chunk), int(subspace), _ptr(out), out.size))
         return out
 
+    def get_stalta(self, chunk, subspace, W):
+        out = np.empty(self.num_lags(chunk), dtype=np.float32)
+        self._check(self._L.dtx_get_stalta(self._h, int(chunk), int(subspace), int(W), _ptr(out), out.size))
+        return out
+
     def rowstats(self):
         n = self.nchunks * self._run_S
         mx = np.empty(n, dtype=np.float32)
@@ -151,6 +156,11 @@ class Engine(object):
         ms = C.c_float()
         self._check(self._L.dtx_last_k1_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def launch_count(self):
+        n = C.c_int64()
+        self._check(self._L.dtx_launch_count(self._h, C.byref(n)))
+        return n.value
 
     # -------------------------------------------------------------------- ccx
     def ccx(self, X, Nc, row_begin=0, row_end=None, engine="fp64"):

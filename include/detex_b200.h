@@ -97,6 +97,9 @@ int dtx_num_lags(dtx_ctx* ctx, int chunk, int64_t* T);
 /* dense DS row (CorDF.SSdetect[name], detect.py:268) */
 int dtx_get_ds(dtx_ctx* ctx, int chunk, int subspace, float* out, int64_t count);
 int dtx_get_ds64(dtx_ctx* ctx, int chunk, int subspace, double* out, int64_t count);
+/* dense |DS| / LTA (CorDF.STALTA with triggerSTATime = 0, _getStaLtaArray detect.py:501-515),
+ * W = LTA window in samples; filled with NaN when the row is shorter than W */
+int dtx_get_stalta(dtx_ctx* ctx, int chunk, int subspace, int W, float* out, int64_t count);
 /* maxds[chunk*S+s] = CorDF.MaxDS (detect.py:275-281); flags bit0 = row has NaN, bit1 = infs zeroed */
 int dtx_get_rowstats(dtx_ctx* ctx, float* maxds, int32_t* flags, int64_t count);
 /* hist[s*400+b] accumulated over every run since the last reset (histdic, detect.py:146,181) */
@@ -109,6 +112,8 @@ int dtx_get_candidates(dtx_ctx* ctx, dtx_cand* out, int64_t cap, int64_t* n);
 /* Timing aid for bench.py: device milliseconds of the dominant kernel (K1) in the last
  * dtx_detect_run, measured with CUDA events on the context's stream. */
 int dtx_last_k1_ms(dtx_ctx* ctx, float* ms);
+/* Number of CUDA kernels this context has launched since creation (bench.py's gpu_launches). */
+int dtx_launch_count(dtx_ctx* ctx, int64_t* n);
 
 /* Pairwise CCX ---------------------------------------------------------------------------
  * Replaces construct._makeDFcclags / _CCX2 / _subSamp (construct.py:369-466) for the N

@@ -1,0 +1,103 @@
+"""Generate the golden vectors under tests/golden/ from the UNMODIFIED reference.
+
+Run in the build container (where /root/reference exists):
+    python tests/golden/make_golden.py
+The reference functions are imported through oracle/ref_shim.py and fed seeded synthetic
+inputs; inputs and the reference's outputs are stored together so that the oracle and the
+CUDA path can be checked against them anywhere (the GPU box has no /root/reference).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from detex_b200 import synth  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    R = ref_shim.RefFunctions()
+    # ---- detection statistic (_MPXDS, detect.py:559-578; _MPXSSCorr, fas.py:120-134)
+    cases = {}
+    specs = [
+        ("nc3", dict(seed=101, nchunks=2, Ls=6000, ns=300, Nc=3, ranks=[1, 3, 5, 8], planted=2)),
+        ("nc1", dict(seed=102, nchunks=1, Ls=8000, ns=250, Nc=1, ranks=[2, 4], planted=2)),
+        ("nc2odd", dict(seed=103, nchunks=1, Ls=5003, ns=333, Nc=2, ranks=[3, 16], planted=1)),
+    ]
+    for name, kw in specs:
+        chunks, bases, truth = synth.detection_case(**kw)
+        if name == "nc3":
+            chunks[1] = chunks[1] + 250.0      # DC level (fillZeros-like conditioning case)
+        cases[name + "_Nc"] = kw["Nc"]
+        cases[name + "_nchunks"] = len(chunks)
+        cases[name + "_nbases"] = len(bases)
+        for ci, c in enumerate(chunks):
+            cases["%s_chunk%d" % (name, ci)] = c
+        for si, U in enumerate(bases):
+            cases["%s_U%d" % (name, si)] = U
+            for ci, c in enumerate(chunks):
+                ds = R.MPXDS(c, U, kw["Nc"])
+                ds2 = R.MPXSSCorr(c, U, kw["Nc"])
+                assert np.abs(ds - ds2).max() == 0.0
+                cases["%s_DS_%d_%d" % (name, ci, si)] = ds
+    # singleton: unit-norm, non-demeaned template (detect.py:356-357)
+    rng = np.random.default_rng(104)
+    x = synth.multiplex(synth.bandpassed_noise(rng, 5000, nchan=3))
+    tem = x[3000:3000 + 900].copy() + 0.3
+    U = (tem / np.linalg.norm(tem))[None, :]
+    cases["single_chunk"] = x
+    cases["single_U"] = U
+    cases["single_DS"] = R.MPXDS(x, U, 3)
+    np.savez_compressed(os.path.join(OUT, "ds_golden.npz"), **cases)
+
+    # ---- STA/LTA + greedy trigger picking (detect.py:390-445, 501-557)
+    ds = cases["nc3_DS_0_1"]
+    trig = {}
+    for lta, sta in ((50.0, 0), (500.0, 0), (50.0, 7.0)):
+        trig["stalta_%g_%g" % (lta, sta)] = R.getStaLtaArray(ds, lta, sta)
+    rng = np.random.default_rng(7)
+    syn = rng.uniform(0, 0.2, size=20000)
+    for pos, val in ((5, .8), (1500, .9), (2300, .85), (3600, .7), (3601, .7), (9000, .95), (10990, .6),
+                     (11050, .9), (19990, .75), (14000, .5), (14000 + 1999, .45), (14000 + 2000, .44)):
+        syn[pos] = val
+    stl = R.getStaLtaArray(syn, 500.0, 0)
+    df = R.CreateCoeffArray(syn, stl, 100.0, 1.0e9, 0.4, [1.0, 2.5, 4.0])
+    trig["syn_DS"] = syn
+    trig["syn_stalta"] = stl
+    trig["syn_trig_DS"] = df.DS.values.astype(float)
+    trig["syn_trig_STMP"] = df.STMP.values.astype(float)
+    trig["syn_trig_STALTA"] = df.DS_STALTA.values.astype(float)
+    trig["syn_trig_MSTAMPmin"] = df.MSTAMPmin.values.astype(float)
+    trig["syn_trig_MSTAMPmax"] = df.MSTAMPmax.values.astype(float)
+    np.savez_compressed(os.path.join(OUT, "trigger_golden.npz"), **trig)
+
+    # ---- CCX (_makeDFcclags / _CCX2 / _subSamp, construct.py:369-466)
+    ccx = {}
+    for name, (seed, nfam, per, ns, Nc) in {"nc3": (201, 3, 4, 200, 3), "nc1": (202, 2, 3, 301, 1)}.items():
+        X = synth.event_families(seed, nfam, per, ns, Nc, max_shift=20)
+        if name == "nc3":
+            X[5] = 0.0          # an all-zero waveform (zeroed-out event, construct.py:457-461)
+            X[7] = X[2]         # identical pair
+        cc, lag, sub = R.makeDFcclags(X, Nc)
+        ccx[name + "_X"] = X
+        ccx[name + "_Nc"] = Nc
+        ccx[name + "_cc"] = cc.values.astype(float)
+        ccx[name + "_lag"] = lag.values.astype(float)
+        ccx[name + "_sub"] = sub.values.astype(float)
+    np.savez_compressed(os.path.join(OUT, "ccx_golden.npz"), **ccx)
+
+    # ---- multiplex (construct.py:928-987)
+    chans = [np.arange(6.0), np.arange(6.0) + 10, np.arange(7.0) + 20]
+    np.savez_compressed(os.path.join(OUT, "multiplex_golden.npz"), c0=chans[0], c1=chans[1], c2=chans[2],
+                        out=R.multiplex(chans))
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""world_size-2 gloo test of the N>1 plumbing (runs on CPU): chunk sharding, gather of the
+variable-length candidate records, histogram / FAS all-reduce, CCX row-block gather."""
+import os
+import socket
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from detex_b200 import parallel
+from detex_b200._lib import CAND_DTYPE
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        nchunks, S = 7, 3
+        lo, hi = parallel.shard_range(nchunks, rank, world)
+        # every rank "detects" on its own chunks: deterministic fake candidates per chunk
+        recs = []
+        for c in range(lo, hi):
+            rng = np.random.default_rng(100 + c)
+            k = int(rng.integers(0, 5))
+            r = np.zeros(k, dtype=CAND_DTYPE)
+            r["row"] = c * S + rng.integers(0, S, size=k)
+            r["t"] = rng.integers(0, 1000, size=k)
+            r["ds"] = rng.uniform(0.3, 1, size=k)
+            recs.append(r)
+        local = np.concatenate(recs) if recs else np.zeros(0, dtype=CAND_DTYPE)
+        allc = parallel.gather_records(local)
+        hist = np.zeros((S, 400), dtype=np.int64)
+        for c in range(lo, hi):
+            hist[c % S, c] += c + 1
+        hist = parallel.allreduce_sum(hist)
+        fasst = parallel.allreduce_sum(np.full((S, 5), float(rank + 1)))
+        N = 9
+        blocks = parallel.ccx_row_blocks(N, world)
+        b0, b1 = blocks[rank]
+        blk = np.arange(b0, b1, dtype=np.float64)[:, None] * np.ones((1, N))
+        full = parallel.gather_row_blocks(blk, blocks, N)
+        if rank == 0:
+            q.put((allc, hist, fasst, full))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gather_equals_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    allc, hist, fasst, full = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process expectation
+    S = 3
+    exp = []
+    for c in range(7):
+        rng = np.random.default_rng(100 + c)
+        k = int(rng.integers(0, 5))
+        r = np.zeros(k, dtype=CAND_DTYPE)
+        r["row"] = c * S + rng.integers(0, S, size=k)
+        r["t"] = rng.integers(0, 1000, size=k)
+        r["ds"] = rng.uniform(0.3, 1, size=k)
+        exp.append(r)
+    exp = np.concatenate(exp)
+    assert np.array_equal(allc, exp)
+    eh = np.zeros((S, 400), dtype=np.int64)
+    for c in range(7):
+        eh[c % S, c] += c + 1
+    assert np.array_equal(hist, eh)
+    assert np.all(fasst == 3.0)
+    assert np.array_equal(full[:, 0], np.arange(8, dtype=np.float64))

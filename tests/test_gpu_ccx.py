@@ -1,0 +1,65 @@
+"""Parity of the CUDA CCX path against the golden vectors / oracle: CC within 1e-5
+(float64 engine: 1e-10), lags bit-exact."""
+import numpy as np
+import pytest
+
+from detex_b200 import construct, synth
+from oracle import detex_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", ["nc3", "nc1"])
+def test_ccx_matches_reference_golden(engine, ccx_golden, case):
+    g = ccx_golden
+    X, Nc = g[case + "_X"], int(g[case + "_Nc"])
+    cc, lag, sub = engine.ccx(X, Nc)
+    N = X.shape[0]
+    iu = np.triu_indices(N, 1)
+    rcc, rlag, rsub = g[case + "_cc"][iu[0], iu[1] - 1], g[case + "_lag"][iu[0], iu[1] - 1], g[case + "_sub"][iu[0], iu[1] - 1]
+    assert np.abs(cc[iu] - rcc).max() < 1e-10
+    assert np.array_equal(lag[iu].astype(float), rlag)
+    assert np.nanmax(np.abs(sub[iu] - rsub)) < 1e-7
+
+
+def test_ccx_row_blocks_equal_full(engine, ccx_golden):
+    X = ccx_golden["nc3_X"]
+    cc, lag, sub = engine.ccx(X, 3)
+    for b0, b1 in ((0, 4), (4, 9), (9, 11)):
+        c2, l2, s2 = engine.ccx(X, 3, row_begin=b0, row_end=b1)
+        for r in range(b0, b1):
+            assert np.array_equal(c2[r - b0, r + 1:], cc[r, r + 1:])
+            assert np.array_equal(l2[r - b0, r + 1:], lag[r, r + 1:])
+
+
+def test_makeDFcclags_frames(engine, ccx_golden):
+    import pandas as pd
+    g = ccx_golden
+    X = g["nc3_X"]
+    evs = ["ev%02d" % i for i in range(len(X))]
+    row = pd.Series({"MPtd": {e: X[i] for i, e in enumerate(evs)}, "MPfd": {e: None for e in evs},
+                     "Channels": {e: ["E", "N", "Z"] for e in evs}})
+    DFcc, DFlag, DFsub = construct._makeDFcclags(evs, row, engine=engine)
+    assert list(DFcc.columns) == list(range(1, len(X))) and list(DFcc.index) == list(range(len(X) - 1))
+    a = DFcc.values.astype(float)
+    assert np.array_equal(np.isnan(a), np.isnan(g["nc3_cc"]))
+    m = ~np.isnan(a)
+    assert np.abs(a[m] - g["nc3_cc"][m]).max() < 1e-10
+    assert np.array_equal(DFlag.values.astype(float)[m], g["nc3_lag"][m])
+    link = construct.cluster_link(DFcc)
+    assert np.allclose(link, orc.cluster_link(g["nc3_cc"]), atol=1e-9)
+    cc1 = construct._CCX2(None, None, X[0], X[1], "ENZ", "ENZ", engine=engine)
+    assert abs(cc1[0] - g["nc3_cc"][0, 0]) < 1e-10 and cc1[1] == g["nc3_lag"][0, 0]
+    with pytest.raises(Exception):
+        construct._CCX2(None, None, X[0], X[1][:-3], "ENZ", "ENZ", engine=engine)
+
+
+def test_ccx_config3_shape_subset(engine):
+    """config 3 waveform shape (3 ch x 10 s x 100 Hz, n = 3000, 1001 lags), 24 events."""
+    X = synth.event_families(3003, 4, 6, 1000, 3, max_shift=100)
+    cc, lag, sub = engine.ccx(X, 3)
+    rcc, rlag, rsub = orc.make_cclags(X, 3, fft=True)
+    iu = np.triu_indices(len(X), 1)
+    assert np.abs(cc[iu] - rcc[iu[0], iu[1] - 1]).max() < 1e-10
+    assert np.array_equal(lag[iu].astype(float), rlag[iu[0], iu[1] - 1])
+    assert cc[0, 1] > 0.4 and abs(lag[0, 1]) <= 600 and lag[0, 1] % 3 == 0

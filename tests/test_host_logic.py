@@ -1,0 +1,92 @@
+"""Host-side logic of the package (no GPU): greedy pick on compacted candidates, beta fit
+from sufficient statistics, SVD basis selection, shard arithmetic."""
+import numpy as np
+import scipy.stats
+
+from detex_b200 import detect, fas, parallel, subspace, synth
+from oracle import detex_oracle as orc
+
+
+def test_greedy_pick_sparse_equals_dense_reference_loop(trig_golden):
+    g = trig_golden
+    ds = g["syn_DS"]
+    thr = 0.4
+    idx = np.nonzero(ds >= thr)[0]
+    picks = detect.greedy_pick(idx, ds[idx], len(ds), 100.0)
+    got = ds[idx[picks]]
+    assert np.array_equal(got, g["syn_trig_DS"])
+    assert np.array_equal(idx[picks] / 100.0 + 1.0e9, g["syn_trig_STMP"])
+
+
+def test_greedy_pick_random_against_oracle():
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        T = int(rng.integers(3000, 30000))
+        ds = rng.uniform(0, 0.3, size=T)
+        for _ in range(int(rng.integers(0, 12))):
+            ds[int(rng.integers(0, T))] = rng.uniform(0.3, 1.0)
+        sr = float(rng.choice([20.0, 40.0, 100.0]))
+        rows = orc.greedy_triggers(ds, 0.25, sr, 0.0, [0.0])
+        idx = np.nonzero(ds >= 0.25)[0]
+        picks = detect.greedy_pick(idx, ds[idx], T, sr)
+        assert [int(idx[k]) for k in picks] == [r["index"] for r in rows]
+
+
+def test_createcoeffarray_columns(trig_golden):
+    import pandas as pd
+    g = trig_golden
+    cs = pd.Series({"SSdetect": g["syn_DS"], "STALTA": g["syn_stalta"], "SampRate": 100.0,
+                    "TimeStamp": 1.0e9, "Nc": 1})
+    df = detect._CreateCoeffArray(cs, "SS0", {"SS0": 0.4}, "STA", {"SS0": [1.0, 2.5, 4.0]})
+    assert list(df.columns) == ['DS', 'DS_STALTA', 'STMP', 'Name', 'Sta', 'MSTAMPmin', 'MSTAMPmax', 'Mag',
+                                'SNR', 'ProEnMag']
+    assert np.array_equal(df.DS.values, g["syn_trig_DS"])
+    assert np.allclose(df.DS_STALTA.values, g["syn_trig_STALTA"], rtol=0, atol=1e-12)
+    assert np.array_equal(df.MSTAMPmin.values, g["syn_trig_MSTAMPmin"])
+
+
+def test_beta_fit_from_stats_matches_scipy():
+    rng = np.random.default_rng(1)
+    for a0, b0 in ((1.5, 4000.0), (3.0, 2500.0), (8.0, 900.0)):
+        x = rng.beta(a0, b0, size=100000)
+        st = orc.beta_sufficient_stats(x)
+        a, b, loc, scale = fas.beta_fit_from_stats(*st)
+        ra, rb, _, _ = scipy.stats.beta.fit(x, floc=0, fscale=1)
+        assert abs(a - ra) < 1e-8 * ra and abs(b - rb) < 1e-8 * rb
+        nn = fas.beta_nnlf_from_stats(a, b, st[0], st[3], st[4])
+        assert abs(nn - scipy.stats.beta.nnlf((ra, rb, 0, 1), x)) < 1e-6 * abs(nn)
+
+
+def test_svd_basis_matches_oracle():
+    rng = np.random.default_rng(2)
+    base = synth.wavelet_basis(rng, 200, 3, 3)
+    ev = np.array([rng.standard_normal(3) @ base + 0.05 * rng.standard_normal(600) for _ in range(9)])
+    a = subspace.svd_basis(ev)
+    b = orc.svd_basis(ev)
+    assert a["NumBasis"] == b["ndim"] and a["NumBasis"] >= 3
+    assert np.allclose(a["U"], b["U"])
+    assert np.allclose(a["U"] @ a["U"].T, np.eye(a["NumBasis"]), atol=1e-12)
+    th = subspace.threshold_from_fas({"betadist": (2.0, 3000.0, 0, 1)}, Pf=1e-12)
+    assert abs(th - orc.threshold_from_beta(2.0, 3000.0, 1e-12)) < 1e-15
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 720, 5760):
+        for w in (1, 2, 3, 8):
+            r = [parallel.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_ccx_row_blocks_balanced():
+    for N in (5, 81, 4096):
+        for w in (1, 2, 4, 8):
+            blocks = parallel.ccx_row_blocks(N, w)
+            assert blocks[0][0] == 0 and blocks[-1][1] == N - 1
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+            pairs = [sum(N - 1 - b for b in range(b0, b1)) for b0, b1 in blocks]
+            assert sum(pairs) == N * (N - 1) // 2
+            if N == 4096:
+                assert max(pairs) / (sum(pairs) / w) < 1.01
