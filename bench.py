@@ -381,8 +381,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunks", type=int, default=CHUNKS_PER_STATION, help="chunks per GPU (720 = 30 days)")
     ap.add_argument("--nsub", type=int, default=NSUB)
-    ap.add_argument("--batch", type=int, default=24, help="chunks per detect_run (DS buffer = batch*S*T*4 B)")
-    ap.add_argument("--kblk", type=int, default=1)
+    ap.add_argument("--batch", type=int, default=48, help="chunks per detect_run (DS buffer = batch*S*T*4 B)")
+    ap.add_argument("--kblk", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -246,11 +246,10 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
     lay.u_exp = eu;
     lay.u_inv_scale = std::ldexp(1.0f, -eu);
     for (int b = 0; b < lay.nblocks; ++b) {
-        int slot = 0, maxrank = 1;
-        for (int s : members[b]) maxrank = std::max(maxrank, rank_off[s + 1] - rank_off[s]);
+        int slot = 0;
         for (int i = 0; i < VEC_PER_BLOCK; ++i) {
             BlockInfo& bi = binfo[static_cast<size_t>(b) * VEC_PER_BLOCK + i];
-            bi.sumU = 0.f; bi.out_row = -1; bi.nrows = 0; bi.maxrank = maxrank;
+            bi.sumU = 0.f; bi.out_row = -1; bi.nrows = 0; bi.seg_end = i + 1;
         }
         for (int s : members[b]) {
             const int r = rank_off[s + 1] - rank_off[s];
@@ -263,6 +262,7 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
                 bi.sumU = static_cast<float>(su);
                 bi.out_row = s;
                 bi.nrows = (k == 0) ? r : 0;
+                bi.seg_end = slot - k + r;
             }
         }
     }
@@ -345,7 +345,7 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
     if (it == ctx->sets.end()) return fail(ctx, DTX_ERR_STATE, "dtx_detect_run: unknown basis set");
     if (ctx->nchunks < 1 || !ctx->d_raw) return fail(ctx, DTX_ERR_STATE, "dtx_detect_run: no chunks loaded");
     if (engine != DTX_ENGINE_TCGEN05 && engine != DTX_ENGINE_FP64) return fail(ctx, DTX_ERR_ARG, "bad engine");
-    if (kblk == 0) kblk = 1;
+    if (kblk == 0) kblk = 2;  // default: drain every 128 taps (bias <= ~2e-6 at DS = 1)
     if (kblk < 1 || kblk > 64) return fail(ctx, DTX_ERR_ARG, "kblk out of range");
     BasisSet& bs = it->second;
     const BasisLayout& lay = bs.lay;

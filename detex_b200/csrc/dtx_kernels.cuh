@@ -48,7 +48,7 @@ struct BlockInfo {   // one per (basis block, vector slot)
     float sumU;      // sum of the basis vector's entries (true units)
     int out_row;     // DS row of the subspace this vector belongs to, -1 = padding
     int nrows;       // rank of the subspace if this slot is its first vector, else 0
-    int maxrank;     // largest rank in the block (same value in all 16 slots)
+    int seg_end;     // slot index one past the last vector of this slot's subspace
 };
 
 struct BasisLayout {

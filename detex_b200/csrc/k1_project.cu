@@ -255,21 +255,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) k1_kernel(const __grid_constant__
                 if (b == 0) mbar_wait(&normfull[nm.idx], nm.phase);
                 const BlockInfo bi = P.a.binfo[b * VEC_PER_BLOCK + kl];
                 const bool head = bi.nrows > 0 && bi.out_row >= 0;
-                float* dsrow = P.a.DS + cd.ds_off +
-                               static_cast<long long>(head ? bi.out_row : 0) * cd.Tpad +
-                               static_cast<long long>(it.y) * TILE_T;
-                const int maxrank = bi.maxrank;
+                const long long row_off = cd.ds_off + static_cast<long long>(head ? bi.out_row : 0) * cd.Tpad +
+                                          static_cast<long long>(it.y) * TILE_T + 1024 * colhalf + p;
+                float* dsrow = P.a.DS + row_off;
+                const float* pmu = smu + 1024 * colhalf + p;
+                const float* pie = sie + 1024 * colhalf + p;
+                const float nsumU = -bi.sumU;
+                // segmented suffix sum over the vector slots of a subspace (lanes 2 apart share a
+                // phase): 4 fixed doubling steps cover ranks up to 16, branch free so the 128
+                // unrolled lags interleave
+                const bool j1 = kl + 1 < bi.seg_end, j2 = kl + 2 < bi.seg_end, j4 = kl + 4 < bi.seg_end,
+                           j8 = kl + 8 < bi.seg_end;
 #pragma unroll
                 for (int i = 0; i < 128; ++i) {
-                    const int tl = 8 * (128 * colhalf + i) + p;
-                    const float c = fmaf(sums[i], sc, -smu[tl] * bi.sumU);
-                    const float v = c * c;
-                    float tot = v;
-                    for (int d = 1; d < maxrank; ++d) {
-                        const float o = __shfl_down_sync(0xffffffffu, v, 2 * d);
-                        if (d < bi.nrows) tot += o;
-                    }
-                    if (head) dsrow[tl] = tot * sie[tl];
+                    const float c = fmaf(sums[i], sc, pmu[8 * i] * nsumU);
+                    float v = c * c;
+                    float o = __shfl_down_sync(0xffffffffu, v, 2);
+                    v += j1 ? o : 0.f;
+                    o = __shfl_down_sync(0xffffffffu, v, 4);
+                    v += j2 ? o : 0.f;
+                    o = __shfl_down_sync(0xffffffffu, v, 8);
+                    v += j4 ? o : 0.f;
+                    o = __shfl_down_sync(0xffffffffu, v, 16);
+                    v += j8 ? o : 0.f;
+                    if (head) dsrow[8 * i] = v * pie[8 * i];
                 }
             }
             __syncwarp();

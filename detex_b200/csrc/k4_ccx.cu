@@ -22,6 +22,7 @@ constexpr int CT = 256;          // threads
 constexpr int LT = 4 * CT;       // lags per tile (4 per thread)
 constexpr int JT = 256;          // taps per tile
 constexpr int X2ROW = (JT + LT) / 4 + 2;
+constexpr double CC_GUARD = 1e-9;
 
 template <typename T>
 __global__ void __launch_bounds__(CT)
@@ -190,10 +191,13 @@ ccx_kernel(const T* __restrict__ X, int N, int n, int Nc, int trunc, int nl, int
         double maxcc = 0.0, ss = 0.0;
         int lg = 0;
         if (ml.cnt > 0) {
-            if (ml.mx > 1.0 || ml.mn < -1.0) {
+            // `if maxcc > 1. or mincc < -1.` (construct.py:457): meant for the infs of zeroed-out
+            // waveforms.  A Pearson coefficient of exactly 1 can come out as 1 + 2e-16 depending on
+            // summation order, so the comparison carries a round-off guard band.
+            if (ml.mx > 1.0 + CC_GUARD || ml.mn < -1.0 - CC_GUARD) {
                 for (int i = tid; i < nl; i += CT) {
                     const double v = res[i];
-                    if (v > 1.0 || v < -1.0) res[i] = 0.0;
+                    if (v > 1.0 + CC_GUARD || v < -1.0 - CC_GUARD) res[i] = 0.0;
                 }
                 __syncthreads();
                 ml = block_maxloc(res, nl, shml);

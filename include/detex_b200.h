@@ -88,7 +88,7 @@ int dtx_attach_device_chunks(dtx_ctx* ctx, int nchunks, const void* dev_base,
  * per subspace, candidate compaction against the thresholds, LTA of |DS| over
  * `lta_window` samples at the candidates, and (want_fas) the beta-fit sufficient
  * statistics of fas._initFAS (fas.py:74-84).
- * kblk: 64-tap chunks accumulated in TMEM between drains (1, 2 or 4; 0 = default). */
+ * kblk: 64-tap chunks accumulated in TMEM between drains (0 = default 2). */
 int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_lo, double hist_hi,
                    int lta_window, int want_fas, int keep_ds64);
 

@@ -124,9 +124,13 @@ def test_constant_run_gives_nan_row(engine):
     """A window of constant data is 0/0: the row carries NaN, MaxDS is NaN, nothing triggers
     and the chunk's histogram is skipped (np.histogram raises -> detect.py:182-185)."""
     Nc, ns, Ls = 1, 100, 3000
-    chunks, bases, _ = synth.detection_case(25, 1, Ls, ns, Nc, [2])
-    x = chunks[0]
-    x[1000:1400] = 3.25
+    _, bases, _ = synth.detection_case(25, 1, Ls, ns, Nc, [2])
+    # integer-valued samples with an exactly-zero sum: centring is exact in every
+    # implementation, so the all-zero run below is exactly 0/0 everywhere
+    x = np.random.default_rng(25).integers(-50, 51, size=Ls).astype(np.float64)
+    x[1000:1400] = 0.0
+    x[0] -= x.sum()
+    assert x.sum() == 0.0
     engine.set_bases(18, bases, Nc, thresholds=[0.2])
     engine.hist(18, reset=True)
     engine.load_chunks([x])
