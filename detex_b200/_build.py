@@ -15,7 +15,7 @@ LIB = os.path.join(OUT_DIR, "libdetex_b200.so")
 SOURCES = ["dtx_api.cu", "k0_prep.cu", "k1_project.cu", "k_direct.cu", "k3_post.cu", "k4_ccx.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false",
+    "-Xcompiler", "-fPIC", "-shared", "-Xlinker", "--no-undefined", "--use_fast_math=false",
 ]
 
 

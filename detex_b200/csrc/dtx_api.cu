@@ -16,11 +16,6 @@
 
 using namespace dtx;
 
-namespace dtx {
-void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int row_begin, int row_end,
-                     double* d_cc, int* d_lag, double* d_sub, int num_sms, cudaStream_t st);
-}
-
 namespace {
 
 template <typename T>
@@ -337,17 +332,9 @@ int dtx_attach_device_chunks(dtx_ctx* ctx, int nchunks, const void* dev_base, co
     return DTX_OK;
 }
 
-int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_lo, double hist_hi,
-                   int lta_window, int want_fas, int keep_ds64) {
-    if (!ctx) return DTX_ERR_ARG;
-    DTX_CUDA(cudaSetDevice(ctx->device));
-    auto it = ctx->sets.find(set_id);
-    if (it == ctx->sets.end()) return fail(ctx, DTX_ERR_STATE, "dtx_detect_run: unknown basis set");
-    if (ctx->nchunks < 1 || !ctx->d_raw) return fail(ctx, DTX_ERR_STATE, "dtx_detect_run: no chunks loaded");
-    if (engine != DTX_ENGINE_TCGEN05 && engine != DTX_ENGINE_FP64) return fail(ctx, DTX_ERR_ARG, "bad engine");
-    if (kblk == 0) kblk = 2;  // default: drain every 128 taps (bias <= ~2e-6 at DS = 1, DESIGN.md)
-    if (kblk < 1 || kblk > 64) return fail(ctx, DTX_ERR_ARG, "kblk out of range");
-    BasisSet& bs = it->second;
+// K0 + (K1 | fp64 direct) on the loaded chunks; leaves DS in ctx->d_DS.
+static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mode, int keep_ds64,
+                       const int* blk_hi) {
     const BasisLayout& lay = bs.lay;
     const int Nc = lay.Nc, n = lay.n, ns = lay.ns, S = lay.S;
     const int Kc = round_up(ns + 7, CHUNK_TAPS);
@@ -370,7 +357,8 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
         cd.Tpad = cd.ntiles * TILE_T;
         cd.Lpad = round_up(cd.Tpad + Kc, 64);
         cd.sig_off = sig; cd.norm_off = nrm; cd.ds_off = ds;
-        cd.pad0 = cd.pad1 = 0;
+        cd.blk_lo = 0;
+        cd.blk_hi = blk_hi ? blk_hi[i] : lay.nblocks;
         sig += 2LL * Nc * cd.Lpad;
         nrm += cd.Tpad;
         ds += static_cast<long long>(S) * cd.Tpad;
@@ -379,10 +367,14 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
         maxT = std::max(maxT, cd.T);
         nitems += cd.ntiles;
     }
+    // K1 tile: 2048 lags (N = 256), or 1024 (N = 128) when no chunk has more than 1024 lags
+    const int nq = maxT <= TILE_T / 2 ? 128 : 256;
     std::vector<int2> items;
-    items.reserve(nitems);
-    for (int i = 0; i < nchunks; ++i)
-        for (int t = 0; t < ctx->h_chunks[i].ntiles; ++t) items.push_back(make_int2(i, t));
+    items.reserve(nitems * 2);
+    for (int i = 0; i < nchunks; ++i) {
+        const int nt = (ctx->h_chunks[i].T + 8 * nq - 1) / (8 * nq);
+        for (int t = 0; t < nt; ++t) items.push_back(make_int2(i, t));
+    }
 
     DTX_CUDA(ctx->d_chunks.reserve(nchunks));
     DTX_CUDA(ctx->d_items.reserve(items.size()));
@@ -417,7 +409,7 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
         a.Aimg = bs.d_Aimg.p; a.xsplit = ctx->d_xsplit.p; a.mu = ctx->d_mu.p; a.invE = ctx->d_invE.p;
         a.chunk_scale = ctx->d_scale.p; a.chunks = ctx->d_chunks.p; a.items = ctx->d_items.p;
         a.binfo = bs.d_binfo.p; a.DS = ctx->d_DS.p; a.nitems = static_cast<int>(items.size());
-        a.kblk = kblk; a.num_sms = ctx->num_sms;
+        a.kblk = kblk; a.num_sms = ctx->num_sms; a.nq = nq; a.mode = mode;
         DTX_CUDA(cudaEventRecord(ctx->ev0, st));
         launch_k1(a, lay, st);
         DTX_CUDA(cudaEventRecord(ctx->ev1, st));
@@ -436,6 +428,25 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
         ctx->launches += 1;
     }
     DTX_CUDA(cudaGetLastError());
+    ctx->run_S = bs.lay.S;
+    return DTX_OK;
+}
+
+int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_lo, double hist_hi,
+                   int lta_window, int want_fas, int keep_ds64) {
+    if (!ctx) return DTX_ERR_ARG;
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    auto it = ctx->sets.find(set_id);
+    if (it == ctx->sets.end()) return fail(ctx, DTX_ERR_STATE, "dtx_detect_run: unknown basis set");
+    if (ctx->nchunks < 1 || !ctx->d_raw) return fail(ctx, DTX_ERR_STATE, "dtx_detect_run: no chunks loaded");
+    if (engine != DTX_ENGINE_TCGEN05 && engine != DTX_ENGINE_FP64) return fail(ctx, DTX_ERR_ARG, "bad engine");
+    if (kblk == 0) kblk = 2;  // default: drain every 128 taps (bias <= ~2e-6 at DS = 1, DESIGN.md)
+    if (kblk < 1 || kblk > 64) return fail(ctx, DTX_ERR_ARG, "kblk out of range");
+    BasisSet& bs = it->second;
+    const int rc = project_run(ctx, bs, engine, kblk, 0, keep_ds64, nullptr);
+    if (rc != DTX_OK) return rc;
+    const int nchunks = ctx->nchunks, S = bs.lay.S;
+    cudaStream_t st = ctx->stream;
     launch_k3(ctx->d_DS.p, ctx->d_chunks.p, nchunks, S, bs.d_thr.p, ctx->d_rowmax.p, ctx->d_rowflags.p,
               bs.d_hist.p, hist_lo, hist_hi, ctx->d_cand.p, ctx->cand_cap, ctx->d_ncand.p,
               want_fas ? bs.d_fas.p : nullptr, st);
@@ -586,6 +597,88 @@ int dtx_launch_count(dtx_ctx* ctx, int64_t* n) {
     return DTX_OK;
 }
 
+static const int CCX_SET_ID = -77;
+
+// Tensor-core CCX: events [row_begin,row_end) as rank-1 templates, padded events as chunks.
+static int ccx_tcgen05(dtx_ctx* ctx, const void* X, int dtype, const void* dX, int N, int n, int Nc, int row_begin,
+                       int row_end, const double* wa, const double* wb, const double* es, const double* ed,
+                       double* dcc, int* dlag, double* dsub, std::vector<int2>& flagged) {
+    const int ns = n / Nc, trunc = n / (2 * Nc) - 1, nl = 2 * ns - 1 - 2 * trunc;
+    const int rows = row_end - row_begin;
+    cudaStream_t st = ctx->stream;
+    // templates: x / ||x - mean||  (zero rows for zeroed-out waveforms)
+    std::vector<double> U(static_cast<size_t>(rows) * n);
+    std::vector<int32_t> roff(rows + 1);
+    for (int r = 0; r <= rows; ++r) roff[r] = r;
+    for (int r = 0; r < rows; ++r) {
+        const size_t src = static_cast<size_t>(row_begin + r) * n;
+        long double s1 = 0;
+        for (int i = 0; i < n; ++i)
+            s1 += dtype == DTX_F32 ? static_cast<const float*>(X)[src + i] : static_cast<const double*>(X)[src + i];
+        const double mean = static_cast<double>(s1 / n);
+        long double s2 = 0;
+        for (int i = 0; i < n; ++i) {
+            const double v = (dtype == DTX_F32 ? static_cast<const float*>(X)[src + i]
+                                               : static_cast<const double*>(X)[src + i]) - mean;
+            s2 += v * v;
+        }
+        const double nrm = std::sqrt(static_cast<double>(s2));
+        for (int i = 0; i < n; ++i) {
+            const double v = dtype == DTX_F32 ? static_cast<const float*>(X)[src + i]
+                                              : static_cast<const double*>(X)[src + i];
+            U[static_cast<size_t>(r) * n + i] = nrm > 0 ? v / nrm : 0.0;
+        }
+    }
+    int rc = dtx_set_bases(ctx, CCX_SET_ID, U.data(), roff.data(), rows, n, Nc, nullptr);
+    if (rc != DTX_OK) return rc;
+    BasisSet& bs = ctx->sets[CCX_SET_ID];
+    const int P = ns - trunc - 1;
+    const int Lc = nl + ns - 1;
+    const long long Lm = static_cast<long long>(Lc) * Nc;
+    // batch of signals bounded by the DS buffer (rows x Tpad floats per signal)
+    const long long per_sig = static_cast<long long>(rows) * ((nl + TILE_T - 1) / TILE_T * TILE_T) * 4;
+    int batch = static_cast<int>(std::max<long long>(1, std::min<long long>(512, (4LL << 30) / per_sig)));
+    DevBuf<double> dpad;
+    DevBuf<int> dnflag;
+    DevBuf<int2> dflag;
+    const int flag_cap = 1 << 20;
+    DTX_CUDA(dpad.reserve(static_cast<size_t>(batch) * Lm));
+    DTX_CUDA(dnflag.reserve(1));
+    DTX_CUDA(dflag.reserve(flag_cap));
+    DTX_CUDA(cudaMemsetAsync(dnflag.p, 0, sizeof(int), st));
+    std::vector<int64_t> offs, lens;
+    std::vector<int> blk_hi;
+    for (int c0 = row_begin + 1; c0 < N; c0 += batch) {
+        const int nsig = std::min(batch, N - c0);
+        launch_ccx_pad(dX, dtype == DTX_F32, n, Nc, c0, nsig, P, Lc, dpad.p, st);
+        DTX_CUDA(cudaGetLastError());
+        offs.resize(nsig); lens.resize(nsig); blk_hi.resize(nsig);
+        for (int i = 0; i < nsig; ++i) {
+            offs[i] = static_cast<int64_t>(i) * Lm;
+            lens[i] = Lm;
+            const int nrow = std::min(c0 + i, row_end) - row_begin;   // templates b < c
+            blk_hi[i] = (nrow + VEC_PER_BLOCK - 1) / VEC_PER_BLOCK;
+        }
+        rc = dtx_attach_device_chunks(ctx, nsig, dpad.p, offs.data(), lens.data(), DTX_F64);
+        if (rc != DTX_OK) return rc;
+        rc = project_run(ctx, bs, DTX_ENGINE_TCGEN05, 2, 1, 0, blk_hi.data());
+        if (rc != DTX_OK) return rc;
+        launch_ccx_post(ctx->d_DS.p, ctx->d_chunks.p, c0, nsig, dX, dtype == DTX_F32, N, n, Nc, row_begin, row_end,
+                        wa, wb, es, ed, dcc, dlag, dsub, dnflag.p, dflag.p, flag_cap, st);
+        DTX_CUDA(cudaGetLastError());
+        ctx->launches += 2;
+    }
+    int nflag = 0;
+    DTX_CUDA(cudaMemcpyAsync(&nflag, dnflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaStreamSynchronize(st));
+    if (nflag > flag_cap) return fail(ctx, DTX_ERR_CAPACITY, "dtx_ccx: too many degenerate pairs");
+    flagged.resize(nflag);
+    if (nflag) DTX_CUDA(cudaMemcpy(flagged.data(), dflag.p, sizeof(int2) * nflag, cudaMemcpyDeviceToHost));
+    dpad.release(); dnflag.release(); dflag.release();
+    ctx->ran = false;  // the detection results of this context were overwritten
+    return DTX_OK;
+}
+
 int dtx_ccx(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int row_begin, int row_end,
             int engine, double* cc, int32_t* lag, double* subsamp) {
     if (!ctx) return DTX_ERR_ARG;
@@ -594,31 +687,71 @@ int dtx_ccx(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int ro
         return fail(ctx, DTX_ERR_ARG, "dtx_ccx: lengths not equal / not a multiple of Nc (construct.py:430-436)");
     if (row_begin < 0 || row_end > N || row_begin >= row_end) return fail(ctx, DTX_ERR_ARG, "dtx_ccx: bad row range");
     if (dtype != DTX_F64 && dtype != DTX_F32) return fail(ctx, DTX_ERR_ARG, "dtx_ccx: bad dtype");
-    (void)engine;  // both engines currently run the float64 kernel
+    if (engine != DTX_ENGINE_TCGEN05 && engine != DTX_ENGINE_FP64) return fail(ctx, DTX_ERR_ARG, "dtx_ccx: bad engine");
     DTX_CUDA(cudaSetDevice(ctx->device));
+    const int ns = n / Nc, trunc = n / (2 * Nc) - 1, nl = 2 * ns - 1 - 2 * trunc;
     const size_t esz = dtype == DTX_F32 ? 4 : 8;
     const size_t rows = static_cast<size_t>(row_end - row_begin);
     DevBuf<uint8_t> dX;
-    DevBuf<double> dcc, dsub;
+    DevBuf<double> dcc, dsub, wa, wb, es, ed;
     DevBuf<int> dlag;
     DTX_CUDA(dX.reserve(static_cast<size_t>(N) * n * esz));
     DTX_CUDA(dcc.reserve(rows * N));
     DTX_CUDA(dsub.reserve(rows * N));
     DTX_CUDA(dlag.reserve(rows * N));
+    DTX_CUDA(wa.reserve(static_cast<size_t>(N) * nl));
+    DTX_CUDA(wb.reserve(static_cast<size_t>(N) * nl));
+    DTX_CUDA(es.reserve(N));
+    DTX_CUDA(ed.reserve(N));
     cudaStream_t st = ctx->stream;
     DTX_CUDA(cudaMemcpyAsync(dX.p, X, static_cast<size_t>(N) * n * esz, cudaMemcpyHostToDevice, st));
     DTX_CUDA(cudaMemsetAsync(dcc.p, 0, rows * N * sizeof(double), st));
     DTX_CUDA(cudaMemsetAsync(dsub.p, 0, rows * N * sizeof(double), st));
     DTX_CUDA(cudaMemsetAsync(dlag.p, 0, rows * N * sizeof(int), st));
-    launch_ccx_fp64(dX.p, dtype == DTX_F32, N, n, Nc, row_begin, row_end, dcc.p, dlag.p, dsub.p,
-                    ctx->num_sms, st);
+    launch_ccx_stats(dX.p, dtype == DTX_F32, N, n, Nc, wa.p, wb.p, es.p, ed.p, st);
     DTX_CUDA(cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 1;
+    if (engine == DTX_ENGINE_FP64 || nl < 16) {  // tiny templates: not worth a GEMM
+        launch_ccx_fp64(dX.p, dtype == DTX_F32, N, n, Nc, row_begin, row_end, wa.p, wb.p, es.p, ed.p, dcc.p, dlag.p,
+                        dsub.p, ctx->num_sms, st);
+        DTX_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+    } else {
+        std::vector<int2> flagged;
+        const int rc = ccx_tcgen05(ctx, X, dtype, dX.p, N, n, Nc, row_begin, row_end, wa.p, wb.p, es.p, ed.p, dcc.p,
+                                   dlag.p, dsub.p, flagged);
+        if (rc != DTX_OK) return rc;
+        if (!flagged.empty()) {
+            // degenerate pairs (|res| > 1 from zero-variance windows, or a crowded maximum): the
+            // float64 kernel re-does their rows; only the flagged entries are taken from it
+            std::vector<int> frows;
+            for (const int2& f : flagged) frows.push_back(f.x);
+            std::sort(frows.begin(), frows.end());
+            frows.erase(std::unique(frows.begin(), frows.end()), frows.end());
+            DevBuf<double> tcc, tsub;
+            DevBuf<int> tlag;
+            DTX_CUDA(tcc.reserve(N)); DTX_CUDA(tsub.reserve(N)); DTX_CUDA(tlag.reserve(N));
+            for (int b : frows) {
+                launch_ccx_fp64(dX.p, dtype == DTX_F32, N, n, Nc, b, b + 1, wa.p, wb.p, es.p, ed.p, tcc.p, tlag.p,
+                                tsub.p, ctx->num_sms, st);
+                DTX_CUDA(cudaGetLastError());
+                for (const int2& f : flagged)
+                    if (f.x == b) {
+                        const size_t o = static_cast<size_t>(b - row_begin) * N + f.y;
+                        DTX_CUDA(cudaMemcpyAsync(dcc.p + o, tcc.p + f.y, sizeof(double), cudaMemcpyDeviceToDevice, st));
+                        DTX_CUDA(cudaMemcpyAsync(dsub.p + o, tsub.p + f.y, sizeof(double), cudaMemcpyDeviceToDevice, st));
+                        DTX_CUDA(cudaMemcpyAsync(dlag.p + o, tlag.p + f.y, sizeof(int), cudaMemcpyDeviceToDevice, st));
+                    }
+            }
+            DTX_CUDA(cudaStreamSynchronize(st));
+            tcc.release(); tsub.release(); tlag.release();
+        }
+    }
     DTX_CUDA(cudaMemcpyAsync(cc, dcc.p, rows * N * sizeof(double), cudaMemcpyDeviceToHost, st));
     DTX_CUDA(cudaMemcpyAsync(lag, dlag.p, rows * N * sizeof(int), cudaMemcpyDeviceToHost, st));
     DTX_CUDA(cudaMemcpyAsync(subsamp, dsub.p, rows * N * sizeof(double), cudaMemcpyDeviceToHost, st));
     DTX_CUDA(cudaStreamSynchronize(st));
-    dX.release(); dcc.release(); dsub.release(); dlag.release();
+    dX.release(); dcc.release(); dsub.release(); dlag.release(); wa.release(); wb.release(); es.release(); ed.release();
     return DTX_OK;
 }
 

@@ -34,7 +34,7 @@ struct ChunkDesc {
     int ntiles;          // ceil(T / TILE_T)
     int Lpad;            // padded per-channel length of the split arrays
     int Tpad;            // ntiles * TILE_T
-    int pad0, pad1;
+    int blk_lo, blk_hi;  // basis blocks K1 runs for this chunk: [blk_lo, blk_hi)
 };
 
 struct Seg {
@@ -86,6 +86,8 @@ struct K1Args {
     int nitems;
     int kblk;      // 64-tap chunks accumulated in TMEM between drains
     int num_sms;
+    int nq;        // MMA N: 256 (tiles of 2048 lags) or 128 (tiles of 1024 lags)
+    int mode;      // 0 = detection statistic, 1 = signed correlation coefficient (CCX)
 };
 void launch_k1(const K1Args& a, const BasisLayout& lay, cudaStream_t st);
 int k1_smem_bytes();
@@ -108,6 +110,19 @@ void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, c
                double* d_fas /*[S][4] or null*/, cudaStream_t st);
 void launch_lta(const float* DS, const ChunkDesc* d_chunks, int S, const int* d_rowflags,
                 Candidate* d_cand, const int* d_ncand, int cand_cap, int W, cudaStream_t st);
+
+// k4_ccx.cu : pairwise CCX
+void launch_ccx_stats(const void* d_X, int dtype_f32, int N, int n, int Nc, double* wa, double* wb, double* es,
+                      double* ed, cudaStream_t st);
+void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int row_begin, int row_end,
+                     const double* wa, const double* wb, const double* es, const double* ed, double* d_cc,
+                     int* d_lag, double* d_sub, int num_sms, cudaStream_t st);
+void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int nsig, int P, int Lc, double* out,
+                    cudaStream_t st);
+void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsig, const void* d_X, int dtype_f32,
+                     int N, int n, int Nc, int row_begin, int row_end, const double* wa, const double* wb,
+                     const double* es, const double* ed, double* d_cc, int* d_lag, double* d_sub, int* d_nflag,
+                     int2* d_flagged, int flag_cap, cudaStream_t st);
 
 void launch_stalta_dense(const float* row, int T, int W, int zero_inf, float* out, cudaStream_t st);
 

@@ -4,7 +4,9 @@
 // Replaces, for ALL subspaces of a station at once, the per-subspace FFT correlation
 //   m1 = ssFD * MPconFD ; if1 = real(ifft(m1))[:, n-1:L] - av_norm ; sum(if1^2)/b ; [::Nc]
 // of `_SSDetex._MPXDS` (reference detex/detect.py:559-578) == `fas._MPXSSCorr`
-// (detex/fas.py:120-134).
+// (detex/fas.py:120-134).  In MODE 1 the same contraction yields the signed normalised
+// cross-correlation series of `construct._CCX2` (detex/construct.py:438-453) with events as
+// rank-1 templates and zero-padded events as the data.
 //
 // Math (per channel c, de-multiplexed; exact because only channel-aligned lags are kept):
 //   P[k,t]  = sum_c sum_j U_c[k,j] x_c[t+j]
@@ -17,7 +19,7 @@
 // * A (M = 128 rows = 16 basis vectors x 8 phases) is a plain matrix: pre-built once per
 //   basis set in HBM in the exact no-swizzle K-major smem image (Aimg) and streamed through a
 //   4-stage ring with 32 KB bulk copies (UBLKCP); it is L2-resident across the 148 CTAs.
-// * B (N = 256 rows) is a HANKEL matrix and is never materialised: row q starts 8 elements
+// * B (N = NQ rows) is a HANKEL matrix and is never materialised: row q starts 8 elements
 //   = 16 B after row q-1, which is exactly the row pitch inside a core matrix.  A K-major
 //   no-swizzle descriptor with LBO = 16 B (next K core matrix) and SBO = 128 B (next 8 rows)
 //   makes the tensor core read overlapping core matrices straight out of the 1-D signal
@@ -29,7 +31,7 @@
 //   chunks; 8 drain warps pull each partial sum out of TMEM (double-buffered accumulators)
 //   and add it to register accumulators with round-to-nearest.
 //
-// One persistent CTA per SM; work item = (chunk, tile of 2048 lags); inner loop over the
+// One persistent CTA per SM; work item = (chunk, tile of 8*NQ lags); inner loop over the
 // basis blocks so all CTAs stream the same A block from L2 at about the same time.
 #include "dtx_kernels.cuh"
 #include "tc_common.cuh"
@@ -37,23 +39,23 @@
 namespace dtx {
 namespace {
 
-constexpr int NQ = 256;
 constexpr int STAGES = 4;
 constexpr int STAGE_BYTES = 32768;                      // A_hi tile | A_lo tile (16 KB each)
 constexpr int TILE_BYTES = 16384;
-constexpr int SIG_HALFS = TILE_T + MAX_SEG_TAPS;        // per hi or lo span
+constexpr int SIG_HALFS = TILE_T + MAX_SEG_TAPS;        // per hi or lo span (sized for NQ = 256)
 constexpr int SIG_BUF_BYTES = 2 * SIG_HALFS * 2;        // hi + lo
 constexpr int NORM_BUF_BYTES = 2 * TILE_T * 4;          // mu + invE
 constexpr int NTHREADS = 384;                           // warps 0-3: producer, MMA, 2 idle; warps 4-11: drain
 constexpr int FIRST_DRAIN_WARP = 4;
-constexpr int REGS_CTRL = 56, REGS_DRAIN = 224;        // setmaxnreg budgets (128*56 + 256*224 = 64512)
 constexpr int NDRAIN_WARPS = 8;
+constexpr int REGS_CTRL = 56, REGS_DRAIN = 224;         // setmaxnreg budgets (128*56 + 256*224 = 64512)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * SIG_BUF_BYTES + 2 * NORM_BUF_BYTES;
 
 struct K1Params {
     K1Args a;
     int nblocks, nchunks, nseg;
     float u_inv_scale;
+    float inv_cn;  // n / (n-1)
     Seg seg[MAX_SEGS];
 };
 
@@ -76,17 +78,215 @@ struct Ring {
     }
 };
 
+struct Smem {
+    uint8_t* stage;
+    uint8_t* sig;
+    uint8_t* norm;
+    uint64_t *full, *empty, *sigfull, *sigempty, *accfull, *accempty, *normfull, *normempty;
+};
+
+// ------------------------------------------------------------------ producer (1 thread)
+template <int NQ>
+__device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) {
+    constexpr int TT = 8 * NQ;
+    Ring st(STAGES), sg(2), nm(2);
+    for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
+        const int2 it = P.a.items[item];
+        const ChunkDesc cd = P.a.chunks[it.x];
+        // window mean / inverse energy of this tile
+        mbar_wait(&S.normempty[nm.idx], nm.phase ^ 1);
+        mbar_arrive_expect_tx(&S.normfull[nm.idx], 2 * TT * 4);
+        bulk_g2s(S.norm + nm.idx * NORM_BUF_BYTES, P.a.mu + cd.norm_off + static_cast<long long>(it.y) * TT,
+                 TT * 4, &S.normfull[nm.idx]);
+        bulk_g2s(S.norm + nm.idx * NORM_BUF_BYTES + TILE_T * 4,
+                 P.a.invE + cd.norm_off + static_cast<long long>(it.y) * TT, TT * 4, &S.normfull[nm.idx]);
+        nm.advance();
+        const __half* sig0 = P.a.xsplit + cd.sig_off + static_cast<long long>(it.y) * TT;
+        for (int b = cd.blk_lo; b < cd.blk_hi; ++b) {
+            const uint8_t* ablk = P.a.Aimg + static_cast<size_t>(b) * P.nchunks * STAGE_BYTES;
+            for (int g = 0; g < P.nseg; ++g) {
+                const Seg sgm = P.seg[g];
+                const uint32_t bytes = (TT + sgm.ntaps) * 2;
+                mbar_wait(&S.sigempty[sg.idx], sg.phase ^ 1);
+                mbar_arrive_expect_tx(&S.sigfull[sg.idx], 2 * bytes);
+                const __half* src = sig0 + static_cast<long long>(sgm.chan * 2) * cd.Lpad + sgm.tap0;
+                bulk_g2s(S.sig + sg.idx * SIG_BUF_BYTES, src, bytes, &S.sigfull[sg.idx]);
+                bulk_g2s(S.sig + sg.idx * SIG_BUF_BYTES + SIG_HALFS * 2, src + cd.Lpad, bytes,
+                         &S.sigfull[sg.idx]);
+                sg.advance();
+                const int nck = sgm.ntaps / CHUNK_TAPS;
+                for (int kc = 0; kc < nck; ++kc) {
+                    mbar_wait(&S.empty[st.idx], st.phase ^ 1);
+                    mbar_arrive_expect_tx(&S.full[st.idx], STAGE_BYTES);
+                    bulk_g2s(S.stage + st.idx * STAGE_BYTES,
+                             ablk + static_cast<size_t>(sgm.chunk0 + kc) * STAGE_BYTES, STAGE_BYTES,
+                             &S.full[st.idx]);
+                    st.advance();
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- MMA issuer (1 thread)
+template <int NQ>
+__device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint32_t tmem) {
+    const int kblk = P.a.kblk;
+    const uint32_t idesc = idesc_f16_f32(128, NQ);
+    const uint64_t a_base = smem_desc_kmajor_noswz(0, A_LBO, A_SBO);
+    const uint64_t b_base = smem_desc_kmajor_noswz(0, B_LBO, B_SBO);
+    const uint32_t stage0 = smem_u32(S.stage), sig0 = smem_u32(S.sig);
+    Ring st(STAGES), sg(2), ac(2);
+    for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
+        const int2 it = P.a.items[item];
+        const int blk_lo = P.a.chunks[it.x].blk_lo, blk_hi = P.a.chunks[it.x].blk_hi;
+        for (int b = blk_lo; b < blk_hi; ++b) {
+            int cib = 0, done = 0;
+            for (int g = 0; g < P.nseg; ++g) {
+                const int nck = P.seg[g].ntaps / CHUNK_TAPS;
+                mbar_wait(&S.sigfull[sg.idx], sg.phase);
+                tc_fence_after();
+                const uint32_t sh = sig0 + sg.idx * SIG_BUF_BYTES;
+                const uint32_t sl = sh + SIG_HALFS * 2;
+                for (int kc = 0; kc < nck; ++kc) {
+                    mbar_wait(&S.full[st.idx], st.phase);
+                    if (cib == 0) mbar_wait(&S.accempty[ac.idx], ac.phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem + ac.idx * 256;
+                    const uint32_t ah = stage0 + st.idx * STAGE_BYTES;
+                    const uint32_t al = ah + TILE_BYTES;
+                    const uint32_t bo = kc * (CHUNK_TAPS * 2);
+#pragma unroll
+                    for (int kk = 0; kk < CHUNK_TAPS / 16; ++kk) {
+                        const uint64_t dah = a_base | ((ah + kk * 256) >> 4);
+                        const uint64_t dal = a_base | ((al + kk * 256) >> 4);
+                        const uint64_t dbh = b_base | ((sh + bo + kk * 32) >> 4);
+                        const uint64_t dbl = b_base | ((sl + bo + kk * 32) >> 4);
+                        umma_f16(d, dah, dbh, idesc, (cib | kk) ? 1u : 0u);
+                        umma_f16(d, dah, dbl, idesc, 1u);
+                        umma_f16(d, dal, dbh, idesc, 1u);
+                    }
+                    umma_commit(&S.empty[st.idx]);
+                    st.advance();
+                    ++cib;
+                    ++done;
+                    if (cib == kblk || done == P.nchunks) {
+                        umma_commit(&S.accfull[ac.idx]);
+                        ac.advance();
+                        cib = 0;
+                    }
+                }
+                umma_commit(&S.sigempty[sg.idx]);
+                sg.advance();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------- drain + epilogue (8 warps, 256 threads)
+template <int NQ, int MODE>
+__device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uint32_t tmem, int warp,
+                                           int lane) {
+    constexpr int TT = 8 * NQ;
+    constexpr int NCOL = NQ / 2;                 // accumulator columns per thread
+    const int dw = warp - FIRST_DRAIN_WARP;      // 0..7
+    const int lq = warp & 3;                     // TMEM lane quarter this warp may read
+    const int colhalf = dw >> 2;                 // which half of the NQ accumulator columns
+    const int p = 2 * lq + (lane & 1);           // phase of this thread's row
+    const int kl = lane >> 1;                    // basis-vector slot of this thread's row
+    const uint32_t taddr0 = tmem + (static_cast<uint32_t>(lq * 32) << 16) + colhalf * NCOL;
+    const int kblk = P.a.kblk;
+    const int ndrains = (P.nchunks + kblk - 1) / kblk;
+    Ring ac(2), nm(2);
+    float sums[NCOL];
+    for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
+        const int2 it = P.a.items[item];
+        const ChunkDesc cd = P.a.chunks[it.x];
+        const float sc = P.a.chunk_scale[it.x] * P.u_inv_scale;
+        const float* smu = reinterpret_cast<const float*>(S.norm + nm.idx * NORM_BUF_BYTES);
+        const float* sie = smu + TILE_T;
+        for (int b = cd.blk_lo; b < cd.blk_hi; ++b) {
+#pragma unroll
+            for (int i = 0; i < NCOL; ++i) sums[i] = 0.f;
+            for (int dr = 0; dr < ndrains; ++dr) {
+                mbar_wait(&S.accfull[ac.idx], ac.phase);
+                tc_fence_after();
+                const uint32_t ta = taddr0 + ac.idx * 256;
+#pragma unroll
+                for (int i = 0; i < NCOL / 32; ++i) {
+                    uint32_t v[32];
+                    tmem_ld_x32(ta + i * 32, v);
+                    tmem_wait_ld();
+                    if (i == NCOL / 32 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&S.accempty[ac.idx]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sums[i * 32 + j] += __uint_as_float(v[j]);
+                }
+                ac.advance();
+            }
+            // ---------------------------------------------------- K2 epilogue
+            if (b == cd.blk_lo) mbar_wait(&S.normfull[nm.idx], nm.phase);
+            const BlockInfo bi = P.a.binfo[b * VEC_PER_BLOCK + kl];
+            const bool head = bi.nrows > 0 && bi.out_row >= 0;
+            const long long row_off = cd.ds_off + static_cast<long long>(head ? bi.out_row : 0) * cd.Tpad +
+                                      static_cast<long long>(it.y) * TT + 8 * NCOL * colhalf + p;
+            float* dsrow = P.a.DS + row_off;
+            const float* pmu = smu + 8 * NCOL * colhalf + p;
+            const float* pie = sie + 8 * NCOL * colhalf + p;
+            const float nsumU = -bi.sumU;
+            if (MODE == 0) {
+                // segmented suffix sum over the vector slots of a subspace (lanes 2 apart share a
+                // phase): 4 fixed doubling steps cover ranks up to 16, branch free so the
+                // unrolled lags interleave
+                const bool j1 = kl + 1 < bi.seg_end, j2 = kl + 2 < bi.seg_end, j4 = kl + 4 < bi.seg_end,
+                           j8 = kl + 8 < bi.seg_end;
+#pragma unroll
+                for (int i = 0; i < NCOL; ++i) {
+                    const float c = fmaf(sums[i], sc, pmu[8 * i] * nsumU);
+                    float v = c * c;
+                    float o = __shfl_down_sync(0xffffffffu, v, 2);
+                    v += j1 ? o : 0.f;
+                    o = __shfl_down_sync(0xffffffffu, v, 4);
+                    v += j2 ? o : 0.f;
+                    o = __shfl_down_sync(0xffffffffu, v, 8);
+                    v += j4 ? o : 0.f;
+                    o = __shfl_down_sync(0xffffffffu, v, 16);
+                    v += j8 ? o : 0.f;
+                    if (head) dsrow[8 * i] = v * pie[8 * i];
+                }
+            } else {
+                // signed Pearson coefficient: templates are pre-scaled by 1/||x1 - mean||, so
+                // res = c / sqrt(E) = c * sqrt(invE * n/(n-1))
+#pragma unroll
+                for (int i = 0; i < NCOL; ++i) {
+                    const float c = fmaf(sums[i], sc, pmu[8 * i] * nsumU);
+                    if (head) dsrow[8 * i] = c * sqrtf(pie[8 * i] * P.inv_cn);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.normempty[nm.idx]);
+        nm.advance();
+    }
+}
+
+template <int NQ, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) k1_kernel(const __grid_constant__ K1Params P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sStage = smem;
-    uint8_t* sSig = smem + STAGES * STAGE_BYTES;
-    uint8_t* sNorm = sSig + 2 * SIG_BUF_BYTES;
     __shared__ uint64_t full[STAGES], empty[STAGES];
     __shared__ uint64_t sigfull[2], sigempty[2], accfull[2], accempty[2], normfull[2], normempty[2];
     __shared__ uint32_t tmem_base_s;
+    Smem S;
+    S.stage = smem;
+    S.sig = smem + STAGES * STAGE_BYTES;
+    S.norm = S.sig + 2 * SIG_BUF_BYTES;
+    S.full = full; S.empty = empty; S.sigfull = sigfull; S.sigempty = sigempty;
+    S.accfull = accfull; S.accempty = accempty; S.normfull = normfull; S.normempty = normempty;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
@@ -110,181 +310,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k1_kernel(const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    const int kblk = P.a.kblk;
 
+    // setmaxnreg must sit at the top of each role branch for ptxas to budget the branch
     if (warp < FIRST_DRAIN_WARP) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
-      if (warp == 0) {
-        // =============================================================== producer
-        if (lane == 0) {
-            Ring st(STAGES), sg(2), nm(2);
-            for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
-                const int2 it = P.a.items[item];
-                const ChunkDesc cd = P.a.chunks[it.x];
-                // window mean / inverse energy of this tile
-                mbar_wait(&normempty[nm.idx], nm.phase ^ 1);
-                mbar_arrive_expect_tx(&normfull[nm.idx], NORM_BUF_BYTES);
-                bulk_g2s(sNorm + nm.idx * NORM_BUF_BYTES,
-                         P.a.mu + cd.norm_off + static_cast<long long>(it.y) * TILE_T, TILE_T * 4,
-                         &normfull[nm.idx]);
-                bulk_g2s(sNorm + nm.idx * NORM_BUF_BYTES + TILE_T * 4,
-                         P.a.invE + cd.norm_off + static_cast<long long>(it.y) * TILE_T, TILE_T * 4,
-                         &normfull[nm.idx]);
-                nm.advance();
-                const __half* sig0 = P.a.xsplit + cd.sig_off + static_cast<long long>(it.y) * TILE_T;
-                for (int b = 0; b < P.nblocks; ++b) {
-                    const uint8_t* ablk =
-                        P.a.Aimg + static_cast<size_t>(b) * P.nchunks * STAGE_BYTES;
-                    for (int g = 0; g < P.nseg; ++g) {
-                        const Seg sgm = P.seg[g];
-                        const uint32_t bytes = (TILE_T + sgm.ntaps) * 2;
-                        mbar_wait(&sigempty[sg.idx], sg.phase ^ 1);
-                        mbar_arrive_expect_tx(&sigfull[sg.idx], 2 * bytes);
-                        const __half* src =
-                            sig0 + static_cast<long long>(sgm.chan * 2) * cd.Lpad + sgm.tap0;
-                        bulk_g2s(sSig + sg.idx * SIG_BUF_BYTES, src, bytes, &sigfull[sg.idx]);
-                        bulk_g2s(sSig + sg.idx * SIG_BUF_BYTES + SIG_HALFS * 2, src + cd.Lpad, bytes,
-                                 &sigfull[sg.idx]);
-                        sg.advance();
-                        const int nck = sgm.ntaps / CHUNK_TAPS;
-                        for (int kc = 0; kc < nck; ++kc) {
-                            mbar_wait(&empty[st.idx], st.phase ^ 1);
-                            mbar_arrive_expect_tx(&full[st.idx], STAGE_BYTES);
-                            bulk_g2s(sStage + st.idx * STAGE_BYTES,
-                                     ablk + static_cast<size_t>(sgm.chunk0 + kc) * STAGE_BYTES,
-                                     STAGE_BYTES, &full[st.idx]);
-                            st.advance();
-                        }
-                    }
-                }
-            }
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
+        if (warp == 0 && lane == 0) {
+            producer_loop<NQ>(P, S);
+        } else if (warp == 1 && lane == 0) {
+            mma_loop<NQ>(P, S, tmem);
         }
-      } else if (warp == 1) {
-        // ============================================================= MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = idesc_f16_f32(128, NQ);
-            const uint64_t a_base = smem_desc_kmajor_noswz(0, A_LBO, A_SBO);
-            const uint64_t b_base = smem_desc_kmajor_noswz(0, B_LBO, B_SBO);
-            const uint32_t stage0 = smem_u32(sStage), sig0 = smem_u32(sSig);
-            Ring st(STAGES), sg(2), ac(2);
-            for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
-                for (int b = 0; b < P.nblocks; ++b) {
-                    int cib = 0, done = 0;
-                    for (int g = 0; g < P.nseg; ++g) {
-                        const int nck = P.seg[g].ntaps / CHUNK_TAPS;
-                        mbar_wait(&sigfull[sg.idx], sg.phase);
-                        tc_fence_after();
-                        const uint32_t sh = sig0 + sg.idx * SIG_BUF_BYTES;
-                        const uint32_t sl = sh + SIG_HALFS * 2;
-                        for (int kc = 0; kc < nck; ++kc) {
-                            mbar_wait(&full[st.idx], st.phase);
-                            if (cib == 0) mbar_wait(&accempty[ac.idx], ac.phase ^ 1);
-                            tc_fence_after();
-                            const uint32_t d = tmem + ac.idx * NQ;
-                            const uint32_t ah = stage0 + st.idx * STAGE_BYTES;
-                            const uint32_t al = ah + TILE_BYTES;
-                            const uint32_t bo = kc * (CHUNK_TAPS * 2);
-#pragma unroll
-                            for (int kk = 0; kk < CHUNK_TAPS / 16; ++kk) {
-                                const uint64_t dah = a_base | ((ah + kk * 256) >> 4);
-                                const uint64_t dal = a_base | ((al + kk * 256) >> 4);
-                                const uint64_t dbh = b_base | ((sh + bo + kk * 32) >> 4);
-                                const uint64_t dbl = b_base | ((sl + bo + kk * 32) >> 4);
-                                umma_f16(d, dah, dbh, idesc, (cib | kk) ? 1u : 0u);
-                                umma_f16(d, dah, dbl, idesc, 1u);
-                                umma_f16(d, dal, dbh, idesc, 1u);
-                            }
-                            umma_commit(&empty[st.idx]);
-                            st.advance();
-                            ++cib;
-                            ++done;
-                            if (cib == kblk || done == P.nchunks) {
-                                umma_commit(&accfull[ac.idx]);
-                                ac.advance();
-                                cib = 0;
-                            }
-                        }
-                        umma_commit(&sigempty[sg.idx]);
-                        sg.advance();
-                    }
-                }
-            }
-        }
-      }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_DRAIN));
-        // ================================================== drain + epilogue warps
-        const int dw = warp - FIRST_DRAIN_WARP;  // 0..7
-        const int lq = warp & 3;            // TMEM lane quarter this warp may read
-        const int colhalf = dw >> 2;        // which 128 of the 256 accumulator columns
-        const int p = 2 * lq + (lane & 1);  // phase of this thread's row
-        const int kl = lane >> 1;           // basis-vector slot of this thread's row
-        const uint32_t taddr0 = tmem + (static_cast<uint32_t>(lq * 32) << 16) + colhalf * 128;
-        const int ndrains = (P.nchunks + kblk - 1) / kblk;
-        Ring ac(2), nm(2);
-        float sums[128];
-        for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
-            const int2 it = P.a.items[item];
-            const ChunkDesc cd = P.a.chunks[it.x];
-            const float sc = P.a.chunk_scale[it.x] * P.u_inv_scale;
-            const float* smu = reinterpret_cast<const float*>(sNorm + nm.idx * NORM_BUF_BYTES);
-            const float* sie = smu + TILE_T;
-            for (int b = 0; b < P.nblocks; ++b) {
-#pragma unroll
-                for (int i = 0; i < 128; ++i) sums[i] = 0.f;
-                for (int dr = 0; dr < ndrains; ++dr) {
-                    mbar_wait(&accfull[ac.idx], ac.phase);
-                    tc_fence_after();
-                    const uint32_t ta = taddr0 + ac.idx * NQ;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint32_t v[32];
-                        tmem_ld_x32(ta + i * 32, v);
-                        tmem_wait_ld();
-                        if (i == 3) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&accempty[ac.idx]);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) sums[i * 32 + j] += __uint_as_float(v[j]);
-                    }
-                    ac.advance();
-                }
-                // ------------------------------------------------ K2 epilogue
-                if (b == 0) mbar_wait(&normfull[nm.idx], nm.phase);
-                const BlockInfo bi = P.a.binfo[b * VEC_PER_BLOCK + kl];
-                const bool head = bi.nrows > 0 && bi.out_row >= 0;
-                const long long row_off = cd.ds_off + static_cast<long long>(head ? bi.out_row : 0) * cd.Tpad +
-                                          static_cast<long long>(it.y) * TILE_T + 1024 * colhalf + p;
-                float* dsrow = P.a.DS + row_off;
-                const float* pmu = smu + 1024 * colhalf + p;
-                const float* pie = sie + 1024 * colhalf + p;
-                const float nsumU = -bi.sumU;
-                // segmented suffix sum over the vector slots of a subspace (lanes 2 apart share a
-                // phase): 4 fixed doubling steps cover ranks up to 16, branch free so the 128
-                // unrolled lags interleave
-                const bool j1 = kl + 1 < bi.seg_end, j2 = kl + 2 < bi.seg_end, j4 = kl + 4 < bi.seg_end,
-                           j8 = kl + 8 < bi.seg_end;
-#pragma unroll
-                for (int i = 0; i < 128; ++i) {
-                    const float c = fmaf(sums[i], sc, pmu[8 * i] * nsumU);
-                    float v = c * c;
-                    float o = __shfl_down_sync(0xffffffffu, v, 2);
-                    v += j1 ? o : 0.f;
-                    o = __shfl_down_sync(0xffffffffu, v, 4);
-                    v += j2 ? o : 0.f;
-                    o = __shfl_down_sync(0xffffffffu, v, 8);
-                    v += j4 ? o : 0.f;
-                    o = __shfl_down_sync(0xffffffffu, v, 16);
-                    v += j8 ? o : 0.f;
-                    if (head) dsrow[8 * i] = v * pie[8 * i];
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&normempty[nm.idx]);
-            nm.advance();
-        }
+        drain_loop<NQ, MODE>(P, S, tmem, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -334,6 +371,12 @@ basis_image_kernel(const double* __restrict__ U, const int* __restrict__ slot_ro
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(out);
 }
 
+template <int NQ, int MODE>
+void launch_k1_t(const K1Params& P, int grid, cudaStream_t st) {
+    cudaFuncSetAttribute(k1_kernel<NQ, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    k1_kernel<NQ, MODE><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+}
+
 }  // namespace
 
 int k1_smem_bytes() { return SMEM_BYTES; }
@@ -346,17 +389,23 @@ void launch_basis_image(const double* d_U, const int* d_slot_row, const BasisLay
 }
 
 void launch_k1(const K1Args& a, const BasisLayout& lay, cudaStream_t st) {
-    cudaFuncSetAttribute(k1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     K1Params P;
     P.a = a;
     P.nblocks = lay.nblocks;
     P.nchunks = lay.nchunks;
     P.nseg = lay.nseg;
     P.u_inv_scale = lay.u_inv_scale;
+    P.inv_cn = static_cast<float>(static_cast<double>(lay.n) / (lay.n - 1.0));
     for (int i = 0; i < lay.nseg; ++i) P.seg[i] = lay.seg[i];
-    int grid = a.nitems < a.num_sms ? a.nitems : a.num_sms;
+    const int grid = a.nitems < a.num_sms ? a.nitems : a.num_sms;
     if (grid < 1) return;
-    k1_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+    if (a.nq == 128) {
+        if (a.mode == 1) launch_k1_t<128, 1>(P, grid, st);
+        else launch_k1_t<128, 0>(P, grid, st);
+    } else {
+        if (a.mode == 1) launch_k1_t<256, 1>(P, grid, st);
+        else launch_k1_t<256, 0>(P, grid, st);
+    }
 }
 
 }  // namespace dtx

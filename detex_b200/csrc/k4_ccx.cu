@@ -225,19 +225,160 @@ ccx_kernel(const T* __restrict__ X, int N, int n, int Nc, int trunc, int nl, int
     }
 }
 
+
+// ===================================================================== tensor-core engine
+// Events as rank-1 templates of the Hankel GEMM (k1_project.cu, MODE 1), zero-padded events
+// as its "chunks".  The GEMM returns the float32 correlation series of every pair; this
+// kernel finds the arg-max neighbourhood in it and RE-SCORES those few lags in float64 from
+// the original waveforms, so cc / lag / subsamp come out with float64 accuracy.
+
+// padded "chunk" of event c: per channel [P zeros | x_c | zeros], P = ns - trunc - 1, so that
+// lag m of the Hankel output is the shift kappa = m + trunc + 1 - ns of _CCX2.
+template <typename T>
+__global__ void __launch_bounds__(256)
+ccx_pad_kernel(const T* __restrict__ X, int n, int Nc, int c0, int P, int Lc, double* __restrict__ out) {
+    const int c = c0 + blockIdx.y;
+    const long long Lm = static_cast<long long>(Lc) * Nc;
+    const T* x = X + static_cast<long long>(c) * n;
+    double* o = out + static_cast<long long>(blockIdx.y) * Lm;
+    for (long long i = blockIdx.x * 256 + threadIdx.x; i < Lm; i += static_cast<long long>(gridDim.x) * 256) {
+        const long long j = i - static_cast<long long>(P) * Nc;
+        o[i] = (j >= 0 && j < n) ? static_cast<double>(x[j]) : 0.0;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ double ccx_exact(const T* __restrict__ x1, const T* __restrict__ x2, int n, int Nc,
+                                            int kappa, double sum1, double a, double sb, double std1, int lane) {
+    const int sh = kappa * Nc;
+    double acc = 0.0;
+    const int lo = max(0, -sh), hi = min(n, n - sh);
+    for (int i = lo + lane; i < hi; i += 32) acc = fma(static_cast<double>(x1[i]), static_cast<double>(x2[i + sh]), acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return (acc - sum1 * a) / (static_cast<double>(n) * sb * std1);
+}
+
+constexpr int CCX_MAXCAND = 8;
+constexpr float CCX_CAND_BAND = 3e-5f;   // float32 series is within ~2e-6 of float64; generous band
+
+// one warp per (signal chunk ci, template row r)
+template <typename T>
+__global__ void __launch_bounds__(256)
+ccx_post_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, int c0, const T* __restrict__ X,
+                int N, int n, int Nc, int trunc, int nl, int row_begin, int row_end,
+                const double* __restrict__ wa, const double* __restrict__ wb, const double* __restrict__ evsum,
+                const double* __restrict__ evstd, double* __restrict__ cc, int* __restrict__ lag,
+                double* __restrict__ sub, int* __restrict__ nflag, int2* __restrict__ flagged, int flag_cap) {
+    const int ci = blockIdx.y;
+    const int c = c0 + ci;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int b = row_begin + r;
+    if (b >= row_end || b >= c) return;
+    const ChunkDesc cd = chunks[ci];
+    const float* row = DS + cd.ds_off + static_cast<long long>(r) * cd.Tpad;
+    const long long o = static_cast<long long>(r) * N + c;
+    const double std1 = evstd[b], std2 = evstd[c];
+    if (!(std1 > 0.0) || !(std2 > 0.0)) {  // zeroed-out waveform: the reference's all-NaN branch
+        if (lane == 0) { cc[o] = 0.0; lag[o] = 0; sub[o] = 0.0; }
+        return;
+    }
+    float mx = -INFINITY, mn = INFINITY;
+    int cnt = 0;
+    for (int m = lane; m < nl; m += 32) {
+        const float v = row[m];
+        if (!isnan(v)) { mx = fmaxf(mx, v); mn = fminf(mn, v); ++cnt; }
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+    }
+    if (cnt == 0) {
+        if (lane == 0) { cc[o] = 0.0; lag[o] = 0; sub[o] = 0.0; }
+        return;
+    }
+    bool fallback = (mx > 1.001f) || (mn < -1.001f);
+    // candidates: every lag whose float32 value is within the band of the maximum
+    int cand[CCX_MAXCAND];
+    int ncand = 0;
+    if (!fallback) {
+        const float thr = mx - CCX_CAND_BAND;
+        for (int m0 = 0; m0 < nl && !fallback; m0 += 32) {
+            const int m = m0 + lane;
+            const bool hit = m < nl && row[m] >= thr;
+            unsigned bal = __ballot_sync(0xffffffffu, hit);
+            while (bal) {
+                const int l = __ffs(bal) - 1;
+                bal &= bal - 1;
+                if (ncand < CCX_MAXCAND) cand[ncand++] = m0 + l;
+                else fallback = true;
+            }
+        }
+    }
+    const T* x1 = X + static_cast<long long>(b) * n;
+    const T* x2 = X + static_cast<long long>(c) * n;
+    const int ns = n / Nc;
+    const double sum1 = evsum[b];
+    const double* wac = wa + static_cast<long long>(c) * nl;
+    const double* wbc = wb + static_cast<long long>(c) * nl;
+    double best = 0.0;
+    int ind = -1;
+    if (!fallback) {
+        for (int k = 0; k < ncand; ++k) {
+            const int m = cand[k];
+            const double v = ccx_exact(x1, x2, n, Nc, m + trunc + 1 - ns, sum1, wac[m], wbc[m], std1, lane);
+            if (isnan(v)) continue;
+            if (ind < 0 || v > best) { best = v; ind = m; }
+        }
+        if (ind < 0 || best > 1.0 + CC_GUARD) fallback = true;
+    }
+    if (fallback) {
+        if (lane == 0) {
+            const int k = atomicAdd(nflag, 1);
+            if (k < flag_cap) flagged[k] = make_int2(b, c);
+        }
+        return;
+    }
+    double ss = 0.0;
+    if (ind != 0 && ind != nl - 1) {
+        const double cb4 = ccx_exact(x1, x2, n, Nc, ind - 1 + trunc + 1 - ns, sum1, wac[ind - 1], wbc[ind - 1], std1, lane);
+        const double caf = ccx_exact(x1, x2, n, Nc, ind + 1 + trunc + 1 - ns, sum1, wac[ind + 1], wbc[ind + 1], std1, lane);
+        const double alpha = acos((cb4 + caf) / (2 * best));
+        const double alsi = sin(alpha);
+        const double tau = -(atan((cb4 - caf) / (2 * best * alsi)) / alpha);
+        ss = (fabs(tau) > 0.5) ? static_cast<double>(ind) : tau;
+    }
+    if (lane == 0) {
+        cc[o] = best;
+        lag[o] = (ind + 1 + trunc) * Nc - n;
+        sub[o] = ss;
+    }
+}
+
 }  // namespace
 
-void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int row_begin, int row_end,
-                     double* d_cc, int* d_lag, double* d_sub, int num_sms, cudaStream_t st) {
+void launch_ccx_stats(const void* d_X, int dtype_f32, int N, int n, int Nc, double* wa, double* wb, double* es,
+                      double* ed, cudaStream_t st) {
     const int ns = n / Nc;
     const int trunc = n / (2 * Nc) - 1;
     const int nl = 2 * ns - 1 - 2 * trunc;
-    double *wa = nullptr, *wb = nullptr, *es = nullptr, *ed = nullptr;
-    cudaMallocAsync(reinterpret_cast<void**>(&wa), sizeof(double) * N * nl, st);
-    cudaMallocAsync(reinterpret_cast<void**>(&wb), sizeof(double) * N * nl, st);
-    cudaMallocAsync(reinterpret_cast<void**>(&es), sizeof(double) * N, st);
-    cudaMallocAsync(reinterpret_cast<void**>(&ed), sizeof(double) * N, st);
     const size_t sm_stats = sizeof(double) * 2 * Nc * (ns + 1);
+    if (dtype_f32) {
+        cudaFuncSetAttribute(ccx_stats<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_stats));
+        ccx_stats<float><<<N, CT, sm_stats, st>>>(static_cast<const float*>(d_X), N, n, Nc, trunc, nl, wa, wb, es, ed);
+    } else {
+        cudaFuncSetAttribute(ccx_stats<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_stats));
+        ccx_stats<double><<<N, CT, sm_stats, st>>>(static_cast<const double*>(d_X), N, n, Nc, trunc, nl, wa, wb, es, ed);
+    }
+}
+
+void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int row_begin, int row_end,
+                     const double* wa, const double* wb, const double* es, const double* ed, double* d_cc,
+                     int* d_lag, double* d_sub, int num_sms, cudaStream_t st) {
+    const int ns = n / Nc;
+    const int trunc = n / (2 * Nc) - 1;
+    const int nl = 2 * ns - 1 - 2 * trunc;
     const size_t sm_res = sizeof(double) * nl;
     const int rows = row_end - row_begin;
     int gx = (2 * num_sms + rows - 1) / rows;
@@ -245,22 +386,42 @@ void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int r
     if (gx > N) gx = N;
     const dim3 grid(gx, rows);
     if (dtype_f32) {
-        cudaFuncSetAttribute(ccx_stats<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_stats));
         cudaFuncSetAttribute(ccx_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_res));
-        ccx_stats<float><<<N, CT, sm_stats, st>>>(static_cast<const float*>(d_X), N, n, Nc, trunc, nl, wa, wb, es, ed);
         ccx_kernel<float><<<grid, CT, sm_res, st>>>(static_cast<const float*>(d_X), N, n, Nc, trunc, nl, row_begin,
                                                     wa, wb, es, ed, d_cc, d_lag, d_sub);
     } else {
-        cudaFuncSetAttribute(ccx_stats<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_stats));
         cudaFuncSetAttribute(ccx_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_res));
-        ccx_stats<double><<<N, CT, sm_stats, st>>>(static_cast<const double*>(d_X), N, n, Nc, trunc, nl, wa, wb, es, ed);
         ccx_kernel<double><<<grid, CT, sm_res, st>>>(static_cast<const double*>(d_X), N, n, Nc, trunc, nl, row_begin,
                                                      wa, wb, es, ed, d_cc, d_lag, d_sub);
     }
-    cudaFreeAsync(wa, st);
-    cudaFreeAsync(wb, st);
-    cudaFreeAsync(es, st);
-    cudaFreeAsync(ed, st);
+}
+
+void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int nsig, int P, int Lc, double* out,
+                    cudaStream_t st) {
+    const dim3 grid(32, nsig);
+    if (dtype_f32)
+        ccx_pad_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(d_X), n, Nc, c0, P, Lc, out);
+    else
+        ccx_pad_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(d_X), n, Nc, c0, P, Lc, out);
+}
+
+void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsig, const void* d_X, int dtype_f32,
+                     int N, int n, int Nc, int row_begin, int row_end, const double* wa, const double* wb,
+                     const double* es, const double* ed, double* d_cc, int* d_lag, double* d_sub, int* d_nflag,
+                     int2* d_flagged, int flag_cap, cudaStream_t st) {
+    const int ns = n / Nc;
+    const int trunc = n / (2 * Nc) - 1;
+    const int nl = 2 * ns - 1 - 2 * trunc;
+    const int rows = row_end - row_begin;
+    const dim3 grid((rows + 7) / 8, nsig);
+    if (dtype_f32)
+        ccx_post_kernel<float><<<grid, 256, 0, st>>>(DS, d_chunks, c0, static_cast<const float*>(d_X), N, n, Nc, trunc,
+                                                     nl, row_begin, row_end, wa, wb, es, ed, d_cc, d_lag, d_sub,
+                                                     d_nflag, d_flagged, flag_cap);
+    else
+        ccx_post_kernel<double><<<grid, 256, 0, st>>>(DS, d_chunks, c0, static_cast<const double*>(d_X), N, n, Nc,
+                                                      trunc, nl, row_begin, row_end, wa, wb, es, ed, d_cc, d_lag,
+                                                      d_sub, d_nflag, d_flagged, flag_cap);
 }
 
 }  // namespace dtx

@@ -63,3 +63,33 @@ def test_ccx_config3_shape_subset(engine):
     assert np.abs(cc[iu] - rcc[iu[0], iu[1] - 1]).max() < 1e-10
     assert np.array_equal(lag[iu].astype(float), rlag[iu[0], iu[1] - 1])
     assert cc[0, 1] > 0.4 and abs(lag[0, 1]) <= 600 and lag[0, 1] % 3 == 0
+
+
+@pytest.mark.parametrize("case", ["nc3", "nc1"])
+def test_ccx_tensor_engine_matches_reference_golden(engine, ccx_golden, case):
+    """tcgen05 engine: float32 correlation series from the Hankel GEMM, arg-max neighbourhood
+    re-scored in float64 -> same accuracy as the float64 engine, lags bit-exact."""
+    g = ccx_golden
+    X, Nc = g[case + "_X"], int(g[case + "_Nc"])
+    cc, lag, sub = engine.ccx(X, Nc, engine="tcgen05")
+    N = X.shape[0]
+    iu = np.triu_indices(N, 1)
+    rcc, rlag, rsub = g[case + "_cc"][iu[0], iu[1] - 1], g[case + "_lag"][iu[0], iu[1] - 1], g[case + "_sub"][iu[0], iu[1] - 1]
+    assert np.abs(cc[iu] - rcc).max() < 1e-10
+    assert np.array_equal(lag[iu].astype(float), rlag)
+    assert np.nanmax(np.abs(sub[iu] - rsub)) < 1e-7
+
+
+def test_ccx_tensor_engine_config3_shape_and_row_blocks(engine):
+    X = synth.event_families(3003, 6, 8, 1000, 3, max_shift=100)      # 48 events, n = 3000, 1001 lags
+    cc, lag, sub = engine.ccx(X, 3, engine="tcgen05")
+    c64, l64, s64 = engine.ccx(X, 3, engine="fp64")
+    iu = np.triu_indices(len(X), 1)
+    assert np.abs(cc[iu] - c64[iu]).max() < 1e-12
+    assert np.array_equal(lag[iu], l64[iu])
+    assert np.nanmax(np.abs(sub[iu] - s64[iu])) < 1e-9
+    for b0, b1 in ((0, 17), (17, 40), (40, 47)):
+        c2, l2, s2 = engine.ccx(X, 3, row_begin=b0, row_end=b1, engine="tcgen05")
+        for r in range(b0, b1):
+            assert np.array_equal(c2[r - b0, r + 1:], cc[r, r + 1:])
+            assert np.array_equal(l2[r - b0, r + 1:], lag[r, r + 1:])
