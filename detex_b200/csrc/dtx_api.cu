@@ -86,7 +86,7 @@ struct dtx_ctx {
     bool have_ds64 = false;
     std::vector<ChunkDesc> h_chunks;
     DevBuf<ChunkDesc> d_chunks;
-    DevBuf<int2> d_items;
+    DevBuf<int4> d_items;
     DevBuf<__half> d_xsplit;
     DevBuf<float> d_mu, d_invE, d_DS, d_scale, d_rowmax;
     DevBuf<double> d_DS64, d_sum;
@@ -369,11 +369,22 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     }
     // K1 tile: 2048 lags (N = 256), or 1024 (N = 128) when no chunk has more than 1024 lags
     const int nq = maxT <= TILE_T / 2 ? 128 : 256;
-    std::vector<int2> items;
-    items.reserve(nitems * 2);
-    for (int i = 0; i < nchunks; ++i) {
-        const int nt = (ctx->h_chunks[i].T + 8 * nq - 1) / (8 * nq);
-        for (int t = 0; t < nt; ++t) items.push_back(make_int2(i, t));
+    // work items (chunk, tile, basis block), ordered (chunk group, block, tile): all CTAs share
+    // the current A block in L2 and the group's split signal (<= ~40 MB) stays L2 resident
+    const int tiles_per_chunk = std::max(1, (maxT + 8 * nq - 1) / (8 * nq));
+    const int group = std::max(8, (4 * ctx->num_sms + tiles_per_chunk - 1) / tiles_per_chunk);
+    std::vector<int4> items;
+    items.reserve(static_cast<size_t>(nitems) * 2 * lay.nblocks);
+    for (int g0 = 0; g0 < nchunks; g0 += group) {
+        const int g1 = std::min(nchunks, g0 + group);
+        int max_blk = 0;
+        for (int i = g0; i < g1; ++i) max_blk = std::max(max_blk, ctx->h_chunks[i].blk_hi);
+        for (int b = 0; b < max_blk; ++b)
+            for (int i = g0; i < g1; ++i) {
+                if (b < ctx->h_chunks[i].blk_lo || b >= ctx->h_chunks[i].blk_hi) continue;
+                const int nt = (ctx->h_chunks[i].T + 8 * nq - 1) / (8 * nq);
+                for (int t = 0; t < nt; ++t) items.push_back(make_int4(i, t, b, 0));
+            }
     }
 
     DTX_CUDA(ctx->d_chunks.reserve(nchunks));
@@ -393,7 +404,7 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     cudaStream_t st = ctx->stream;
     DTX_CUDA(cudaMemcpyAsync(ctx->d_chunks.p, ctx->h_chunks.data(), sizeof(ChunkDesc) * nchunks,
                              cudaMemcpyHostToDevice, st));
-    DTX_CUDA(cudaMemcpyAsync(ctx->d_items.p, items.data(), sizeof(int2) * items.size(),
+    DTX_CUDA(cudaMemcpyAsync(ctx->d_items.p, items.data(), sizeof(int4) * items.size(),
                              cudaMemcpyHostToDevice, st));
     DTX_CUDA(cudaMemsetAsync(ctx->d_ncand.p, 0, sizeof(int), st));
 
@@ -451,7 +462,7 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
               bs.d_hist.p, hist_lo, hist_hi, ctx->d_cand.p, ctx->cand_cap, ctx->d_ncand.p,
               want_fas ? bs.d_fas.p : nullptr, st);
     DTX_CUDA(cudaGetLastError());
-    ctx->launches += 1;
+    ctx->launches += 2;  // k3_fast_kernel + k3_kernel (flagged rows only)
     if (bs.has_thr && lta_window > 0) {
         launch_lta(ctx->d_DS.p, ctx->d_chunks.p, S, ctx->d_rowflags.p, ctx->d_cand.p, ctx->d_ncand.p,
                    ctx->cand_cap, lta_window, st);

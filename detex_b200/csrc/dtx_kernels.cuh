@@ -80,7 +80,7 @@ struct K1Args {
     const float* invE;
     const float* chunk_scale;
     const ChunkDesc* chunks;
-    const int2* items;
+    const int4* items;     // (chunk, tile, basis block, 0)
     const BlockInfo* binfo;
     float* DS;
     int nitems;

@@ -31,8 +31,10 @@
 //   chunks; 8 drain warps pull each partial sum out of TMEM (double-buffered accumulators)
 //   and add it to register accumulators with round-to-nearest.
 //
-// One persistent CTA per SM; work item = (chunk, tile of 8*NQ lags); inner loop over the
-// basis blocks so all CTAs stream the same A block from L2 at about the same time.
+// One persistent CTA per SM; work item = (chunk, tile of 8*NQ lags, basis block).  The host
+// orders the items (chunk group, block, tile) so that at any time all 148 CTAs stream the SAME
+// 4.6 MB A block from L2 and a group's split signal stays L2-resident: DRAM traffic is then
+// about the algorithmic minimum (inputs once per group + the dense DS write).
 #include "dtx_kernels.cuh"
 #include "tc_common.cuh"
 
@@ -91,7 +93,7 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
     constexpr int TT = 8 * NQ;
     Ring st(STAGES), sg(2), nm(2);
     for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
-        const int2 it = P.a.items[item];
+        const int4 it = P.a.items[item];
         const ChunkDesc cd = P.a.chunks[it.x];
         // window mean / inverse energy of this tile
         mbar_wait(&S.normempty[nm.idx], nm.phase ^ 1);
@@ -102,7 +104,8 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
                  P.a.invE + cd.norm_off + static_cast<long long>(it.y) * TT, TT * 4, &S.normfull[nm.idx]);
         nm.advance();
         const __half* sig0 = P.a.xsplit + cd.sig_off + static_cast<long long>(it.y) * TT;
-        for (int b = cd.blk_lo; b < cd.blk_hi; ++b) {
+        {
+            const int b = it.z;
             const uint8_t* ablk = P.a.Aimg + static_cast<size_t>(b) * P.nchunks * STAGE_BYTES;
             for (int g = 0; g < P.nseg; ++g) {
                 const Seg sgm = P.seg[g];
@@ -138,9 +141,7 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
     const uint32_t stage0 = smem_u32(S.stage), sig0 = smem_u32(S.sig);
     Ring st(STAGES), sg(2), ac(2);
     for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
-        const int2 it = P.a.items[item];
-        const int blk_lo = P.a.chunks[it.x].blk_lo, blk_hi = P.a.chunks[it.x].blk_hi;
-        for (int b = blk_lo; b < blk_hi; ++b) {
+        {
             int cib = 0, done = 0;
             for (int g = 0; g < P.nseg; ++g) {
                 const int nck = P.seg[g].ntaps / CHUNK_TAPS;
@@ -200,12 +201,13 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
     Ring ac(2), nm(2);
     float sums[NCOL];
     for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
-        const int2 it = P.a.items[item];
+        const int4 it = P.a.items[item];
         const ChunkDesc cd = P.a.chunks[it.x];
         const float sc = P.a.chunk_scale[it.x] * P.u_inv_scale;
         const float* smu = reinterpret_cast<const float*>(S.norm + nm.idx * NORM_BUF_BYTES);
         const float* sie = smu + TILE_T;
-        for (int b = cd.blk_lo; b < cd.blk_hi; ++b) {
+        {
+            const int b = it.z;
 #pragma unroll
             for (int i = 0; i < NCOL; ++i) sums[i] = 0.f;
             for (int dr = 0; dr < ndrains; ++dr) {
@@ -228,7 +230,7 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
                 ac.advance();
             }
             // ---------------------------------------------------- K2 epilogue
-            if (b == cd.blk_lo) mbar_wait(&S.normfull[nm.idx], nm.phase);
+            mbar_wait(&S.normfull[nm.idx], nm.phase);
             const BlockInfo bi = P.a.binfo[b * VEC_PER_BLOCK + kl];
             const bool head = bi.nrows > 0 && bi.out_row >= 0;
             const long long row_off = cd.ds_off + static_cast<long long>(head ? bi.out_row : 0) * cd.Tpad +

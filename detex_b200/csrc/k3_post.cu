@@ -34,6 +34,16 @@ __device__ __forceinline__ int hist_bin(float xf, double lo, double hi, double s
     return i;
 }
 
+// Float32 pre-binning: the exact float64 edge comparison is only needed when the value sits
+// within 1e-3 of a bin edge (float32 rounding of (x - lo) * 400 is ~1e-5 of a bin).
+__device__ __forceinline__ int hist_bin_fast(float x, float flo, float finv, double lo, double hi, double step) {
+    const float t = (x - flo) * finv;
+    const float fl = floorf(t);
+    const float fr = t - fl;
+    if (fr > 1e-3f && fr < 0.999f && t > 0.f && t < static_cast<float>(HIST_BINS)) return static_cast<int>(fl);
+    return hist_bin(x, lo, hi, step);
+}
+
 constexpr int K3_THREADS = 256;
 
 __global__ void __launch_bounds__(K3_THREADS)
@@ -41,10 +51,11 @@ k3_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, in
           const float* __restrict__ thr, float* __restrict__ rowmax, int* __restrict__ rowflags,
           unsigned long long* __restrict__ hist, double hlo, double hhi,
           Candidate* __restrict__ cand, int cand_cap, int* __restrict__ ncand,
-          double* __restrict__ fas) {
+          double* __restrict__ fas, int only_flagged) {
     const ChunkDesc cd = chunks[blockIdx.y];
     const int s = blockIdx.x;
     const int row = blockIdx.y * S + s;
+    if (only_flagged && !(rowflags[row] & 4)) return;  // the single-pass kernel already did this row
     const float* x = DS + cd.ds_off + static_cast<long long>(s) * cd.Tpad;
     const int T = cd.T;
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
@@ -143,6 +154,110 @@ k3_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, in
     }
 }
 
+
+// Single-pass version for the common case (no NaN / inf in the row): 128-bit loads, per-thread
+// run-length histogram (noise DS sits in one or two bins, so almost no shared atomics),
+// candidates staged in shared memory.  Rows with NaN / inf or more than K3_STAGE candidates
+// are flagged (bit 2) and redone by k3_kernel, which carries the reference's corner rules.
+constexpr int K3_STAGE = 1024;
+__global__ void __launch_bounds__(K3_THREADS)
+k3_fast_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, int S,
+               const float* __restrict__ thr, float* __restrict__ rowmax, int* __restrict__ rowflags,
+               unsigned long long* __restrict__ hist, double hlo, double hhi,
+               Candidate* __restrict__ cand, int cand_cap, int* __restrict__ ncand,
+               double* __restrict__ fas) {
+    const ChunkDesc cd = chunks[blockIdx.y];
+    const int s = blockIdx.x;
+    const int row = blockIdx.y * S + s;
+    const float* x = DS + cd.ds_off + static_cast<long long>(s) * cd.Tpad;
+    const int T = cd.T;
+    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    __shared__ int sh_hist[HIST_BINS];
+    __shared__ int2 sh_cand[K3_STAGE];
+    __shared__ int sh_ncand, sh_bad, sh_base;
+    __shared__ float sh_max[8];
+    __shared__ double sh_d[8][4];
+    for (int i = tid; i < HIST_BINS; i += K3_THREADS) sh_hist[i] = 0;
+    if (tid == 0) { sh_ncand = 0; sh_bad = 0; }
+    __syncthreads();
+    const double step = (hhi - hlo) / HIST_BINS;
+    const float flo = static_cast<float>(hlo), finv = static_cast<float>(HIST_BINS / (hhi - hlo));
+    const float th = thr ? thr[s] : INFINITY;
+    float mfin = -INFINITY;
+    int bad = 0, cur = -1, cnt = 0;
+    double f1 = 0, f2 = 0, f3 = 0, f4 = 0;
+    auto one = [&](float a, int i) {
+        if (isnan(a) || isinf(a)) { bad = 1; return; }
+        mfin = fmaxf(mfin, a);
+        const int b = hist_bin_fast(a, flo, finv, hlo, hhi, step);
+        if (b == cur) ++cnt;
+        else {
+            if (cnt > 0 && cur >= 0) atomicAdd(&sh_hist[cur], cnt);
+            cur = b;
+            cnt = 1;
+        }
+        if (a >= th) {
+            const int k = atomicAdd(&sh_ncand, 1);
+            if (k < K3_STAGE) sh_cand[k] = make_int2(i, __float_as_int(a));
+        }
+        if (fas) {
+            const double d = static_cast<double>(a);
+            f1 += d; f2 += d * d;
+            f3 += static_cast<double>(logf(a));
+            f4 += static_cast<double>(log1pf(-a));
+        }
+    };
+    const int T4 = T & ~3;
+    for (int i = tid * 4; i < T4; i += K3_THREADS * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(x + i);
+        one(v.x, i); one(v.y, i + 1); one(v.z, i + 2); one(v.w, i + 3);
+    }
+    for (int i = T4 + tid; i < T; i += K3_THREADS) one(x[i], i);
+    if (cnt > 0 && cur >= 0) atomicAdd(&sh_hist[cur], cnt);
+    mfin = warp_max(mfin);
+    if (__any_sync(0xffffffffu, bad) && l == 0) sh_bad = 1;
+    if (l == 0) sh_max[w] = mfin;
+    if (fas) {
+        f1 = warp_sum(f1); f2 = warp_sum(f2); f3 = warp_sum(f3); f4 = warp_sum(f4);
+        if (l == 0) { sh_d[w][0] = f1; sh_d[w][1] = f2; sh_d[w][2] = f3; sh_d[w][3] = f4; }
+    }
+    __syncthreads();
+    const int nc = sh_ncand;
+    if (sh_bad || nc > K3_STAGE) {          // hand the row to the two-pass kernel
+        if (tid == 0) rowflags[row] = 4;
+        return;
+    }
+    float mx = sh_max[0];
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, sh_max[i]);
+    const bool trig = mx > th;               // _evalTrigCon: strict >
+    if (tid == 0) {
+        rowmax[row] = mx;
+        rowflags[row] = 0;
+        sh_base = (trig && nc > 0) ? atomicAdd(ncand, nc) : 0;
+    }
+    for (int i = tid; i < HIST_BINS; i += K3_THREADS) {
+        const int c = sh_hist[i];
+        if (c) atomicAdd(&hist[static_cast<long long>(s) * HIST_BINS + i], static_cast<unsigned long long>(c));
+    }
+    if (fas) {
+        if (tid < 4) {
+            double t = 0;
+            for (int i = 0; i < 8; ++i) t += sh_d[i][tid];
+            atomicAdd(&fas[s * 5 + 1 + tid], t);
+        }
+        if (tid == 4) atomicAdd(&fas[s * 5], static_cast<double>(T));
+    }
+    __syncthreads();
+    if (trig)
+        for (int i = tid; i < nc; i += K3_THREADS) {
+            const int k = sh_base + i;
+            if (k < cand_cap) {
+                Candidate c; c.row = row; c.t = sh_cand[i].x; c.ds = __int_as_float(sh_cand[i].y); c.lta = 0.f;
+                cand[k] = c;
+            }
+        }
+}
+
 // One warp per candidate: centred rolling mean of |DS| with pandas' window placement and
 // _replaceNanWithMean's edge rule (detect.py:517-524).
 __global__ void __launch_bounds__(256)
@@ -233,9 +348,10 @@ void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, c
                double hist_hi, Candidate* d_cand, int cand_cap, int* d_ncand, double* d_fas,
                cudaStream_t st) {
     const dim3 grid(S, nchunks);
-    k3_kernel<<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist,
-                                           hist_lo, hist_hi,
-                                           d_cand, cand_cap, d_ncand, d_fas);
+    k3_fast_kernel<<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist, hist_lo,
+                                                hist_hi, d_cand, cand_cap, d_ncand, d_fas);
+    k3_kernel<<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist, hist_lo, hist_hi,
+                                           d_cand, cand_cap, d_ncand, d_fas, 1);
 }
 
 void launch_lta(const float* DS, const ChunkDesc* d_chunks, int S, const int* d_rowflags,
