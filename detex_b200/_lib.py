@@ -21,7 +21,7 @@ EXPORTS = [
     "dtx_version", "dtx_create", "dtx_destroy", "dtx_last_error", "dtx_sync", "dtx_set_bases",
     "dtx_load_chunks", "dtx_attach_device_chunks", "dtx_detect_run", "dtx_num_lags", "dtx_get_ds",
     "dtx_get_ds64", "dtx_get_stalta", "dtx_get_rowstats", "dtx_get_hist", "dtx_get_fas", "dtx_get_candidates",
-    "dtx_last_k1_ms", "dtx_launch_count", "dtx_ccx",
+    "dtx_sta_lta_max", "dtx_set_events", "dtx_est_mags", "dtx_last_k1_ms", "dtx_launch_count", "dtx_ccx",
 ]
 
 
@@ -68,6 +68,9 @@ def load():
     L.dtx_get_fas.argtypes = [p, C.c_int, p, C.c_int64, C.c_int]
     L.dtx_get_candidates.argtypes = [p, p, C.c_int64, C.POINTER(C.c_int64)]
     L.dtx_last_k1_ms.argtypes = [p, C.POINTER(C.c_float)]
+    L.dtx_sta_lta_max.argtypes = [p, C.c_int, C.c_int, C.c_int, C.c_int, p, C.c_int64]
+    L.dtx_set_events.argtypes = [p, C.c_int, C.c_int, C.c_int, p, p, p, C.c_int]
+    L.dtx_est_mags.argtypes = [p, C.c_int, C.c_int, p, p, p, p]
     L.dtx_launch_count.argtypes = [p, C.POINTER(C.c_int64)]
     L.dtx_ccx.argtypes = [p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p, p, p]
     for name in EXPORTS:

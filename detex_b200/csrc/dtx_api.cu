@@ -55,7 +55,12 @@ struct BasisSet {
     DevBuf<float> d_thr;
     DevBuf<unsigned long long> d_hist;
     DevBuf<double> d_fas;
+    // magnitude estimation (N1): one blob per subspace [ewf | mags | mean | std | wfu_var]
+    std::map<int, DevBuf<double>> ev_blob;
+    std::map<int, std::pair<int, int>> ev_meta;  // subspace -> (nev, is_single)
     void release() {
+        for (auto& kv : ev_blob) kv.second.release();
+        ev_blob.clear(); ev_meta.clear();
         d_U.release(); d_rank_off.release(); d_slot_row.release(); d_binfo.release();
         d_Aimg.release(); d_thr.release(); d_hist.release(); d_fas.release();
     }
@@ -599,6 +604,127 @@ int dtx_last_k1_ms(dtx_ctx* ctx, float* ms) {
     DTX_CUDA(cudaSetDevice(ctx->device));
     DTX_CUDA(cudaEventSynchronize(ctx->ev1));
     DTX_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return DTX_OK;
+}
+
+int dtx_sta_lta_max(dtx_ctx* ctx, int Nc, int chan, int nsta, int nlta, float* out, int64_t count) {
+    if (!ctx || !out) return DTX_ERR_ARG;
+    if (ctx->nchunks < 1 || !ctx->d_raw) return fail(ctx, DTX_ERR_STATE, "dtx_sta_lta_max: no chunks loaded");
+    if (Nc < 1 || chan < 0 || chan >= Nc || nsta < 1 || nlta <= nsta)
+        return fail(ctx, DTX_ERR_ARG, "dtx_sta_lta_max: need 0 <= chan < Nc and 1 <= nsta < nlta");
+    if (count < ctx->nchunks) return fail(ctx, DTX_ERR_CAPACITY, "dtx_sta_lta_max: buffer too small");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    const int nch = ctx->nchunks;
+    std::vector<long long> off(nch);
+    std::vector<int> Ls(nch);
+    int maxLs = 0;
+    for (int i = 0; i < nch; ++i) {
+        off[i] = ctx->raw_off[i];
+        Ls[i] = static_cast<int>(ctx->rawL[i] / Nc);
+        maxLs = std::max(maxLs, Ls[i]);
+    }
+    DevBuf<long long> doff;
+    DevBuf<int> dLs;
+    DevBuf<unsigned> dout;
+    DTX_CUDA(doff.reserve(nch)); DTX_CUDA(dLs.reserve(nch)); DTX_CUDA(dout.reserve(nch));
+    cudaStream_t st = ctx->stream;
+    DTX_CUDA(cudaMemcpyAsync(doff.p, off.data(), sizeof(long long) * nch, cudaMemcpyHostToDevice, st));
+    DTX_CUDA(cudaMemcpyAsync(dLs.p, Ls.data(), sizeof(int) * nch, cudaMemcpyHostToDevice, st));
+    launch_stalta_max(ctx->d_raw, ctx->dtype == DTX_F32, doff.p, dLs.p, nch, maxLs, Nc, chan, nsta, nlta, dout.p, st);
+    DTX_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    static_assert(sizeof(float) == sizeof(unsigned), "bit copy");
+    DTX_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(float) * nch, cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaStreamSynchronize(st));
+    doff.release(); dLs.release(); dout.release();
+    return DTX_OK;
+}
+
+int dtx_set_events(dtx_ctx* ctx, int set_id, int subspace, int nev, const double* ewf, const double* mags,
+                   const double* wfu_var, int is_single) {
+    if (!ctx || !ewf || !mags) return DTX_ERR_ARG;
+    auto it = ctx->sets.find(set_id);
+    if (it == ctx->sets.end()) return fail(ctx, DTX_ERR_STATE, "dtx_set_events: unknown basis set");
+    BasisSet& bs = it->second;
+    if (subspace < 0 || subspace >= bs.lay.S || nev < 1) return fail(ctx, DTX_ERR_ARG, "dtx_set_events: bad index");
+    if (!is_single && !wfu_var) return fail(ctx, DTX_ERR_ARG, "dtx_set_events: wfu_var required for subspaces");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    const int n = bs.lay.n;
+    std::vector<double> blob(static_cast<size_t>(nev) * n + 4 * static_cast<size_t>(nev));
+    double* pm = blob.data() + static_cast<size_t>(nev) * n;
+    for (int i = 0; i < nev; ++i) {
+        const double* e = ewf + static_cast<size_t>(i) * n;
+        std::copy(e, e + n, blob.data() + static_cast<size_t>(i) * n);
+        long double s = 0;
+        for (int j = 0; j < n; ++j) s += e[j];
+        const double mean = static_cast<double>(s / n);
+        long double v = 0;
+        for (int j = 0; j < n; ++j) v += (e[j] - mean) * (e[j] - mean);
+        pm[i] = mags[i];
+        pm[nev + i] = mean;
+        pm[2 * nev + i] = std::sqrt(static_cast<double>(v / n));
+        pm[3 * nev + i] = wfu_var ? wfu_var[i] : 0.0;
+    }
+    DevBuf<double>& d = bs.ev_blob[subspace];
+    DTX_CUDA(d.reserve(blob.size()));
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    DTX_CUDA(cudaMemcpy(d.p, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice));
+    bs.ev_meta[subspace] = std::make_pair(nev, is_single);
+    return DTX_OK;
+}
+
+int dtx_est_mags(dtx_ctx* ctx, int set_id, int ntrig, const int32_t* chunk, const int32_t* subspace,
+                 const int32_t* t, double* out) {
+    if (!ctx || !chunk || !subspace || !t || !out || ntrig < 0) return DTX_ERR_ARG;
+    if (ntrig == 0) return DTX_OK;
+    auto it = ctx->sets.find(set_id);
+    if (it == ctx->sets.end()) return fail(ctx, DTX_ERR_STATE, "dtx_est_mags: unknown basis set");
+    if (!ctx->ran || ctx->run_set != set_id) return fail(ctx, DTX_ERR_STATE, "dtx_est_mags: run dtx_detect_run on this set first");
+    BasisSet& bs = it->second;
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    const int n = bs.lay.n, S = bs.lay.S;
+    std::vector<MagSubspace> subs(S);
+    for (int s = 0; s < S; ++s) {
+        MagSubspace& m = subs[s];
+        std::memset(&m, 0, sizeof(m));
+        m.row0 = bs.rank_off[s];
+        m.rank = bs.rank_off[s + 1] - bs.rank_off[s];
+        auto e = bs.ev_meta.find(s);
+        if (e == bs.ev_meta.end()) continue;
+        const int nev = e->second.first;
+        const double* base = bs.ev_blob[s].p;
+        m.nev = nev;
+        m.is_single = e->second.second;
+        m.ewf = base;
+        m.mags = base + static_cast<size_t>(nev) * n;
+        m.ev_mean = m.mags + nev;
+        m.ev_std = m.mags + 2 * nev;
+        m.wfu_var = m.mags + 3 * nev;
+    }
+    std::vector<MagTrigger> trig(ntrig);
+    for (int i = 0; i < ntrig; ++i) {
+        if (chunk[i] < 0 || chunk[i] >= ctx->nchunks || subspace[i] < 0 || subspace[i] >= S || t[i] < 0 ||
+            t[i] >= ctx->h_chunks[chunk[i]].T)
+            return fail(ctx, DTX_ERR_ARG, "dtx_est_mags: trigger out of range");
+        if (subs[subspace[i]].nev == 0) return fail(ctx, DTX_ERR_STATE, "dtx_est_mags: dtx_set_events missing for a subspace");
+        trig[i].chunk = chunk[i]; trig[i].subspace = subspace[i]; trig[i].t = t[i]; trig[i].pad = 0;
+    }
+    const int stride = 6 * n + 8;
+    DevBuf<MagSubspace> dsubs;
+    DevBuf<MagTrigger> dtrig;
+    DevBuf<double> dscr, dout;
+    DTX_CUDA(dsubs.reserve(S)); DTX_CUDA(dtrig.reserve(ntrig));
+    DTX_CUDA(dscr.reserve(static_cast<size_t>(ntrig) * stride)); DTX_CUDA(dout.reserve(static_cast<size_t>(ntrig) * 3));
+    cudaStream_t st = ctx->stream;
+    DTX_CUDA(cudaMemcpyAsync(dsubs.p, subs.data(), sizeof(MagSubspace) * S, cudaMemcpyHostToDevice, st));
+    DTX_CUDA(cudaMemcpyAsync(dtrig.p, trig.data(), sizeof(MagTrigger) * ntrig, cudaMemcpyHostToDevice, st));
+    launch_mag(ctx->d_raw, ctx->dtype == DTX_F32, ctx->d_chunks.p, ctx->d_sum.p, dtrig.p, ntrig, dsubs.p, bs.d_U.p, n,
+               bs.lay.Nc, dscr.p, stride, dout.p, st);
+    DTX_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    DTX_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * 3 * ntrig, cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaStreamSynchronize(st));
+    dsubs.release(); dtrig.release(); dscr.release(); dout.release();
     return DTX_OK;
 }
 

@@ -124,6 +124,26 @@ void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsi
                      const double* es, const double* ed, double* d_cc, int* d_lag, double* d_sub, int* d_nflag,
                      int2* d_flagged, int flag_cap, cudaStream_t st);
 
+// k7_mag.cu : per-detection magnitude / SNR estimates (_estMag)
+struct MagTrigger {
+    int chunk, subspace, t, pad;
+};
+struct MagSubspace {
+    int is_single, row0, rank, nev;
+    const double* ewf;      // [nev][n] event waveforms (single: WFU[0])
+    const double* mags;     // [nev]
+    const double* ev_mean;  // [nev]
+    const double* ev_std;   // [nev] population std
+    const double* wfu_var;  // [nev] var(WFU_i), population
+};
+void launch_mag(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, const double* d_sum,
+                const MagTrigger* d_trig, int ntrig, const MagSubspace* d_subs, const double* d_U, int n, int Nc,
+                double* d_scratch, int scratch_stride, double* d_out, cudaStream_t st);
+
+// k6_stalta.cu : classic STA/LTA screen of raw chunks (fas._checkSTALTA)
+void launch_stalta_max(const void* raw, int dtype_f32, const long long* d_raw_off, const int* d_Ls, int nchunks,
+                       int maxLs, int Nc, int chan, int nsta, int nlta, unsigned* d_out_bits, cudaStream_t st);
+
 void launch_stalta_dense(const float* row, int T, int W, int zero_inf, float* out, cudaStream_t st);
 
 }  // namespace dtx

@@ -95,7 +95,7 @@ class SSDetex(object):
 
     def __init__(self, ssTD, threshold, offsets, Nc, sta="", engine=None, set_id=0,
                  triggerLTATime=5, triggerSTATime=0, fillZeros=False, calcHist=True,
-                 kernel="tcgen05", kblk=0):
+                 kernel="tcgen05", kblk=0, ewf=None, mags=None, issubspace=True, estimateMags=None):
         self.names = sorted(ssTD.keys())
         if not self.names:
             raise ValueError("no subspaces")
@@ -126,6 +126,20 @@ class SSDetex(object):
                                   thresholds=[self.threshold[k] for k in names])
             self.set_ids[n] = sid
         self.histdic = {na: np.zeros(len(HIST_BINS) - 1, dtype=np.int64) for na in self.names}
+        # magnitude / SNR estimation (_estMag, detect.py:447-499): needs the event waveforms and
+        # magnitudes _loadMPSubSpace keeps per subspace (ewf, mags; detect.py:346-381)
+        self.estimateMags = (ewf is not None and mags is not None) if estimateMags is None else estimateMags
+        self.issubspace = issubspace
+        if self.estimateMags:
+            if ewf is None or mags is None:
+                raise ValueError("estimateMags needs ewf and mags")
+            for n, names in self.groups.items():
+                for si, name in enumerate(names):
+                    W = np.atleast_2d(np.asarray(ewf[name], dtype=np.float64))
+                    U = self.ssTD[name]
+                    wfu = (W @ U.T) @ U                      # WFU = WFs . UtU (detect.py:381)
+                    self.engine.set_events(self.set_ids[n], si, W if issubspace else wfu[:1], mags[name],
+                                           wfu_var=np.var(wfu, axis=1), is_single=not issubspace)
 
     # ------------------------------------------------------------------ core
     def run_chunks(self, chunks, sr, starts, keep_ds=False):
@@ -173,15 +187,19 @@ class SSDetex(object):
                         raise Exception('over 4000 events found in single data block on %s for %s'
                                         % (self.sta, name))
                     minof, maxof = np.min(self.offsets[name]), np.max(self.offsets[name])
-                    for k in picks:
+                    if self.estimateMags and len(picks):
+                        tt = np.asarray(sel["t"][picks], dtype=np.int32)
+                        mg = eng.est_mags(sid, np.full(len(tt), gi), np.full(len(tt), si), tt)
+                    for pi, k in enumerate(picks):
                         coef = float(sel["ds"][k])
                         times = float(sel["t"][k]) / sr + starts[ci]      # detect.py:413
                         if self.fillZeros:
                             sl = 0.0
                         else:
                             sl = abs(coef) / float(sel["lta"][k])         # STA == |DS|, detect.py:505-507
+                        pe_mag, st_mag, snr = (mg[pi] if self.estimateMags else (np.nan, np.nan, np.nan))
                         rows.append([coef, sl, times, name, self.sta, times - maxof, times - minof,
-                                     np.nan, np.nan, np.nan])
+                                     st_mag, snr, pe_mag])       # Mag = stMag, ProEnMag = peMag (detect.py:428,442)
             if self.calcHist:
                 h = eng.hist(sid, reset=True)
                 for si, name in enumerate(names):

@@ -157,6 +157,28 @@ class Engine(object):
         self._check(self._L.dtx_last_k1_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def sta_lta_max(self, Nc, chan, nsta, nlta):
+        """max of ObsPy's classic STA/LTA of channel `chan` for every loaded chunk (fas.py:175-205)."""
+        out = np.empty(self.nchunks, dtype=np.float32)
+        self._check(self._L.dtx_sta_lta_max(self._h, int(Nc), int(chan), int(nsta), int(nlta), _ptr(out), out.size))
+        return out
+
+    def set_events(self, set_id, subspace, ewf, mags, wfu_var=None, is_single=False):
+        ewf = np.ascontiguousarray(np.atleast_2d(np.asarray(ewf, dtype=np.float64)))
+        mags = np.ascontiguousarray(np.asarray(mags, dtype=np.float64))
+        wv = None if wfu_var is None else np.ascontiguousarray(np.asarray(wfu_var, dtype=np.float64))
+        self._check(self._L.dtx_set_events(self._h, int(set_id), int(subspace), ewf.shape[0], _ptr(ewf), _ptr(mags),
+                                           _ptr(wv) if wv is not None else None, int(bool(is_single))))
+
+    def est_mags(self, set_id, chunk, subspace, t):
+        """(ntrig, 3) array of ProEnMag, Mag, SNR for triggers of the current batch (_estMag)."""
+        chunk = np.ascontiguousarray(np.asarray(chunk, dtype=np.int32))
+        subspace = np.ascontiguousarray(np.asarray(subspace, dtype=np.int32))
+        t = np.ascontiguousarray(np.asarray(t, dtype=np.int32))
+        out = np.empty((len(t), 3), dtype=np.float64)
+        self._check(self._L.dtx_est_mags(self._h, int(set_id), len(t), _ptr(chunk), _ptr(subspace), _ptr(t), _ptr(out)))
+        return out
+
     def launch_count(self):
         n = C.c_int64()
         self._check(self._L.dtx_launch_count(self._h, C.byref(n)))

@@ -53,6 +53,41 @@ def beta_nnlf_from_stats(a, b, N, slog, slog1m):
     return -((a - 1) * slog + (b - 1) * slog1m - N * sc.betaln(a, b))
 
 
+def screen_chunks(chunks, Nc, sr, zchan=None, STATime=0.5, LTATime=5, staltalimit=8.0, engine=None, batch=32):
+    """`_checkSTALTA` for every candidate chunk (fas.py:175-205): True where the classic
+    STA/LTA of the screening channel (Z = last channel in ObsPy's sorted order by default)
+    never exceeds `staltalimit`.  staltalimit=None passes everything."""
+    if staltalimit is None:
+        return [True] * len(chunks)
+    eng = engine or default_engine()
+    zchan = Nc - 1 if zchan is None else zchan
+    out = []
+    for i in range(0, len(chunks), batch):
+        eng.load_chunks(chunks[i:i + batch])
+        mx = eng.sta_lta_max(Nc, zchan, int(STATime * sr), int(LTATime * sr))
+        out.extend(bool(m <= staltalimit) for m in mx)
+    return out
+
+
+def select_null_chunks(passes, conDatNum):
+    """Chunk bookkeeping of `_getDSVect` / `_initFAS` (fas.py:56-71, 96-112): keep screened
+    chunks in order until conDatNum are kept; if <= 25 % pass, drop the screen."""
+    def walk(flags):
+        kept, count = [], 0
+        for i, ok in enumerate(flags):
+            count += 1
+            if not ok:
+                continue
+            if len(kept) >= conDatNum:
+                break
+            kept.append(i)
+        return kept, count
+    kept, count = walk(passes)
+    if count and float(len(kept)) / count <= .25:
+        kept, count = walk([True] * len(passes))
+    return kept
+
+
 def initFAS(bases, chunks, Nc, numBins=401, engine=None, set_id=900, kernel="tcgen05", batch=16):
     """Array part of `_initFAS` (fas.py:23-86).  bases: list of (r, n) arrays (one per
     subspace / single, same n); chunks: the null-space multiplexed chunks that passed the

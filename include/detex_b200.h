@@ -109,6 +109,25 @@ int dtx_get_fas(dtx_ctx* ctx, int set_id, double* fas, int64_t count, int reset)
 /* candidates of the last run; *n receives the number produced (may exceed cap: truncated) */
 int dtx_get_candidates(dtx_ctx* ctx, dtx_cand* out, int64_t cap, int64_t* n);
 
+/* STA/LTA screen of the loaded chunks -----------------------------------------------------
+ * Replaces fas._checkSTALTA (fas.py:175-205): out[i] = max over the chunk of ObsPy's
+ * classic_sta_lta (obspy 1.0.2, obspy/signal/src/stalta.c) of channel `chan` (0-based position
+ * in the multiplexed order; Detex screens the Z component) with nsta / nlta samples.  A chunk
+ * passes the FAS screen when out[i] <= staltalimit. */
+int dtx_sta_lta_max(dtx_ctx* ctx, int Nc, int chan, int nsta, int nlta, float* out, int64_t count);
+
+/* Per-detection magnitude / SNR (next row N1) ------------------------------------------------
+ * Replaces _SSDetex._estMag with _estPEMag / _estSTDMag (detect.py:447-499, 637-664) and
+ * construct.fast_normcorr (construct.py:469-483).  dtx_set_events uploads, per subspace, what
+ * _loadMPSubSpace keeps for it (detect.py:346-381): the trimmed aligned event waveforms
+ * ewf[nev][n], their magnitudes, and var(WFU_i) of the events projected into the subspace
+ * (singles: nev = 1, ewf = the trimmed template, wfu_var ignored).  dtx_est_mags evaluates the
+ * triggers (chunk, subspace, lag) of the current batch; out[i] = {ProEnMag, Mag, SNR}. */
+int dtx_set_events(dtx_ctx* ctx, int set_id, int subspace, int nev, const double* ewf, const double* mags,
+                   const double* wfu_var, int is_single);
+int dtx_est_mags(dtx_ctx* ctx, int set_id, int ntrig, const int32_t* chunk, const int32_t* subspace,
+                 const int32_t* t, double* out);
+
 /* Timing aid for bench.py: device milliseconds of the dominant kernel (K1) in the last
  * dtx_detect_run, measured with CUDA events on the context's stream. */
 int dtx_last_k1_ms(dtx_ctx* ctx, float* ms);

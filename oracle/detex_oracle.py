@@ -36,20 +36,21 @@ from scipy.cluster.hierarchy import linkage
 
 
 def _window_sums(x, n):
-    """S1[t] = sum x[t:t+n], S2[t] = sum x[t:t+n]**2 for t = 0..len(x)-n (float64,
-    long-double prefix sums so the subtraction of prefixes does not lose digits)."""
+    """S1[t] = sum x[t:t+n], S2[t] = sum x[t:t+n]**2 for t = 0..len(x)-n.  float64 prefix sums
+    of the (already centred, see callers) data: the prefix of ~1e6 unit-variance samples is
+    exact to ~1e-10, i.e. 1e-14 of a window's energy."""
     x = np.asarray(x, dtype=np.float64)
-    c1 = np.concatenate(([0.0], np.cumsum(x.astype(np.longdouble))))
-    c2 = np.concatenate(([0.0], np.cumsum(np.square(x.astype(np.longdouble)))))
-    s1 = (c1[n:] - c1[:-n]).astype(np.float64)
-    s2 = (c2[n:] - c2[:-n]).astype(np.float64)
-    return s1, s2
+    c1 = np.concatenate(([0.0], np.cumsum(x)))
+    c2 = np.concatenate(([0.0], np.cumsum(np.square(x))))
+    return c1[n:] - c1[:-n], c2[n:] - c2[:-n]
 
 
 def rolling_mean(x, n):
     """pd.rolling_mean(x, n)[n-1:]"""
-    s1, _ = _window_sums(x, n)
-    return s1 / n
+    x = np.asarray(x, dtype=np.float64)
+    m = x.mean()
+    s1, _ = _window_sums(x - m, n)
+    return s1 / n + m
 
 
 def rolling_var(x, n):
@@ -437,3 +438,112 @@ def single_basis(x):
     """Singleton template: unit-norm, NOT demeaned (detect.py:356-357, fas.py:144)."""
     x = np.asarray(x, dtype=np.float64)
     return (x / np.linalg.norm(x))[None, :]
+
+
+# --------------------------------------------------------------------------
+# a14 (screen)  fas._checkSTALTA  (fas.py:175-205)
+# The arithmetic is ObsPy's classic_sta_lta (obspy 1.0.2, pinned in the reference's
+# environment.txt, NOT vendored): restated from obspy/signal/trigger.py::classic_sta_lta_py
+# == obspy/signal/src/stalta.c.  ObsPy is not installable here, so THIS function's parity is
+# unpinned; everything downstream of the screen is pinned.
+# --------------------------------------------------------------------------
+
+
+def classic_sta_lta(a, nsta, nlta):
+    a = np.asarray(a, dtype=np.float64)
+    nsta, nlta = int(nsta), int(nlta)
+    sta = np.cumsum(a ** 2)
+    lta = sta.copy()
+    sta[nsta:] = sta[nsta:] - sta[:-nsta]
+    sta /= nsta
+    lta[nlta:] = lta[nlta:] - lta[:-nlta]
+    lta /= nlta
+    sta[:nlta - 1] = 0
+    dtiny = np.finfo(0.0).tiny
+    lta[lta < dtiny] = dtiny
+    return sta / lta
+
+
+def check_stalta(z, sr, STATime, LTATime, limit):
+    """`_checkSTALTA` on the screening channel (fas.py:191-197)."""
+    if limit is None:
+        return True
+    cft = classic_sta_lta(z, STATime * sr, LTATime * sr)
+    return bool(np.max(cft) <= limit)
+
+
+def select_null_chunks(passes, conDatNum):
+    """Bookkeeping of `_getDSVect` / `_initFAS` (fas.py:56-71, 96-112): walk the candidate
+    chunks in order, keep those that pass the screen until conDatNum are kept; if <= 25 %
+    pass, drop the screen.  Returns the kept indices."""
+    def walk(flags):
+        kept, count = [], 0
+        for i, ok in enumerate(flags):
+            count += 1
+            if not ok:
+                continue
+            if len(kept) >= conDatNum:
+                break
+            kept.append(i)
+        return kept, count
+    kept, count = walk(passes)
+    if count and float(len(kept)) / count <= .25:
+        kept, count = walk([True] * len(passes))
+    return kept
+
+
+# --------------------------------------------------------------------------
+# N1  per-detection magnitude / SNR  (detect.py:447-499, 637-664; construct.py:469-483)
+# --------------------------------------------------------------------------
+
+
+def fast_normcorr(t, s):
+    """`construct.fast_normcorr` (construct.py:469-483)."""
+    t = np.asarray(t, dtype=np.float64)
+    s = np.asarray(s, dtype=np.float64)
+    if len(t) > len(s):
+        t, s = s, t
+    n = len(t)
+    nt = (t - np.mean(t)) / (np.std(t) * n)
+    sum_nt = nt.sum()
+    a = rolling_mean(s, n)
+    b = rolling_std(s, n) * np.sqrt((n - 1.0) / n)
+    c = np.convolve(nt[::-1], s, mode="valid")
+    return (c - sum_nt * a) / b
+
+
+def est_mag(trigIndex, MPcon, Nc, U, ewf, mags, issubspace=True):
+    """`_SSDetex._estMag` (detect.py:447-499).  U: (r, n) basis; ewf: (events, n) trimmed
+    waveforms (single: the trimmed template); returns (ProEnMag, Mag, SNR)."""
+    MPcon = np.asarray(MPcon, dtype=np.float64)
+    U = np.atleast_2d(np.asarray(U, dtype=np.float64))
+    ewf = np.atleast_2d(np.asarray(ewf, dtype=np.float64))
+    mags = np.asarray(mags, dtype=np.float64)
+    WFU = (ewf @ U.T) @ U                                    # detect.py:381 without the n x n UtU
+    WFlen = WFU.shape[1]
+    ConDat = MPcon[trigIndex * Nc: trigIndex * Nc + WFlen]
+    if issubspace:
+        ssCon = U.T @ (U @ ConDat)                           # detect.py:460
+        proEn = np.var(ssCon) / np.var(WFU, axis=1)          # :462
+    if trigIndex * Nc > 5 * WFlen:                           # :465-470
+        pe = MPcon[trigIndex * Nc - 5 * WFlen: trigIndex * Nc]
+    else:
+        pe = MPcon[trigIndex * Nc: trigIndex * Nc + WFlen + 6 * WFlen]
+    rstd = rolling_std(pe, WFlen) if len(pe) >= WFlen else np.array([])
+    baseNoise = np.median(rstd) if len(rstd) else np.nan
+    SNR = np.std(ConDat) / baseNoise
+    touse = mags > -15
+    if issubspace:
+        if not np.any(touse):
+            return np.nan, np.nan, SNR
+        cors = np.array([fast_normcorr(x, ConDat)[0] for x in ewf])
+        den = np.sum(np.square(cors[touse]))
+        pe_mag = sum((mags[i] + np.log10(np.sqrt(proEn[i]))) * cors[i] ** 2 for i in range(len(mags)) if mags[i] > -15) / den
+        st_mag = sum((mags[i] + np.log10(np.std(ConDat) / np.std(ewf[i]))) * cors[i] ** 2
+                     for i in range(len(mags)) if mags[i] > -15) / den
+        return pe_mag, st_mag, SNR
+    if np.isnan(mags[0]) or mags[0] < -15:
+        return np.nan, np.nan, SNR
+    d1 = np.dot(ConDat, WFU[0])
+    d2 = np.dot(WFU[0], WFU[0])
+    return mags[0] + d1 / d2, mags[0] + np.log10(np.std(ConDat) / np.std(WFU[0])), SNR

@@ -171,6 +171,18 @@ class RefFunctions(object):
                                    {name: None}, None, {name: None}, None, {name: None},
                                    {name: None})
 
+    # detex/detect.py:447-499
+    def estMag(self, trigIndex, MPcon, Nc, U, ewf, mags, issubspace=True):
+        s = self._ssd
+        s.issubspace = issubspace
+        U = np.atleast_2d(U)
+        UtU = np.dot(np.transpose(U), U)                 # detect.py:367
+        WFU = np.dot(np.atleast_2d(ewf), UtU)            # detect.py:381
+        cs = pd.Series({"Nc": Nc})
+        evs = ["e%d" % i for i in range(len(mags))]
+        return s._estMag(trigIndex, cs, MPcon, np.asarray(mags, dtype=float), evs, WFU, UtU, np.atleast_2d(ewf), 0.0,
+                         0.0, "SS0", "STA")
+
     # detex/construct.py:928-987
     def multiplex(self, chans):
         st = [types.SimpleNamespace(data=np.asarray(c)) for c in chans]

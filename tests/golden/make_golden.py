@@ -90,6 +90,27 @@ def main():
         ccx[name + "_sub"] = sub.values.astype(float)
     np.savez_compressed(os.path.join(OUT, "ccx_golden.npz"), **ccx)
 
+    # ---- magnitude / SNR estimates (_estMag, detect.py:447-499)
+    from oracle import detex_oracle as orc
+    rng = np.random.default_rng(301)
+    Nc, ns = 3, 120
+    n = Nc * ns
+    fam = synth.wavelet_basis(rng, ns, Nc, 3)
+    ewf = np.array([rng.standard_normal(3) @ fam * rng.uniform(50, 500) + 5.0 * rng.standard_normal(n) for _ in range(7)])
+    Umag = orc.svd_basis(ewf, select_value=0.9)["U"]
+    mags = np.array([1.1, 2.3, -20.0, 0.7, 1.9, 2.8, 1.4])
+    x = synth.multiplex(synth.bandpassed_noise(rng, 3000, nchan=Nc)) * 20.0
+    trigs = [100, 1500, 2700]                         # early (post-event noise), middle, late
+    for t in trigs:
+        x[t * Nc:t * Nc + n] += 0.8 * ewf[t % 7]
+    single = ewf[1][30:330].copy()
+    mag = {"x": x, "Nc": Nc, "U": Umag, "ewf": ewf, "mags": mags, "trigs": np.array(trigs), "single": single}
+    mag["sub_out"] = np.array([R.estMag(t, x, Nc, Umag, ewf, mags, True) for t in trigs], dtype=float)
+    us = (single / np.linalg.norm(single))[None, :]
+    mag["single_out"] = np.array([R.estMag(t, x, Nc, us, single[None, :], np.array([1.7]), False) for t in trigs], dtype=float)
+    mag["nomag_out"] = np.array(R.estMag(1500, x, Nc, Umag, ewf, np.full(7, -99.0), True), dtype=float)
+    np.savez_compressed(os.path.join(OUT, "mag_golden.npz"), **mag)
+
     # ---- multiplex (construct.py:928-987)
     chans = [np.arange(6.0), np.arange(6.0) + 10, np.arange(7.0) + 20]
     np.savez_compressed(os.path.join(OUT, "multiplex_golden.npz"), c0=chans[0], c1=chans[1], c2=chans[2],

@@ -71,3 +71,72 @@ def test_corDat_triggers_match_reference_loop(engine):
     assert abs(cor.MaxDS["SS1"] - ds0.max()) < 1e-5
     st = orc.sta_lta(ds0, 5 * sr, 0)
     assert np.abs(cor.STALTA["SS1"] - st).max() < 2e-3 * st.max()
+
+
+def test_stalta_screen_matches_oracle(engine):
+    """fas._checkSTALTA on the GPU vs the restated ObsPy classic_sta_lta (parity of that
+    third-party function itself is unpinned: ObsPy is not installable)."""
+    rng = np.random.default_rng(41)
+    Nc, Ls, sr = 3, 20000, 100.0
+    chunks = []
+    for i in range(6):
+        ch = synth.bandpassed_noise(rng, Ls - 7 * i, nchan=Nc)
+        if i % 2:
+            ch[2, 5000 + 100 * i: 5300 + 100 * i] *= 12.0      # a transient on Z
+        chunks.append(synth.multiplex(ch))
+    engine.load_chunks(chunks)
+    mx = engine.sta_lta_max(Nc, 2, int(0.5 * sr), int(5 * sr))
+    ref = [orc.classic_sta_lta(c[2::Nc], 0.5 * sr, 5 * sr).max() for c in chunks]
+    assert np.allclose(mx, ref, rtol=1e-6)
+    passes = fas.screen_chunks(chunks, Nc, sr, engine=engine, batch=4)
+    assert passes == [orc.check_stalta(c[2::Nc], sr, 0.5, 5, 8.0) for c in chunks]
+    assert passes == [True, False, True, False, True, False]
+    assert fas.select_null_chunks(passes, 2) == orc.select_null_chunks(passes, 2) == [0, 2]
+    assert fas.select_null_chunks([False] * 7 + [True], 3) == [0, 1, 2]      # <= 25 % pass: screen dropped
+
+
+def test_est_mags_matches_reference_golden(engine):
+    """N1: per-detection ProEnMag / Mag / SNR on the GPU against `_estMag` of the reference."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mag_golden.npz"))
+    x, Nc, U, ewf, mags = g["x"], int(g["Nc"]), g["U"], g["ewf"], g["mags"]
+    trigs = g["trigs"].astype(np.int32)
+    engine.set_bases(40, [U], Nc, thresholds=[0.5])
+    engine.load_chunks([x, x[: len(x) - 30]])
+    engine.detect_run(40)
+    wfu = (ewf @ U.T) @ U
+    engine.set_events(40, 0, ewf, mags, wfu_var=np.var(wfu, axis=1))
+    out = engine.est_mags(40, np.zeros(3, np.int32), np.zeros(3, np.int32), trigs)
+    assert np.allclose(out, g["sub_out"], rtol=0, atol=1e-9)
+    out1 = engine.est_mags(40, np.ones(2, np.int32), np.zeros(2, np.int32), trigs[:2])   # second chunk
+    assert np.allclose(out1, g["sub_out"][:2], rtol=0, atol=1e-9)
+    engine.set_events(40, 0, ewf, np.full(7, -99.0), wfu_var=np.var(wfu, axis=1))
+    o = engine.est_mags(40, [0], [0], [1500])[0]
+    assert np.isnan(o[0]) and np.isnan(o[1]) and abs(o[2] - g["nomag_out"][2]) < 1e-9
+    # singleton
+    single = g["single"]
+    us = (single / np.linalg.norm(single))[None, :]
+    engine.set_bases(41, [us], Nc, thresholds=[0.5])
+    engine.load_chunks([x])
+    engine.detect_run(41)
+    engine.set_events(41, 0, single[None, :], [1.7], is_single=True)
+    outs = engine.est_mags(41, np.zeros(3, np.int32), np.zeros(3, np.int32), trigs)
+    assert np.allclose(outs, g["single_out"], rtol=0, atol=1e-9)
+
+
+def test_corDat_fills_magnitude_columns(engine):
+    rng = np.random.default_rng(51)
+    Nc, ns, Ls, sr = 3, 200, 9000, 100.0
+    n = Nc * ns
+    fam = synth.wavelet_basis(rng, ns, Nc, 2)
+    ewf = np.array([rng.standard_normal(2) @ fam * 100 + rng.standard_normal(n) for _ in range(5)])
+    U = orc.svd_basis(ewf, select_value=0.9)["U"]
+    mags = np.array([1.0, 1.5, 2.0, 0.5, 1.2])
+    x = synth.multiplex(synth.bandpassed_noise(rng, Ls, nchan=Nc))
+    x[4000 * Nc:4000 * Nc + n] += 0.2 * ewf[2]
+    det = detect.SSDetex({"SS0": U}, {"SS0": 0.4}, {"SS0": [1.0, 2.0]}, Nc, sta="TST", engine=engine, set_id=9,
+                         ewf={"SS0": ewf}, mags={"SS0": mags})
+    df, _ = det.corDat([x], sr, [0.0])
+    assert len(df) == 1 and abs(df.STMP[0] - 40.0) < 0.05
+    ref = orc.est_mag(int(round(df.STMP[0] * sr)), x, Nc, U, ewf, mags, True)
+    assert abs(df.ProEnMag[0] - ref[0]) < 1e-9 and abs(df.Mag[0] - ref[1]) < 1e-9 and abs(df.SNR[0] - ref[2]) < 1e-9

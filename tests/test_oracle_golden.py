@@ -110,3 +110,16 @@ def test_fas_stats_consistent():
     assert abs(a - 3.0) < 0.2 and abs(b - 2000.0) < 150
     th = orc.threshold_from_beta(a, b, Pf=1e-12)
     assert 0 < th < 0.1
+
+
+def test_est_mag_matches_reference():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mag_golden.npz"))
+    x, Nc, U, ewf, mags = g["x"], int(g["Nc"]), g["U"], g["ewf"], g["mags"]
+    for t, ref in zip(g["trigs"], g["sub_out"]):
+        assert np.allclose(orc.est_mag(int(t), x, Nc, U, ewf, mags, True), ref, rtol=0, atol=1e-12)
+    single = g["single"]
+    us = (single / np.linalg.norm(single))[None, :]
+    for t, ref in zip(g["trigs"], g["single_out"]):
+        assert np.allclose(orc.est_mag(int(t), x, Nc, us, single[None, :], np.array([1.7]), False), ref, rtol=0, atol=1e-12)
+    out = orc.est_mag(1500, x, Nc, U, ewf, np.full(7, -99.0), True)
+    assert np.isnan(out[0]) and np.isnan(out[1]) and abs(out[2] - g["nomag_out"][2]) < 1e-12
