@@ -48,6 +48,7 @@ struct BasisSet {
     int R = 0;
     std::vector<int> rank_off;
     bool has_thr = false;
+    bool has_split = false;   // some subspace has rank > 16 (pieces accumulate into DS)
     DevBuf<double> d_U;
     DevBuf<int> d_rank_off, d_slot_row;
     DevBuf<BlockInfo> d_binfo;
@@ -190,8 +191,7 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
     const int R = rank_off[S];
     for (int s = 0; s < S; ++s) {
         const int r = rank_off[s + 1] - rank_off[s];
-        if (r < 1 || r > VEC_PER_BLOCK)
-            return fail(ctx, DTX_ERR_ARG, "dtx_set_bases: subspace rank must be in 1..16");
+        if (r < 1) return fail(ctx, DTX_ERR_ARG, "dtx_set_bases: subspace rank must be >= 1");
     }
     BasisSet& bs = ctx->sets[set_id];
     BasisLayout& lay = bs.lay;
@@ -219,22 +219,31 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
     lay.nseg = nseg;
     lay.nchunks = chunk0;
 
-    // pack subspaces into blocks of 16 vector slots, first-fit decreasing by rank
-    std::vector<int> order(S);
-    for (int s = 0; s < S; ++s) order[s] = s;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        return (rank_off[a + 1] - rank_off[a]) > (rank_off[b + 1] - rank_off[b]);
-    });
-    std::vector<int> used;                    // slots used per block
-    std::vector<std::vector<int>> members;    // subspaces per block
-    for (int s : order) {
+    // pack subspaces into blocks of 16 vector slots, first-fit decreasing by rank.  A subspace
+    // of rank > 16 is cut into pieces of <= 16 vectors; DS is additive over the pieces
+    // (sum of squared projections), so their epilogues accumulate into the same DS row.
+    struct Piece { int s, row0, r; bool split; };
+    std::vector<Piece> pieces;
+    bs.has_split = false;
+    for (int s = 0; s < S; ++s) {
         const int r = rank_off[s + 1] - rank_off[s];
+        for (int k0 = 0; k0 < r; k0 += VEC_PER_BLOCK)
+            pieces.push_back(Piece{s, rank_off[s] + k0, std::min(VEC_PER_BLOCK, r - k0), r > VEC_PER_BLOCK});
+        if (r > VEC_PER_BLOCK) bs.has_split = true;
+    }
+    std::vector<int> order(pieces.size());
+    for (size_t i = 0; i < pieces.size(); ++i) order[i] = static_cast<int>(i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pieces[a].r > pieces[b].r; });
+    std::vector<int> used;                    // slots used per block
+    std::vector<std::vector<int>> members;    // pieces per block
+    for (int pi : order) {
+        const int r = pieces[pi].r;
         int b = -1;
         for (size_t i = 0; i < used.size(); ++i)
             if (used[i] + r <= VEC_PER_BLOCK) { b = static_cast<int>(i); break; }
         if (b < 0) { used.push_back(0); members.emplace_back(); b = static_cast<int>(used.size()) - 1; }
         used[b] += r;
-        members[b].push_back(s);
+        members[b].push_back(pi);
     }
     lay.nblocks = static_cast<int>(used.size());
     std::vector<int> slot_row(static_cast<size_t>(lay.nblocks) * VEC_PER_BLOCK, -1);
@@ -251,17 +260,18 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
             BlockInfo& bi = binfo[static_cast<size_t>(b) * VEC_PER_BLOCK + i];
             bi.sumU = 0.f; bi.out_row = -1; bi.nrows = 0; bi.seg_end = i + 1;
         }
-        for (int s : members[b]) {
-            const int r = rank_off[s + 1] - rank_off[s];
+        for (int pi : members[b]) {
+            const Piece& pc = pieces[pi];
+            const int r = pc.r, s = pc.s;
             for (int k = 0; k < r; ++k, ++slot) {
-                const int row = rank_off[s] + k;
+                const int row = pc.row0 + k;
                 slot_row[static_cast<size_t>(b) * VEC_PER_BLOCK + slot] = row;
                 BlockInfo& bi = binfo[static_cast<size_t>(b) * VEC_PER_BLOCK + slot];
                 long double su = 0;
                 for (int j = 0; j < n; ++j) su += U[static_cast<long long>(row) * n + j];
                 bi.sumU = static_cast<float>(su);
                 bi.out_row = s;
-                bi.nrows = (k == 0) ? r : 0;
+                bi.nrows = (k == 0) ? (pc.split ? -r : r) : 0;   // negative: accumulate into the row
                 bi.seg_end = slot - k + r;
             }
         }
@@ -426,6 +436,7 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         a.chunk_scale = ctx->d_scale.p; a.chunks = ctx->d_chunks.p; a.items = ctx->d_items.p;
         a.binfo = bs.d_binfo.p; a.DS = ctx->d_DS.p; a.nitems = static_cast<int>(items.size());
         a.kblk = kblk; a.num_sms = ctx->num_sms; a.nq = nq; a.mode = mode;
+        if (bs.has_split) DTX_CUDA(cudaMemsetAsync(ctx->d_DS.p, 0, sizeof(float) * ds, st));
         DTX_CUDA(cudaEventRecord(ctx->ev0, st));
         launch_k1(a, lay, st);
         DTX_CUDA(cudaEventRecord(ctx->ev1, st));
@@ -707,6 +718,7 @@ int dtx_est_mags(dtx_ctx* ctx, int set_id, int ntrig, const int32_t* chunk, cons
             t[i] >= ctx->h_chunks[chunk[i]].T)
             return fail(ctx, DTX_ERR_ARG, "dtx_est_mags: trigger out of range");
         if (subs[subspace[i]].nev == 0) return fail(ctx, DTX_ERR_STATE, "dtx_est_mags: dtx_set_events missing for a subspace");
+        if (subs[subspace[i]].rank > MAG_MAX_RANK) return fail(ctx, DTX_ERR_ARG, "dtx_est_mags: rank > 64 not supported");
         trig[i].chunk = chunk[i]; trig[i].subspace = subspace[i]; trig[i].t = t[i]; trig[i].pad = 0;
     }
     const int stride = 6 * n + 8;

@@ -47,7 +47,8 @@ struct Seg {
 struct BlockInfo {   // one per (basis block, vector slot)
     float sumU;      // sum of the basis vector's entries (true units)
     int out_row;     // DS row of the subspace this vector belongs to, -1 = padding
-    int nrows;       // rank of the subspace if this slot is its first vector, else 0
+    int nrows;       // rank of the piece if this slot is its first vector, else 0; negative =
+                     // piece of a rank > 16 subspace (epilogue accumulates into the DS row)
     int seg_end;     // slot index one past the last vector of this slot's subspace
 };
 
@@ -125,6 +126,7 @@ void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsi
                      int2* d_flagged, int flag_cap, cudaStream_t st);
 
 // k7_mag.cu : per-detection magnitude / SNR estimates (_estMag)
+constexpr int MAG_MAX_RANK = 64;
 struct MagTrigger {
     int chunk, subspace, t, pad;
 };

@@ -232,7 +232,8 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
             // ---------------------------------------------------- K2 epilogue
             mbar_wait(&S.normfull[nm.idx], nm.phase);
             const BlockInfo bi = P.a.binfo[b * VEC_PER_BLOCK + kl];
-            const bool head = bi.nrows > 0 && bi.out_row >= 0;
+            const bool head = bi.nrows != 0 && bi.out_row >= 0;
+            const bool accum = bi.nrows < 0;   // piece of a rank > 16 subspace
             const long long row_off = cd.ds_off + static_cast<long long>(head ? bi.out_row : 0) * cd.Tpad +
                                       static_cast<long long>(it.y) * TT + 8 * NCOL * colhalf + p;
             float* dsrow = P.a.DS + row_off;
@@ -257,7 +258,10 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
                     v += j4 ? o : 0.f;
                     o = __shfl_down_sync(0xffffffffu, v, 16);
                     v += j8 ? o : 0.f;
-                    if (head) dsrow[8 * i] = v * pie[8 * i];
+                    if (head) {
+                        if (accum) atomicAdd(&dsrow[8 * i], v * pie[8 * i]);
+                        else dsrow[8 * i] = v * pie[8 * i];
+                    }
                 }
             } else {
                 // signed Pearson coefficient: templates are pre-scaled by 1/||x1 - mean||, so

@@ -132,8 +132,9 @@ k3_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, in
         if (fas) {
             const double d = static_cast<double>(a);
             f1 += d; f2 += d * d;
-            f3 += static_cast<double>(logf(a));
-            f4 += static_cast<double>(log1pf(-a));
+            // float32 DS can round to exactly 0 (or 1) where float64 would not: keep the logs finite
+            f3 += static_cast<double>(logf(fmaxf(a, 1e-30f)));
+            f4 += static_cast<double>(log1pf(-fminf(a, 0.99999994f)));
         }
     }
     __syncthreads();
@@ -203,8 +204,9 @@ k3_fast_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunk
         if (fas) {
             const double d = static_cast<double>(a);
             f1 += d; f2 += d * d;
-            f3 += static_cast<double>(logf(a));
-            f4 += static_cast<double>(log1pf(-a));
+            // float32 DS can round to exactly 0 (or 1) where float64 would not: keep the logs finite
+            f3 += static_cast<double>(logf(fmaxf(a, 1e-30f)));
+            f4 += static_cast<double>(log1pf(-fminf(a, 0.99999994f)));
         }
     };
     const int T4 = T & ~3;

@@ -70,7 +70,7 @@ mag_kernel(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks, cons
     const int tid = threadIdx.x;
     __shared__ double sh[MT / 32];
     __shared__ unsigned hist[256];
-    __shared__ double coef[VEC_PER_BLOCK];
+    __shared__ double coef[MAG_MAX_RANK];
     double* scr = scratch + static_cast<long long>(blockIdx.x) * scratch_stride;
     const double nn = static_cast<double>(n);
 

@@ -27,44 +27,47 @@ direct_kernel(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
     const double mean = sum[blockIdx.z] / static_cast<double>(cd.L);
     const T* x = raw + cd.raw_off;
     __shared__ double Us[RMAX][JT];
-    double acc[RMAX];
-#pragma unroll
-    for (int k = 0; k < RMAX; ++k) acc[k] = 0.0;
-    double s1 = 0.0, s2 = 0.0, su[RMAX];
-#pragma unroll
-    for (int k = 0; k < RMAX; ++k) su[k] = 0.0;
     const bool live = t < cd.T;
     const long long o = static_cast<long long>(live ? t : 0) * Nc;
-    for (int j0 = 0; j0 < n; j0 += JT) {
-        const int jn = min(JT, n - j0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < RMAX * JT; i += 128) {
-            const int k = i / JT, j = i % JT;
-            Us[k][j] = (k < r && j < jn) ? U[static_cast<long long>(k0 + k) * n + j0 + j] : 0.0;
-        }
-        __syncthreads();
-        for (int j = 0; j < jn; ++j) {
-            const double xv = static_cast<double>(x[o + j0 + j]) - mean;
-            s1 += xv;
-            s2 += xv * xv;
+    double s1 = 0.0, s2 = 0.0, num = 0.0;
+    const double nn = static_cast<double>(n);
+    for (int kc = 0; kc < r; kc += RMAX) {   // ranks above RMAX: several passes over the window
+        const int rc = min(RMAX, r - kc);
+        double acc[RMAX], su[RMAX];
 #pragma unroll
-            for (int k = 0; k < RMAX; ++k) {
-                acc[k] = fma(Us[k][j], xv, acc[k]);
-                su[k] += Us[k][j];
+        for (int k = 0; k < RMAX; ++k) { acc[k] = 0.0; su[k] = 0.0; }
+        double p1 = 0.0, p2 = 0.0;
+        for (int j0 = 0; j0 < n; j0 += JT) {
+            const int jn = min(JT, n - j0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < RMAX * JT; i += 128) {
+                const int k = i / JT, j = i % JT;
+                Us[k][j] = (k < rc && j < jn) ? U[static_cast<long long>(k0 + kc + k) * n + j0 + j] : 0.0;
             }
+            __syncthreads();
+            for (int j = 0; j < jn; ++j) {
+                const double xv = static_cast<double>(x[o + j0 + j]) - mean;
+                p1 += xv;
+                p2 += xv * xv;
+#pragma unroll
+                for (int k = 0; k < RMAX; ++k) {
+                    acc[k] = fma(Us[k][j], xv, acc[k]);
+                    su[k] += Us[k][j];
+                }
+            }
+        }
+        s1 = p1;
+        s2 = p2;
+        const double mu = s1 / nn;
+#pragma unroll
+        for (int k = 0; k < RMAX; ++k) {
+            const double c = acc[k] - mu * su[k];
+            num += (k < rc) ? c * c : 0.0;
         }
     }
     if (!live) return;
-    const double nn = static_cast<double>(n);
-    const double mu = s1 / nn;
     double E = s2 - s1 * s1 / nn;
     if (E < 0.0) E = 0.0;
-    double num = 0.0;
-#pragma unroll
-    for (int k = 0; k < RMAX; ++k) {
-        const double c = acc[k] - mu * su[k];
-        num += (k < r) ? c * c : 0.0;
-    }
     const double ds = ((nn - 1.0) / nn) * num / E;
     const long long idx = cd.ds_off + static_cast<long long>(s) * cd.Tpad + t;
     if (DS) DS[idx] = static_cast<float>(ds);

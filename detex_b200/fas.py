@@ -30,6 +30,8 @@ def _MPXSSCorr(MPcon, reqlen, ssArrayTD, ssArrayFD, Nc, engine=None, kernel="tcg
 def beta_fit_from_stats(N, sx, sxx, slog, slog1m):
     """scipy.stats.beta.fit(data, floc=0, fscale=1) from the data's sufficient statistics
     (scipy/stats/_continuous_distns.py, beta_gen.fit, fixed loc and scale branch)."""
+    if not all(np.isfinite(v) for v in (N, sx, sxx, slog, slog1m)) or N < 2:
+        raise RuntimeError("beta fit failed: non-finite sufficient statistics (DS outside (0, 1)?)")
     xbar = sx / N
     var = sxx / N - xbar * xbar
     fac = xbar * (1 - xbar) / var - 1

@@ -65,7 +65,8 @@ int dtx_sync(dtx_ctx* ctx);
  * _loadMPSingles (fas.py:137-172): U holds the rows `row.SVD[k] for k in row.UsedSVDKeys`
  * of S subspaces (or the unit-norm singleton templates) back to back, each of length n
  * multiplexed samples (n % Nc == 0); subspace s owns rows rank_off[s]..rank_off[s+1]-1
- * (rank <= 16).  thresholds[s] (may be NULL) is row.Threshold.  The library copies. */
+ * (any rank >= 1; ranks above 16 are split into 16-vector pieces whose DS contributions
+ * are accumulated).  thresholds[s] (may be NULL) is row.Threshold.  The library copies. */
 int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank_off, int S, int n,
                   int Nc, const double* thresholds);
 

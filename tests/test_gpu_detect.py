@@ -206,3 +206,33 @@ def test_full_size_chunk_properties(engine):
     engine.detect_run(20)
     for ci in range(2):
         assert np.abs(engine.get_ds(ci, 0) - ds[ci]).max() < 2 * TOL
+
+
+def test_rank_above_16_is_split_and_accumulated(engine):
+    Nc, ns, Ls = 3, 200, 5000
+    ranks = [37, 3, 16, 17, 1]
+    chunks, bases, _ = synth.detection_case(26, 2, Ls, ns, Nc, ranks, planted=2)
+    engine.set_bases(21, bases, Nc)
+    engine.load_chunks(chunks)
+    for eng_name in ("tcgen05", "fp64"):
+        engine.detect_run(21, engine=eng_name)
+        for ci, c in enumerate(chunks):
+            for si, U in enumerate(bases):
+                assert np.abs(engine.get_ds(ci, si) - orc.mpx_ds_direct(c, U, Nc)).max() < TOL, (eng_name, ci, si)
+
+
+def test_short_chunks_use_the_1024_lag_tile(engine):
+    """Chunks with <= 1024 lags run the N = 128 variant of the Hankel GEMM (tiles of 1024 lags)."""
+    Nc, ns = 3, 300
+    ranks = [2, 5, 8]
+    chunks, bases, _ = synth.detection_case(27, 3, 1200, ns, Nc, ranks, planted=1)
+    chunks[1] = chunks[1][:(ns + 40) * Nc]      # 41 lags
+    chunks[2] = chunks[2][:(ns + 1023) * Nc]    # exactly 1024 lags
+    engine.set_bases(22, bases, Nc, thresholds=[0.3] * 3)
+    engine.load_chunks(chunks)
+    engine.detect_run(22, lta_window=20)
+    for ci, c in enumerate(chunks):
+        for si, U in enumerate(bases):
+            ref = orc.mpx_ds_direct(c, U, Nc)
+            ds = engine.get_ds(ci, si)
+            assert ds.shape == ref.shape and np.abs(ds - ref).max() < TOL
