@@ -194,6 +194,10 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
         if (r < 1) return fail(ctx, DTX_ERR_ARG, "dtx_set_bases: subspace rank must be >= 1");
     }
     BasisSet& bs = ctx->sets[set_id];
+    for (auto& kv : bs.ev_blob) kv.second.release();   // events belong to the previous bases
+    bs.ev_blob.clear();
+    bs.ev_meta.clear();
+    if (ctx->run_set == set_id) ctx->ran = false;      // results of the old bases are stale
     BasisLayout& lay = bs.lay;
     lay = BasisLayout{};
     lay.Nc = Nc;
@@ -267,7 +271,7 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
                 const int row = pc.row0 + k;
                 slot_row[static_cast<size_t>(b) * VEC_PER_BLOCK + slot] = row;
                 BlockInfo& bi = binfo[static_cast<size_t>(b) * VEC_PER_BLOCK + slot];
-                long double su = 0;
+                double su = 0;   // |sum| <= sqrt(n): plain double summation is exact to ~1e-13
                 for (int j = 0; j < n; ++j) su += U[static_cast<long long>(row) * n + j];
                 bi.sumU = static_cast<float>(su);
                 bi.out_row = s;
@@ -761,17 +765,17 @@ static int ccx_tcgen05(dtx_ctx* ctx, const void* X, int dtype, const void* dX, i
     for (int r = 0; r <= rows; ++r) roff[r] = r;
     for (int r = 0; r < rows; ++r) {
         const size_t src = static_cast<size_t>(row_begin + r) * n;
-        long double s1 = 0;
+        double s1 = 0;
         for (int i = 0; i < n; ++i)
             s1 += dtype == DTX_F32 ? static_cast<const float*>(X)[src + i] : static_cast<const double*>(X)[src + i];
-        const double mean = static_cast<double>(s1 / n);
-        long double s2 = 0;
+        const double mean = s1 / n;
+        double s2 = 0;
         for (int i = 0; i < n; ++i) {
             const double v = (dtype == DTX_F32 ? static_cast<const float*>(X)[src + i]
                                                : static_cast<const double*>(X)[src + i]) - mean;
             s2 += v * v;
         }
-        const double nrm = std::sqrt(static_cast<double>(s2));
+        const double nrm = std::sqrt(s2);
         for (int i = 0; i < n; ++i) {
             const double v = dtype == DTX_F32 ? static_cast<const float*>(X)[src + i]
                                               : static_cast<const double*>(X)[src + i];
@@ -824,7 +828,10 @@ static int ccx_tcgen05(dtx_ctx* ctx, const void* X, int dtype, const void* dX, i
     flagged.resize(nflag);
     if (nflag) DTX_CUDA(cudaMemcpy(flagged.data(), dflag.p, sizeof(int2) * nflag, cudaMemcpyDeviceToHost));
     dpad.release(); dnflag.release(); dflag.release();
-    ctx->ran = false;  // the detection results of this context were overwritten
+    // the detection state of this context was overwritten and the padded chunks are gone
+    ctx->ran = false;
+    ctx->d_raw = nullptr;
+    ctx->nchunks = 0;
     return DTX_OK;
 }
 
