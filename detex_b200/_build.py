@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libdetex_b200.so")
-SOURCES = ["dtx_api.cu", "k0_prep.cu", "k1_project.cu", "k_direct.cu", "k3_post.cu", "k4_ccx.cu", "k6_stalta.cu", "k7_mag.cu"]
+SOURCES = ["dtx_api.cu", "k0_prep.cu", "k1_project.cu", "k_direct.cu", "k3_post.cu", "k4_ccx.cu", "k6_stalta.cu", "k7_mag.cu", "k8_preproc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-Xlinker", "--no-undefined", "--use_fast_math=false",

@@ -19,7 +19,7 @@ HIST_BINS = 400
 
 EXPORTS = [
     "dtx_version", "dtx_create", "dtx_destroy", "dtx_last_error", "dtx_sync", "dtx_set_bases",
-    "dtx_load_chunks", "dtx_attach_device_chunks", "dtx_detect_run", "dtx_num_lags", "dtx_get_ds",
+    "dtx_load_chunks", "dtx_attach_device_chunks", "dtx_preprocess_chunks", "dtx_get_chunk", "dtx_detect_run", "dtx_num_lags", "dtx_get_ds",
     "dtx_get_ds64", "dtx_get_stalta", "dtx_get_rowstats", "dtx_get_hist", "dtx_get_fas", "dtx_get_candidates",
     "dtx_sta_lta_max", "dtx_set_events", "dtx_est_mags", "dtx_last_k1_ms", "dtx_launch_count", "dtx_ccx",
 ]
@@ -57,6 +57,8 @@ def load():
     L.dtx_set_bases.argtypes = [p, C.c_int, p, p, C.c_int, C.c_int, C.c_int, p]
     L.dtx_load_chunks.argtypes = [p, C.c_int, p, p, C.c_int]
     L.dtx_attach_device_chunks.argtypes = [p, C.c_int, p, p, p, C.c_int]
+    L.dtx_preprocess_chunks.argtypes = [p, C.c_int, C.c_int, p, p, C.c_int, p, C.c_int, C.c_int, C.c_int]
+    L.dtx_get_chunk.argtypes = [p, C.c_int, p, C.c_int64, C.POINTER(C.c_int64)]
     L.dtx_detect_run.argtypes = [p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                  C.c_int, C.c_int]
     L.dtx_num_lags.argtypes = [p, C.c_int, C.POINTER(C.c_int64)]

@@ -622,6 +622,90 @@ int dtx_last_k1_ms(dtx_ctx* ctx, float* ms) {
     return DTX_OK;
 }
 
+int dtx_preprocess_chunks(dtx_ctx* ctx, int nchunks, int Nc, const void* const* chan_ptrs,
+                          const int64_t* chan_len, int dtype, const double* sos, int nsos, int zerophase,
+                          int detrend) {
+    if (!ctx || !chan_ptrs || !chan_len) return DTX_ERR_ARG;
+    if (nchunks < 1 || Nc < 1 || nsos < 0 || (nsos > 0 && !sos)) return fail(ctx, DTX_ERR_ARG, "dtx_preprocess_chunks: bad arguments");
+    if (dtype != DTX_F64 && dtype != DTX_F32) return fail(ctx, DTX_ERR_ARG, "dtx_preprocess_chunks: bad dtype");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    const int ntr = nchunks * Nc;
+    std::vector<long long> off(ntr), out_off(nchunks);
+    std::vector<int> len(ntr), minlen(nchunks);
+    std::vector<int64_t> L(nchunks);
+    long long tot = 0, otot = 0;
+    int maxlen = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        int mn = INT32_MAX;
+        for (int c = 0; c < Nc; ++c) {
+            const int64_t l = chan_len[ch * Nc + c];
+            if (l < 1 || l > (1LL << 30)) return fail(ctx, DTX_ERR_ARG, "dtx_preprocess_chunks: trace length out of range");
+            off[ch * Nc + c] = tot;
+            len[ch * Nc + c] = static_cast<int>(l);
+            tot += (l + 1) & ~1LL;
+            mn = std::min<int>(mn, static_cast<int>(l));
+            maxlen = std::max<int>(maxlen, static_cast<int>(l));
+        }
+        minlen[ch] = mn;            // multiplex trims to the shortest channel (construct.py:972-974)
+        L[ch] = static_cast<int64_t>(mn) * Nc;
+        out_off[ch] = otot;
+        otot += (L[ch] + 1) & ~1LL;
+    }
+    cudaStream_t st = ctx->stream;
+    DevBuf<double> dbuf, dstats, dseg;
+    DevBuf<long long> doff, dooff;
+    DevBuf<int> dlen, dmin;
+    const int maxseg = (maxlen + preproc_seg() - 1) / preproc_seg();
+    DTX_CUDA(dbuf.reserve(tot)); DTX_CUDA(dstats.reserve(2 * static_cast<size_t>(ntr)));
+    DTX_CUDA(dseg.reserve(static_cast<size_t>(ntr) * maxseg * 2));
+    DTX_CUDA(doff.reserve(ntr)); DTX_CUDA(dlen.reserve(ntr)); DTX_CUDA(dmin.reserve(nchunks)); DTX_CUDA(dooff.reserve(nchunks));
+    std::vector<double> conv;
+    for (int t = 0; t < ntr; ++t) {
+        const void* src = chan_ptrs[t];
+        if (dtype == DTX_F32) {   // the reference filters float32 traces in float64 as well (scipy sosfilt)
+            conv.resize(len[t]);
+            const float* f = static_cast<const float*>(chan_ptrs[t]);
+            for (int i = 0; i < len[t]; ++i) conv[i] = f[i];
+            DTX_CUDA(cudaMemcpy(dbuf.p + off[t], conv.data(), sizeof(double) * len[t], cudaMemcpyHostToDevice));
+        } else {
+            DTX_CUDA(cudaMemcpyAsync(dbuf.p + off[t], src, sizeof(double) * len[t], cudaMemcpyHostToDevice, st));
+        }
+    }
+    DTX_CUDA(cudaMemcpyAsync(doff.p, off.data(), sizeof(long long) * ntr, cudaMemcpyHostToDevice, st));
+    DTX_CUDA(cudaMemcpyAsync(dlen.p, len.data(), sizeof(int) * ntr, cudaMemcpyHostToDevice, st));
+    DTX_CUDA(cudaMemcpyAsync(dmin.p, minlen.data(), sizeof(int) * nchunks, cudaMemcpyHostToDevice, st));
+    DTX_CUDA(cudaMemcpyAsync(dooff.p, out_off.data(), sizeof(long long) * nchunks, cudaMemcpyHostToDevice, st));
+    launch_preproc(dbuf.p, doff.p, dlen.p, ntr, maxlen, sos, nsos, zerophase, detrend, dstats.p, dseg.p, st);
+    DTX_CUDA(cudaGetLastError());
+    ctx->launches += (detrend ? 2 : 0) + 3 * nsos * (zerophase ? 2 : 1);
+    // multiplexed result becomes the loaded batch
+    int rc = set_chunk_table(ctx, nchunks, L.data(), nullptr, DTX_F64);
+    if (rc) return rc;
+    for (int ch = 0; ch < nchunks; ++ch)
+        if (ctx->raw_off[ch] != out_off[ch]) return fail(ctx, DTX_ERR_STATE, "dtx_preprocess_chunks: layout mismatch");
+    DTX_CUDA(ctx->raw_own.reserve(static_cast<size_t>(otot) * 8));
+    launch_multiplex(dbuf.p, doff.p, dmin.p, dooff.p, nchunks, Nc, maxlen, reinterpret_cast<double*>(ctx->raw_own.p), st);
+    DTX_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    ctx->d_raw = ctx->raw_own.p;
+    DTX_CUDA(cudaStreamSynchronize(st));   // host trace buffers may be released by the caller
+    dbuf.release(); dstats.release(); dseg.release(); doff.release(); dooff.release(); dlen.release(); dmin.release();
+    return DTX_OK;
+}
+
+int dtx_get_chunk(dtx_ctx* ctx, int chunk, double* out, int64_t count, int64_t* L) {
+    if (!ctx || !out) return DTX_ERR_ARG;
+    if (!ctx->d_raw || chunk < 0 || chunk >= ctx->nchunks) return fail(ctx, DTX_ERR_STATE, "dtx_get_chunk: no such chunk");
+    if (ctx->dtype != DTX_F64) return fail(ctx, DTX_ERR_STATE, "dtx_get_chunk: float64 chunks only");
+    if (L) *L = ctx->rawL[chunk];
+    if (count < ctx->rawL[chunk]) return fail(ctx, DTX_ERR_CAPACITY, "dtx_get_chunk: buffer too small");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    DTX_CUDA(cudaMemcpyAsync(out, static_cast<const double*>(ctx->d_raw) + ctx->raw_off[chunk],
+                             sizeof(double) * ctx->rawL[chunk], cudaMemcpyDeviceToHost, ctx->stream));
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DTX_OK;
+}
+
 int dtx_sta_lta_max(dtx_ctx* ctx, int Nc, int chan, int nsta, int nlta, float* out, int64_t count) {
     if (!ctx || !out) return DTX_ERR_ARG;
     if (ctx->nchunks < 1 || !ctx->d_raw) return fail(ctx, DTX_ERR_STATE, "dtx_sta_lta_max: no chunks loaded");

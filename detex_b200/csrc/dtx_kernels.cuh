@@ -142,6 +142,13 @@ void launch_mag(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, const
                 const MagTrigger* d_trig, int ntrig, const MagSubspace* d_subs, const double* d_U, int n, int Nc,
                 double* d_scratch, int scratch_stride, double* d_out, cudaStream_t st);
 
+// k8_preproc.cu : detrend + SOS filter + multiplex (construct._applyFilter array part)
+void launch_preproc(double* d_buf, const long long* d_off, const int* d_len, int ntr, int maxlen, const double* sos,
+                    int nsos, int zerophase, int detrend, double* d_stats, double* d_segstate, cudaStream_t st);
+void launch_multiplex(const double* d_buf, const long long* d_off, const int* d_minlen, const long long* d_out_off,
+                      int nchunks, int Nc, int maxlen, double* d_out, cudaStream_t st);
+int preproc_seg();
+
 // k6_stalta.cu : classic STA/LTA screen of raw chunks (fas._checkSTALTA)
 void launch_stalta_max(const void* raw, int dtype_f32, const long long* d_raw_off, const int* d_Ls, int nchunks,
                        int maxLs, int Nc, int chan, int nsta, int nlta, unsigned* d_out_bits, cudaStream_t st);

@@ -148,9 +148,19 @@ class SSDetex(object):
         Returns (ss_df rows as DataFrame with the reference's columns, per-chunk dicts
         {name: MaxDS}, and optionally the dense DS arrays {(chunk, name): ndarray}).
         Chunks the reference would skip (detect.py:262-274) are dropped with a warning."""
+        return self._run(chunks, [len(c) for c in chunks], sr, starts, keep_ds, raw_filt=None)
+
+    def run_raw_chunks(self, traces, sr, starts, filt=(1, 10, 2, True), keep_ds=False):
+        """As run_chunks, but from RAW per-channel traces (list of chunks, each a list of channel
+        arrays in sorted order): linear detrend + band-pass + multiplex run on the device too
+        (`_applyFilter` + `multiplex`, detect.py:231-241), so the samples cross PCIe once."""
+        lens = [min(len(t) for t in ch) * self.Nc for ch in traces]
+        return self._run(traces, lens, sr, starts, keep_ds, raw_filt=(filt,))
+
+    def _run(self, chunks, lens, sr, starts, keep_ds, raw_filt):
         good = []
         for i, c in enumerate(chunks):
-            L = len(c) // self.Nc * self.Nc
+            L = lens[i] // self.Nc * self.Nc
             nmax = max(self.groups.keys())
             if L <= nmax or (L - nmax) // self.Nc + 1 < 10:
                 log.warning("current data block on %s starting %s is shorter than template, skipping",
@@ -163,7 +173,11 @@ class SSDetex(object):
         if not good:
             return pd.DataFrame(columns=SAR_COLS), maxds, dense
         eng = self.engine
-        eng.load_chunks([chunks[i] for i in good])
+        if raw_filt is None:
+            eng.load_chunks([chunks[i] for i in good])
+        else:
+            from . import preprocess
+            preprocess.applyFilter([chunks[i] for i in good], sr, raw_filt[0], engine=eng)
         W = int(self.triggerLTATime * sr)
         for n, names in sorted(self.groups.items()):
             sid = self.set_ids[n]

@@ -84,6 +84,34 @@ class Engine(object):
         self._keep = arrs  # async H2D: keep the host arrays alive until the next sync
         self.nchunks = len(arrs)
 
+    def preprocess_chunks(self, traces, sos, zerophase=True, detrend=True):
+        """traces: list (chunks) of lists (channels, ObsPy sort order) of 1-D host arrays.  Detrend,
+        SOS-filter and multiplex on the device; the result becomes the loaded batch."""
+        Nc = len(traces[0])
+        f32 = all(np.asarray(t).dtype == np.float32 for ch in traces for t in ch)
+        dt = np.float32 if f32 else np.float64
+        arrs = [np.ascontiguousarray(np.asarray(t, dtype=dt)) for ch in traces for t in ch]
+        if any(len(ch) != Nc for ch in traces):
+            raise DtxError(2, "every chunk needs the same number of channels")
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        lens = np.array([a.shape[0] for a in arrs], dtype=np.int64)
+        sos = np.ascontiguousarray(np.atleast_2d(np.asarray(sos, dtype=np.float64)))
+        self._check(self._L.dtx_preprocess_chunks(self._h, len(traces), Nc, ptrs, _ptr(lens),
+                                                  _lib.DTX_F32 if f32 else _lib.DTX_F64, _ptr(sos), sos.shape[0],
+                                                  int(bool(zerophase)), int(bool(detrend))))
+        self.nchunks = len(traces)
+        return [int(min(len(t) for t in ch)) * Nc for ch in traces]
+
+    def get_chunk(self, chunk):
+        L = C.c_int64()
+        probe = np.empty(1, dtype=np.float64)
+        rc = self._L.dtx_get_chunk(self._h, int(chunk), _ptr(probe), 0, C.byref(L))
+        if rc not in (0, _lib.DTX_ERR_CAPACITY):
+            self._check(rc)
+        out = np.empty(L.value, dtype=np.float64)
+        self._check(self._L.dtx_get_chunk(self._h, int(chunk), _ptr(out), out.size, C.byref(L)))
+        return out
+
     def attach_device_chunks(self, base_ptr, elem_offsets, lengths, f32=False):
         off = np.ascontiguousarray(np.asarray(elem_offsets, dtype=np.int64))
         L = np.ascontiguousarray(np.asarray(lengths, dtype=np.int64))

@@ -81,6 +81,21 @@ int dtx_load_chunks(dtx_ctx* ctx, int nchunks, const void* const* host_ptrs, con
 int dtx_attach_device_chunks(dtx_ctx* ctx, int nchunks, const void* dev_base,
                              const int64_t* elem_offsets, const int64_t* L, int dtype);
 
+/* On-device pre-processing (next row N2) ----------------------------------------------------
+ * Replaces the array part of construct._applyFilter (construct.py:1017-1029) + multiplex
+ * (construct.py:928-987): every trace is linearly detrended (scipy.signal.detrend, which is what
+ * ObsPy 1.0.2's Trace.detrend('linear') calls), filtered with the given second-order sections
+ * exactly as obspy/signal/filter.py::bandpass does (sosfilt from a zero state; zerophase = a
+ * second pass over the reversed trace), channels are trimmed to the shortest one and
+ * interleaved.  The multiplexed float64 chunks become the context's loaded chunks (as after
+ * dtx_load_chunks).  chan_ptrs[chunk*Nc + c] / chan_len[...] are host arrays; sos is
+ * [nsos][6] = b0 b1 b2 a0 a1 a2 (scipy layout), designed by the caller. */
+int dtx_preprocess_chunks(dtx_ctx* ctx, int nchunks, int Nc, const void* const* chan_ptrs,
+                          const int64_t* chan_len, int dtype, const double* sos, int nsos, int zerophase,
+                          int detrend);
+/* the multiplexed chunk as the device holds it (MPcon of detect.py:241), float64 chunks only */
+int dtx_get_chunk(dtx_ctx* ctx, int chunk, double* out, int64_t count, int64_t* L);
+
 /* Detection statistic ------------------------------------------------------------------
  * Replaces the `for ind,row in CorDF.iterrows(): _MPXDS(...)` loop of _SSDetex._getRA
  * (detect.py:259-281) and fas._MPXSSCorr (fas.py:120-134) for every loaded chunk and every

@@ -547,3 +547,31 @@ def est_mag(trigIndex, MPcon, Nc, U, ewf, mags, issubspace=True):
     d1 = np.dot(ConDat, WFU[0])
     d2 = np.dot(WFU[0], WFU[0])
     return mags[0] + d1 / d2, mags[0] + np.log10(np.std(ConDat) / np.std(WFU[0])), SNR
+
+
+# --------------------------------------------------------------------------
+# N2  pre-processing: array part of construct._applyFilter (construct.py:1017-1029)
+# ObsPy 1.0.2 (not vendored): Trace.detrend('linear') -> scipy.signal.detrend(type='linear');
+# Trace.filter('bandpass') -> obspy/signal/filter.py::bandpass (iirfilter + zpk2sos + sosfilt,
+# zerophase = second sosfilt over the reversed trace).  ObsPy is not installable here, so the
+# ObsPy-side wiring is restated from its published source (parity of this step unpinned); the
+# arithmetic itself is SciPy's, which IS run here.
+# --------------------------------------------------------------------------
+
+
+def apply_filter(chans, sr, filt=(1, 10, 2, True)):
+    """chans: list of 1-D channel arrays (sorted order).  Returns the multiplexed chunk."""
+    import scipy.signal
+    out = []
+    for x in chans:
+        y = scipy.signal.detrend(np.asarray(x, dtype=np.float64), type="linear")
+        if filt is not None:
+            fe = 0.5 * sr
+            z, p, k = scipy.signal.iirfilter(filt[2], [filt[0] / fe, filt[1] / fe], btype="band", ftype="butter",
+                                             output="zpk")
+            sos = scipy.signal.zpk2sos(z, p, k)
+            y = scipy.signal.sosfilt(sos, y)
+            if filt[3]:
+                y = scipy.signal.sosfilt(sos, y[::-1])[::-1]
+        out.append(y)
+    return multiplex(out)
