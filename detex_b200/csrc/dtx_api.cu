@@ -93,6 +93,8 @@ struct dtx_ctx {
     std::vector<ChunkDesc> h_chunks;
     DevBuf<ChunkDesc> d_chunks;
     DevBuf<int4> d_items;
+    std::vector<int> items_key;   // shape signature of the cached work-item list
+    int n_items = 0;
     DevBuf<__half> d_xsplit;
     DevBuf<float> d_mu, d_invE, d_DS, d_scale, d_rowmax;
     DevBuf<double> d_DS64, d_sum;
@@ -392,9 +394,16 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     // the current A block in L2 and the group's split signal (<= ~40 MB) stays L2 resident
     const int tiles_per_chunk = std::max(1, (maxT + 8 * nq - 1) / (8 * nq));
     const int group = std::max(8, (4 * ctx->num_sms + tiles_per_chunk - 1) / tiles_per_chunk);
+    // the list only depends on the batch's shape: reuse the device copy when it has not changed
+    std::vector<int> sig_key{nq, lay.nblocks, group, nchunks};
+    for (int i = 0; i < nchunks; ++i) {
+        sig_key.push_back(ctx->h_chunks[i].T);
+        sig_key.push_back(ctx->h_chunks[i].blk_hi);
+    }
+    const bool items_cached = sig_key == ctx->items_key && ctx->d_items.p != nullptr;
     std::vector<int4> items;
-    items.reserve(static_cast<size_t>(nitems) * 2 * lay.nblocks);
-    for (int g0 = 0; g0 < nchunks; g0 += group) {
+    if (!items_cached) items.reserve(static_cast<size_t>(nitems) * 2 * lay.nblocks);
+    for (int g0 = 0; g0 < nchunks && !items_cached; g0 += group) {
         const int g1 = std::min(nchunks, g0 + group);
         int max_blk = 0;
         for (int i = g0; i < g1; ++i) max_blk = std::max(max_blk, ctx->h_chunks[i].blk_hi);
@@ -407,7 +416,11 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     }
 
     DTX_CUDA(ctx->d_chunks.reserve(nchunks));
-    DTX_CUDA(ctx->d_items.reserve(items.size()));
+    if (!items_cached) {
+        DTX_CUDA(ctx->d_items.reserve(items.size()));
+        ctx->items_key = sig_key;
+        ctx->n_items = static_cast<int>(items.size());
+    }
     DTX_CUDA(ctx->d_xsplit.reserve(sig));
     DTX_CUDA(ctx->d_mu.reserve(nrm));
     DTX_CUDA(ctx->d_invE.reserve(nrm));
@@ -423,8 +436,9 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     cudaStream_t st = ctx->stream;
     DTX_CUDA(cudaMemcpyAsync(ctx->d_chunks.p, ctx->h_chunks.data(), sizeof(ChunkDesc) * nchunks,
                              cudaMemcpyHostToDevice, st));
-    DTX_CUDA(cudaMemcpyAsync(ctx->d_items.p, items.data(), sizeof(int4) * items.size(),
-                             cudaMemcpyHostToDevice, st));
+    if (!items_cached)
+        DTX_CUDA(cudaMemcpyAsync(ctx->d_items.p, items.data(), sizeof(int4) * items.size(),
+                                 cudaMemcpyHostToDevice, st));
     DTX_CUDA(cudaMemsetAsync(ctx->d_ncand.p, 0, sizeof(int), st));
 
     const int f32 = ctx->dtype == DTX_F32;
@@ -438,7 +452,7 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         K1Args a;
         a.Aimg = bs.d_Aimg.p; a.xsplit = ctx->d_xsplit.p; a.mu = ctx->d_mu.p; a.invE = ctx->d_invE.p;
         a.chunk_scale = ctx->d_scale.p; a.chunks = ctx->d_chunks.p; a.items = ctx->d_items.p;
-        a.binfo = bs.d_binfo.p; a.DS = ctx->d_DS.p; a.nitems = static_cast<int>(items.size());
+        a.binfo = bs.d_binfo.p; a.DS = ctx->d_DS.p; a.nitems = ctx->n_items;
         a.kblk = kblk; a.num_sms = ctx->num_sms; a.nq = nq; a.mode = mode;
         if (bs.has_split) DTX_CUDA(cudaMemsetAsync(ctx->d_DS.p, 0, sizeof(float) * ds, st));
         DTX_CUDA(cudaEventRecord(ctx->ev0, st));
