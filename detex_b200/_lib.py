@@ -21,7 +21,7 @@ EXPORTS = [
     "dtx_version", "dtx_create", "dtx_destroy", "dtx_last_error", "dtx_sync", "dtx_set_bases",
     "dtx_load_chunks", "dtx_attach_device_chunks", "dtx_preprocess_chunks", "dtx_get_chunk", "dtx_detect_run", "dtx_num_lags", "dtx_get_ds",
     "dtx_get_ds64", "dtx_get_stalta", "dtx_get_rowstats", "dtx_get_hist", "dtx_get_fas", "dtx_get_candidates",
-    "dtx_sta_lta_max", "dtx_set_events", "dtx_est_mags", "dtx_last_k1_ms", "dtx_launch_count", "dtx_ccx",
+    "dtx_sta_lta_max", "dtx_set_events", "dtx_est_mags", "dtx_last_k1_ms", "dtx_launch_count", "dtx_ccx", "dtx_corr_zero_lag",
 ]
 
 
@@ -74,6 +74,7 @@ def load():
     L.dtx_set_events.argtypes = [p, C.c_int, C.c_int, C.c_int, p, p, p, C.c_int]
     L.dtx_est_mags.argtypes = [p, C.c_int, C.c_int, p, p, p, p]
     L.dtx_launch_count.argtypes = [p, C.POINTER(C.c_int64)]
+    L.dtx_corr_zero_lag.argtypes = [p, p, C.c_int, C.c_int, p]
     L.dtx_ccx.argtypes = [p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p, p, p]
     for name in EXPORTS:
         if name not in ("dtx_destroy", "dtx_last_error"):

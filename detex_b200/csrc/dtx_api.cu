@@ -848,6 +848,24 @@ int dtx_launch_count(dtx_ctx* ctx, int64_t* n) {
     return DTX_OK;
 }
 
+int dtx_corr_zero_lag(dtx_ctx* ctx, const double* X, int N, int n, double* out) {
+    if (!ctx || !X || !out) return DTX_ERR_ARG;
+    if (N < 1 || n < 2) return fail(ctx, DTX_ERR_ARG, "dtx_corr_zero_lag: bad shape");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<double> dX, dout;
+    DTX_CUDA(dX.reserve(static_cast<size_t>(N) * n));
+    DTX_CUDA(dout.reserve(static_cast<size_t>(N) * N));
+    cudaStream_t st = ctx->stream;
+    DTX_CUDA(cudaMemcpyAsync(dX.p, X, sizeof(double) * N * n, cudaMemcpyHostToDevice, st));
+    launch_corr0(dX.p, N, n, dout.p, st);
+    DTX_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    DTX_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaStreamSynchronize(st));
+    dX.release(); dout.release();
+    return DTX_OK;
+}
+
 static const int CCX_SET_ID = -77;
 
 // Tensor-core CCX: events [row_begin,row_end) as rank-1 templates, padded events as chunks.

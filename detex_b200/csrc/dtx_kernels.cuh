@@ -118,6 +118,7 @@ void launch_ccx_stats(const void* d_X, int dtype_f32, int N, int n, int Nc, doub
 void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int row_begin, int row_end,
                      const double* wa, const double* wb, const double* es, const double* ed, double* d_cc,
                      int* d_lag, double* d_sub, int num_sms, cudaStream_t st);
+void launch_corr0(const double* d_X, int N, int n, double* d_out, cudaStream_t st);
 void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int nsig, int P, int Lc, double* out,
                     cudaStream_t st);
 void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsig, const void* d_X, int dtype_f32,

@@ -425,3 +425,47 @@ void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsi
 }
 
 }  // namespace dtx
+
+// ------------------------------------------------------------------ zero-lag Pearson matrix
+// `SubSpace.validateClusters` (reference detex/subspace.py:738-773) calls
+// construct.fast_normcorr(t, s) on every pair of ALIGNED, trimmed waveforms of a cluster; at
+// equal lengths that is the single zero-lag Pearson coefficient.  One CTA per pair, float64.
+namespace dtx {
+namespace {
+__global__ void __launch_bounds__(256)
+corr0_kernel(const double* __restrict__ X, int N, int n, double* __restrict__ out) {
+    const int b = blockIdx.y, c = blockIdx.x;
+    if (c < b) return;
+    const double* x1 = X + static_cast<long long>(b) * n;
+    const double* x2 = X + static_cast<long long>(c) * n;
+    double s1 = 0, s2 = 0, q1 = 0, q2 = 0, p = 0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double a = x1[i], d = x2[i];
+        s1 += a; s2 += d; q1 += a * a; q2 += d * d; p += a * d;
+    }
+    __shared__ double sh[8][5];
+    double v[5] = {s1, s2, q1, q2, p};
+    for (int k = 0; k < 5; ++k)
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 5; ++k) sh[threadIdx.x >> 5][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[5] = {0, 0, 0, 0, 0};
+        for (int w = 0; w < 8; ++w)
+            for (int k = 0; k < 5; ++k) t[k] += sh[w][k];
+        const double nn = n;
+        const double cov = t[4] - t[0] * t[1] / nn;
+        const double v1 = t[2] - t[0] * t[0] / nn, v2 = t[3] - t[1] * t[1] / nn;
+        const double r = cov / sqrt(v1 * v2);
+        out[static_cast<long long>(b) * N + c] = r;
+        out[static_cast<long long>(c) * N + b] = r;
+    }
+}
+}  // namespace
+
+void launch_corr0(const double* d_X, int N, int n, double* d_out, cudaStream_t st) {
+    const dim3 grid(N, N);
+    corr0_kernel<<<grid, 256, 0, st>>>(d_X, N, n, d_out);
+}
+}  // namespace dtx

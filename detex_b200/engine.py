@@ -212,6 +212,13 @@ class Engine(object):
         self._check(self._L.dtx_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def corr_zero_lag(self, X):
+        X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+        N, n = X.shape
+        out = np.empty((N, N), dtype=np.float64)
+        self._check(self._L.dtx_corr_zero_lag(self._h, _ptr(X), N, n, _ptr(out)))
+        return out
+
     # -------------------------------------------------------------------- ccx
     def ccx(self, X, Nc, row_begin=0, row_end=None, engine="fp64"):
         X = np.asarray(X)

@@ -33,6 +33,18 @@ def svd_basis(aligned, selectCriteria=2, selectValue=0.9, normalize=False):
                 FracEnergy={'Average': avg, 'Minimum': mn}, NumBasis=ndim)
 
 
+def validate_cluster(aligned, ccreq, engine=None):
+    """`SubSpace.validateClusters` for one cluster (subspace.py:738-773): aligned is the
+    (events, n) array of aligned + trimmed members in `row.Events` order.  Returns the indices
+    of the events that fail (max CC with every LATER member < ccreq), in the order the
+    reference would remove them.  The pairwise zero-lag coefficients come from the GPU."""
+    from .detect import default_engine
+    eng = engine or default_engine()
+    cc = eng.corr_zero_lag(aligned)
+    N = cc.shape[0]
+    return [i for i in range(N - 1) if np.max(cc[i, i + 1:]) < ccreq]
+
+
 def single_basis(mptd):
     """Singleton template: unit norm, not demeaned (detect.py:356-357; fas.py:144)."""
     x = np.asarray(mptd, dtype=np.float64)

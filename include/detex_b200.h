@@ -160,6 +160,11 @@ int dtx_launch_count(dtx_ctx* ctx, int64_t* n);
 int dtx_ccx(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int row_begin, int row_end,
             int engine, double* cc, int32_t* lag, double* subsamp);
 
+/* Zero-lag Pearson matrix of N equal-length waveforms (next row N3, validateClusters,
+ * subspace.py:738-773: fast_normcorr of every pair of aligned, trimmed cluster members).
+ * out is the dense symmetric [N][N] matrix. */
+int dtx_corr_zero_lag(dtx_ctx* ctx, const double* X, int N, int n, double* out);
+
 #ifdef __cplusplus
 }
 #endif

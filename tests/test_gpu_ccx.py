@@ -93,3 +93,18 @@ def test_ccx_tensor_engine_config3_shape_and_row_blocks(engine):
         for r in range(b0, b1):
             assert np.array_equal(c2[r - b0, r + 1:], cc[r, r + 1:])
             assert np.array_equal(l2[r - b0, r + 1:], lag[r, r + 1:])
+
+
+def test_validate_cluster_zero_lag_cc(engine):
+    """N3 (part): validateClusters' pairwise zero-lag fast_normcorr on the GPU."""
+    from detex_b200 import subspace
+    rng = np.random.default_rng(71)
+    base = synth.multiplex(synth.bandpassed_noise(rng, 400, nchan=3))
+    W = np.array([base + s * synth.multiplex(synth.bandpassed_noise(rng, 400, nchan=3)) for s in (0.2, 0.3, 3.0, 0.25, 4.0)])
+    cc = engine.corr_zero_lag(W)
+    for i in range(5):
+        for j in range(5):
+            assert abs(cc[i, j] - orc.fast_normcorr(W[i], W[j])[0]) < 1e-12
+    bad = subspace.validate_cluster(W, 0.5, engine=engine)
+    exp = [i for i in range(4) if max(orc.fast_normcorr(W[i], W[j])[0] for j in range(i + 1, 5)) < 0.5]
+    assert bad == exp and 2 in bad
