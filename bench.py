@@ -233,7 +233,7 @@ def gpu_arm(args):
         for b in range(nbatch):
             lo, hi = b * args.batch, min(args.chunks, (b + 1) * args.batch)
             eng.attach_device_chunks(data.data_ptr(), offs_all[lo:hi], lens_all[lo:hi])
-            eng.detect_run(0, engine="tcgen05", kblk=args.kblk, lta_window=int(5 * SR))
+            eng.detect_run(0, engine=args.engine, kblk=args.kblk, lta_window=int(5 * SR))
             c = eng.candidates()
             c["row"] += lo * args.nsub
             cands.append(c)
@@ -323,7 +323,7 @@ def gpu_arm(args):
         for b in range(nbatch):
             lo, hi = b * args.batch, min(args.chunks, (b + 1) * args.batch)
             eng.load_chunks([hnp[i] for i in range(lo, hi)])                  # H2D (pinned)
-            eng.detect_run(0, engine="tcgen05", kblk=args.kblk, lta_window=int(5 * SR))
+            eng.detect_run(0, engine=args.engine, kblk=args.kblk, lta_window=int(5 * SR))
             mx, fl = eng.rowstats()                                            # D2H
             c = eng.candidates()                                               # D2H
             c["row"] += lo * args.nsub
@@ -383,6 +383,7 @@ def main():
     ap.add_argument("--nsub", type=int, default=NSUB)
     ap.add_argument("--batch", type=int, default=48, help="chunks per detect_run (DS buffer = batch*S*T*4 B)")
     ap.add_argument("--kblk", type=int, default=2)
+    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "tcgen05_x8", "tcgen05_auto"])
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

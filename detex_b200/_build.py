@@ -30,21 +30,23 @@ def _stale():
     return os.path.getmtime(inc) > t
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile the library.  `extra_flags` / `out` build experiment variants next to it."""
+    if out is None and not force and not _stale():
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     if verbose:
         flags += ["-Xptxas", "-v"]
-    cmd = [nvcc] + flags + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    target = out or LIB
+    cmd = [nvcc] + flags + list(extra_flags) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", target]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -14,7 +14,9 @@ DTX_OK = 0
 DTX_ERR_SHORT_CHUNK = 4
 DTX_ERR_CAPACITY = 6
 DTX_F64, DTX_F32 = 0, 1
-ENGINE_TCGEN05, ENGINE_FP64 = 0, 1
+ENGINE_TCGEN05, ENGINE_FP64, ENGINE_TCGEN05_X8, ENGINE_TCGEN05_AUTO = 0, 1, 2, 3
+ENGINES = {"tcgen05": ENGINE_TCGEN05, "fp64": ENGINE_FP64, "tcgen05_x8": ENGINE_TCGEN05_X8,
+           "tcgen05_auto": ENGINE_TCGEN05_AUTO}
 HIST_BINS = 400
 
 EXPORTS = [
@@ -22,6 +24,7 @@ EXPORTS = [
     "dtx_load_chunks", "dtx_attach_device_chunks", "dtx_preprocess_chunks", "dtx_get_chunk", "dtx_detect_run", "dtx_num_lags", "dtx_get_ds",
     "dtx_get_ds64", "dtx_get_stalta", "dtx_get_rowstats", "dtx_get_hist", "dtx_get_fas", "dtx_get_candidates",
     "dtx_sta_lta_max", "dtx_set_events", "dtx_est_mags", "dtx_last_k1_ms", "dtx_launch_count", "dtx_ccx", "dtx_corr_zero_lag",
+    "dtx_set_x8_tolerance", "dtx_get_chunk_modes",
 ]
 
 
@@ -43,9 +46,10 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_build.LIB):
+    path = os.environ.get("DETEX_B200_LIB", _build.LIB)   # experiment variants (see experiments/ab_issue.sh)
+    if path == _build.LIB and not os.path.exists(path):
         _build.build()
-    L = C.CDLL(_build.LIB)
+    L = C.CDLL(path)
     p = C.c_void_p
     L.dtx_version.restype = C.c_int
     L.dtx_create.argtypes = [C.c_int, p, C.POINTER(p)]
@@ -54,6 +58,8 @@ def load():
     L.dtx_last_error.argtypes = [p]
     L.dtx_last_error.restype = C.c_char_p
     L.dtx_sync.argtypes = [p]
+    L.dtx_set_x8_tolerance.argtypes = [p, C.c_double]
+    L.dtx_get_chunk_modes.argtypes = [p, p]
     L.dtx_set_bases.argtypes = [p, C.c_int, p, p, C.c_int, C.c_int, C.c_int, p]
     L.dtx_load_chunks.argtypes = [p, C.c_int, p, p, C.c_int]
     L.dtx_attach_device_chunks.argtypes = [p, C.c_int, p, p, p, C.c_int]

@@ -5,6 +5,9 @@
   _makeDFcclags(eventList, row)                      construct.py:369-394
   cluster_link(DFcc)                                 construct.py:152-157 (linkage stays on CPU:
                                                      SciPy single linkage is an O(N^2) MST)
+  get_delays(DFcc, DFlag) / alignTD(delays, MPtd)    construct.py:272-286, 486-503, 710-812
+                                                     (dendrogram-walk alignment, O(N^2) instead of
+                                                     the reference's O(N^3) pandas loops)
 """
 import numpy as np
 import pandas as pd
@@ -65,3 +68,75 @@ def cluster_link(DFcc):
     """createCluster tail (construct.py:152-157)."""
     cx = _flatNoNan(1.0000001 - np.asarray(DFcc, dtype=np.float64))
     return linkage(cx)
+
+
+def get_delays(DFcc, DFlag):
+    """`_getDelays` + `_traceEventDendro` (construct.py:710-761) without the condensed lag vector.
+
+    The reference walks the single linkage in merge order; for the pair (ev1 < ev2) whose distance
+    caused the merge it reads that pair's *current* lag, delays every event of the merged cluster
+    that does not contain ev1 by it, and rewrites all affected entries of the N(N-1)/2 lag vector
+    (`_updateLags`, construct.py:764-793: pairs (b, j > b) += lag, pairs (a < b, b) -= lag).  Those
+    updates are exactly `lag(i, j) = lag0(i, j) + d[i] - d[j]` with d the per-event delay so far,
+    so only d is kept: one vectorised add per merge, O(N^2) in total (N = 4096: seconds; the
+    reference's per-merge DataFrame scans and Python loops are O(N^3)).
+
+    DFcc, DFlag: (N-1) x (N-1) frames / arrays as `_makeDFcclags` returns them.  Returns
+    (link, delays) with delays the int64 `lagSeries` of construct.py:742 in event order.
+    Duplicate coefficients raise (the reference perturbs them with unseeded random numbers,
+    construct.py:814-835)."""
+    cc = np.asarray(DFcc, dtype=np.float64)
+    lagm = np.asarray(DFlag, dtype=np.float64)
+    N = cc.shape[0]                                   # events - 1
+    iu = np.triu_indices(N)                           # (row b, column c-1) with c-1 >= b
+    cx = 1.0000001 - cc[iu]
+    if np.isnan(cx).any():
+        raise ValueError("get_delays: NaN in the upper triangle of DFcc")
+    order = np.argsort(cx, kind="stable")
+    if N > 1 and (np.diff(cx[order]) == 0).any():
+        raise ValueError("get_delays: duplicate correlation coefficients (construct.py:814-835)")
+    lag0 = lagm[iu]
+    link = linkage(cx)
+    members = [None] * (2 * N + 1)
+    for i in range(N + 1):
+        members[i] = np.array([i], dtype=np.int64)
+    owner = np.arange(N + 1, dtype=np.int64)          # current cluster id of every event
+    d = np.zeros(N + 1, dtype=np.int64)
+    sorted_cx = cx[order]
+    for a in range(N):
+        i1, i2 = int(link[a, 0]), int(link[a, 1])
+        p = int(order[np.searchsorted(sorted_cx, link[a, 2])])
+        ev1, ev2 = int(iu[0][p]), int(iu[1][p]) + 1
+        cl22 = members[i2] if owner[ev1] == i1 else members[i1]
+        cur = int(np.round(lag0[p] + d[ev1] - d[ev2]))
+        d[cl22] += cur
+        new = N + 1 + a
+        members[new] = np.concatenate([members[i1], members[i2]])
+        owner[members[new]] = new
+        members[i1] = members[i2] = None
+    return link, d
+
+
+def alignTD(delays, MPtd):
+    """`_alignTD` (construct.py:486-503) on the shifted delays of construct.py:283-284:
+    returns (aligned [N][len], SampleDelays).  Raises like the reference's
+    `detex.log(level='error')` when nothing is left."""
+    d = np.asarray(delays, dtype=np.int64)
+    d = d - int(d.min())
+    length = len(MPtd[0]) - int(d.max())
+    if length <= 0:
+        raise Exception('Alignment of multiplexed stream failing, try raising ccreq or widenning '
+                        'trim window')
+    return np.array([np.asarray(x)[k:k + length] for x, k in zip(MPtd, d)]), d
+
+
+def update_start_times(stats, sample_delays, origin_times, magnitudes):
+    """`_updateStartTimes` (construct.py:346-366): start time after the alignment trim, predicted
+    origin-to-window offset.  stats: list of dicts {Nc, sampling_rate, starttime, ...}."""
+    out = []
+    for st, k, ot, mag in zip(stats, sample_delays, origin_times, magnitudes):
+        st = dict(st)
+        new = st['starttime'] + k / (st['sampling_rate'] * st['Nc'])
+        st.update(starttime=new, origintime=ot, magnitude=mag, offset=new - ot)
+        out.append(st)
+    return out

@@ -53,6 +53,9 @@ struct BasisSet {
     DevBuf<int> d_rank_off, d_slot_row;
     DevBuf<BlockInfo> d_binfo;
     DevBuf<uint8_t> d_Aimg;
+    DevBuf<uint8_t> d_Aimg8;  // image of the 8-bit cross-term engine, built on first use
+    bool have_img8 = false;
+    double nu4 = 1.0;         // max over basis vectors of sum u^4 / (sum u^2)^2 (precision policy)
     DevBuf<float> d_thr;
     DevBuf<unsigned long long> d_hist;
     DevBuf<double> d_fas;
@@ -63,7 +66,7 @@ struct BasisSet {
         for (auto& kv : ev_blob) kv.second.release();
         ev_blob.clear(); ev_meta.clear();
         d_U.release(); d_rank_off.release(); d_slot_row.release(); d_binfo.release();
-        d_Aimg.release(); d_thr.release(); d_hist.release(); d_fas.release();
+        d_Aimg.release(); d_Aimg8.release(); have_img8 = false; d_thr.release(); d_hist.release(); d_fas.release();
     }
 };
 
@@ -98,7 +101,9 @@ struct dtx_ctx {
     DevBuf<__half> d_xsplit;
     DevBuf<float> d_mu, d_invE, d_DS, d_scale, d_rowmax;
     DevBuf<double> d_DS64, d_sum;
-    DevBuf<unsigned> d_maxbits;
+    DevBuf<unsigned> d_maxbits, d_k4bits;
+    DevBuf<int> d_chunk_mode;     // per chunk: 1 = 8-bit cross terms in the last run
+    double x8_eps = 2e-6;         // adaptive engine: admitted RMS error of a normalised projection
     DevBuf<int> d_rowflags, d_ncand;
     DevBuf<Candidate> d_cand;
     int cand_cap = 1 << 20;
@@ -168,6 +173,7 @@ void dtx_destroy(dtx_ctx* ctx) {
     ctx->raw_own.release(); ctx->d_chunks.release(); ctx->d_items.release(); ctx->d_xsplit.release();
     ctx->d_mu.release(); ctx->d_invE.release(); ctx->d_DS.release(); ctx->d_scale.release();
     ctx->d_rowmax.release(); ctx->d_DS64.release(); ctx->d_sum.release(); ctx->d_maxbits.release();
+    ctx->d_k4bits.release(); ctx->d_chunk_mode.release();
     ctx->d_rowflags.release(); ctx->d_ncand.release(); ctx->d_cand.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -259,6 +265,17 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
     int eu = 0;
     if (umax > 0 && std::isfinite(umax)) eu = 13 - std::ilogb(umax);  // max|U| * 2^eu in [2^13, 2^14)
     lay.u_exp = eu;
+    bs.nu4 = 0.0;
+    for (int k = 0; k < R; ++k) {
+        double s2 = 0, s4 = 0;
+        for (int j = 0; j < n; ++j) {
+            const double v = U[static_cast<long long>(k) * n + j];
+            s2 += v * v;
+            s4 += (v * v) * (v * v);
+        }
+        const double q = s2 > 0 ? s4 / (s2 * s2) : 1.0;
+        bs.nu4 = std::max(bs.nu4, std::isfinite(q) ? q : 1.0);
+    }
     lay.u_inv_scale = std::ldexp(1.0f, -eu);
     for (int b = 0; b < lay.nblocks; ++b) {
         int slot = 0;
@@ -303,7 +320,8 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
     DTX_CUDA(cudaMemcpy(bs.d_thr.p, thr.data(), sizeof(float) * S, cudaMemcpyHostToDevice));
     DTX_CUDA(cudaMemset(bs.d_hist.p, 0, sizeof(unsigned long long) * S * HIST_BINS));
     DTX_CUDA(cudaMemset(bs.d_fas.p, 0, sizeof(double) * S * 5));
-    launch_basis_image(bs.d_U.p, bs.d_slot_row.p, lay, bs.d_Aimg.p, ctx->stream);
+    launch_basis_image(bs.d_U.p, bs.d_slot_row.p, lay, bs.d_Aimg.p, 0, ctx->stream);
+    bs.have_img8 = false;
     ctx->launches += 1;
     DTX_CUDA(cudaGetLastError());
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -429,6 +447,8 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     DTX_CUDA(ctx->d_scale.reserve(nchunks));
     DTX_CUDA(ctx->d_sum.reserve(nchunks));
     DTX_CUDA(ctx->d_maxbits.reserve(nchunks));
+    DTX_CUDA(ctx->d_k4bits.reserve(nchunks));
+    DTX_CUDA(ctx->d_chunk_mode.reserve(nchunks));
     DTX_CUDA(ctx->d_rowmax.reserve(static_cast<size_t>(nchunks) * S));
     DTX_CUDA(ctx->d_rowflags.reserve(static_cast<size_t>(nchunks) * S));
     DTX_CUDA(ctx->d_ncand.reserve(1));
@@ -442,15 +462,34 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     DTX_CUDA(cudaMemsetAsync(ctx->d_ncand.p, 0, sizeof(int), st));
 
     const int f32 = ctx->dtype == DTX_F32;
+    // 8-bit cross terms: forced, or per chunk where the random-rounding model
+    //   rms error of (u . w)/(|u||w|)  <=  X8_C * (K4 * nu4)^(1/4)
+    // (Cauchy-Schwarz on sum u^2 x^2; K4, nu4 = fourth-moment concentration of the worst window
+    // and of the worst basis vector) stays below ctx->x8_eps.  X8_C = rms relative error of the two
+    // 8-bit cross products per tap, relative to |u_j x_j|.
+    constexpr double X8_C = 1.6e-5;
+    const int x8 = (engine == DTX_ENGINE_TCGEN05_X8) ? X8_FORCE
+                 : (engine == DTX_ENGINE_TCGEN05_AUTO && mode == 0) ? X8_AUTO : X8_OFF;
+    const float k4_limit = static_cast<float>(std::pow(ctx->x8_eps / X8_C, 4.0) / bs.nu4);
+    if (x8 && !bs.have_img8) {
+        DTX_CUDA(bs.d_Aimg8.reserve(static_cast<size_t>(lay.nblocks) * lay.nchunks * 32768));
+        launch_basis_image(bs.d_U.p, bs.d_slot_row.p, lay, bs.d_Aimg8.p, 1, st);
+        bs.have_img8 = true;
+        ctx->launches += 1;
+    }
     launch_k0(ctx->d_raw, f32, ctx->d_chunks.p, nchunks, Nc, n, max_Lpad, max_ntiles, ctx->d_sum.p,
-              ctx->d_maxbits.p, ctx->d_scale.p, ctx->d_xsplit.p, ctx->d_mu.p, ctx->d_invE.p, st);
+              ctx->d_maxbits.p, ctx->d_scale.p, ctx->d_xsplit.p, ctx->d_mu.p, ctx->d_invE.p, x8, k4_limit,
+              ctx->d_k4bits.p, ctx->d_chunk_mode.p, st);
     DTX_CUDA(cudaGetLastError());
     ctx->launches += 3;  // k0_stats, k0_split, k0_norm
     ctx->have_ds64 = false;
     ctx->k1_timed = false;
-    if (engine == DTX_ENGINE_TCGEN05) {
+    if (engine != DTX_ENGINE_FP64) {
         K1Args a;
-        a.Aimg = bs.d_Aimg.p; a.xsplit = ctx->d_xsplit.p; a.mu = ctx->d_mu.p; a.invE = ctx->d_invE.p;
+        a.Aimg = bs.d_Aimg.p; a.Aimg8 = x8 ? bs.d_Aimg8.p : nullptr;
+        a.chunk_mode = x8 ? ctx->d_chunk_mode.p : nullptr;
+        a.kblk8 = (3 * kblk + 1) / 2;   // same number of MMAs per TMEM accumulation as the 3-MMA mode
+        a.xsplit = ctx->d_xsplit.p; a.mu = ctx->d_mu.p; a.invE = ctx->d_invE.p;
         a.chunk_scale = ctx->d_scale.p; a.chunks = ctx->d_chunks.p; a.items = ctx->d_items.p;
         a.binfo = bs.d_binfo.p; a.DS = ctx->d_DS.p; a.nitems = ctx->n_items;
         a.kblk = kblk; a.num_sms = ctx->num_sms; a.nq = nq; a.mode = mode;
@@ -484,7 +523,9 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
     auto it = ctx->sets.find(set_id);
     if (it == ctx->sets.end()) return fail(ctx, DTX_ERR_STATE, "dtx_detect_run: unknown basis set");
     if (ctx->nchunks < 1 || !ctx->d_raw) return fail(ctx, DTX_ERR_STATE, "dtx_detect_run: no chunks loaded");
-    if (engine != DTX_ENGINE_TCGEN05 && engine != DTX_ENGINE_FP64) return fail(ctx, DTX_ERR_ARG, "bad engine");
+    if (engine != DTX_ENGINE_TCGEN05 && engine != DTX_ENGINE_FP64 && engine != DTX_ENGINE_TCGEN05_X8 &&
+        engine != DTX_ENGINE_TCGEN05_AUTO)
+        return fail(ctx, DTX_ERR_ARG, "bad engine");
     if (kblk == 0) kblk = 2;  // default: drain every 128 taps (bias <= ~2e-6 at DS = 1)
     if (kblk < 1 || kblk > 64) return fail(ctx, DTX_ERR_ARG, "kblk out of range");
     BasisSet& bs = it->second;
@@ -506,6 +547,23 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
     ctx->run_set = set_id;
     ctx->run_S = S;
     ctx->ran = true;
+    return DTX_OK;
+}
+
+int dtx_set_x8_tolerance(dtx_ctx* ctx, double eps) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (!(eps >= 0.0) || !std::isfinite(eps)) return fail(ctx, DTX_ERR_ARG, "dtx_set_x8_tolerance: eps must be >= 0");
+    ctx->x8_eps = eps;
+    return DTX_OK;
+}
+
+int dtx_get_chunk_modes(dtx_ctx* ctx, int32_t* modes) {
+    if (!ctx || !modes) return DTX_ERR_ARG;
+    if (!ctx->ran) return fail(ctx, DTX_ERR_STATE, "dtx_get_chunk_modes: no run");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    DTX_CUDA(cudaMemcpyAsync(modes, ctx->d_chunk_mode.p, sizeof(int32_t) * ctx->nchunks,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
     return DTX_OK;
 }
 

@@ -12,6 +12,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 namespace dtx {
@@ -22,6 +23,10 @@ constexpr int VEC_PER_BLOCK = 16;   // basis vectors per K1 basis block (x 8 pha
 constexpr int MAX_SEG_TAPS = 3072;  // taps per K segment (bounded by the smem signal span)
 constexpr int MAX_SEGS = 48;
 constexpr int HIST_BINS = 400;
+// 8-bit cross-term engine: u_lo * 2^6 and u_hi * 2^-6 fit e4m3 (max|u * 2^eu| < 2^14), x_hi * 2^-6 and
+// x_lo * 2^6 fit e5m2 (max|x * 2^ex| < 2^15); the shifts cancel in each product.
+constexpr int X8_SHIFT = 6;
+enum { X8_OFF = 0, X8_AUTO = 1, X8_FORCE = 2 };   // per-run policy handed to k0_split
 
 struct ChunkDesc {
     long long raw_off;   // element offset of the chunk in the raw buffer
@@ -67,15 +72,18 @@ struct BasisLayout {
 // k0_prep.cu
 void launch_k0(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nchunks, int Nc, int n,
                int max_Lpad, int max_ntiles, double* d_sum, unsigned* d_maxbits, float* d_scale,
-               __half* d_xsplit, float* d_mu, float* d_invE, cudaStream_t st);
+               __half* d_xsplit, float* d_mu, float* d_invE, int x8_policy, float k4_limit,
+               unsigned* d_k4bits, int* d_chunk_mode, cudaStream_t st);
 
 // basis image (k1_project.cu)
 void launch_basis_image(const double* d_U, const int* d_slot_row, const BasisLayout& lay,
-                        uint8_t* d_Aimg, cudaStream_t st);
+                        uint8_t* d_Aimg, int x8, cudaStream_t st);
 
 // k1_project.cu : tcgen05 Hankel projection + normalisation -> DS
 struct K1Args {
-    const uint8_t* Aimg;
+    const uint8_t* Aimg;      // fp16 hi | fp16 lo tiles (3 MMAs per K step)
+    const uint8_t* Aimg8;     // fp16 hi | (e4m3 u_lo, e4m3 u_hi) byte-pair tiles (2 MMAs per K step), may be null
+    const int* chunk_mode;    // per chunk: 1 = 8-bit cross terms (written by k0_split)
     const __half* xsplit;
     const float* mu;
     const float* invE;
@@ -85,7 +93,8 @@ struct K1Args {
     const BlockInfo* binfo;
     float* DS;
     int nitems;
-    int kblk;      // 64-tap chunks accumulated in TMEM between drains
+    int kblk;      // 64-tap chunks accumulated in TMEM between drains (fp16 cross terms)
+    int kblk8;     // same for chunks in 8-bit cross-term mode
     int num_sms;
     int nq;        // MMA N: 256 (tiles of 2048 lags) or 128 (tiles of 1024 lags)
     int mode;      // 0 = detection statistic, 1 = signed correlation coefficient (CCX)

@@ -4,11 +4,13 @@
 // detex/fas.py:126-127) and the de-multiplexing implied by `result[::Nc]` (detect.py:578).
 //
 //   k0_stats : per chunk sum(x) and max|x|                     (HBM-bound, 1 read)
-//   k0_split : x -> (x - mean) * 2^ex -> fp16 hi + lo per channel, zero padded
 //   k0_norm  : window mean mu[t] and invE[t] = ((n-1)/n) / (S2 - S1^2/n) for every
 //              channel-aligned lag t, float64 running sums (block scan of the in/out
 //              differences), so the denominator never suffers the cancellation a
-//              float32 prefix sum would.
+//              float32 prefix sum would.  For the adaptive engine also the worst window
+//              kurtosis of the chunk (precision policy, see k0_split).
+//   k0_split : x -> (x - mean) * 2^ex -> fp16 hi + lo per channel, zero padded; the lo plane
+//              holds fp16 residuals or, for chunks in 8-bit cross-term mode, e5m2 byte pairs
 //
 // DS is invariant to adding a constant to x and to scaling x, so centring on the chunk
 // mean and scaling by a power of two change nothing mathematically; they put the data in
@@ -63,8 +65,15 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k0_split(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
          const double* __restrict__ sum, const unsigned* __restrict__ maxbits,
-         float* __restrict__ scale_out, __half* __restrict__ xsplit, int Nc) {
+         float* __restrict__ scale_out, __half* __restrict__ xsplit, int Nc, int x8_policy,
+         float k4_limit, const unsigned* __restrict__ k4bits, int* __restrict__ chunk_mode) {
     const ChunkDesc cd = chunks[blockIdx.y];
+    // precision mode of this chunk ("8-bit cross terms"): off, forced, or chosen from the
+    // worst window kurtosis K4 = sum (x - chunk mean)^4 / ||w - window mean||^4 that k0_norm found
+    // (NaN / inf / zero-energy windows give K4 = 3e38, i.e. the fp16 cross terms)
+    const bool x8 = x8_policy == X8_FORCE ||
+                    (x8_policy == X8_AUTO && __uint_as_float(k4bits[blockIdx.y]) <= k4_limit);
+    if (blockIdx.x == 0 && threadIdx.x == 0) chunk_mode[blockIdx.y] = x8 ? 1 : 0;
     const double mean = sum[blockIdx.y] / static_cast<double>(cd.L);
     const int ex = scale_exp(__uint_as_float(maxbits[blockIdx.y]), mean);
     if (blockIdx.x == 0 && threadIdx.x == 0) scale_out[blockIdx.y] = exp2f(static_cast<float>(-ex));
@@ -78,7 +87,15 @@ k0_split(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
         float v = 0.f;
         if (j < cd.L) v = static_cast<float>(ldexp(static_cast<double>(x[j]) - mean, ex));
         const __half hi = __float2half_rn(v);
-        const __half lo = __float2half_rn(v - __half2float(hi));
+        __half lo;
+        if (!x8) lo = __float2half_rn(v - __half2float(hi));
+        else {
+            // 8-bit cross-term plane: byte 0 = e5m2(x_hi * 2^-X8_S), byte 1 = e5m2(x_lo * 2^X8_S)
+            const float fh = __half2float(hi);
+            const unsigned b0 = __nv_cvt_float_to_fp8(ldexpf(fh, -X8_SHIFT), __NV_SATFINITE, __NV_E5M2);
+            const unsigned b1 = __nv_cvt_float_to_fp8(ldexpf(v - fh, X8_SHIFT), __NV_SATFINITE, __NV_E5M2);
+            lo = __ushort_as_half(static_cast<unsigned short>(b0 | (b1 << 8)));
+        }
         out[static_cast<long long>(c * 2 + 0) * cd.Lpad + i] = hi;
         out[static_cast<long long>(c * 2 + 1) * cd.Lpad + i] = lo;
     }
@@ -89,54 +106,61 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k0_norm(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
         const double* __restrict__ sum, float* __restrict__ mu, float* __restrict__ invE, int Nc,
-        int n) {
+        int n, unsigned* __restrict__ k4bits) {
     const ChunkDesc cd = chunks[blockIdx.y];
     if (blockIdx.x >= cd.ntiles) return;
     const double mean = sum[blockIdx.y] / static_cast<double>(cd.L);
     const T* x = raw + cd.raw_off;
     const int t0 = blockIdx.x * TILE_T;
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
-    __shared__ double sh1[8], sh2[8];
-    __shared__ double base1, base2;
+    __shared__ double sh1[8], sh2[8], sh4[8];
+    __shared__ double base1, base2, base4;
 
     // window sums at t0 (t0 < T always holds for an existing tile)
-    double a1 = 0.0, a2 = 0.0;
+    // (the fourth-power sums only feed the precision policy; k4bits == nullptr skips them)
+    const bool want4 = k4bits != nullptr;
+    double a1 = 0.0, a2 = 0.0, a4 = 0.0;
     {
         const long long o = static_cast<long long>(t0) * Nc;
         for (int j = tid; j < n; j += 256) {
             const double v = static_cast<double>(x[o + j]) - mean;
             a1 += v;
             a2 += v * v;
+            a4 += (v * v) * (v * v);
         }
         for (int s = 16; s > 0; s >>= 1) {
             a1 += __shfl_xor_sync(0xffffffffu, a1, s);
             a2 += __shfl_xor_sync(0xffffffffu, a2, s);
+            a4 += __shfl_xor_sync(0xffffffffu, a4, s);
         }
         if (l == 0) {
             sh1[w] = a1;
             sh2[w] = a2;
+            sh4[w] = a4;
         }
         __syncthreads();
         if (tid == 0) {
-            double b1 = 0, b2 = 0;
+            double b1 = 0, b2 = 0, b4 = 0;
             for (int i = 0; i < 8; ++i) {
                 b1 += sh1[i];
                 b2 += sh2[i];
+                b4 += sh4[i];
             }
             base1 = b1;
             base2 = b2;
+            base4 = b4;
         }
         __syncthreads();
     }
     // differences: d[i] moves the window from t0+i-1 to t0+i (i >= 1); thread owns 8 lags
     constexpr int PER = TILE_T / 256;
-    double d1[PER], d2[PER];
-    double r1 = 0.0, r2 = 0.0;
+    double d1[PER], d2[PER], d4[PER];
+    double r1 = 0.0, r2 = 0.0, r4 = 0.0;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         const int i = tid * PER + k;
         const int t = t0 + i;
-        double e1 = 0.0, e2 = 0.0;
+        double e1 = 0.0, e2 = 0.0, e4 = 0.0;
         if (i >= 1 && t < cd.T) {
             const long long o = static_cast<long long>(t - 1) * Nc;
             for (int c = 0; c < Nc; ++c) {
@@ -144,38 +168,46 @@ k0_norm(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
                 const double vout = static_cast<double>(x[o + c]) - mean;
                 e1 += vin - vout;
                 e2 += vin * vin - vout * vout;
+                if (want4) e4 += (vin * vin) * (vin * vin) - (vout * vout) * (vout * vout);
             }
         }
         r1 += e1;
         r2 += e2;
+        r4 += e4;
         d1[k] = r1;
         d2[k] = r2;
+        d4[k] = r4;
     }
     // exclusive scan of per-thread totals across the block
-    double p1 = r1, p2 = r2;
+    double p1 = r1, p2 = r2, p4 = r4;
     for (int s = 1; s < 32; s <<= 1) {
         const double q1 = __shfl_up_sync(0xffffffffu, p1, s);
         const double q2 = __shfl_up_sync(0xffffffffu, p2, s);
+        const double q4 = __shfl_up_sync(0xffffffffu, p4, s);
         if (l >= s) {
             p1 += q1;
             p2 += q2;
+            p4 += q4;
         }
     }
     __syncthreads();
     if (l == 31) {
         sh1[w] = p1;
         sh2[w] = p2;
+        sh4[w] = p4;
     }
     __syncthreads();
-    double o1 = p1 - r1, o2 = p2 - r2;  // exclusive within warp
+    double o1 = p1 - r1, o2 = p2 - r2, o4 = p4 - r4;  // exclusive within warp
     for (int i = 0; i < w; ++i) {
         o1 += sh1[i];
         o2 += sh2[i];
+        o4 += sh4[i];
     }
     const double nn = static_cast<double>(n);
     const double cn = (nn - 1.0) / nn;
     float* pm = mu + cd.norm_off + t0;
     float* pe = invE + cd.norm_off + t0;
+    float k4 = 0.f;   // worst window of the tile: sum (x - chunk mean)^4 / (window energy)^2
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         const int i = tid * PER + k;
@@ -188,17 +220,28 @@ k0_norm(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
             if (E < 0.0) E = 0.0;
             fm = static_cast<float>(s1 / nn);
             fe = static_cast<float>(cn / E);  // E == 0 -> +inf, as the reference's x/0
+            if (want4) {
+                const float r = static_cast<float>((base4 + o4 + d4[k]) / (E * E));
+                k4 = fmaxf(k4, r >= 0.f && r < 3e38f ? r : 3e38f);   // NaN / inf -> never 8-bit
+            }
         }
         pm[i] = fm;
         pe[i] = fe;
+    }
+    if (want4) {
+        for (int s = 16; s > 0; s >>= 1) k4 = fmaxf(k4, __shfl_xor_sync(0xffffffffu, k4, s));
+        if (l == 0) atomicMax(&k4bits[blockIdx.y], __float_as_uint(k4));  // k4 >= 0: uint order == float order
     }
 }
 
 void launch_k0(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nchunks, int Nc, int n,
                int max_Lpad, int max_ntiles, double* d_sum, unsigned* d_maxbits, float* d_scale,
-               __half* d_xsplit, float* d_mu, float* d_invE, cudaStream_t st) {
+               __half* d_xsplit, float* d_mu, float* d_invE, int x8_policy, float k4_limit,
+               unsigned* d_k4bits, int* d_chunk_mode, cudaStream_t st) {
     cudaMemsetAsync(d_sum, 0, sizeof(double) * nchunks, st);
     cudaMemsetAsync(d_maxbits, 0, sizeof(unsigned) * nchunks, st);
+    cudaMemsetAsync(d_k4bits, 0, sizeof(unsigned) * nchunks, st);
+    unsigned* k4 = x8_policy == X8_AUTO ? d_k4bits : nullptr;   // k0_norm runs before k0_split reads it
     const dim3 g1(64, nchunks);
     long long tot = static_cast<long long>(Nc) * max_Lpad;
     int gx = static_cast<int>((tot + 256 * 8 - 1) / (256 * 8));
@@ -208,13 +251,15 @@ void launch_k0(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nc
     if (dtype_f32) {
         const float* r = static_cast<const float*>(raw);
         k0_stats<float><<<g1, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits);
-        k0_split<float><<<g2, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits, d_scale, d_xsplit, Nc);
-        k0_norm<float><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n);
+        k0_norm<float><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n, k4);
+        k0_split<float><<<g2, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits, d_scale, d_xsplit, Nc, x8_policy,
+                                            k4_limit, d_k4bits, d_chunk_mode);
     } else {
         const double* r = static_cast<const double*>(raw);
         k0_stats<double><<<g1, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits);
-        k0_split<double><<<g2, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits, d_scale, d_xsplit, Nc);
-        k0_norm<double><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n);
+        k0_norm<double><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n, k4);
+        k0_split<double><<<g2, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits, d_scale, d_xsplit, Nc, x8_policy,
+                                             k4_limit, d_k4bits, d_chunk_mode);
     }
 }
 

@@ -53,6 +53,21 @@ constexpr int NDRAIN_WARPS = 8;
 constexpr int REGS_CTRL = 56, REGS_DRAIN = 224;         // setmaxnreg budgets (128*56 + 256*224 = 64512)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * SIG_BUF_BYTES + 2 * NORM_BUF_BYTES;
 
+// Issue style of the producer / MMA warps.  Default: ONE lane runs the role loop (ptxas wraps
+// every UTCHMMA / UBLKCP in an ELECT loop, ~128 cycles per MMA: the issuer paces the tensor
+// pipe).  -DDTX_CONVERGED_ISSUE: the whole warp runs the loop converged and an elected lane
+// issues (descriptors stay in uniform registers, 12 MMAs back to back).  A/B in
+// experiments/ab_issue.sh; see DESIGN.md section 7.
+#ifdef DTX_CONVERGED_ISSUE
+#define ISSUE_LANE elect_one()
+#define ISSUE_SYNC() __syncwarp()
+#define ROLE_LANES(lane) true
+#else
+#define ISSUE_LANE true
+#define ISSUE_SYNC() ((void)0)
+#define ROLE_LANES(lane) ((lane) == 0)
+#endif
+
 struct K1Params {
     K1Args a;
     int nblocks, nchunks, nseg;
@@ -87,6 +102,11 @@ struct Smem {
     uint64_t *full, *empty, *sigfull, *sigempty, *accfull, *accempty, *normfull, *normempty;
 };
 
+// precision mode of a chunk: 1 = both cross terms in one 8-bit MMA (decided on the device by k0_split)
+__device__ __forceinline__ int item_x8(const K1Params& P, int chunk) {
+    return P.a.chunk_mode ? P.a.chunk_mode[chunk] : 0;
+}
+
 // ------------------------------------------------------------------ producer (1 thread)
 template <int NQ>
 __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) {
@@ -97,33 +117,43 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
         const ChunkDesc cd = P.a.chunks[it.x];
         // window mean / inverse energy of this tile
         mbar_wait(&S.normempty[nm.idx], nm.phase ^ 1);
-        mbar_arrive_expect_tx(&S.normfull[nm.idx], 2 * TT * 4);
-        bulk_g2s(S.norm + nm.idx * NORM_BUF_BYTES, P.a.mu + cd.norm_off + static_cast<long long>(it.y) * TT,
-                 TT * 4, &S.normfull[nm.idx]);
-        bulk_g2s(S.norm + nm.idx * NORM_BUF_BYTES + TILE_T * 4,
-                 P.a.invE + cd.norm_off + static_cast<long long>(it.y) * TT, TT * 4, &S.normfull[nm.idx]);
+        if (ISSUE_LANE) {
+            mbar_arrive_expect_tx(&S.normfull[nm.idx], 2 * TT * 4);
+            bulk_g2s(S.norm + nm.idx * NORM_BUF_BYTES, P.a.mu + cd.norm_off + static_cast<long long>(it.y) * TT,
+                     TT * 4, &S.normfull[nm.idx]);
+            bulk_g2s(S.norm + nm.idx * NORM_BUF_BYTES + TILE_T * 4,
+                     P.a.invE + cd.norm_off + static_cast<long long>(it.y) * TT, TT * 4, &S.normfull[nm.idx]);
+        }
+        ISSUE_SYNC();
         nm.advance();
         const __half* sig0 = P.a.xsplit + cd.sig_off + static_cast<long long>(it.y) * TT;
         {
             const int b = it.z;
-            const uint8_t* ablk = P.a.Aimg + static_cast<size_t>(b) * P.nchunks * STAGE_BYTES;
+            const uint8_t* ablk = (item_x8(P, it.x) ? P.a.Aimg8 : P.a.Aimg) +
+                                  static_cast<size_t>(b) * P.nchunks * STAGE_BYTES;
             for (int g = 0; g < P.nseg; ++g) {
                 const Seg sgm = P.seg[g];
                 const uint32_t bytes = (TT + sgm.ntaps) * 2;
                 mbar_wait(&S.sigempty[sg.idx], sg.phase ^ 1);
-                mbar_arrive_expect_tx(&S.sigfull[sg.idx], 2 * bytes);
-                const __half* src = sig0 + static_cast<long long>(sgm.chan * 2) * cd.Lpad + sgm.tap0;
-                bulk_g2s(S.sig + sg.idx * SIG_BUF_BYTES, src, bytes, &S.sigfull[sg.idx]);
-                bulk_g2s(S.sig + sg.idx * SIG_BUF_BYTES + SIG_HALFS * 2, src + cd.Lpad, bytes,
-                         &S.sigfull[sg.idx]);
+                if (ISSUE_LANE) {
+                    mbar_arrive_expect_tx(&S.sigfull[sg.idx], 2 * bytes);
+                    const __half* src = sig0 + static_cast<long long>(sgm.chan * 2) * cd.Lpad + sgm.tap0;
+                    bulk_g2s(S.sig + sg.idx * SIG_BUF_BYTES, src, bytes, &S.sigfull[sg.idx]);
+                    bulk_g2s(S.sig + sg.idx * SIG_BUF_BYTES + SIG_HALFS * 2, src + cd.Lpad, bytes,
+                             &S.sigfull[sg.idx]);
+                }
+                ISSUE_SYNC();
                 sg.advance();
                 const int nck = sgm.ntaps / CHUNK_TAPS;
                 for (int kc = 0; kc < nck; ++kc) {
                     mbar_wait(&S.empty[st.idx], st.phase ^ 1);
-                    mbar_arrive_expect_tx(&S.full[st.idx], STAGE_BYTES);
-                    bulk_g2s(S.stage + st.idx * STAGE_BYTES,
-                             ablk + static_cast<size_t>(sgm.chunk0 + kc) * STAGE_BYTES, STAGE_BYTES,
-                             &S.full[st.idx]);
+                    if (ISSUE_LANE) {
+                        mbar_arrive_expect_tx(&S.full[st.idx], STAGE_BYTES);
+                        bulk_g2s(S.stage + st.idx * STAGE_BYTES,
+                                 ablk + static_cast<size_t>(sgm.chunk0 + kc) * STAGE_BYTES, STAGE_BYTES,
+                                 &S.full[st.idx]);
+                    }
+                    ISSUE_SYNC();
                     st.advance();
                 }
             }
@@ -134,13 +164,18 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
 // ---------------------------------------------------------------- MMA issuer (1 thread)
 template <int NQ>
 __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint32_t tmem) {
-    const int kblk = P.a.kblk;
     const uint32_t idesc = idesc_f16_f32(128, NQ);
+    const uint32_t idesc8 = idesc_e4m3_e5m2_f32(128, NQ);
     const uint64_t a_base = smem_desc_kmajor_noswz(0, A_LBO, A_SBO);
     const uint64_t b_base = smem_desc_kmajor_noswz(0, B_LBO, B_SBO);
     const uint32_t stage0 = smem_u32(S.stage), sig0 = smem_u32(S.sig);
     Ring st(STAGES), sg(2), ac(2);
+    int x8_next = blockIdx.x < P.a.nitems ? item_x8(P, P.a.items[blockIdx.x].x) : 0;
     for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
+        const bool x8 = x8_next != 0;
+        if (item + static_cast<int>(gridDim.x) < P.a.nitems)   // fetched while this item's MMAs issue
+            x8_next = item_x8(P, P.a.items[item + gridDim.x].x);
+        const int kblk = x8 ? P.a.kblk8 : P.a.kblk;
         {
             int cib = 0, done = 0;
             for (int g = 0; g < P.nseg; ++g) {
@@ -157,27 +192,45 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
                     const uint32_t ah = stage0 + st.idx * STAGE_BYTES;
                     const uint32_t al = ah + TILE_BYTES;
                     const uint32_t bo = kc * (CHUNK_TAPS * 2);
+                    const bool last = (cib + 1 == kblk) || (done + 1 == P.nchunks);
+                    if (ISSUE_LANE) {
+                        if (x8) {
+                            // both cross terms in ONE 8-bit MMA: the "lo" tiles hold byte pairs
+                            // per tap, (u_lo, u_hi) in e4m3 against (x_hi, x_lo) in e5m2
 #pragma unroll
-                    for (int kk = 0; kk < CHUNK_TAPS / 16; ++kk) {
-                        const uint64_t dah = a_base | ((ah + kk * 256) >> 4);
-                        const uint64_t dal = a_base | ((al + kk * 256) >> 4);
-                        const uint64_t dbh = b_base | ((sh + bo + kk * 32) >> 4);
-                        const uint64_t dbl = b_base | ((sl + bo + kk * 32) >> 4);
-                        umma_f16(d, dah, dbh, idesc, (cib | kk) ? 1u : 0u);
-                        umma_f16(d, dah, dbl, idesc, 1u);
-                        umma_f16(d, dal, dbh, idesc, 1u);
+                            for (int kk = 0; kk < CHUNK_TAPS / 16; ++kk) {
+                                const uint64_t dah = a_base | ((ah + kk * 256) >> 4);
+                                const uint64_t dal = a_base | ((al + kk * 256) >> 4);
+                                const uint64_t dbh = b_base | ((sh + bo + kk * 32) >> 4);
+                                const uint64_t dbl = b_base | ((sl + bo + kk * 32) >> 4);
+                                umma_f16(d, dah, dbh, idesc, (cib | kk) ? 1u : 0u);
+                                umma_f8(d, dal, dbl, idesc8, 1u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int kk = 0; kk < CHUNK_TAPS / 16; ++kk) {
+                                const uint64_t dah = a_base | ((ah + kk * 256) >> 4);
+                                const uint64_t dal = a_base | ((al + kk * 256) >> 4);
+                                const uint64_t dbh = b_base | ((sh + bo + kk * 32) >> 4);
+                                const uint64_t dbl = b_base | ((sl + bo + kk * 32) >> 4);
+                                umma_f16(d, dah, dbh, idesc, (cib | kk) ? 1u : 0u);
+                                umma_f16(d, dah, dbl, idesc, 1u);
+                                umma_f16(d, dal, dbh, idesc, 1u);
+                            }
+                        }
+                        umma_commit(&S.empty[st.idx]);
+                        if (last) umma_commit(&S.accfull[ac.idx]);
+                        if (kc == nck - 1) umma_commit(&S.sigempty[sg.idx]);
                     }
-                    umma_commit(&S.empty[st.idx]);
+                    ISSUE_SYNC();
                     st.advance();
                     ++cib;
                     ++done;
-                    if (cib == kblk || done == P.nchunks) {
-                        umma_commit(&S.accfull[ac.idx]);
+                    if (last) {
                         ac.advance();
                         cib = 0;
                     }
                 }
-                umma_commit(&S.sigempty[sg.idx]);
                 sg.advance();
             }
         }
@@ -196,13 +249,13 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
     const int p = 2 * lq + (lane & 1);           // phase of this thread's row
     const int kl = lane >> 1;                    // basis-vector slot of this thread's row
     const uint32_t taddr0 = tmem + (static_cast<uint32_t>(lq * 32) << 16) + colhalf * NCOL;
-    const int kblk = P.a.kblk;
-    const int ndrains = (P.nchunks + kblk - 1) / kblk;
     Ring ac(2), nm(2);
     float sums[NCOL];
     for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
         const int4 it = P.a.items[item];
         const ChunkDesc cd = P.a.chunks[it.x];
+        const int kblk = item_x8(P, it.x) ? P.a.kblk8 : P.a.kblk;
+        const int ndrains = (P.nchunks + kblk - 1) / kblk;
         const float sc = P.a.chunk_scale[it.x] * P.u_inv_scale;
         const float* smu = reinterpret_cast<const float*>(S.norm + nm.idx * NORM_BUF_BYTES);
         const float* sie = smu + TILE_T;
@@ -320,9 +373,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k1_kernel(const __grid_constant__
     // setmaxnreg must sit at the top of each role branch for ptxas to budget the branch
     if (warp < FIRST_DRAIN_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
-        if (warp == 0 && lane == 0) {
+        if (warp == 0 && ROLE_LANES(lane)) {
             producer_loop<NQ>(P, S);
-        } else if (warp == 1 && lane == 0) {
+        } else if (warp == 1 && ROLE_LANES(lane)) {
             mma_loop<NQ>(P, S, tmem);
         }
     } else {
@@ -338,7 +391,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k1_kernel(const __grid_constant__
 // One thread per 16-byte unit (8 taps of one row of one hi/lo tile).
 __global__ void __launch_bounds__(256)
 basis_image_kernel(const double* __restrict__ U, const int* __restrict__ slot_row,
-                   const __grid_constant__ BasisLayout lay, uint8_t* __restrict__ Aimg) {
+                   const __grid_constant__ BasisLayout lay, uint8_t* __restrict__ Aimg, int x8) {
     const long long units_per_tile = 128 * 8;
     const long long total = static_cast<long long>(lay.nblocks) * lay.nchunks * 2 * units_per_tile;
     const long long gid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -370,7 +423,15 @@ basis_image_kernel(const double* __restrict__ U, const int* __restrict__ slot_ro
                 ldexp(U[static_cast<long long>(row) * lay.n + static_cast<long long>(j) * lay.Nc + sg.chan],
                       lay.u_exp));
         const __half hi = __float2half_rn(v);
-        out[jj] = hl == 0 ? hi : __float2half_rn(v - __half2float(hi));
+        if (hl == 0) out[jj] = hi;
+        else if (!x8) out[jj] = __float2half_rn(v - __half2float(hi));
+        else {
+            // 8-bit cross-term image: byte 0 = e4m3(u_lo * 2^X8_S), byte 1 = e4m3(u_hi * 2^-X8_S)
+            const float fh = __half2float(hi);
+            const unsigned b0 = __nv_cvt_float_to_fp8(ldexpf(v - fh, X8_SHIFT), __NV_SATFINITE, __NV_E4M3);
+            const unsigned b1 = __nv_cvt_float_to_fp8(ldexpf(fh, -X8_SHIFT), __NV_SATFINITE, __NV_E4M3);
+            out[jj] = __ushort_as_half(static_cast<unsigned short>(b0 | (b1 << 8)));
+        }
     }
     uint8_t* dst = Aimg + (static_cast<size_t>(b) * lay.nchunks + chunk) * STAGE_BYTES +
                    static_cast<size_t>(hl) * TILE_BYTES + rg * 1024 + kc * 128 + rin * 16;
@@ -388,10 +449,10 @@ void launch_k1_t(const K1Params& P, int grid, cudaStream_t st) {
 int k1_smem_bytes() { return SMEM_BYTES; }
 
 void launch_basis_image(const double* d_U, const int* d_slot_row, const BasisLayout& lay,
-                        uint8_t* d_Aimg, cudaStream_t st) {
+                        uint8_t* d_Aimg, int x8, cudaStream_t st) {
     const long long total = static_cast<long long>(lay.nblocks) * lay.nchunks * 2 * 128 * 8;
     const int grid = static_cast<int>((total + 255) / 256);
-    basis_image_kernel<<<grid, 256, 0, st>>>(d_U, d_slot_row, lay, d_Aimg);
+    basis_image_kernel<<<grid, 256, 0, st>>>(d_U, d_slot_row, lay, d_Aimg, x8);
 }
 
 void launch_k1(const K1Args& a, const BasisLayout& lay, cudaStream_t st) {

@@ -103,6 +103,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, kind::f8f6f4 (8-bit float operands, K = 32 per instruction, fp32 accumulate).
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                        uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // All previously issued MMAs of this thread arrive on `bar` when complete
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -158,6 +168,15 @@ __host__ __device__ constexpr uint32_t idesc_f16_f32(uint32_t M, uint32_t N) {
     return (1u << 4)            // D format = F32
            | (0u << 7)          // A format = F16
            | (0u << 10)         // B format = F16
+           | ((N >> 3) << 17)   // N / 8
+           | ((M >> 4) << 24);  // M / 16
+}
+
+// Instruction descriptor for kind::f8f6f4: A = E4M3, B = E5M2 (both K-major), fp32 D.
+__host__ __device__ constexpr uint32_t idesc_e4m3_e5m2_f32(uint32_t M, uint32_t N) {
+    return (1u << 4)            // D format = F32
+           | (0u << 7)          // A format = E4M3
+           | (1u << 10)         // B format = E5M2
            | ((N >> 3) << 17)   // N / 8
            | ((M >> 4) << 24);  // M / 16
 }

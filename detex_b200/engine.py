@@ -122,7 +122,9 @@ class Engine(object):
     # -------------------------------------------------------------------- run
     def detect_run(self, set_id, engine="tcgen05", kblk=0, hist_range=(0.0, 1.0), lta_window=0,
                    want_fas=False, keep_ds64=False):
-        eng = ENGINE_TCGEN05 if engine == "tcgen05" else ENGINE_FP64
+        if engine not in _lib.ENGINES:
+            raise ValueError("engine must be one of %s" % sorted(_lib.ENGINES))
+        eng = _lib.ENGINES[engine]
         self._check(self._L.dtx_detect_run(self._h, int(set_id), eng, int(kblk), float(hist_range[0]),
                                            float(hist_range[1]), int(lta_window), int(bool(want_fas)),
                                            int(bool(keep_ds64))))
@@ -150,6 +152,16 @@ class Engine(object):
         out = np.empty(self.num_lags(chunk), dtype=np.float32)
         self._check(self._L.dtx_get_stalta(self._h, int(chunk), int(subspace), int(W), _ptr(out), out.size))
         return out
+
+    def set_x8_tolerance(self, eps):
+        """Adaptive engine ("tcgen05_auto"): admitted rms error of a normalised projection."""
+        self._check(self._L.dtx_set_x8_tolerance(self._h, float(eps)))
+
+    def chunk_modes(self):
+        """Per chunk of the last run: 1 = ran with 8-bit cross terms."""
+        m = np.empty(self.nchunks, dtype=np.int32)
+        self._check(self._L.dtx_get_chunk_modes(self._h, _ptr(m)))
+        return m
 
     def rowstats(self):
         n = self.nchunks * self._run_S

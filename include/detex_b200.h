@@ -39,7 +39,13 @@ enum { DTX_F64 = 0, DTX_F32 = 1 };
 /* engine selection for dtx_detect_run / dtx_ccx_run */
 enum {
     DTX_ENGINE_TCGEN05 = 0, /* production: Hankel-tiled tcgen05 GEMM, split fp16 x3 */
-    DTX_ENGINE_FP64 = 1     /* validation: float64 CUDA-core closed form */
+    DTX_ENGINE_FP64 = 1,    /* validation: float64 CUDA-core closed form */
+    DTX_ENGINE_TCGEN05_X8 = 2, /* detection only, opt-in: hi*hi in fp16, both cross terms in ONE
+                                  e4m3 x e5m2 MMA (2 MMAs per K step instead of 3).  Its error is
+                                  statistical, not worst-case bounded */
+    DTX_ENGINE_TCGEN05_AUTO = 3 /* detection only, opt-in: per chunk, 8-bit cross terms where the
+                                   fourth-moment error model admits them (dtx_set_x8_tolerance),
+                                   fp16 cross terms everywhere else */
 };
 
 /* One candidate trigger: a lag whose statistic is >= the subspace threshold
@@ -108,7 +114,15 @@ int dtx_get_chunk(dtx_ctx* ctx, int chunk, double* out, int64_t count, int64_t* 
 int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_lo, double hist_hi,
                    int lta_window, int want_fas, int keep_ds64);
 
+/* DTX_ENGINE_TCGEN05_AUTO: admitted rms error of a normalised projection (u.w)/(|u||w|) under the
+ * random-rounding model (default 2e-6: the 8-bit terms then add 2 sqrt(DS) eps <= 4e-6 per model
+ * standard deviation; measured maxima are 0.2-0.6 of that, profiles/r01_x8_engine.md);
+ * 0 turns the 8-bit mode off for every chunk. */
+int dtx_set_x8_tolerance(dtx_ctx* ctx, double eps);
+
 /* Results (each call synchronises the stream) ------------------------------------------ */
+/* modes[chunk] of the last dtx_detect_run: 1 = the chunk ran with 8-bit cross terms */
+int dtx_get_chunk_modes(dtx_ctx* ctx, int32_t* modes);
 int dtx_num_lags(dtx_ctx* ctx, int chunk, int64_t* T);
 /* dense DS row (CorDF.SSdetect[name], detect.py:268) */
 int dtx_get_ds(dtx_ctx* ctx, int chunk, int subspace, float* out, int64_t count);

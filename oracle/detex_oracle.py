@@ -359,6 +359,63 @@ def cluster_link(cc):
 
 
 # --------------------------------------------------------------------------
+# N3  alignment from the dendrogram  (construct.py:272-286, 486-503, 710-812)
+# --------------------------------------------------------------------------
+
+
+def _triangular(n):
+    return n * (n + 1) // 2
+
+
+def get_delays(cc, lag):
+    """`_getDelays` + `_traceEventDendro` (construct.py:710-761), literally: walk the single
+    linkage of `1.0000001 - cc` in merge order; the pair (ev1 < ev2) whose distance made the merge
+    gives `currentLag = round(lag of that pair, as updated so far)`; every event b of the merged
+    cluster that does NOT contain ev1 is delayed by it, and the condensed lag vector is updated
+    with `_updateLags` (construct.py:764-793): pairs (b, j > b) += currentLag, pairs (a < b, b)
+    -= currentLag.  cc, lag: (N-1) x (N-1) arrays laid out as DFcc / DFlag (row b, column c-1,
+    NaN below the diagonal).  Coefficients must be unique (the reference perturbs duplicates with
+    unseeded random numbers, construct.py:814-835; that branch cannot be pinned).
+    Returns (link, delays[int64 per event])."""
+    cc = np.asarray(cc, dtype=np.float64)
+    cx = flat_no_nan(cc)
+    if len(np.unique(cx)) != len(cx):
+        raise ValueError("duplicate correlation coefficients (construct.py:814-835)")
+    lagm = np.asarray(lag, dtype=np.float64).flatten()
+    lags = lagm[~np.isnan(lagm)].copy()
+    link = linkage(cx)
+    N = len(link)                      # events - 1
+    members = {i: [i] for i in range(N + 1)}
+    for a in range(N):                 # _getClustDict, construct.py:799-811
+        members[N + 1 + a] = members[int(link[a, 0])] + members[int(link[a, 1])]
+    delays = np.zeros(N + 1, dtype=np.int64)
+    for a in range(N):
+        p = int(np.where(cx == link[a, 2])[0][0])
+        ev1 = 0
+        while p >= _triangular(N) - _triangular(N - (ev1 + 1)):
+            ev1 += 1
+        i1, i2 = int(link[a, 0]), int(link[a, 1])
+        cl22 = members[i2] if ev1 in members[i1] else members[i1]
+        cur = int(np.round(lags[p]))
+        for b in cl22:
+            delays[b] += cur
+            acr0 = _triangular(N) - _triangular(N - b)            # _getAcr
+            for k in range(N - b):
+                lags[acr0 + k] += cur
+            for k in range(b):                                    # _getDow
+                lags[_triangular(N - 1) - 1 + b - _triangular(N - 1 - k)] -= cur
+    return link, delays
+
+
+def align_td(delays, X):
+    """`_alignTD` (construct.py:486-503) after `delays - min(delays)` (construct.py:283-284):
+    drop the first SampleDelays samples of each multiplexed waveform, keep the common length."""
+    d = np.asarray(delays, dtype=np.int64) - int(np.min(delays))
+    length = len(X[0]) - int(d.max())
+    return np.array([np.asarray(x)[k:][:length] for x, k in zip(X, d)])
+
+
+# --------------------------------------------------------------------------
 # a14-a15  FAS statistics and thresholds  (fas.py:74-84, subspace.py:1027-1047,1110-1140)
 # --------------------------------------------------------------------------
 

@@ -191,3 +191,41 @@ class RefFunctions(object):
     # detex/construct.py:469-483
     def fast_normcorr(self, t, s):
         return self.construct.fast_normcorr(t, s)
+
+    # detex/construct.py:272-281, 710-786, 486-503: linkage -> per-event alignment delays.
+    # `_getDelays` itself stores a list into a DataFrame cell through `.loc` (construct.py:725),
+    # which today's pandas refuses, so its bookkeeping lines 711-728 are replayed here with the
+    # same content and the arithmetic -- `_traceEventDendro`, `_updateLags`, `_getDow`, `_getAcr`,
+    # `_makeCC2LagMap`, `_getClustDict`, `_ensureUnique`, `_flatNoNan`, `_alignTD` -- is the
+    # reference's own, unmodified.
+    def getDelays(self, DFcc, DFlag):
+        from scipy.cluster.hierarchy import linkage
+        C = self.construct
+        cxdf = 1.0000001 - DFcc
+        cx = C._flatNoNan(cxdf)
+        cx, cxdf = C._ensureUnique(cx, cxdf)
+        lags = C._flatNoNan(DFlag)
+        link = linkage(cx)
+        CCtoLag = C._makeCC2LagMap(cx, lags)
+        N = len(link)
+        linkup = np.append(link, np.arange(N + 1, 2 * N + 1).reshape(N, 1), 1)
+        clustDict = C._getClustDict(linkup, len(linkup))
+        rows = []
+        for r in linkup:
+            tempdf = cxdf[cxdf == r[2]].dropna(how='all').dropna(axis=1)
+            rows.append(dict(i1=r[0], i2=r[1], cc=r[2], num=r[3], clust=r[4],
+                             II=clustDict[int(r[0])].tolist() + clustDict[int(r[1])].tolist(),
+                             ev1=tempdf.index[0], ev2=tempdf.columns[0]))
+        dflink = pd.DataFrame(rows).astype(object)
+        delays = C._traceEventDendro(dflink, cx, lags, CCtoLag, clustDict, clustDict.iloc[-1])
+        return link, np.asarray(delays.values, dtype=np.int64)
+
+    # detex/construct.py:283-286, 486-503
+    def alignTD(self, delays, X):
+        evs = ["ev%04d" % i for i in range(len(X))]
+        delayNP = -1 * np.min(delays)
+        delayDF = pd.DataFrame(np.asarray(delays) + delayNP, columns=['SampleDelays'])
+        delayDF['Events'] = [evs[x] for x in delayDF.index]
+        srow = pd.Series({"MPtd": {e: X[i] for i, e in enumerate(evs)}, "Station": "STA"})
+        al = self.construct._alignTD(delayDF, srow)
+        return np.array([al[e] for e in evs])

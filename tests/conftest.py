@@ -53,3 +53,8 @@ def trig_golden():
 @pytest.fixture(scope="session")
 def ccx_golden():
     return np.load(os.path.join(GOLDEN, "ccx_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def align_golden():
+    return np.load(os.path.join(GOLDEN, "align_golden.npz"))

@@ -90,6 +90,32 @@ def main():
         ccx[name + "_sub"] = sub.values.astype(float)
     np.savez_compressed(os.path.join(OUT, "ccx_golden.npz"), **ccx)
 
+    # ---- alignment from the dendrogram (_getDelays/_traceEventDendro/_alignTD,
+    #      construct.py:272-286, 486-503, 710-812): reference CCX output -> reference delays
+    import pandas as pd
+    al = {}
+    X = synth.event_families(203, 3, 5, 240, 3, max_shift=25)
+    cc, lag, _ = R.makeDFcclags(X, 3)
+    link, delays = R.getDelays(cc.astype(float), lag.astype(float))
+    al.update(fam_X=X, fam_cc=cc.values.astype(float), fam_lag=lag.values.astype(float), fam_link=link,
+              fam_delays=delays, fam_aligned=R.alignTD(delays, X))
+    rng = np.random.default_rng(204)
+    for name, N in (("rand2", 2), ("rand3", 3), ("rand24", 24)):
+        true = rng.integers(-40, 40, N)
+        iu = np.triu_indices(N - 1)
+        ccm = np.full((N - 1, N - 1), np.nan)
+        lgm = np.full((N - 1, N - 1), np.nan)
+        ccm[iu] = rng.permutation(np.linspace(0.2, 0.97, len(iu[0])))
+        noise = 3 * rng.integers(-2, 3, len(iu[0])) * (rng.random(len(iu[0])) < 0.4)
+        lgm[iu] = (true[iu[1] + 1] - true[iu[0]]) * 3 + noise      # inconsistent lags on purpose
+        idx, cols = range(N - 1), range(1, N)
+        link, delays = R.getDelays(pd.DataFrame(ccm, index=idx, columns=cols),
+                                   pd.DataFrame(lgm, index=idx, columns=cols))
+        Xr = rng.standard_normal((N, 900))
+        al.update({name + "_cc": ccm, name + "_lag": lgm, name + "_link": link, name + "_delays": delays,
+                   name + "_X": Xr, name + "_aligned": R.alignTD(delays, Xr)})
+    np.savez_compressed(os.path.join(OUT, "align_golden.npz"), **al)
+
     # ---- magnitude / SNR estimates (_estMag, detect.py:447-499)
     from oracle import detex_oracle as orc
     rng = np.random.default_rng(301)

@@ -3,7 +3,9 @@ from sufficient statistics, SVD basis selection, shard arithmetic."""
 import numpy as np
 import scipy.stats
 
-from detex_b200 import detect, fas, parallel, subspace, synth
+import pytest
+
+from detex_b200 import construct, detect, fas, parallel, subspace, synth
 from oracle import detex_oracle as orc
 
 
@@ -90,3 +92,66 @@ def test_ccx_row_blocks_balanced():
             assert sum(pairs) == N * (N - 1) // 2
             if N == 4096:
                 assert max(pairs) / (sum(pairs) / w) < 1.01
+
+
+# ---- N3: alignment from the dendrogram (construct.py:272-286, 486-503, 710-812)
+
+@pytest.mark.parametrize("case", ["fam", "rand2", "rand3", "rand24"])
+def test_get_delays_matches_reference_golden(align_golden, case):
+    g = align_golden
+    link, delays = construct.get_delays(g[case + "_cc"], g[case + "_lag"])
+    assert np.array_equal(link, g[case + "_link"])
+    assert np.array_equal(delays, g[case + "_delays"])
+    aligned, sd = construct.alignTD(delays, g[case + "_X"])
+    assert np.array_equal(aligned, g[case + "_aligned"])
+    assert sd.min() == 0 and np.array_equal(sd, delays - delays.min())
+
+
+def _random_cc_lag(rng, N, consistent):
+    true = rng.integers(-50, 50, N)
+    iu = np.triu_indices(N - 1)
+    cc = np.full((N - 1, N - 1), np.nan)
+    lag = np.full((N - 1, N - 1), np.nan)
+    cc[iu] = rng.permutation(np.linspace(0.1, 0.99, len(iu[0])))
+    lag[iu] = (true[iu[1] + 1] - true[iu[0]]) * 3
+    if not consistent:
+        lag[iu] += 3 * rng.integers(-3, 4, len(iu[0]))
+    return cc, lag, true
+
+
+def test_get_delays_random_against_oracle():
+    rng = np.random.default_rng(11)
+    for N in (2, 3, 4, 7, 16, 41):
+        for consistent in (True, False):
+            cc, lag, _ = _random_cc_lag(rng, N, consistent)
+            l1, d1 = orc.get_delays(cc, lag)
+            l2, d2 = construct.get_delays(cc, lag)
+            assert np.array_equal(l1, l2) and np.array_equal(d1, d2)
+
+
+def test_get_delays_recovers_consistent_shifts_at_scale():
+    """With mutually consistent lags the walk must return the true shifts (up to a constant),
+    whatever the merge order; N = 1500 runs in about a second (the reference is O(N^3))."""
+    rng = np.random.default_rng(12)
+    cc, lag, true = _random_cc_lag(rng, 1500, True)
+    _, d = construct.get_delays(cc, lag)
+    # positive lag(i, j) = event j is delayed relative to i -> j is trimmed by more samples
+    assert np.array_equal(d - d.min(), 3 * (true - true.min()))
+
+
+def test_get_delays_rejects_duplicates_and_alignTD_raises_when_empty():
+    cc, lag, _ = _random_cc_lag(np.random.default_rng(13), 5, True)
+    cc[0, 1] = cc[0, 0]
+    with pytest.raises(ValueError):
+        construct.get_delays(cc, lag)
+    with pytest.raises(Exception):
+        construct.alignTD(np.array([0, 50, 120]), np.zeros((3, 100)))
+
+
+def test_update_start_times():
+    st = [dict(Nc=3, sampling_rate=100.0, starttime=1000.0), dict(Nc=3, sampling_rate=100.0, starttime=2000.0)]
+    out = construct.update_start_times(st, [0, 30], [990.0, 1995.0], [1.5, 2.0])
+    assert out[0]["starttime"] == 1000.0 and out[0]["offset"] == 10.0
+    assert out[1]["starttime"] == 2000.0 + 30 / 300.0 and out[1]["magnitude"] == 2.0
+    assert abs(out[1]["offset"] - (5.0 + 0.1)) < 1e-12
+    assert st[1]["starttime"] == 2000.0          # inputs untouched

@@ -123,3 +123,14 @@ def test_est_mag_matches_reference():
         assert np.allclose(orc.est_mag(int(t), x, Nc, us, single[None, :], np.array([1.7]), False), ref, rtol=0, atol=1e-12)
     out = orc.est_mag(1500, x, Nc, U, ewf, np.full(7, -99.0), True)
     assert np.isnan(out[0]) and np.isnan(out[1]) and abs(out[2] - g["nomag_out"][2]) < 1e-12
+
+
+@pytest.mark.parametrize("case", ["fam", "rand2", "rand3", "rand24"])
+def test_alignment_delays_match_reference(align_golden, case):
+    """`_getDelays` / `_traceEventDendro` / `_alignTD` (construct.py:486-503, 710-812): integer
+    work, exact."""
+    g = align_golden
+    link, delays = orc.get_delays(g[case + "_cc"], g[case + "_lag"])
+    assert np.array_equal(link, g[case + "_link"])
+    assert np.array_equal(delays, g[case + "_delays"])
+    assert np.array_equal(orc.align_td(delays, g[case + "_X"]), g[case + "_aligned"])

@@ -64,3 +64,21 @@ def test_multiplex(R):
     ch = [np.arange(5.0), np.arange(5.0) * 2, np.arange(6.0) * 3]
     assert np.array_equal(R.multiplex(ch), orc.multiplex(ch))
     assert np.array_equal(synth.multiplex([c[:5] for c in ch]), orc.multiplex(ch))
+
+
+@pytest.mark.parametrize("seed,N", [(31, 2), (32, 6), (33, 19)])
+def test_alignment_delays(R, seed, N):
+    """construct.py:710-812 through the reference's own `_traceEventDendro` / `_alignTD`."""
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    iu = np.triu_indices(N - 1)
+    cc = np.full((N - 1, N - 1), np.nan)
+    lag = np.full((N - 1, N - 1), np.nan)
+    cc[iu] = rng.permutation(np.linspace(0.2, 0.95, len(iu[0])))
+    lag[iu] = 3 * rng.integers(-60, 60, len(iu[0]))
+    idx, cols = range(N - 1), range(1, N)
+    link, delays = R.getDelays(pd.DataFrame(cc, index=idx, columns=cols), pd.DataFrame(lag, index=idx, columns=cols))
+    l2, d2 = orc.get_delays(cc, lag)
+    assert np.array_equal(link, l2) and np.array_equal(delays, d2)
+    X = rng.standard_normal((N, 1500))
+    assert np.array_equal(R.alignTD(delays, X), orc.align_td(d2, X))
