@@ -44,6 +44,14 @@ METRIC = "subspace_detector_template_samples_per_sec"
 UNIT = "template*samples/s"
 
 
+DTYPES = {
+    "tcgen05": "fp16x3-split (fp32-equivalent), f64 window energy",
+    "tcgen05_x8": "fp16 hi*hi + e4m3 x e5m2 cross terms, fp32 accumulate, f64 window energy",
+    "tcgen05_auto": "per chunk: fp16x3-split, or fp16 hi*hi + e4m3 x e5m2 cross terms where the error "
+                    "model admits them; fp32 accumulate, f64 window energy",
+}
+
+
 def ranks_list(nsub):
     return [(i % 8) + 1 for i in range(nsub)]
 
@@ -164,7 +172,7 @@ def workload_config(args):
         "chunks_per_gpu": args.chunks, "subspaces": args.nsub, "basis_vectors": sum(ranks_list(args.nsub)),
         "n": N_MUX, "lags_per_chunk": T_PER_CHUNK, "batch_chunks": args.batch,
         "l2": "inputs (%.1f GB/GPU) larger than L2" % (args.chunks * LS * NC * 8 / 1e9),
-        "input_dtype": "f64", "kblk": args.kblk,
+        "input_dtype": "f64", "kblk": args.kblk, "engine": args.engine,
     }
 
 
@@ -226,18 +234,21 @@ def gpu_arm(args):
     flops_per_chunk = 2.0 * N_MUX * sum(ranks) * T_PER_CHUNK
 
     k1_ms = []
+    x8_chunks = [0]
 
-    def step_resident():
+    def step_resident(engine=args.engine):
         """One pass over the station with the chunks resident in HBM."""
         cands = []
         for b in range(nbatch):
             lo, hi = b * args.batch, min(args.chunks, (b + 1) * args.batch)
             eng.attach_device_chunks(data.data_ptr(), offs_all[lo:hi], lens_all[lo:hi])
-            eng.detect_run(0, engine=args.engine, kblk=args.kblk, lta_window=int(5 * SR))
+            eng.detect_run(0, engine=engine, kblk=args.kblk, lta_window=int(5 * SR))
             c = eng.candidates()
             c["row"] += lo * args.nsub
             cands.append(c)
             k1_ms.append((eng.k1_ms(), hi - lo))
+            if engine != "tcgen05":
+                x8_chunks[0] += int(eng.chunk_modes().sum())
         c = np.concatenate(cands)
         hist = eng.hist(0, reset=True)
         if world > 1:                      # the only exchange: trigger lists + histograms
@@ -271,6 +282,7 @@ def gpu_arm(args):
     for _ in range(args.warmup):
         step_resident()
     k1_ms.clear()
+    x8_chunks[0] = 0
     launches0 = eng.launch_count()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -307,9 +319,54 @@ def gpu_arm(args):
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k1_kernel (tcgen05 Hankel projection + normalisation)",
                 "peak_source": peak_src, "k1_ms_per_launch": k1_avg_ms, "k1_share_of_step": tot_ms / 1e3 / (step_s * args.steps),
-                "issued_tflops": achieved * 3.0 * (3 * 3008.0 / N_MUX),
                 "note": "algorithmic flops = 2*n*R per lag; fp32-equivalent precision costs 3 fp16 MMAs per "
                         "product, so frac is bounded by 1/3"}
+    # tensor-pipe slots issued per algorithmic product: 3 fp16 MMAs, or 2 (fp16 + one 8-bit MMA of
+    # twice the K) for the chunks that ran with 8-bit cross terms; K padded 3000 -> 3008 per channel
+    x8_frac = x8_chunks[0] / float(args.chunks * args.steps)
+    roofline["issued_tflops"] = achieved * (3.0 - x8_frac) * (3 * 3008.0 / N_MUX)
+    if args.engine != "tcgen05":
+        roofline["note"] = ("algorithmic flops = 2*n*R per lag; %.0f %% of the chunks ran with 8-bit cross terms "
+                            "(2 tensor-pipe slots per product, frac bounded by 1/2), the rest with fp16 cross "
+                            "terms (3 slots, 1/3)" % (100 * x8_frac))
+
+    # ------------------------------------------------- parity spot check at full size (untimed)
+    # the planted chunk of day 0 against the float64 closed form on the device, first 8 subspaces
+    npar = min(8, args.nsub)
+    eng.set_bases(1, bases[:npar], NC)
+
+    def parity_check(engine):
+        ci = min(args.chunks - 1, 7)
+        eng.attach_device_chunks(data.data_ptr(), offs_all[ci:ci + 1], lens_all[ci:ci + 1])
+        eng.detect_run(1, engine=engine, kblk=args.kblk, keep_ds64=True)
+        perr, pmax = 0.0, 0.0
+        for si in range(npar):
+            d64 = eng.get_ds64(0, si)
+            perr = max(perr, float(np.abs(eng.get_ds(0, si) - d64).max()))
+            pmax = max(pmax, float(d64.max()))
+        assert perr < 1e-5, "detection statistic out of tolerance against the float64 closed form: %g" % perr
+        return {"max_abs_err_vs_fp64": perr, "tol": 1e-5, "max_ds": pmax, "chunk": ci, "subspaces": npar,
+                "lags": T_PER_CHUNK, "x8_mode": int(eng.chunk_modes()[0])}
+
+    parity = parity_check(args.engine)
+
+    # -------------------- the opt-in adaptive-precision engine on the same resident data (reported
+    # beside the headline, which stays on the worst-case-bounded default engine)
+    alt = None
+    if args.engine == "tcgen05" and not args.no_alt:
+        x8_chunks[0] = 0
+        k1_ms.clear()
+        step_resident("tcgen05_auto")
+        x8_chunks[0] = 0
+        k1_ms.clear()
+        ms_a, wall_a, (cands_a, hist_a) = timed(lambda: step_resident("tcgen05_auto"), args.steps)
+        alt = {"engine": "tcgen05_auto", "dtype": DTYPES["tcgen05_auto"],
+               "value": ts_per_step / (max(ms_a / 1e3, wall_a) / args.steps), "unit": UNIT,
+               "x8_chunk_fraction": x8_chunks[0] / float(args.chunks * args.steps),
+               "k1_ms_per_launch": sum(m for m, _ in k1_ms) / len(k1_ms),
+               "candidates_per_step": int(len(cands_a)),
+               "hist_bins_moved_vs_default": int(np.abs(hist_a - hist).sum() // 2),
+               "parity_check": parity_check("tcgen05_auto")}
 
     # ---------------------------------------------------------------- end-to-end (host buffers)
     host = torch.empty((args.chunks, L), dtype=torch.float64, pin_memory=True)
@@ -346,13 +403,17 @@ def gpu_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp16x3-split (fp32-equivalent), f64 window energy", "data": "synthetic",
+        "dtype": DTYPES[args.engine], "data": "synthetic",
         "config": workload_config(args),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(args.chunks) * L * 8,
                 "d2h_bytes_per_step": int(d2h[0] // max(1, args.steps))},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
-        "candidates_per_step": int(len(cands)), "hist_total": int(hist.sum()),
+        "candidates_per_step": int(len(cands)), "hist_total": int(hist.sum()), "parity_check": parity,
     }
+    if args.engine != "tcgen05":
+        line["x8_chunk_fraction"] = x8_frac
+    if alt is not None:
+        line["adaptive_engine"] = alt
     if rank == 0 and world == 1 and not args.no_cpu:
         import multiprocessing as mp
         os.environ.setdefault("OMP_NUM_THREADS", "1")
@@ -385,6 +446,7 @@ def main():
     ap.add_argument("--kblk", type=int, default=2)
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "tcgen05_x8", "tcgen05_auto"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the extra pass with the adaptive-precision engine")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -88,3 +88,30 @@ def event_families(seed, nfam, per_fam, ns, Nc, sr=100.0, max_shift=100, noise=0
             w = w + noise * w.std() * bandpassed_noise(rng, ns, sr=sr, nchan=Nc)
             out.append(multiplex(w))
     return np.array(out)
+
+
+def detection_table(seed, nev=80, stas=("TA.M17A", "TA.M18A", "TA.N17A"), t0=1.4e9, n_templates=6):
+    """A shuffled multi-station detections table (columns of detect.py:397-398) plus a template
+    key whose origins coincide with some of the events: input of the N4 results path."""
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    rows, times = [], []
+    for e in range(nev):
+        te = t0 + e * 400.0 + float(rng.uniform(0, 50))
+        times.append(te)
+        for sta in stas:
+            if rng.random() < 0.7:
+                for _ in range(int(rng.integers(1, 3))):          # sometimes two detectors fire
+                    t = te + float(rng.uniform(-1.5, 1.5))
+                    rows.append([float(rng.uniform(0.3, 0.95)), float(rng.uniform(3, 9)), t + 3.0,
+                                 "SS%d" % int(rng.integers(0, 3)), sta, t, t + float(rng.uniform(1, 4)),
+                                 float(rng.choice([np.nan, 1.5, 2.0, 2.7])), float(rng.uniform(1, 5)),
+                                 float(rng.choice([np.nan, 1.1, 1.9]))])
+    cols = ['DS', 'DS_STALTA', 'STMP', 'Name', 'Sta', 'MSTAMPmin', 'MSTAMPmax', 'Mag', 'SNR', 'ProEnMag']
+    det = pd.DataFrame(rows, columns=cols)
+    det = det.iloc[rng.permutation(len(det))].reset_index(drop=True)
+    pick = np.sort(rng.choice(nev, size=n_templates, replace=False))
+    temkey = pd.DataFrame({"NAME": ["ev%02d" % i for i in range(n_templates)][::-1],   # not in time order
+                           "TIME": [times[k] + 1.0 for k in pick], "MAG": np.linspace(1, 3, n_templates)})
+    temkey["STMP"] = temkey["TIME"].astype(float)
+    return det, temkey

@@ -37,6 +37,24 @@ def _rolling(fn):
     return f
 
 
+class _UTCDateTime(object):
+    """Stand-in for obspy.UTCDateTime on the results path (results.py:421, 478-479): `.timestamp`
+    from epoch seconds or an ISO string, `str()` as ObsPy prints it."""
+
+    def __init__(self, x):
+        import datetime
+        if isinstance(x, (int, float, np.integer, np.floating)):
+            self.timestamp = float(x)
+        else:
+            d = datetime.datetime.fromisoformat(str(x).replace("Z", ""))
+            self.timestamp = d.replace(tzinfo=datetime.timezone.utc).timestamp()
+
+    def __str__(self):
+        import datetime
+        d = datetime.datetime(1970, 1, 1) + datetime.timedelta(microseconds=int(round(self.timestamp * 1e6)))
+        return d.strftime("%Y-%m-%dT%H:%M:%S.%fZ")
+
+
 _loaded = None
 
 
@@ -87,6 +105,13 @@ def load():
     import collections.abc
     if not hasattr(collections, "Iterable"):
         collections.Iterable = collections.abc.Iterable
+    if not hasattr(pd.DataFrame, "iteritems"):       # removed alias of .items() (util.py:925, results.py:519)
+        pd.DataFrame.iteritems = pd.DataFrame.items
+        pd.Series.iteritems = pd.Series.items
+    # the only ObsPy object the results path needs: epoch seconds <-> ISO string
+    sys.modules["obspy"].UTCDateTime = _UTCDateTime
+    sys.modules["obspy"].core.UTCDateTime = _UTCDateTime
+    sys.modules["obspy.core"].UTCDateTime = _UTCDateTime
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     import detex  # noqa: E402
@@ -229,3 +254,19 @@ class RefFunctions(object):
         srow = pd.Series({"MPtd": {e: X[i] for i, e in enumerate(evs)}, "Station": "STA"})
         al = self.construct._alignTD(delayDF, srow)
         return np.array([al[e] for e in evs])
+
+    # detex/util.py:870-893 (pandas_dbms.write_frame / get_schema)
+    def saveSQLite(self, DF, db, table):
+        import detex.util
+        return detex.util.saveSQLite(DF, db, table)
+
+    # detex/results.py:371-401 (reads the table back through detex.util.loadSQLite)
+    def deleteDetDups(self, db, associateBuffer, table="ss_df", trigCon=0, trigParameter=0.0):
+        import detex.results
+        return detex.results._deleteDetDups(db, trigCon, trigParameter, associateBuffer, None, None, None, table)
+
+    # detex/results.py:404-466, associateReq = 0
+    def associateDetections(self, ssdf, requiredNumStations, associateBuffer, temkey, exceptionalThreshold=None):
+        import detex.results
+        return detex.results._associateDetections(ssdf.copy(), 0, requiredNumStations, associateBuffer, None,
+                                                  temkey.copy(), exceptionalThreshold)

@@ -116,6 +116,39 @@ def main():
                    name + "_X": Xr, name + "_aligned": R.alignTD(delays, Xr)})
     np.savez_compressed(os.path.join(OUT, "align_golden.npz"), **al)
 
+    # ---- results tables (N4): SQLite wire format, duplicate removal, association
+    #      (util.py:870-931, pandas_dbms.py:214-251, results.py:371-515) run by the reference itself
+    import sqlite3
+    import tempfile
+    from detex_b200.synth import detection_table
+    res = {}
+    det, temkey = detection_table(401)
+    with tempfile.TemporaryDirectory() as td:
+        db = os.path.join(td, "ref.db")
+        R.saveSQLite(det, db, "ss_df")
+        R.saveSQLite(det.iloc[:7], db, "ss_df")          # append path
+        con = sqlite3.connect(db)
+        res["schema"] = np.array(con.execute("select sql from sqlite_master").fetchall()[0][0])
+        res["nrows"] = np.array(con.execute("select count(*) from ss_df").fetchall()[0][0])
+        con.close()
+        dd = R.deleteDetDups(db, 1.0)
+    num = [c for c in dd.columns if c not in ("Name", "Sta")]
+    res["dedup_num"] = dd[num].to_numpy(dtype=float)
+    res["dedup_cols"] = np.array(num)
+    res["dedup_name"] = dd["Name"].to_numpy(dtype=str)
+    res["dedup_sta"] = dd["Sta"].to_numpy(dtype=str)
+    evnum = ["DSav", "DSmax", "NumStations", "DS_STALTA", "MSTAMPmin", "MSTAMPmax", "Mag", "ProEnMag"]
+    for tag, (req, exc) in {"req2": (2, None), "req3": (3, None), "req3_exc": (3, 0.9),
+                            "req3_excdict": (3, {"TA.M17A": 0.8}), "req1": (1, None)}.items():
+        dt, at = R.associateDetections(dd, req, 1.0, temkey, exc)
+        for kind, t in (("det", dt), ("auto", at)):
+            res["%s_%s_num" % (tag, kind)] = t[evnum].to_numpy(dtype=float).reshape(len(t), len(evnum))
+            res["%s_%s_event" % (tag, kind)] = t["Event"].to_numpy(dtype=str)
+            res["%s_%s_nd" % (tag, kind)] = np.array([len(g) for g in t["Dets"]], dtype=np.int64)
+            res["%s_%s_dets_stmp" % (tag, kind)] = (np.concatenate([g["STMP"].to_numpy(dtype=float) for g in t["Dets"]])
+                                                    if len(t) else np.zeros(0))
+    np.savez_compressed(os.path.join(OUT, "results_golden.npz"), **res)
+
     # ---- magnitude / SNR estimates (_estMag, detect.py:447-499)
     from oracle import detex_oracle as orc
     rng = np.random.default_rng(301)
