@@ -53,12 +53,13 @@ constexpr int NDRAIN_WARPS = 8;
 constexpr int REGS_CTRL = 56, REGS_DRAIN = 224;         // setmaxnreg budgets (128*56 + 256*224 = 64512)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * SIG_BUF_BYTES + 2 * NORM_BUF_BYTES;
 
-// Issue style of the producer / MMA warps.  Default: ONE lane runs the role loop (ptxas wraps
-// every UTCHMMA / UBLKCP in an ELECT loop, ~128 cycles per MMA: the issuer paces the tensor
-// pipe).  -DDTX_CONVERGED_ISSUE: the whole warp runs the loop converged and an elected lane
-// issues (descriptors stay in uniform registers, 12 MMAs back to back).  A/B in
-// experiments/ab_issue.sh; see DESIGN.md section 7.
-#ifdef DTX_CONVERGED_ISSUE
+// Issue style of the producer / MMA warps.  Default: the whole warp runs the role loop converged
+// and an elected lane issues (descriptors stay in uniform registers, the MMAs of a stage go out
+// back to back).  -DDTX_SINGLE_LANE_ISSUE: ONE lane runs the loop (ptxas then wraps every UTCHMMA /
+// UBLKCP in an ELECT loop, ~128 cycles per MMA, i.e. the issuer paces the tensor pipe).  Same-box
+// A/B (experiments/gpu_round1k.sh, profiles/r01_issue_ab.md): converged is +0.8 % with 3 MMAs per
+// K step and +2.2 % with the 8-bit cross terms, where the pipe is not saturated.
+#ifndef DTX_SINGLE_LANE_ISSUE
 #define ISSUE_LANE elect_one()
 #define ISSUE_SYNC() __syncwarp()
 #define ROLE_LANES(lane) true
