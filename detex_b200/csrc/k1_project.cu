@@ -51,7 +51,15 @@ constexpr int NTHREADS = 384;                           // warps 0-3: producer, 
 constexpr int FIRST_DRAIN_WARP = 4;
 constexpr int NDRAIN_WARPS = 8;
 constexpr int REGS_CTRL = 56, REGS_DRAIN = 224;         // setmaxnreg budgets (128*56 + 256*224 = 64512)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * SIG_BUF_BYTES + 2 * NORM_BUF_BYTES;
+// Epilogue transposition buffer (one per half of the accumulator columns): the 8 phases of a lag
+// octet live in 4 different warps, so DS is staged [slot][128 lags] in smem and written out as
+// 512-byte rows.  Row stride +4 floats keeps rows 16 B aligned; slots >= 8 store with column ^ 2 so
+// the 32 lanes of a store hit 32 banks.
+constexpr int EPI_QC = 16;                               // accumulator columns per chunk
+constexpr int EPI_LAGS = EPI_QC * 8;                     // = 128 lags per chunk
+constexpr int EPI_STRIDE = EPI_LAGS + 4;                 // floats
+constexpr int EPI_BUF_BYTES = VEC_PER_BLOCK * EPI_STRIDE * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * SIG_BUF_BYTES + 2 * NORM_BUF_BYTES + 2 * EPI_BUF_BYTES;
 
 // Issue style of the producer / MMA warps.  Default: the whole warp runs the role loop converged
 // and an elected lane issues (descriptors stay in uniform registers, the MMAs of a stage go out
@@ -100,6 +108,7 @@ struct Smem {
     uint8_t* stage;
     uint8_t* sig;
     uint8_t* norm;
+    uint8_t* epi;
     uint64_t *full, *empty, *sigfull, *sigempty, *accfull, *accempty, *normfull, *normempty;
 };
 
@@ -284,47 +293,56 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
                 ac.advance();
             }
             // ---------------------------------------------------- K2 epilogue
+            // Every thread turns its accumulators into normalised projections c (squared for the
+            // detection statistic) and parks them in smem as [slot][lag]; the four warps of this
+            // column half then sum the slots of each subspace and write 512-byte DS rows.
             mbar_wait(&S.normfull[nm.idx], nm.phase);
-            const BlockInfo bi = P.a.binfo[b * VEC_PER_BLOCK + kl];
-            const bool head = bi.nrows != 0 && bi.out_row >= 0;
-            const bool accum = bi.nrows < 0;   // piece of a rank > 16 subspace
-            const long long row_off = cd.ds_off + static_cast<long long>(head ? bi.out_row : 0) * cd.Tpad +
-                                      static_cast<long long>(it.y) * TT + 8 * NCOL * colhalf + p;
-            float* dsrow = P.a.DS + row_off;
+            const float nsumU = -P.a.binfo[b * VEC_PER_BLOCK + kl].sumU;
+            float* ebuf = reinterpret_cast<float*>(S.epi + colhalf * EPI_BUF_BYTES);
+            float* wr = ebuf + kl * EPI_STRIDE + (p ^ (kl >= 8 ? 2 : 0));
             const float* pmu = smu + 8 * NCOL * colhalf + p;
-            const float* pie = sie + 8 * NCOL * colhalf + p;
-            const float nsumU = -bi.sumU;
-            if (MODE == 0) {
-                // segmented suffix sum over the vector slots of a subspace (lanes 2 apart share a
-                // phase): 4 fixed doubling steps cover ranks up to 16, branch free so the
-                // unrolled lags interleave
-                const bool j1 = kl + 1 < bi.seg_end, j2 = kl + 2 < bi.seg_end, j4 = kl + 4 < bi.seg_end,
-                           j8 = kl + 8 < bi.seg_end;
+            const float* pie4 = sie + 8 * NCOL * colhalf + lane * 4;
+            float* dsbase = P.a.DS + cd.ds_off + static_cast<long long>(it.y) * TT + 8 * NCOL * colhalf + lane * 4;
+            // read-out role of this warp: the subspaces whose first slot is lq, lq+4, lq+8, lq+12
+            BlockInfo hb[4];
 #pragma unroll
-                for (int i = 0; i < NCOL; ++i) {
-                    const float c = fmaf(sums[i], sc, pmu[8 * i] * nsumU);
-                    float v = c * c;
-                    float o = __shfl_down_sync(0xffffffffu, v, 2);
-                    v += j1 ? o : 0.f;
-                    o = __shfl_down_sync(0xffffffffu, v, 4);
-                    v += j2 ? o : 0.f;
-                    o = __shfl_down_sync(0xffffffffu, v, 8);
-                    v += j4 ? o : 0.f;
-                    o = __shfl_down_sync(0xffffffffu, v, 16);
-                    v += j8 ? o : 0.f;
-                    if (head) {
-                        if (accum) atomicAdd(&dsrow[8 * i], v * pie[8 * i]);
-                        else dsrow[8 * i] = v * pie[8 * i];
+            for (int k = 0; k < 4; ++k) hb[k] = P.a.binfo[b * VEC_PER_BLOCK + lq + 4 * k];
+#pragma unroll
+            for (int c = 0; c < NCOL / EPI_QC; ++c) {
+#pragma unroll
+                for (int j = 0; j < EPI_QC; ++j) {
+                    const int i = c * EPI_QC + j;
+                    const float cc = fmaf(sums[i], sc, pmu[8 * i] * nsumU);
+                    wr[8 * j] = MODE == 0 ? cc * cc : cc;
+                }
+                named_bar_sync(1 + colhalf, 128);
+                float4 ie = *reinterpret_cast<const float4*>(pie4 + c * EPI_LAGS);
+                if (MODE == 1) {
+                    // signed Pearson coefficient: templates are pre-scaled by 1/||x1 - mean||, so
+                    // res = c / sqrt(E) = c * sqrt(invE * n/(n-1))
+                    ie.x = sqrtf(ie.x * P.inv_cn); ie.y = sqrtf(ie.y * P.inv_cn);
+                    ie.z = sqrtf(ie.z * P.inv_cn); ie.w = sqrtf(ie.w * P.inv_cn);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int slot = lq + 4 * k;
+                    if (hb[k].nrows == 0 || hb[k].out_row < 0) continue;   // not the first slot of a subspace
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int sl = slot; sl < hb[k].seg_end; ++sl) {
+                        const float4 v = *reinterpret_cast<const float4*>(ebuf + sl * EPI_STRIDE + lane * 4);
+                        if (sl >= 8) { acc.x += v.z; acc.y += v.w; acc.z += v.x; acc.w += v.y; }
+                        else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+                    }
+                    acc.x *= ie.x; acc.y *= ie.y; acc.z *= ie.z; acc.w *= ie.w;
+                    float* dst = dsbase + static_cast<long long>(hb[k].out_row) * cd.Tpad + c * EPI_LAGS;
+                    if (hb[k].nrows < 0) {   // piece of a rank > 16 subspace: accumulate into the row
+                        atomicAdd(dst, acc.x); atomicAdd(dst + 1, acc.y);
+                        atomicAdd(dst + 2, acc.z); atomicAdd(dst + 3, acc.w);
+                    } else {
+                        *reinterpret_cast<float4*>(dst) = acc;
                     }
                 }
-            } else {
-                // signed Pearson coefficient: templates are pre-scaled by 1/||x1 - mean||, so
-                // res = c / sqrt(E) = c * sqrt(invE * n/(n-1))
-#pragma unroll
-                for (int i = 0; i < NCOL; ++i) {
-                    const float c = fmaf(sums[i], sc, pmu[8 * i] * nsumU);
-                    if (head) dsrow[8 * i] = c * sqrtf(pie[8 * i] * P.inv_cn);
-                }
+                named_bar_sync(1 + colhalf, 128);
             }
         }
         __syncwarp();
@@ -343,6 +361,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k1_kernel(const __grid_constant__
     S.stage = smem;
     S.sig = smem + STAGES * STAGE_BYTES;
     S.norm = S.sig + 2 * SIG_BUF_BYTES;
+    S.epi = S.norm + 2 * NORM_BUF_BYTES;
     S.full = full; S.empty = empty; S.sigfull = sigfull; S.sigempty = sigempty;
     S.accfull = accfull; S.accempty = accempty; S.normfull = normfull; S.normempty = normempty;
 

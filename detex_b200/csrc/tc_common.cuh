@@ -113,6 +113,10 @@ __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Named barrier among `nthreads` threads (whole warps) of the CTA; id 0 is __syncthreads().
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // All previously issued MMAs of this thread arrive on `bar` when complete
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
