@@ -411,7 +411,10 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     // work items (chunk, tile, basis block), ordered (chunk group, block, tile): all CTAs share
     // the current A block in L2 and the group's split signal (<= ~40 MB) stays L2 resident
     const int tiles_per_chunk = std::max(1, (maxT + 8 * nq - 1) / (8 * nq));
-    const int group = std::max(8, (4 * ctx->num_sms + tiles_per_chunk - 1) / tiles_per_chunk);
+    // (>= 4 waves of items per (group, block) pass.  Group size 8 vs 4 long chunks makes no measurable
+    // difference in time or DRAM traffic: ncu shows ~17-20 GB of L2 read misses per 48-chunk launch
+    // either way, see profiles/r01_k1_ncu_summary.md)
+    const int group = std::max(1, (4 * ctx->num_sms + tiles_per_chunk - 1) / tiles_per_chunk);
     // the list only depends on the batch's shape: reuse the device copy when it has not changed
     std::vector<int> sig_key{nq, lay.nblocks, group, nchunks};
     for (int i = 0; i < nchunks; ++i) {

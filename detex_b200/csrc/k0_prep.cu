@@ -225,7 +225,9 @@ k0_norm(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
                 k4 = fmaxf(k4, r >= 0.f && r < 3e38f ? r : 3e38f);   // NaN / inf -> never 8-bit
             }
         }
-        pm[i] = fm;
+        // mu is stored phase-major inside every 1024-lag group, [group][t % 8][t / 8 % 128], the
+        // order K1's epilogue threads (one phase, consecutive accumulator columns) read it in
+        pm[(i & ~1023) + (i & 7) * 128 + ((i & 1023) >> 3)] = fm;
         pe[i] = fe;
     }
     if (want4) {

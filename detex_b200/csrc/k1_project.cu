@@ -112,6 +112,18 @@ struct Smem {
     uint64_t *full, *empty, *sigfull, *sigempty, *accfull, *accempty, *normfull, *normempty;
 };
 
+// 64-tap stages accumulated in TMEM before accumulation `nacc` of a work item is drained.  The
+// first FIRST_LONG_ACCS accumulations of an item are twice as long: while the drain warps are
+// still in the previous item's epilogue the MMA warp then has four instead of two kblk's of work
+// before it runs out of accumulators (the truncation bias of those two partial sums doubles, over
+// ~3 % of the taps).
+#ifndef DTX_FIRST_LONG_ACCS
+#define DTX_FIRST_LONG_ACCS 2
+#endif
+__device__ __forceinline__ int acc_stages(int nacc, int kblk) {
+    return nacc < DTX_FIRST_LONG_ACCS ? 2 * kblk : kblk;
+}
+
 // precision mode of a chunk: 1 = both cross terms in one 8-bit MMA (decided on the device by k0_split)
 __device__ __forceinline__ int item_x8(const K1Params& P, int chunk) {
     return P.a.chunk_mode ? P.a.chunk_mode[chunk] : 0;
@@ -187,7 +199,7 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
             x8_next = item_x8(P, P.a.items[item + gridDim.x].x);
         const int kblk = x8 ? P.a.kblk8 : P.a.kblk;
         {
-            int cib = 0, done = 0;
+            int cib = 0, done = 0, nacc = 0;
             for (int g = 0; g < P.nseg; ++g) {
                 const int nck = P.seg[g].ntaps / CHUNK_TAPS;
                 mbar_wait(&S.sigfull[sg.idx], sg.phase);
@@ -202,7 +214,7 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
                     const uint32_t ah = stage0 + st.idx * STAGE_BYTES;
                     const uint32_t al = ah + TILE_BYTES;
                     const uint32_t bo = kc * (CHUNK_TAPS * 2);
-                    const bool last = (cib + 1 == kblk) || (done + 1 == P.nchunks);
+                    const bool last = (cib + 1 == acc_stages(nacc, kblk)) || (done + 1 == P.nchunks);
                     if (ISSUE_LANE) {
                         if (x8) {
                             // both cross terms in ONE 8-bit MMA: the "lo" tiles hold byte pairs
@@ -239,6 +251,7 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
                     if (last) {
                         ac.advance();
                         cib = 0;
+                        ++nacc;
                     }
                 }
                 sg.advance();
@@ -248,6 +261,26 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
 }
 
 // ------------------------------------------------- drain + epilogue (8 warps, 256 threads)
+// Rare path of the epilogue read-out, kept out of the unrolled code: a piece of a rank > 16
+// subspace accumulates into its DS row.
+__device__ __noinline__ void epi_accumulate(float* dst, float4 acc) {
+    atomicAdd(dst, acc.x); atomicAdd(dst + 1, acc.y);
+    atomicAdd(dst + 2, acc.z); atomicAdd(dst + 3, acc.w);
+}
+
+// DS rows are written with the streaming (evict-first) hint so that the 18 GB DS stream of a launch
+// does not evict the L2-resident inputs; -DDTX_DS_STREAM=0 uses plain stores.
+#ifndef DTX_DS_STREAM
+#define DTX_DS_STREAM 1
+#endif
+__device__ __forceinline__ void store_ds_row(float* dst, float4 v) {
+#if DTX_DS_STREAM
+    __stcs(reinterpret_cast<float4*>(dst), v);
+#else
+    *reinterpret_cast<float4*>(dst) = v;
+#endif
+}
+
 template <int NQ, int MODE>
 __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uint32_t tmem, int warp,
                                            int lane) {
@@ -265,7 +298,8 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
         const int4 it = P.a.items[item];
         const ChunkDesc cd = P.a.chunks[it.x];
         const int kblk = item_x8(P, it.x) ? P.a.kblk8 : P.a.kblk;
-        const int ndrains = (P.nchunks + kblk - 1) / kblk;
+        int ndrains = 0;
+        for (int rem = P.nchunks; rem > 0; ++ndrains) rem -= acc_stages(ndrains, kblk);
         const float sc = P.a.chunk_scale[it.x] * P.u_inv_scale;
         const float* smu = reinterpret_cast<const float*>(S.norm + nm.idx * NORM_BUF_BYTES);
         const float* sie = smu + TILE_T;
@@ -300,7 +334,8 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
             const float nsumU = -P.a.binfo[b * VEC_PER_BLOCK + kl].sumU;
             float* ebuf = reinterpret_cast<float*>(S.epi + colhalf * EPI_BUF_BYTES);
             float* wr = ebuf + kl * EPI_STRIDE + (p ^ (kl >= 8 ? 2 : 0));
-            const float* pmu = smu + 8 * NCOL * colhalf + p;
+            // mu tile is phase-major per 1024-lag group (k0_norm): this thread's 128 columns are contiguous
+            const float* pmu = smu + (8 * NCOL * colhalf / 1024) * 1024 + p * 128 + (NCOL * colhalf) % 128;
             const float* pie4 = sie + 8 * NCOL * colhalf + lane * 4;
             float* dsbase = P.a.DS + cd.ds_off + static_cast<long long>(it.y) * TT + 8 * NCOL * colhalf + lane * 4;
             // read-out role of this warp: the subspaces whose first slot is lq, lq+4, lq+8, lq+12
@@ -310,10 +345,15 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
 #pragma unroll
             for (int c = 0; c < NCOL / EPI_QC; ++c) {
 #pragma unroll
-                for (int j = 0; j < EPI_QC; ++j) {
-                    const int i = c * EPI_QC + j;
-                    const float cc = fmaf(sums[i], sc, pmu[8 * i] * nsumU);
-                    wr[8 * j] = MODE == 0 ? cc * cc : cc;
+                for (int j4 = 0; j4 < EPI_QC / 4; ++j4) {
+                    const float4 m4 = *reinterpret_cast<const float4*>(pmu + c * EPI_QC + 4 * j4);
+                    const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = 4 * j4 + jj;
+                        const float cc = fmaf(sums[c * EPI_QC + j], sc, mm[jj] * nsumU);
+                        wr[8 * j] = MODE == 0 ? cc * cc : cc;
+                    }
                 }
                 named_bar_sync(1 + colhalf, 128);
                 float4 ie = *reinterpret_cast<const float4*>(pie4 + c * EPI_LAGS);
@@ -335,12 +375,15 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
                     }
                     acc.x *= ie.x; acc.y *= ie.y; acc.z *= ie.z; acc.w *= ie.w;
                     float* dst = dsbase + static_cast<long long>(hb[k].out_row) * cd.Tpad + c * EPI_LAGS;
-                    if (hb[k].nrows < 0) {   // piece of a rank > 16 subspace: accumulate into the row
+#ifdef DTX_EPI_INLINE_ATOMICS
+                    if (hb[k].nrows < 0) {
                         atomicAdd(dst, acc.x); atomicAdd(dst + 1, acc.y);
                         atomicAdd(dst + 2, acc.z); atomicAdd(dst + 3, acc.w);
-                    } else {
-                        *reinterpret_cast<float4*>(dst) = acc;
-                    }
+                    } else store_ds_row(dst, acc);
+#else
+                    if (hb[k].nrows < 0) epi_accumulate(dst, acc);
+                    else store_ds_row(dst, acc);
+#endif
                 }
                 named_bar_sync(1 + colhalf, 128);
             }
