@@ -129,7 +129,7 @@ __device__ __forceinline__ int item_x8(const K1Params& P, int chunk) {
     return P.a.chunk_mode ? P.a.chunk_mode[chunk] : 0;
 }
 
-// ------------------------------------------------------------------ producer (1 thread)
+// ------------------------------------------------ producer (warp 0, an elected lane issues)
 template <int NQ>
 __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) {
     constexpr int TT = 8 * NQ;
@@ -183,7 +183,7 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
     }
 }
 
-// ---------------------------------------------------------------- MMA issuer (1 thread)
+// ---------------------------------------------- MMA issuer (warp 1, an elected lane issues)
 template <int NQ>
 __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint32_t tmem) {
     const uint32_t idesc = idesc_f16_f32(128, NQ);

@@ -6,8 +6,10 @@
 //     the quantities scipy.stats.beta.fit(floc=0, fscale=1) and beta.nnlf reduce to)
 // plus the centred LTA mean of |DS| at each candidate (detect.py:501-524).
 //
-// HBM-bound: each row is streamed twice (second pass hits L2 for rows up to ~1.5 MB).
-// One CTA per row, 128-bit loads, shared-memory privatised histogram.
+// HBM-bound: k3_fast_kernel streams each row once (four 128-bit loads in flight per thread,
+// float32 pre-binning, per-thread run-length histogram); rows with NaN / inf or too many
+// candidates are redone by the two-pass k3_kernel (second pass hits L2 for rows up to ~1.5 MB).
+// One CTA per row, shared-memory privatised histogram.
 #include "dtx_kernels.cuh"
 
 namespace dtx {
@@ -171,6 +173,7 @@ k3_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, in
 // candidates staged in shared memory.  Rows with NaN / inf or more than K3_STAGE candidates
 // are flagged (bit 2) and redone by k3_kernel, which carries the reference's corner rules.
 constexpr int K3_STAGE = 1024;
+template <bool FAS>
 __global__ void __launch_bounds__(K3_THREADS)
 k3_fast_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, int S,
                const float* __restrict__ thr, float* __restrict__ rowmax, int* __restrict__ rowflags,
@@ -197,6 +200,13 @@ k3_fast_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunk
     float mfin = -INFINITY;
     int bad = 0, cur = -1, cnt = 0;
     double f1 = 0, f2 = 0, f3 = 0, f4 = 0;
+    auto fas_add = [&](float a) {
+        const double d = static_cast<double>(a);
+        f1 += d; f2 += d * d;
+        // float32 DS can round to exactly 0 (or 1) where float64 would not: keep the logs finite
+        f3 += static_cast<double>(logf(fmaxf(a, 1e-30f)));
+        f4 += static_cast<double>(log1pf(-fminf(a, 0.99999994f)));
+    };
     auto one = [&](float a, int i) {
         if (isnan(a) || isinf(a)) { bad = 1; return; }
         mfin = fmaxf(mfin, a);
@@ -211,47 +221,67 @@ k3_fast_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunk
             const int k = atomicAdd(&sh_ncand, 1);
             if (k < K3_STAGE) sh_cand[k] = make_int2(i, __float_as_int(a));
         }
-        if (fas) {
-            const double d = static_cast<double>(a);
-            f1 += d; f2 += d * d;
-            // float32 DS can round to exactly 0 (or 1) where float64 would not: keep the logs finite
-            f3 += static_cast<double>(logf(fmaxf(a, 1e-30f)));
-            f4 += static_cast<double>(log1pf(-fminf(a, 0.99999994f)));
+        if (FAS) fas_add(a);
+    };
+    // Four values at once, branch free: if all four are finite, sit well inside ONE bin (more than
+    // 1e-3 of a bin away from its edges, so float32 rounding cannot move them), that bin is the
+    // current run's and none reaches the threshold, the run just grows by four.  Noise DS does
+    // that almost always; everything else takes the per-value path above.
+    const float toff = -flo * finv;
+    auto quad = [&](const float4 v, int i) {
+        const float curf = static_cast<float>(cur);
+        const float t0 = fmaf(v.x, finv, toff), t1 = fmaf(v.y, finv, toff), t2 = fmaf(v.z, finv, toff),
+                    t3 = fmaf(v.w, finv, toff);
+        const float g0 = floorf(t0), g1 = floorf(t1), g2 = floorf(t2), g3 = floorf(t3);
+        const bool inside = fabsf(t0 - g0 - 0.5f) < 0.499f && fabsf(t1 - g1 - 0.5f) < 0.499f &&
+                            fabsf(t2 - g2 - 0.5f) < 0.499f && fabsf(t3 - g3 - 0.5f) < 0.499f;
+        const bool same = cur >= 0 && g0 == curf && g1 == curf && g2 == curf && g3 == curf;
+        const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        if (inside && same && m4 < th) {
+            cnt += 4;
+            mfin = fmaxf(mfin, m4);
+            if (FAS) {
+                // quad partial sums in float32 (4 terms), accumulated in float64
+                f1 += static_cast<double>((v.x + v.y) + (v.z + v.w));
+                f2 += static_cast<double>(fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w));
+                f3 += static_cast<double>((logf(fmaxf(v.x, 1e-30f)) + logf(fmaxf(v.y, 1e-30f))) +
+                                          (logf(fmaxf(v.z, 1e-30f)) + logf(fmaxf(v.w, 1e-30f))));
+                f4 += static_cast<double>((log1pf(-fminf(v.x, 0.99999994f)) + log1pf(-fminf(v.y, 0.99999994f))) +
+                                          (log1pf(-fminf(v.z, 0.99999994f)) + log1pf(-fminf(v.w, 0.99999994f))));
+            }
+        } else {
+            one(v.x, i); one(v.y, i + 1); one(v.z, i + 2); one(v.w, i + 3);
         }
     };
     const int T4 = T & ~3;
     constexpr int STRIDE = K3_THREADS * 4;
     int i0 = tid * 4;
-    // four independent 128-bit loads in flight per thread (the per-element work below is a
-    // dependent chain; without this the kernel is latency-bound at a third of the HBM rate)
+    // four independent 128-bit loads in flight per thread
     for (; i0 + 3 * STRIDE < T4; i0 += 4 * STRIDE) {
         const float4 v0 = __ldcs(reinterpret_cast<const float4*>(x + i0));
         const float4 v1 = __ldcs(reinterpret_cast<const float4*>(x + i0 + STRIDE));
         const float4 v2 = __ldcs(reinterpret_cast<const float4*>(x + i0 + 2 * STRIDE));
         const float4 v3 = __ldcs(reinterpret_cast<const float4*>(x + i0 + 3 * STRIDE));
-        one(v0.x, i0); one(v0.y, i0 + 1); one(v0.z, i0 + 2); one(v0.w, i0 + 3);
-        one(v1.x, i0 + STRIDE); one(v1.y, i0 + STRIDE + 1); one(v1.z, i0 + STRIDE + 2); one(v1.w, i0 + STRIDE + 3);
-        one(v2.x, i0 + 2 * STRIDE); one(v2.y, i0 + 2 * STRIDE + 1); one(v2.z, i0 + 2 * STRIDE + 2);
-        one(v2.w, i0 + 2 * STRIDE + 3);
-        one(v3.x, i0 + 3 * STRIDE); one(v3.y, i0 + 3 * STRIDE + 1); one(v3.z, i0 + 3 * STRIDE + 2);
-        one(v3.w, i0 + 3 * STRIDE + 3);
+        quad(v0, i0);
+        quad(v1, i0 + STRIDE);
+        quad(v2, i0 + 2 * STRIDE);
+        quad(v3, i0 + 3 * STRIDE);
     }
-    for (int i = i0; i < T4; i += STRIDE) {
-        const float4 v = *reinterpret_cast<const float4*>(x + i);
-        one(v.x, i); one(v.y, i + 1); one(v.z, i + 2); one(v.w, i + 3);
-    }
+    for (int i = i0; i < T4; i += STRIDE) quad(*reinterpret_cast<const float4*>(x + i), i);
     for (int i = T4 + tid; i < T; i += K3_THREADS) one(x[i], i);
     if (cnt > 0 && cur >= 0) atomicAdd(&sh_hist[cur], cnt);
     mfin = warp_max(mfin);
     if (__any_sync(0xffffffffu, bad) && l == 0) sh_bad = 1;
     if (l == 0) sh_max[w] = mfin;
-    if (fas) {
+    if (FAS) {
         f1 = warp_sum(f1); f2 = warp_sum(f2); f3 = warp_sum(f3); f4 = warp_sum(f4);
         if (l == 0) { sh_d[w][0] = f1; sh_d[w][1] = f2; sh_d[w][2] = f3; sh_d[w][3] = f4; }
     }
     __syncthreads();
     const int nc = sh_ncand;
-    if (sh_bad || nc > K3_STAGE) {          // hand the row to the two-pass kernel
+    const int badrow = sh_bad;
+    __syncthreads();                        // (sh_base below shares a vector load with these two)
+    if (badrow || nc > K3_STAGE) {          // hand the row to the two-pass kernel
         if (tid == 0) rowflags[row] = 4;
         return;
     }
@@ -376,8 +406,12 @@ void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, c
                double hist_hi, Candidate* d_cand, int cand_cap, int* d_ncand, double* d_fas,
                cudaStream_t st) {
     const dim3 grid(S, nchunks);
-    k3_fast_kernel<<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist, hist_lo,
-                                                hist_hi, d_cand, cand_cap, d_ncand, d_fas);
+    if (d_fas)
+        k3_fast_kernel<true><<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist,
+                                                          hist_lo, hist_hi, d_cand, cand_cap, d_ncand, d_fas);
+    else
+        k3_fast_kernel<false><<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist,
+                                                           hist_lo, hist_hi, d_cand, cand_cap, d_ncand, nullptr);
     k3_kernel<<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist, hist_lo, hist_hi,
                                            d_cand, cand_cap, d_ncand, d_fas, 1);
 }
