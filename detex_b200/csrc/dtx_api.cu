@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -190,18 +191,37 @@ int dtx_sync(dtx_ctx* ctx) {
     return DTX_OK;
 }
 
-int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank_off, int S, int n,
-                  int Nc, const double* thresholds) {
-    if (!ctx) return DTX_ERR_ARG;
-    if (!U || !rank_off || S < 1 || Nc < 1 || n < Nc || n % Nc != 0)
-        return fail(ctx, DTX_ERR_ARG, "dtx_set_bases: bad shape (need S>=1, n % Nc == 0)");
-    DTX_CUDA(cudaSetDevice(ctx->device));
+// Basis set from vectors already in bs.d_U ([R][n] float64 on the device; `fill_U`, if given, is
+// called once the buffer exists and puts them there).  All per-vector statistics come from one
+// reduction kernel, so nothing here is O(R*n) on the host.
+static int set_bases_device(dtx_ctx* ctx, int set_id, const std::function<int(double*)>& fill_U,
+                            const int32_t* rank_off, int S, int n, int Nc, const double* thresholds) {
     const int R = rank_off[S];
     for (int s = 0; s < S; ++s) {
         const int r = rank_off[s + 1] - rank_off[s];
         if (r < 1) return fail(ctx, DTX_ERR_ARG, "dtx_set_bases: subspace rank must be >= 1");
     }
+    {   // every argument check comes before the stored vectors are touched
+        const int kc = round_up(n / Nc + 7, CHUNK_TAPS);
+        if (Nc * ((kc + MAX_SEG_TAPS - 1) / MAX_SEG_TAPS) > MAX_SEGS)
+            return fail(ctx, DTX_ERR_ARG, "dtx_set_bases: template too long");
+    }
     BasisSet& bs = ctx->sets[set_id];
+    DTX_CUDA(bs.d_U.reserve(static_cast<size_t>(R) * n));
+    {
+        const int rc = fill_U(bs.d_U.p);
+        if (rc != DTX_OK) return rc;
+    }
+    // per row: sum, max |u|, sum u^2, sum u^4
+    DevBuf<double> d_stats;
+    DTX_CUDA(d_stats.reserve(static_cast<size_t>(R) * 4));
+    launch_basis_row_stats(bs.d_U.p, R, n, d_stats.p, ctx->stream);
+    ctx->launches += 1;
+    DTX_CUDA(cudaGetLastError());
+    std::vector<double> stats(static_cast<size_t>(R) * 4);
+    DTX_CUDA(cudaMemcpyAsync(stats.data(), d_stats.p, sizeof(double) * R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+    d_stats.release();
     for (auto& kv : bs.ev_blob) kv.second.release();   // events belong to the previous bases
     bs.ev_blob.clear();
     bs.ev_meta.clear();
@@ -261,18 +281,13 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
     std::vector<int> slot_row(static_cast<size_t>(lay.nblocks) * VEC_PER_BLOCK, -1);
     std::vector<BlockInfo> binfo(static_cast<size_t>(lay.nblocks) * VEC_PER_BLOCK);
     double umax = 0.0;
-    for (long long i = 0; i < static_cast<long long>(R) * n; ++i) umax = std::max(umax, std::fabs(U[i]));
+    for (int k = 0; k < R; ++k) umax = std::max(umax, stats[static_cast<size_t>(k) * 4 + 1]);
     int eu = 0;
     if (umax > 0 && std::isfinite(umax)) eu = 13 - std::ilogb(umax);  // max|U| * 2^eu in [2^13, 2^14)
     lay.u_exp = eu;
     bs.nu4 = 0.0;
     for (int k = 0; k < R; ++k) {
-        double s2 = 0, s4 = 0;
-        for (int j = 0; j < n; ++j) {
-            const double v = U[static_cast<long long>(k) * n + j];
-            s2 += v * v;
-            s4 += (v * v) * (v * v);
-        }
+        const double s2 = stats[static_cast<size_t>(k) * 4 + 2], s4 = stats[static_cast<size_t>(k) * 4 + 3];
         const double q = s2 > 0 ? s4 / (s2 * s2) : 1.0;
         bs.nu4 = std::max(bs.nu4, std::isfinite(q) ? q : 1.0);
     }
@@ -290,16 +305,13 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
                 const int row = pc.row0 + k;
                 slot_row[static_cast<size_t>(b) * VEC_PER_BLOCK + slot] = row;
                 BlockInfo& bi = binfo[static_cast<size_t>(b) * VEC_PER_BLOCK + slot];
-                double su = 0;   // |sum| <= sqrt(n): plain double summation is exact to ~1e-13
-                for (int j = 0; j < n; ++j) su += U[static_cast<long long>(row) * n + j];
-                bi.sumU = static_cast<float>(su);
+                bi.sumU = static_cast<float>(stats[static_cast<size_t>(row) * 4]);   // float64 block reduction
                 bi.out_row = s;
                 bi.nrows = (k == 0) ? (pc.split ? -r : r) : 0;   // negative: accumulate into the row
                 bi.seg_end = slot - k + r;
             }
         }
     }
-    DTX_CUDA(bs.d_U.reserve(static_cast<size_t>(R) * n));
     DTX_CUDA(bs.d_rank_off.reserve(S + 1));
     DTX_CUDA(bs.d_slot_row.reserve(slot_row.size()));
     DTX_CUDA(bs.d_binfo.reserve(binfo.size()));
@@ -310,7 +322,6 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
     DTX_CUDA(bs.d_Aimg.reserve(img_bytes));
     // synchronous copies: the caller's arrays need not outlive this call
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));
-    DTX_CUDA(cudaMemcpy(bs.d_U.p, U, sizeof(double) * R * n, cudaMemcpyHostToDevice));
     DTX_CUDA(cudaMemcpy(bs.d_rank_off.p, rank_off, sizeof(int) * (S + 1), cudaMemcpyHostToDevice));
     DTX_CUDA(cudaMemcpy(bs.d_slot_row.p, slot_row.data(), sizeof(int) * slot_row.size(), cudaMemcpyHostToDevice));
     DTX_CUDA(cudaMemcpy(bs.d_binfo.p, binfo.data(), sizeof(BlockInfo) * binfo.size(), cudaMemcpyHostToDevice));
@@ -326,6 +337,22 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
     DTX_CUDA(cudaGetLastError());
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));
     return DTX_OK;
+}
+
+int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank_off, int S, int n,
+                  int Nc, const double* thresholds) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (!U || !rank_off || S < 1 || Nc < 1 || n < Nc || n % Nc != 0)
+        return fail(ctx, DTX_ERR_ARG, "dtx_set_bases: bad shape (need S>=1, n % Nc == 0)");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    const size_t count = static_cast<size_t>(rank_off[S]) * n;
+    auto fill = [&](double* d_U) -> int {
+        // synchronous copy: the caller's array need not outlive this call
+        DTX_CUDA(cudaStreamSynchronize(ctx->stream));
+        DTX_CUDA(cudaMemcpy(d_U, U, sizeof(double) * count, cudaMemcpyHostToDevice));
+        return DTX_OK;
+    };
+    return set_bases_device(ctx, set_id, fill, rank_off, S, n, Nc, thresholds);
 }
 
 static int set_chunk_table(dtx_ctx* ctx, int nchunks, const int64_t* L, const int64_t* offs, int dtype) {
@@ -936,30 +963,16 @@ static int ccx_tcgen05(dtx_ctx* ctx, const void* X, int dtype, const void* dX, i
     const int ns = n / Nc, trunc = n / (2 * Nc) - 1, nl = 2 * ns - 1 - 2 * trunc;
     const int rows = row_end - row_begin;
     cudaStream_t st = ctx->stream;
-    // templates: x / ||x - mean||  (zero rows for zeroed-out waveforms)
-    std::vector<double> U(static_cast<size_t>(rows) * n);
+    // templates: x / ||x - mean||  (zero rows for zeroed-out waveforms), built on the device
     std::vector<int32_t> roff(rows + 1);
     for (int r = 0; r <= rows; ++r) roff[r] = r;
-    for (int r = 0; r < rows; ++r) {
-        const size_t src = static_cast<size_t>(row_begin + r) * n;
-        double s1 = 0;
-        for (int i = 0; i < n; ++i)
-            s1 += dtype == DTX_F32 ? static_cast<const float*>(X)[src + i] : static_cast<const double*>(X)[src + i];
-        const double mean = s1 / n;
-        double s2 = 0;
-        for (int i = 0; i < n; ++i) {
-            const double v = (dtype == DTX_F32 ? static_cast<const float*>(X)[src + i]
-                                               : static_cast<const double*>(X)[src + i]) - mean;
-            s2 += v * v;
-        }
-        const double nrm = std::sqrt(s2);
-        for (int i = 0; i < n; ++i) {
-            const double v = dtype == DTX_F32 ? static_cast<const float*>(X)[src + i]
-                                              : static_cast<const double*>(X)[src + i];
-            U[static_cast<size_t>(r) * n + i] = nrm > 0 ? v / nrm : 0.0;
-        }
-    }
-    int rc = dtx_set_bases(ctx, CCX_SET_ID, U.data(), roff.data(), rows, n, Nc, nullptr);
+    auto fill = [&](double* d_U) -> int {
+        launch_ccx_templates(dX, dtype == DTX_F32, n, row_begin, rows, d_U, st);
+        ctx->launches += 1;
+        DTX_CUDA(cudaGetLastError());
+        return DTX_OK;
+    };
+    int rc = set_bases_device(ctx, CCX_SET_ID, fill, roff.data(), rows, n, Nc, nullptr);
     if (rc != DTX_OK) return rc;
     BasisSet& bs = ctx->sets[CCX_SET_ID];
     const int P = ns - trunc - 1;

@@ -76,6 +76,8 @@ void launch_k0(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nc
                unsigned* d_k4bits, int* d_chunk_mode, cudaStream_t st);
 
 // basis image (k1_project.cu)
+// per row of U: {sum, max |u|, sum u^2, sum u^4} (float64)
+void launch_basis_row_stats(const double* d_U, int R, int n, double* d_out, cudaStream_t st);
 void launch_basis_image(const double* d_U, const int* d_slot_row, const BasisLayout& lay,
                         uint8_t* d_Aimg, int x8, cudaStream_t st);
 
@@ -128,6 +130,8 @@ void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int r
                      const double* wa, const double* wb, const double* es, const double* ed, double* d_cc,
                      int* d_lag, double* d_sub, int num_sms, cudaStream_t st);
 void launch_corr0(const double* d_X, int N, int n, double* d_out, cudaStream_t st);
+void launch_ccx_templates(const void* d_X, int dtype_f32, int n, int row_begin, int rows, double* d_U,
+                          cudaStream_t st);
 void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int nsig, int P, int Lc, double* out,
                     cudaStream_t st);
 void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsig, const void* d_X, int dtype_f32,

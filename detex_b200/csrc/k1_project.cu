@@ -509,6 +509,36 @@ void launch_k1_t(const K1Params& P, int grid, cudaStream_t st) {
 
 }  // namespace
 
+// Per basis vector (row of U): sum, max |u|, sum u^2, sum u^4 in float64 -- what dtx_set_bases needs
+// for the mu * sumU correction, the fp16 scale exponent and the precision policy.  One block per row.
+__global__ void __launch_bounds__(256)
+basis_row_stats_kernel(const double* __restrict__ U, int n, double* __restrict__ out) {
+    const double* u = U + static_cast<long long>(blockIdx.x) * n;
+    double s1 = 0, s2 = 0, s4 = 0, mx = 0;
+    for (int j = threadIdx.x; j < n; j += 256) {
+        const double v = u[j];
+        s1 += v;
+        s2 += v * v;
+        s4 += (v * v) * (v * v);
+        mx = fmax(mx, fabs(v));   // NaN-propagating max is not needed: a NaN shows up in s1
+    }
+    __shared__ double sh[4][8];
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        s4 += __shfl_xor_sync(0xffffffffu, s4, o);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = s1; sh[1][w] = s2; sh[2][w] = s4; sh[3][w] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) { s1 += sh[0][i]; s2 += sh[1][i]; s4 += sh[2][i]; mx = fmax(mx, sh[3][i]); }
+        double* o = out + static_cast<long long>(blockIdx.x) * 4;
+        o[0] = s1; o[1] = mx; o[2] = s2; o[3] = s4;
+    }
+}
+
 int k1_smem_bytes() { return SMEM_BYTES; }
 
 void launch_basis_image(const double* d_U, const int* d_slot_row, const BasisLayout& lay,
@@ -516,6 +546,10 @@ void launch_basis_image(const double* d_U, const int* d_slot_row, const BasisLay
     const long long total = static_cast<long long>(lay.nblocks) * lay.nchunks * 2 * 128 * 8;
     const int grid = static_cast<int>((total + 255) / 256);
     basis_image_kernel<<<grid, 256, 0, st>>>(d_U, d_slot_row, lay, d_Aimg, x8);
+}
+
+void launch_basis_row_stats(const double* d_U, int R, int n, double* d_out, cudaStream_t st) {
+    basis_row_stats_kernel<<<R, 256, 0, st>>>(d_U, n, d_out);
 }
 
 void launch_k1(const K1Args& a, const BasisLayout& lay, cudaStream_t st) {

@@ -396,6 +396,49 @@ void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int r
     }
 }
 
+// Events [row_begin, row_begin + rows) as rank-1 templates of the tensor-core engine:
+// x / ||x - mean|| in float64 (zero rows for zeroed-out waveforms).  One block per event.
+template <typename T>
+__global__ void __launch_bounds__(256)
+ccx_templates_kernel(const T* __restrict__ X, int n, int row_begin, double* __restrict__ U) {
+    const T* x = X + static_cast<long long>(row_begin + blockIdx.x) * n;
+    double* u = U + static_cast<long long>(blockIdx.x) * n;
+    __shared__ double sh[8];
+    __shared__ double bc;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    auto block_sum = [&](double v) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if (l == 0) sh[w] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0;
+            for (int i = 0; i < 8; ++i) t += sh[i];
+            bc = t;
+        }
+        __syncthreads();
+        return bc;
+    };
+    double s1 = 0;
+    for (int i = threadIdx.x; i < n; i += 256) s1 += static_cast<double>(x[i]);
+    const double mean = block_sum(s1) / n;
+    double s2 = 0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double v = static_cast<double>(x[i]) - mean;
+        s2 += v * v;
+    }
+    const double nrm = sqrt(block_sum(s2));
+    for (int i = threadIdx.x; i < n; i += 256) u[i] = nrm > 0 ? static_cast<double>(x[i]) / nrm : 0.0;
+}
+
+void launch_ccx_templates(const void* d_X, int dtype_f32, int n, int row_begin, int rows, double* d_U,
+                          cudaStream_t st) {
+    if (dtype_f32)
+        ccx_templates_kernel<float><<<rows, 256, 0, st>>>(static_cast<const float*>(d_X), n, row_begin, d_U);
+    else
+        ccx_templates_kernel<double><<<rows, 256, 0, st>>>(static_cast<const double*>(d_X), n, row_begin, d_U);
+}
+
 void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int nsig, int P, int Lc, double* out,
                     cudaStream_t st) {
     const dim3 grid(32, nsig);
