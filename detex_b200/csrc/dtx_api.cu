@@ -5,6 +5,7 @@
 // launching K0 -> K1 -> K3 on the context's stream.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -104,6 +105,7 @@ struct dtx_ctx {
     DevBuf<double> d_DS64, d_sum;
     DevBuf<unsigned> d_maxbits, d_k4bits;
     DevBuf<int> d_chunk_mode;     // per chunk: 1 = 8-bit cross terms in the last run
+    int sta_window = 0;           // triggerSTATime in samples (0 = reference default: STA = |DS|)
     double x8_eps = 2e-6;         // adaptive engine: admitted RMS error of a normalised projection
     DevBuf<int> d_rowflags, d_ncand;
     DevBuf<Candidate> d_cand;
@@ -441,7 +443,9 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     // (>= 4 waves of items per (group, block) pass.  Group size 8 vs 4 long chunks makes no measurable
     // difference in time or DRAM traffic: ncu shows ~17-20 GB of L2 read misses per 48-chunk launch
     // either way, see profiles/r01_k1_ncu_summary.md)
-    const int group = std::max(1, (4 * ctx->num_sms + tiles_per_chunk - 1) / tiles_per_chunk);
+    int group = std::max(1, (4 * ctx->num_sms + tiles_per_chunk - 1) / tiles_per_chunk);
+    if (const char* g = std::getenv("DTX_K1_GROUP"))   // experiment knob (chunks per group)
+        if (std::atoi(g) > 0) group = std::atoi(g);
     // the list only depends on the batch's shape: reuse the device copy when it has not changed
     std::vector<int> sig_key{nq, lay.nblocks, group, nchunks};
     for (int i = 0; i < nchunks; ++i) {
@@ -570,7 +574,7 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
     ctx->launches += 2;  // k3_fast_kernel + k3_kernel (flagged rows only)
     if (bs.has_thr && lta_window > 0) {
         launch_lta(ctx->d_DS.p, ctx->d_chunks.p, S, ctx->d_rowflags.p, ctx->d_cand.p, ctx->d_ncand.p,
-                   ctx->cand_cap, lta_window, st);
+                   ctx->cand_cap, lta_window, ctx->sta_window, st);
         DTX_CUDA(cudaGetLastError());
         ctx->launches += 1;
     }
@@ -631,6 +635,13 @@ int dtx_get_ds64(dtx_ctx* ctx, int chunk, int subspace, double* out, int64_t cou
     return DTX_OK;
 }
 
+int dtx_set_trigger_sta(dtx_ctx* ctx, int sta_window) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (sta_window < 0) return fail(ctx, DTX_ERR_ARG, "dtx_set_trigger_sta: window must be >= 0");
+    ctx->sta_window = sta_window;
+    return DTX_OK;
+}
+
 int dtx_get_stalta(dtx_ctx* ctx, int chunk, int subspace, int W, float* out, int64_t count) {
     if (!ctx || !out) return DTX_ERR_ARG;
     if (!ctx->ran || chunk < 0 || chunk >= ctx->nchunks || subspace < 0 || subspace >= ctx->run_S || W < 1)
@@ -638,7 +649,8 @@ int dtx_get_stalta(dtx_ctx* ctx, int chunk, int subspace, int W, float* out, int
     const ChunkDesc& cd = ctx->h_chunks[chunk];
     if (count < cd.T) return fail(ctx, DTX_ERR_CAPACITY, "dtx_get_stalta: buffer smaller than T");
     DTX_CUDA(cudaSetDevice(ctx->device));
-    if (cd.T < W) {
+    const int Wsta = ctx->sta_window;
+    if (cd.T < W || cd.T < Wsta) {
         for (int i = 0; i < cd.T; ++i) out[i] = NAN;
         return DTX_OK;
     }
@@ -647,9 +659,9 @@ int dtx_get_stalta(dtx_ctx* ctx, int chunk, int subspace, int W, float* out, int
                              sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));
     DevBuf<float> tmp;
-    DTX_CUDA(tmp.reserve(cd.T));
-    launch_stalta_dense(ctx->d_DS.p + cd.ds_off + static_cast<long long>(subspace) * cd.Tpad, cd.T, W,
-                        (flags & 2) ? 1 : 0, tmp.p, ctx->stream);
+    DTX_CUDA(tmp.reserve(static_cast<size_t>(cd.T) * (Wsta > 0 ? 2 : 1)));
+    launch_stalta_dense(ctx->d_DS.p + cd.ds_off + static_cast<long long>(subspace) * cd.Tpad, cd.T, W, Wsta,
+                        (flags & 2) ? 1 : 0, tmp.p, tmp.p + cd.T, ctx->stream);
     DTX_CUDA(cudaGetLastError());
     DTX_CUDA(cudaMemcpyAsync(out, tmp.p, sizeof(float) * cd.T, cudaMemcpyDeviceToHost, ctx->stream));
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -114,14 +114,14 @@ struct Candidate {
     int row;     // chunk * S + subspace
     int t;       // lag index
     float ds;    // detection statistic
-    float lta;   // centred |DS| mean over the LTA window (filled by launch_lta)
+    float lta;   // denominator of DS_STALTA: |ds| / lta = STA / LTA at t (filled by launch_lta)
 };
 void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, const float* d_thr,
                float* d_rowmax, int* d_rowflags, unsigned long long* d_hist, double hist_lo,
                double hist_hi, Candidate* d_cand, int cand_cap, int* d_ncand,
                double* d_fas /*[S][4] or null*/, cudaStream_t st);
 void launch_lta(const float* DS, const ChunkDesc* d_chunks, int S, const int* d_rowflags,
-                Candidate* d_cand, const int* d_ncand, int cand_cap, int W, cudaStream_t st);
+                Candidate* d_cand, const int* d_ncand, int cand_cap, int W, int Wsta, cudaStream_t st);
 
 // k4_ccx.cu : pairwise CCX
 void launch_ccx_stats(const void* d_X, int dtype_f32, int N, int n, int Nc, double* wa, double* wb, double* es,
@@ -167,6 +167,7 @@ int preproc_seg();
 void launch_stalta_max(const void* raw, int dtype_f32, const long long* d_raw_off, const int* d_Ls, int nchunks,
                        int maxLs, int Nc, int chan, int nsta, int nlta, unsigned* d_out_bits, cudaStream_t st);
 
-void launch_stalta_dense(const float* row, int T, int W, int zero_inf, float* out, cudaStream_t st);
+void launch_stalta_dense(const float* row, int T, int W, int Wsta, int zero_inf, float* out, float* tmp,
+                         cudaStream_t st);
 
 }  // namespace dtx

@@ -129,11 +129,40 @@ __device__ __forceinline__ int item_x8(const K1Params& P, int chunk) {
     return P.a.chunk_mode ? P.a.chunk_mode[chunk] : 0;
 }
 
+// L2 eviction hints of the producer's bulk copies (profiles/r01_k1_traffic_ab.md).
+// DTX_SIG_HINT = 1 (default): the split signal and the norm tiles are copied evict_last -- they are
+// re-read once per basis-block pass (~1 ms apart) and the 18 GB DS write stream of a launch would
+// otherwise push them out (DRAM reads of a 48-chunk launch 16.0 -> 11.2 GB, the level of a build
+// that does not write DS at all).  DTX_A_HINT = 1 marks the basis image evict_first; measured
+// dead end (318 GB of reads: the CTAs stream a block at slightly different times), kept for the record.
+#ifndef DTX_SIG_HINT
+#define DTX_SIG_HINT 1
+#endif
+#ifndef DTX_A_HINT
+#define DTX_A_HINT 0
+#endif
+#if DTX_SIG_HINT
+#define SIG_G2S(dst, src, bytes, bar) bulk_g2s_hint(dst, src, bytes, bar, pol_sig)
+#else
+#define SIG_G2S(dst, src, bytes, bar) bulk_g2s(dst, src, bytes, bar)
+#endif
+#if DTX_A_HINT
+#define A_G2S(dst, src, bytes, bar) bulk_g2s_hint(dst, src, bytes, bar, pol_a)
+#else
+#define A_G2S(dst, src, bytes, bar) bulk_g2s(dst, src, bytes, bar)
+#endif
+
 // ------------------------------------------------ producer (warp 0, an elected lane issues)
 template <int NQ>
 __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) {
     constexpr int TT = 8 * NQ;
     Ring st(STAGES), sg(2), nm(2);
+#if DTX_SIG_HINT
+    const uint64_t pol_sig = l2_policy_evict_last();
+#endif
+#if DTX_A_HINT
+    const uint64_t pol_a = l2_policy_evict_first();
+#endif
     for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
         const int4 it = P.a.items[item];
         const ChunkDesc cd = P.a.chunks[it.x];
@@ -141,9 +170,9 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
         mbar_wait(&S.normempty[nm.idx], nm.phase ^ 1);
         if (ISSUE_LANE) {
             mbar_arrive_expect_tx(&S.normfull[nm.idx], 2 * TT * 4);
-            bulk_g2s(S.norm + nm.idx * NORM_BUF_BYTES, P.a.mu + cd.norm_off + static_cast<long long>(it.y) * TT,
+            SIG_G2S(S.norm + nm.idx * NORM_BUF_BYTES, P.a.mu + cd.norm_off + static_cast<long long>(it.y) * TT,
                      TT * 4, &S.normfull[nm.idx]);
-            bulk_g2s(S.norm + nm.idx * NORM_BUF_BYTES + TILE_T * 4,
+            SIG_G2S(S.norm + nm.idx * NORM_BUF_BYTES + TILE_T * 4,
                      P.a.invE + cd.norm_off + static_cast<long long>(it.y) * TT, TT * 4, &S.normfull[nm.idx]);
         }
         ISSUE_SYNC();
@@ -160,8 +189,8 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
                 if (ISSUE_LANE) {
                     mbar_arrive_expect_tx(&S.sigfull[sg.idx], 2 * bytes);
                     const __half* src = sig0 + static_cast<long long>(sgm.chan * 2) * cd.Lpad + sgm.tap0;
-                    bulk_g2s(S.sig + sg.idx * SIG_BUF_BYTES, src, bytes, &S.sigfull[sg.idx]);
-                    bulk_g2s(S.sig + sg.idx * SIG_BUF_BYTES + SIG_HALFS * 2, src + cd.Lpad, bytes,
+                    SIG_G2S(S.sig + sg.idx * SIG_BUF_BYTES, src, bytes, &S.sigfull[sg.idx]);
+                    SIG_G2S(S.sig + sg.idx * SIG_BUF_BYTES + SIG_HALFS * 2, src + cd.Lpad, bytes,
                              &S.sigfull[sg.idx]);
                 }
                 ISSUE_SYNC();
@@ -171,7 +200,7 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
                     mbar_wait(&S.empty[st.idx], st.phase ^ 1);
                     if (ISSUE_LANE) {
                         mbar_arrive_expect_tx(&S.full[st.idx], STAGE_BYTES);
-                        bulk_g2s(S.stage + st.idx * STAGE_BYTES,
+                        A_G2S(S.stage + st.idx * STAGE_BYTES,
                                  ablk + static_cast<size_t>(sgm.chunk0 + kc) * STAGE_BYTES, STAGE_BYTES,
                                  &S.full[st.idx]);
                     }
@@ -274,6 +303,10 @@ __device__ __noinline__ void epi_accumulate(float* dst, float4 acc) {
 #define DTX_DS_STREAM 1
 #endif
 __device__ __forceinline__ void store_ds_row(float* dst, float4 v) {
+#ifdef DTX_NO_DS_STORE   // traffic experiment only: results are NOT written (except NaN, never true here)
+    if (v.x == 1.2345e30f) *reinterpret_cast<float4*>(dst) = v;
+    return;
+#endif
 #if DTX_DS_STREAM
     __stcs(reinterpret_cast<float4*>(dst), v);
 #else

@@ -317,11 +317,32 @@ k3_fast_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunk
 }
 
 // One warp per candidate: centred rolling mean of |DS| with pandas' window placement and
-// _replaceNanWithMean's edge rule (detect.py:517-524).
+// _replaceNanWithMean's edge rule (detect.py:517-524).  `x` is the DS row, `i` the lag.
+__device__ __forceinline__ float centred_abs_mean(const float* __restrict__ x, int T, int W, int i,
+                                                  bool zero_inf, int l) {
+    if (T < W) return nanf("");
+    const int off = (W - 1) / 2;
+    const int first = W - 1 - off, last = T - 1 - off;  // valid centres
+    if (i < first) i = (first + 1 <= last) ? first + 1 : first;
+    if (i > last) i = last;
+    const int a0 = i - (W - 1) + off;
+    double acc = 0;
+    for (int j = l; j < W; j += 32) {
+        float v = x[a0 + j];
+        if (zero_inf && isinf(v)) v = 0.f;
+        acc += fabs(static_cast<double>(v));
+    }
+    acc = warp_sum(acc);
+    return static_cast<float>(acc / W);
+}
+
+// cand.lta = the denominator of DS_STALTA (`_getStaLtaArray`, detect.py:501-515):
+//   Wsta == 0 (reference default, STA = |DS|):  LTA mean;
+//   Wsta  > 0:  LTA mean * |DS[t]| / STA mean, so that |DS[t]| / lta == STA / LTA in both cases.
 __global__ void __launch_bounds__(256)
 lta_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, int S,
            const int* __restrict__ rowflags, Candidate* __restrict__ cand,
-           const int* __restrict__ ncand, int cand_cap, int W) {
+           const int* __restrict__ ncand, int cand_cap, int W, int Wsta) {
     const int n = min(*ncand, cand_cap);
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
     if (wid >= n) return;
@@ -329,23 +350,11 @@ lta_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, i
     const ChunkDesc cd = chunks[c.row / S];
     const float* x = DS + cd.ds_off + static_cast<long long>(c.row % S) * cd.Tpad;
     const bool zero_inf = (rowflags[c.row] & 2) != 0;
-    const int T = cd.T;
-    float out = nanf("");
-    if (T >= W) {
-        const int off = (W - 1) / 2;
-        const int first = W - 1 - off, last = T - 1 - off;  // valid centres
-        int i = c.t;
-        if (i < first) i = (first + 1 <= last) ? first + 1 : first;
-        if (i > last) i = last;
-        const int a0 = i - (W - 1) + off;
-        double acc = 0;
-        for (int j = l; j < W; j += 32) {
-            float v = x[a0 + j];
-            if (zero_inf && isinf(v)) v = 0.f;
-            acc += fabs(static_cast<double>(v));
-        }
-        acc = warp_sum(acc);
-        out = static_cast<float>(acc / W);
+    float out = centred_abs_mean(x, cd.T, W, c.t, zero_inf, l);
+    if (Wsta > 0) {
+        const float sta = centred_abs_mean(x, cd.T, Wsta, c.t, zero_inf, l);
+        out = static_cast<float>(static_cast<double>(out) * fabs(static_cast<double>(c.ds)) /
+                                 static_cast<double>(sta));
     }
     if (l == 0) cand[wid].lta = out;
 }
@@ -358,7 +367,8 @@ lta_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, i
 // in shared memory as a float64 prefix sum.
 constexpr int SL_TILE = 1024;
 __global__ void __launch_bounds__(256)
-stalta_dense_kernel(const float* __restrict__ x, int T, int W, int zero_inf, float* __restrict__ out) {
+stalta_dense_kernel(const float* __restrict__ x, int T, int W, int zero_inf, int mean_only,
+                    float* __restrict__ out) {
     extern __shared__ double pre[];  // [SL_TILE + W + 1]
     const int off = (W - 1) / 2;
     const int first = W - 1 - off, last = T - 1 - off;
@@ -395,8 +405,15 @@ stalta_dense_kernel(const float* __restrict__ x, int T, int W, int zero_inf, flo
         const double lta = (pre[s0 + W] - pre[s0]) / W;
         float v = x[i];
         if (zero_inf && isinf(v)) v = 0.f;
-        out[i] = static_cast<float>(fabs(static_cast<double>(v)) / lta);
+        out[i] = mean_only ? static_cast<float>(lta) : static_cast<float>(fabs(static_cast<double>(v)) / lta);
     }
+}
+
+// STA / LTA from the two dense rolling means (triggerSTATime != 0)
+__global__ void __launch_bounds__(256)
+ratio_kernel(const float* num, const float* den, int T, float* out) {  // out may alias den
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < T) out[i] = static_cast<float>(static_cast<double>(num[i]) / static_cast<double>(den[i]));
 }
 
 }  // namespace
@@ -417,19 +434,32 @@ void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, c
 }
 
 void launch_lta(const float* DS, const ChunkDesc* d_chunks, int S, const int* d_rowflags,
-                Candidate* d_cand, const int* d_ncand, int cand_cap, int W, cudaStream_t st) {
+                Candidate* d_cand, const int* d_ncand, int cand_cap, int W, int Wsta, cudaStream_t st) {
     // grid sized for the capacity; warps beyond *ncand exit immediately
     const int warps = cand_cap;
     const int grid = (warps * 32 + 255) / 256;
-    lta_kernel<<<grid, 256, 0, st>>>(DS, d_chunks, S, d_rowflags, d_cand, d_ncand, cand_cap, W);
+    lta_kernel<<<grid, 256, 0, st>>>(DS, d_chunks, S, d_rowflags, d_cand, d_ncand, cand_cap, W, Wsta);
 }
 
-void launch_stalta_dense(const float* row, int T, int W, int zero_inf, float* out, cudaStream_t st) {
-    if (T < W) return;
+static void launch_rolling(const float* row, int T, int W, int zero_inf, int mean_only, float* out,
+                           cudaStream_t st) {
     const int grid = (T + SL_TILE - 1) / SL_TILE;
     const size_t sm = sizeof(double) * (SL_TILE + 2 * W + 2);
     cudaFuncSetAttribute(stalta_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
-    stalta_dense_kernel<<<grid, 256, sm, st>>>(row, T, W, zero_inf, out);
+    stalta_dense_kernel<<<grid, 256, sm, st>>>(row, T, W, zero_inf, mean_only, out);
+}
+
+// Wsta == 0: out = |DS| / LTA.  Wsta > 0: out = STA / LTA, `tmp` (T floats) holds the STA means.
+void launch_stalta_dense(const float* row, int T, int W, int Wsta, int zero_inf, float* out, float* tmp,
+                         cudaStream_t st) {
+    if (T < W || T < Wsta) return;
+    if (Wsta <= 0) {
+        launch_rolling(row, T, W, zero_inf, 0, out, st);
+        return;
+    }
+    launch_rolling(row, T, Wsta, zero_inf, 1, tmp, st);
+    launch_rolling(row, T, W, zero_inf, 1, out, st);
+    ratio_kernel<<<(T + 255) / 256, 256, 0, st>>>(tmp, out, T, out);
 }
 
 }  // namespace dtx

@@ -109,10 +109,8 @@ class SSDetex(object):
         self.kblk = kblk
         self.triggerLTATime = triggerLTATime
         self.triggerSTATime = triggerSTATime
-        if triggerSTATime != 0:
-            # reference default is 0 (detex/subspace.py:1745-1761); the STA smoothing path is
-            # not on the GPU yet
-            raise NotImplementedError("triggerSTATime != 0 is not supported")
+        if triggerSTATime < 0:
+            raise ValueError("triggerSTATime must be >= 0")
         self.fillZeros = fillZeros
         self.calcHist = calcHist
         # group by basis length n: one basis set per distinct n (SampleTrims differ per subspace)
@@ -179,6 +177,7 @@ class SSDetex(object):
             from . import preprocess
             preprocess.applyFilter([chunks[i] for i in good], sr, raw_filt[0], engine=eng)
         W = int(self.triggerLTATime * sr)
+        eng.set_trigger_sta(int(self.triggerSTATime * sr))   # detect.py:285-287
         for n, names in sorted(self.groups.items()):
             sid = self.set_ids[n]
             eng.detect_run(sid, engine=self.kernel, kblk=self.kblk, hist_range=(0.0, 1.0),
@@ -210,7 +209,10 @@ class SSDetex(object):
                         if self.fillZeros:
                             sl = 0.0
                         else:
-                            sl = abs(coef) / float(sel["lta"][k])         # STA == |DS|, detect.py:505-507
+                            # |DS| / lta == STA / LTA at the trigger (detect.py:501-515); a chunk shorter
+                            # than a window has no STA/LTA array in the reference -> 0.0 (detect.py:416-419)
+                            den = float(sel["lta"][k])
+                            sl = abs(coef) / den if np.isfinite(den) else 0.0
                         pe_mag, st_mag, snr = (mg[pi] if self.estimateMags else (np.nan, np.nan, np.nan))
                         rows.append([coef, sl, times, name, self.sta, times - maxof, times - minof,
                                      st_mag, snr, pe_mag])       # Mag = stMag, ProEnMag = peMag (detect.py:428,442)
@@ -235,6 +237,7 @@ class SSDetex(object):
         eng.load_chunks([chunk])
         CorDF = pd.DataFrame(index=self.names, columns=CORDF_COLS, dtype=object)
         W = int(self.triggerLTATime * sr)
+        eng.set_trigger_sta(int(self.triggerSTATime * sr))
         for n, names in sorted(self.groups.items()):
             eng.detect_run(self.set_ids[n], engine=self.kernel, kblk=self.kblk)
             mx, _ = eng.rowstats()

@@ -153,6 +153,10 @@ class Engine(object):
         self._check(self._L.dtx_get_stalta(self._h, int(chunk), int(subspace), int(W), _ptr(out), out.size))
         return out
 
+    def set_trigger_sta(self, sta_window):
+        """triggerSTATime in samples (detect.py:282-288): 0 = the reference default STA = |DS|."""
+        self._check(self._L.dtx_set_trigger_sta(self._h, int(sta_window)))
+
     def set_x8_tolerance(self, eps):
         """Adaptive engine ("tcgen05_auto"): admitted rms error of a normalised projection."""
         self._check(self._L.dtx_set_x8_tolerance(self._h, float(eps)))

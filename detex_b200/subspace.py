@@ -29,7 +29,7 @@ def svd_basis(aligned, selectCriteria=2, selectValue=0.9, normalize=False):
         ndim = int(selectValue) + 1
     else:
         raise Exception('selectCriteria of %s is not supported' % selectCriteria)
-    return dict(U=np.ascontiguousarray(U[:, :ndim].T), s=s,
+    return dict(U=np.ascontiguousarray(U[:, :ndim].T), s=s, Ufull=U, cum=cum,
                 FracEnergy={'Average': avg, 'Minimum': mn}, NumBasis=ndim)
 
 

@@ -54,7 +54,9 @@ typedef struct dtx_cand {
     int32_t row;  /* chunk * S + subspace */
     int32_t t;    /* lag index (sample of the chunk, channel-aligned) */
     float ds;     /* detection statistic */
-    float lta;    /* centred rolling mean of |DS| over the LTA window at t (detect.py:501-524) */
+    float lta;    /* denominator of DS_STALTA: |ds| / lta = STA / LTA at t (`_getStaLtaArray`,
+                     detect.py:501-524).  With the default STA = |DS| it is the centred rolling mean of
+                     |DS| over the LTA window; with dtx_set_trigger_sta it is LTA * |ds| / STA */
 } dtx_cand;
 
 int dtx_version(void);
@@ -127,8 +129,12 @@ int dtx_num_lags(dtx_ctx* ctx, int chunk, int64_t* T);
 /* dense DS row (CorDF.SSdetect[name], detect.py:268) */
 int dtx_get_ds(dtx_ctx* ctx, int chunk, int subspace, float* out, int64_t count);
 int dtx_get_ds64(dtx_ctx* ctx, int chunk, int subspace, double* out, int64_t count);
-/* dense |DS| / LTA (CorDF.STALTA with triggerSTATime = 0, _getStaLtaArray detect.py:501-515),
- * W = LTA window in samples; filled with NaN when the row is shorter than W */
+/* triggerSTATime of _SSDetex (detect.py:38, 282-288) in samples: 0 (reference default) makes the
+ * short-term average |DS| itself; > 0 a centred rolling mean of |DS| with the same edge rule as
+ * the LTA.  Applies to the candidates of later dtx_detect_run calls and to dtx_get_stalta. */
+int dtx_set_trigger_sta(dtx_ctx* ctx, int sta_window);
+/* dense STA / LTA (CorDF.STALTA, _getStaLtaArray detect.py:501-515), W = LTA window in samples;
+ * filled with NaN when the row is shorter than a window */
 int dtx_get_stalta(dtx_ctx* ctx, int chunk, int subspace, int W, float* out, int64_t count);
 /* maxds[chunk*S+s] = CorDF.MaxDS (detect.py:275-281); flags bit0 = row has NaN, bit1 = infs zeroed */
 int dtx_get_rowstats(dtx_ctx* ctx, float* maxds, int32_t* flags, int64_t count);

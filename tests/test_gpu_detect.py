@@ -184,6 +184,40 @@ def test_rowstats_histogram_candidates_lta(engine):
         assert np.abs(sl - orc.sta_lta(ds, W, 0)).max() < 1e-3 * np.abs(sl).max()
 
 
+@pytest.mark.parametrize("Wsta,W", [(7, 50), (20, 21), (64, 500)])
+def test_trigger_sta_window(engine, Wsta, W):
+    """triggerSTATime != 0 (`_getStaLtaArray`, detect.py:501-515): STA is a centred rolling mean of
+    |DS| with the same edge rule as the LTA; sparse (candidates) and dense (CorDF.STALTA) paths."""
+    Nc, ns, Ls = 3, 200, 5000
+    chunks, bases, _ = synth.detection_case(29, 2, Ls, ns, Nc, [2, 4], planted=3)
+    engine.set_bases(23, bases, Nc, thresholds=[0.2, 0.25])
+    engine.load_chunks(chunks)
+    engine.set_trigger_sta(Wsta)
+    try:
+        engine.detect_run(23, lta_window=W)
+        cand = engine.candidates()
+        assert len(cand) > 0
+        S = len(bases)
+        seen = set()
+        for c in cand:
+            ci, si = divmod(int(c["row"]), S)
+            ds = engine.get_ds(ci, si).astype(np.float64)
+            ref = orc.sta_lta(ds, W, Wsta)
+            assert abs(abs(float(c["ds"])) / float(c["lta"]) - ref[c["t"]]) < 1e-5 * max(1.0, abs(ref[c["t"]]))
+            if (ci, si) not in seen:
+                seen.add((ci, si))
+                sl = engine.get_stalta(ci, si, W).astype(np.float64)
+                assert np.abs(sl - ref).max() < 1e-5 * np.abs(ref).max()
+    finally:
+        engine.set_trigger_sta(0)
+    # back to the default: STA = |DS|
+    engine.detect_run(23, lta_window=W)
+    c = engine.candidates()[0]
+    ci, si = divmod(int(c["row"]), len(bases))
+    ds = engine.get_ds(ci, si).astype(np.float64)
+    assert abs(abs(float(c["ds"])) / float(c["lta"]) - orc.sta_lta(ds, W, 0)[c["t"]]) < 1e-5
+
+
 def test_full_size_chunk_properties(engine):
     """BASELINE config 2 shape (3 ch x 100 Hz x 3720 s, rank 3, n = 9000): tcgen05 against the
     independent float64 evaluation on the device, plus shift/scale invariance of DS."""

@@ -73,6 +73,35 @@ def test_corDat_triggers_match_reference_loop(engine):
     assert np.abs(cor.STALTA["SS1"] - st).max() < 2e-3 * st.max()
 
 
+def test_corDat_with_trigger_sta_time(engine):
+    """SSDetex(triggerSTATime=0.1): DS_STALTA column against the reference loop restated in the oracle."""
+    Nc, ns, Ls, sr = 3, 200, 8000, 100.0
+    chunks, bases, _ = synth.detection_case(35, 2, Ls, ns, Nc, [2, 3], planted=3)
+    names = ["SS0", "SS1"]
+    ssTD = dict(zip(names, bases))
+    thr = dict(zip(names, [0.3, 0.3]))
+    offs = {n: [0.5, 1.0] for n in names}
+    starts = [5.0e8, 5.0e8 + 3600.0]
+    det = detect.SSDetex(ssTD, thr, offs, Nc, sta="TST", engine=engine, set_id=8, triggerLTATime=2,
+                         triggerSTATime=0.1)
+    try:
+        df, _ = det.corDat(chunks, sr, starts)
+    finally:
+        engine.set_trigger_sta(0)
+    exp = {}
+    for ci, c in enumerate(chunks):
+        for name in names:
+            ds = orc.mpx_ds_direct(c, ssTD[name], Nc)
+            if not orc.eval_trig_con(ds.max(), thr[name]):
+                continue
+            sl = orc.sta_lta(ds, 2 * sr, 0.1 * sr)
+            for r in orc.greedy_triggers(ds, thr[name], sr, starts[ci], offs[name], stalta=sl):
+                exp[(name, r["STMP"])] = r["DS_STALTA"]
+    assert len(df) == len(exp) > 0
+    for name, stmp, sl in zip(df.Name, df.STMP, df.DS_STALTA):
+        assert abs(sl - exp[(name, stmp)]) < 1e-3 * abs(exp[(name, stmp)])
+
+
 def test_stalta_screen_matches_oracle(engine):
     """fas._checkSTALTA on the GPU vs the restated ObsPy classic_sta_lta (parity of that
     third-party function itself is unpinned: ObsPy is not installable)."""
