@@ -115,3 +115,67 @@ def detection_table(seed, nev=80, stas=("TA.M17A", "TA.M18A", "TA.N17A"), t0=1.4
                            "TIME": [times[k] + 1.0 for k in pick], "MAG": np.linspace(1, 3, n_templates)})
     temkey["STMP"] = temkey["TIME"].astype(float)
     return det, temkey
+
+
+def workflow_case(seed, stations=("TA.M17A", "TA.M18A"), nfam=3, per_fam=5, nsingles=2, sr=40.0, Nc=3,
+                  ev_seconds=20.0, nchunks=6, chunk_seconds=300.0, t0=1.3e9, pick_after=5.0):
+    """A small Case1-shaped network for the whole createCluster -> ... -> detex sequence
+    (BASELINE configs[0] stand-in; the reference's Case1 needs IRIS downloads): RAW per-channel
+    event windows and continuous chunks (coloured noise with an offset and a trend, so that the
+    detrend + band-pass step matters), families of similar events, planted family members.
+
+    Returns dict(events, continuous, temkey, stakey, picks, planted, sr, Nc) in the shapes
+    `workflow.ArrayFetcher` / `createCluster` take."""
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    ns = int(ev_seconds * sr)
+    Ls = int(chunk_seconds * sr)
+    nev = nfam * per_fam + nsingles
+    names = ["2010-01-%02dT%02d-00-00" % (1 + i // 20, i % 20) for i in range(nev)]
+    origins = [t0 - 86400.0 * 30 + 3600.0 * i for i in range(nev)]
+    temkey = pd.DataFrame({"NAME": names, "TIME": origins, "LAT": 40.0 + 0.01 * np.arange(nev),
+                           "LON": -110.0 + 0.01 * np.arange(nev), "DEPTH": 5.0,
+                           "MAG": np.round(rng.uniform(1.0, 3.0, nev), 2)})
+    stakey = pd.DataFrame({"NETWORK": [s.split('.')[0] for s in stations],
+                           "STATION": [s.split('.')[1] for s in stations],
+                           "STARTTIME": t0, "ENDTIME": t0 + nchunks * chunk_seconds,
+                           "LAT": 40.5, "LON": -110.5, "ELEVATION": 1500.0, "CHANNELS": "BHE-BHN-BHZ"})
+    events, continuous, picks, planted = {}, {}, [], []
+
+    def raw_noise(nsamp, amp):
+        x = amp * rng.standard_normal((Nc, nsamp))
+        x += 3.0 * amp * rng.standard_normal((Nc, 1))                       # offset
+        x += amp * rng.standard_normal((Nc, 1)) * np.linspace(-1, 1, nsamp)  # trend
+        return x
+
+    for sta in stations:
+        fams = []
+        for f in range(nfam):
+            w = bandpassed_noise(rng, ns // 2, sr=sr, band=(1.5, 8.0), nchan=Nc)
+            fams.append(w * np.hanning(ns // 2)[None, :])
+        events[sta] = {}
+        for i, name in enumerate(names):
+            fam = i // per_fam if i < nfam * per_fam else -1
+            x = raw_noise(ns, 0.15)
+            if fam >= 0:
+                sh = int(rng.integers(-int(0.5 * sr), int(0.5 * sr) + 1))
+                a = float(rng.uniform(0.8, 1.5))
+                s0 = ns // 4 + sh
+                x[:, s0:s0 + ns // 2] += a * fams[fam]
+            else:
+                w = bandpassed_noise(rng, ns // 2, sr=sr, band=(1.5, 8.0), nchan=Nc) * np.hanning(ns // 2)[None, :]
+                x[:, ns // 4: ns // 4 + ns // 2] += w
+            start = origins[i] - 2.0
+            events[sta][name] = ([x[c].copy() for c in range(Nc)], start)
+            picks.append({"TimeStamp": start + pick_after, "Station": sta, "Event": name, "Phase": "P"})
+        continuous[sta] = []
+        for c in range(nchunks):
+            x = raw_noise(Ls, 0.15)
+            if c < nfam + 1:
+                fam = c % nfam
+                t = int(rng.integers(int(20 * sr), Ls - int(40 * sr)))
+                x[:, t:t + ns // 2] += float(rng.uniform(0.8, 1.2)) * fams[fam]
+                planted.append((sta, c, fam, t / sr))
+            continuous[sta].append(([x[k].copy() for k in range(Nc)], t0 + c * chunk_seconds))
+    return dict(events=events, continuous=continuous, temkey=temkey, stakey=stakey,
+                picks=pd.DataFrame(picks), planted=planted, sr=sr, Nc=Nc, chunk_seconds=chunk_seconds)

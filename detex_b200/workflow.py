@@ -22,6 +22,7 @@ import logging
 import os
 import pickle
 import random
+import re
 
 import numpy as np
 import pandas as pd
@@ -40,10 +41,15 @@ def _error(msg, e=Exception):
 
 
 def _timestamp(t):
-    """Epoch seconds from whatever a key holds (float, or anything pandas parses as UTC)."""
+    """Epoch seconds from whatever a key holds: a number, or a UTC date string -- including the
+    reference's own 'YYYY-MM-DDTHH-MM-SS' spelling of template names / times (util.py:574-627)."""
     if isinstance(t, (int, float, np.integer, np.floating)):
         return float(t)
-    ts = pd.Timestamp(str(t).replace('T', ' ').replace('-', '-', 2))
+    txt = str(t)
+    m = re.match(r'^(\d{4}-\d{2}-\d{2})[T ](\d{2})-(\d{2})-(\d{2}(?:\.\d+)?)$', txt)
+    if m:
+        txt = '%s %s:%s:%s' % m.groups()
+    ts = pd.Timestamp(txt)
     if ts.tzinfo is None:
         ts = ts.tz_localize('UTC')
     return ts.timestamp()
@@ -287,7 +293,8 @@ class Cluster(object):
         """subspace.py:305-346.  The reference builds every intermediate cluster of the linkage as a
         Python list and keeps the maximal ones below the cut; those are the flat clusters of
         `fcluster(link, 1 - ccReq, 'distance')` with at least two members, ordered by the height of
-        their top merge (highest first), members in dendrogram-leaf order of that merge."""
+        their top merge (highest first), members in ascending event order (`list(set(...))` of small
+        ints, subspace.py:337)."""
         if newccReq < 0. or newccReq > 1.:
             _error('Parameter ccReq must be between 0 and 1')
         self.ccReq = newccReq
@@ -659,6 +666,11 @@ class SubSpace(object):
                 jobs.append((sta, True))
         if useSingles:
             for sta in self.singles:
+                # the reference tests `isinstance(fas1, dict)` on what is a 1-element LIST for singles
+                # (subspace.py:1722-1727), so it always recalculates; the evident intent is kept here
+                done = [isinstance(f, list) for f in self.singles[sta]['FAS']]
+                if len(done) and all(done) and not recalc:
+                    continue
                 jobs.append((sta, False))
         for sta, issub in jobs:
             names, ssTD, _, _, _, Nc, sr = self._bases(sta, issub)
@@ -751,10 +763,14 @@ class SubSpace(object):
                 self.histSingles = hist
         if useSubSpaces or useSingles:
             ssinfo, sginfo = self._getInfoDF()
+
+            def hframe(h):   # `_getHistograms` (subspace.py:1956-1995)
+                return results.hist_frame({k: v for k, v in h.items() if k != 'Bins'}, bins=h['Bins'])
             results.write_run(subspaceDB, issubspace=True, info=ssinfo if useSubSpaces else None,
-                              hist=self.histSubSpaces if useSubSpaces else None, filt=self.clusters.filt)
+                              hist=hframe(self.histSubSpaces) if useSubSpaces else None, filt=self.clusters.filt)
             if useSingles:
-                results.write_run(subspaceDB, issubspace=False, info=sginfo, hist=self.histSingles, filt=None)
+                results.write_run(subspaceDB, issubspace=False, info=sginfo, hist=hframe(self.histSingles),
+                                  filt=None)
         return out
 
     def _getInfoDF(self):

@@ -1,0 +1,149 @@
+"""The reference's user-facing sequence (createCluster -> updateReqCC -> createSubSpace ->
+attachPickTimes -> SVD -> detex -> SQLite tables) through `detex_b200.workflow`.
+
+CPU (`-m "not gpu"`): the host logic driven by the oracle-backed engine stand-in
+(tests/oracle_engine.py) -- containers, dendrogram cut, alignment, trims, FAS bookkeeping, tables.
+GPU: the same sequence on the CUDA engine, compared with the stand-in's output row by row.
+"""
+import numpy as np
+import pytest
+
+from detex_b200 import results, synth, workflow
+from oracle_engine import OracleEngine
+
+CCREQ = 0.55
+
+
+def _run(eng, tmp_path, seed=77):
+    case = synth.workflow_case(seed)
+    fetcher = workflow.ArrayFetcher(case["events"], case["continuous"], sr=case["sr"], conDatDuration=280,
+                                    conBuff=20, seed=5)
+    cl = workflow.createCluster(CCreq=CCREQ, fetch_arg=fetcher, filt=[1, 10, 2, True], stationKey=case["stakey"],
+                                templateKey=case["temkey"], trim=[2, 18], saveclust=True,
+                                fileName=str(tmp_path / "clust.pkl"), engine=eng)
+    ss = workflow.createSubSpace(Pf=1e-10, clust=cl, engine=eng)
+    ss.attachPickTimes(case["picks"], defaultDuration=8)
+    ss.SVD(selectCriteria=2, selectValue=0.9, conDatNum=3)
+    db = str(tmp_path / "SubSpace.db")
+    found = ss.detex(subspaceDB=db, useSingles=True, estimateMags=True)
+    return case, cl, ss, db, found
+
+
+def _check_structure(case, cl, ss, db):
+    assert len(cl) == 2 and repr(cl).startswith("SSClusterStream with 2 stations")
+    for sta in ("TA.M17A", "TA.M18A"):
+        c = cl[sta]
+        assert c is cl[sta.split(".")[1]]
+        assert sorted(len(x) for x in c.clusts) == [5, 5, 5] and len(c.singles) == 2
+        names = list(case["temkey"].NAME)
+        for k in c.clusts:                                   # families are consecutive blocks of 5 events
+            idx = sorted(names.index(e) for e in k)
+            assert idx[-1] - idx[0] == 4 and idx[0] % 5 == 0
+        sp = ss.subspaces[sta]
+        assert list(sp.Name) == ["SS0", "SS1", "SS2"]
+        for _, row in sp.iterrows():
+            assert row.SVDdefined and 1 <= row.NumBasis <= 5 and len(row.UsedSVDKeys) == row.NumBasis
+            assert row.SampleTrims["Starttime"] % 3 == 0 and row.SampleTrims["Endtime"] % 3 == 0
+            n = row.SampleTrims["Endtime"] - row.SampleTrims["Starttime"]
+            assert all(len(v) == n for v in row.SVD.values())
+            assert 0.05 < row.Threshold < 0.9 and len(row.Offsets) == 3
+            assert set(row.FAS.keys()) == {"bins", "hist", "betadist", "nnlf"}
+        sg = ss.singles[sta]
+        assert list(sg.Name) == ["SG0", "SG1"] and all(0.05 < t < 0.95 for t in sg.Threshold)
+    # the pickled ClusterStream loads and can be cut again
+    import pickle
+    cl2 = pickle.load(open(cl.filename, "rb"))
+    cl2.updateReqCC(0.999)
+    assert all(len(c.clusts) == 0 and len(c.singles) == 17 for c in cl2.clusters)
+    # tables (subspace.py:1883-1902)
+    ssdf = results.loadSQLite(db, "ss_df")
+    info = results.loadSQLite(db, "ss_info")
+    hist = results.loadSQLite(db, "ss_hist")
+    filt = results.loadSQLite(db, "filt_params")
+    assert list(ssdf.columns) == ['DS', 'DS_STALTA', 'STMP', 'Name', 'Sta', 'MSTAMPmin', 'MSTAMPmax', 'Mag', 'SNR',
+                                  'ProEnMag']
+    assert len(info) == 6 and set(info.Sta) == {"TA.M17A", "TA.M18A"}
+    assert len(hist) == 7 and list(filt.iloc[0]) == [1, 10, 2, 1]
+    assert results.loadSQLite(db, "sg_info") is not None
+    # every planted family member is found by a subspace on its station, near where it was put
+    t0 = float(case["stakey"].STARTTIME.iloc[0])
+    for sta, c, fam, tsec in case["planted"]:
+        hit = ssdf[(ssdf.Sta == sta.split(".")[1]) & (np.abs(ssdf.STMP - (t0 + c * case["chunk_seconds"] + tsec)) < 12)]
+        assert len(hit) >= 1 and hit.DS.max() > 0.3, (sta, c, fam)
+    assert np.isfinite(ssdf.Mag).all() and np.isfinite(ssdf.SNR).all()
+    return ssdf
+
+
+def test_workflow_host_logic_with_oracle_engine(tmp_path):
+    case, cl, ss, db, found = _run(OracleEngine(), tmp_path)
+    ssdf = _check_structure(case, cl, ss, db)
+    assert sum(v for (sta, issub), v in found.items() if issub) == len(ssdf)
+
+
+def test_cluster_cut_matches_fcluster():
+    """Cluster.updateReqCC (subspace.py:305-346) against scipy's flat clusters on random linkages."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    rng = np.random.default_rng(3)
+    for N in (2, 5, 12, 40):
+        cx = rng.uniform(0.05, 0.95, N * (N - 1) // 2)
+        link = linkage(cx)
+        key = ["e%02d" % i for i in range(N)]
+        for ccreq in (0.2, 0.5, 0.8):
+            c = workflow.Cluster(None, "TA.X", None, key, link, ccreq, None, None, None, None)
+            T = fcluster(link, 1 - ccreq, criterion="distance")
+            want = {}
+            for e, t in zip(key, T):
+                want.setdefault(t, []).append(e)
+            want = sorted(v for v in want.values() if len(v) > 1)
+            assert sorted(c.clusts) == want
+            assert sorted(c.singles) == sorted(e for e in key if not any(e in v for v in want))
+
+
+def test_workflow_input_errors(tmp_path):
+    case = synth.workflow_case(78, nfam=1, per_fam=2, nsingles=0, nchunks=1)
+    f = workflow.ArrayFetcher(case["events"], case["continuous"], sr=case["sr"])
+    with pytest.raises(TypeError):
+        workflow.createCluster(fetch_arg="EventWaveForms", stationKey=case["stakey"], templateKey=case["temkey"])
+    with pytest.raises(Exception):
+        workflow.createCluster(fetch_arg=f, filt=[1, 10], stationKey=case["stakey"], templateKey=case["temkey"],
+                               engine=OracleEngine())
+    cl = workflow.createCluster(CCreq=0.3, fetch_arg=f, stationKey=case["stakey"], templateKey=case["temkey"],
+                                trim=[2, 18], saveclust=False, engine=OracleEngine())
+    with pytest.raises(Exception):
+        cl.updateReqCC(1.5)
+    ss = workflow.createSubSpace(clust=cl, engine=OracleEngine())
+    with pytest.raises(Exception):                      # SVD not called yet (subspace.py:1858-1861)
+        ss.detex(subspaceDB=str(tmp_path / "x.db"))
+    with pytest.raises(Exception):                      # trigCon != 0 is rejected by the reference too
+        ss.detex(subspaceDB=str(tmp_path / "x.db"), trigCon=1)
+    with pytest.raises(ValueError):
+        ss.SVD(selectCriteria=2, selectValue=1.5)
+
+
+@pytest.mark.gpu
+def test_workflow_on_gpu_matches_oracle_engine(engine, tmp_path):
+    (tmp_path / "gpu").mkdir()
+    (tmp_path / "cpu").mkdir()
+    case, cl, ss, db, _ = _run(engine, tmp_path / "gpu")
+    g = _check_structure(case, cl, ss, db)
+    _, cl0, ss0, db0, _ = _run(OracleEngine(), tmp_path / "cpu")
+    for sta in ("TA.M17A", "TA.M18A"):
+        assert cl[sta].clusts == cl0[sta].clusts and cl[sta].singles == cl0[sta].singles
+        a = cl.trdf[cl.trdf.Station == sta].iloc[0]
+        b = cl0.trdf[cl0.trdf.Station == sta].iloc[0]
+        m = ~np.isnan(b.CCs.values.astype(float))
+        assert np.abs(a.CCs.values.astype(float)[m] - b.CCs.values.astype(float)[m]).max() < 1e-9
+        assert np.array_equal(a.Lags.values.astype(float)[m], b.Lags.values.astype(float)[m])
+        for (_, r), (_, r0) in zip(ss.subspaces[sta].iterrows(), ss0.subspaces[sta].iterrows()):
+            assert r.Events == r0.Events and r.SampleTrims == r0.SampleTrims and r.NumBasis == r0.NumBasis
+            assert abs(r.Threshold - r0.Threshold) < 2e-4
+        for (_, r), (_, r0) in zip(ss.singles[sta].iterrows(), ss0.singles[sta].iterrows()):
+            assert abs(r.Threshold - r0.Threshold) < 2e-4
+    w = results.loadSQLite(db0, "ss_df")
+    # thresholds differ in the 5th digit (float32 DS sums), so compare the detections well above them
+    gs = g[g.DS > 0.3].sort_values(["Sta", "Name", "STMP"]).reset_index(drop=True)
+    ws = w[w.DS > 0.3].sort_values(["Sta", "Name", "STMP"]).reset_index(drop=True)
+    assert len(gs) == len(ws) > 0
+    assert (gs.Name == ws.Name).all() and (gs.STMP == ws.STMP).all()
+    assert np.abs(gs.DS - ws.DS).max() < 1e-5
+    assert np.abs(gs.Mag - ws.Mag).max() < 1e-3 and np.abs(gs.SNR - ws.SNR).max() < 1e-3 * ws.SNR.abs().max()
