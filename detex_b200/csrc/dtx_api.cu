@@ -736,19 +736,23 @@ int dtx_last_k1_ms(dtx_ctx* ctx, float* ms) {
     return DTX_OK;
 }
 
-int dtx_preprocess_chunks(dtx_ctx* ctx, int nchunks, int Nc, const void* const* chan_ptrs,
-                          const int64_t* chan_len, int dtype, const double* sos, int nsos, int zerophase,
-                          int detrend) {
+// Shared body of dtx_preprocess_chunks / dtx_preprocess_chunks_dec.  factor > 1: ObsPy's
+// Trace.decimate (forward-only low-pass SOS `dec_sos`, then data[::factor]) BEFORE detrend and
+// band-pass, the order of construct._applyFilter (construct.py:1017-1029).
+static int preprocess_impl(dtx_ctx* ctx, int nchunks, int Nc, const void* const* chan_ptrs, const int64_t* chan_len,
+                           int dtype, const double* sos, int nsos, int zerophase, int detrend,
+                           const double* dec_sos, int ndec, int factor) {
     if (!ctx || !chan_ptrs || !chan_len) return DTX_ERR_ARG;
     if (nchunks < 1 || Nc < 1 || nsos < 0 || (nsos > 0 && !sos)) return fail(ctx, DTX_ERR_ARG, "dtx_preprocess_chunks: bad arguments");
+    if (factor < 1 || ndec < 0 || (ndec > 0 && !dec_sos)) return fail(ctx, DTX_ERR_ARG, "dtx_preprocess_chunks_dec: bad decimation arguments");
     if (dtype != DTX_F64 && dtype != DTX_F32) return fail(ctx, DTX_ERR_ARG, "dtx_preprocess_chunks: bad dtype");
     DTX_CUDA(cudaSetDevice(ctx->device));
     const int ntr = nchunks * Nc;
-    std::vector<long long> off(ntr), out_off(nchunks);
-    std::vector<int> len(ntr), minlen(nchunks);
+    std::vector<long long> off(ntr), out_off(nchunks), off2(ntr);
+    std::vector<int> len(ntr), minlen(nchunks), len2(ntr);
     std::vector<int64_t> L(nchunks);
-    long long tot = 0, otot = 0;
-    int maxlen = 0;
+    long long tot = 0, tot2 = 0, otot = 0;
+    int maxlen = 0, maxlen2 = 0;
     for (int ch = 0; ch < nchunks; ++ch) {
         int mn = INT32_MAX;
         for (int c = 0; c < Nc; ++c) {
@@ -757,8 +761,13 @@ int dtx_preprocess_chunks(dtx_ctx* ctx, int nchunks, int Nc, const void* const* 
             off[ch * Nc + c] = tot;
             len[ch * Nc + c] = static_cast<int>(l);
             tot += (l + 1) & ~1LL;
-            mn = std::min<int>(mn, static_cast<int>(l));
             maxlen = std::max<int>(maxlen, static_cast<int>(l));
+            const int64_t l2 = (l + factor - 1) / factor;      // len(data[::factor])
+            off2[ch * Nc + c] = tot2;
+            len2[ch * Nc + c] = static_cast<int>(l2);
+            tot2 += (l2 + 1) & ~1LL;
+            maxlen2 = std::max<int>(maxlen2, static_cast<int>(l2));
+            mn = std::min<int>(mn, static_cast<int>(l2));
         }
         minlen[ch] = mn;            // multiplex trims to the shortest channel (construct.py:972-974)
         L[ch] = static_cast<int64_t>(mn) * Nc;
@@ -766,9 +775,9 @@ int dtx_preprocess_chunks(dtx_ctx* ctx, int nchunks, int Nc, const void* const* 
         otot += (L[ch] + 1) & ~1LL;
     }
     cudaStream_t st = ctx->stream;
-    DevBuf<double> dbuf, dstats, dseg;
-    DevBuf<long long> doff, dooff;
-    DevBuf<int> dlen, dmin;
+    DevBuf<double> dbuf, dbuf2, dstats, dseg;
+    DevBuf<long long> doff, doff2, dooff;
+    DevBuf<int> dlen, dlen2, dmin;
     const int maxseg = (maxlen + preproc_seg() - 1) / preproc_seg();
     DTX_CUDA(dbuf.reserve(tot)); DTX_CUDA(dstats.reserve(2 * static_cast<size_t>(ntr)));
     DTX_CUDA(dseg.reserve(static_cast<size_t>(ntr) * maxseg * 2));
@@ -789,7 +798,23 @@ int dtx_preprocess_chunks(dtx_ctx* ctx, int nchunks, int Nc, const void* const* 
     DTX_CUDA(cudaMemcpyAsync(dlen.p, len.data(), sizeof(int) * ntr, cudaMemcpyHostToDevice, st));
     DTX_CUDA(cudaMemcpyAsync(dmin.p, minlen.data(), sizeof(int) * nchunks, cudaMemcpyHostToDevice, st));
     DTX_CUDA(cudaMemcpyAsync(dooff.p, out_off.data(), sizeof(long long) * nchunks, cudaMemcpyHostToDevice, st));
-    launch_preproc(dbuf.p, doff.p, dlen.p, ntr, maxlen, sos, nsos, zerophase, detrend, dstats.p, dseg.p, st);
+    double* work = dbuf.p;
+    const long long* work_off = doff.p;
+    const int* work_len = dlen.p;
+    int work_maxlen = maxlen;
+    if (factor > 1) {
+        // anti-alias low-pass (forward only, no detrend), then keep every factor-th sample
+        launch_preproc(dbuf.p, doff.p, dlen.p, ntr, maxlen, dec_sos, ndec, 0, 0, dstats.p, dseg.p, st);
+        DTX_CUDA(cudaGetLastError());
+        DTX_CUDA(dbuf2.reserve(tot2)); DTX_CUDA(doff2.reserve(ntr)); DTX_CUDA(dlen2.reserve(ntr));
+        DTX_CUDA(cudaMemcpyAsync(doff2.p, off2.data(), sizeof(long long) * ntr, cudaMemcpyHostToDevice, st));
+        DTX_CUDA(cudaMemcpyAsync(dlen2.p, len2.data(), sizeof(int) * ntr, cudaMemcpyHostToDevice, st));
+        launch_decimate(dbuf.p, doff.p, dbuf2.p, doff2.p, dlen2.p, ntr, factor, st);
+        DTX_CUDA(cudaGetLastError());
+        ctx->launches += 3 * ndec + 1;
+        work = dbuf2.p; work_off = doff2.p; work_len = dlen2.p; work_maxlen = maxlen2;
+    }
+    launch_preproc(work, work_off, work_len, ntr, work_maxlen, sos, nsos, zerophase, detrend, dstats.p, dseg.p, st);
     DTX_CUDA(cudaGetLastError());
     ctx->launches += (detrend ? 2 : 0) + 3 * nsos * (zerophase ? 2 : 1);
     // multiplexed result becomes the loaded batch
@@ -798,13 +823,27 @@ int dtx_preprocess_chunks(dtx_ctx* ctx, int nchunks, int Nc, const void* const* 
     for (int ch = 0; ch < nchunks; ++ch)
         if (ctx->raw_off[ch] != out_off[ch]) return fail(ctx, DTX_ERR_STATE, "dtx_preprocess_chunks: layout mismatch");
     DTX_CUDA(ctx->raw_own.reserve(static_cast<size_t>(otot) * 8));
-    launch_multiplex(dbuf.p, doff.p, dmin.p, dooff.p, nchunks, Nc, maxlen, reinterpret_cast<double*>(ctx->raw_own.p), st);
+    launch_multiplex(work, work_off, dmin.p, dooff.p, nchunks, Nc, work_maxlen, reinterpret_cast<double*>(ctx->raw_own.p), st);
     DTX_CUDA(cudaGetLastError());
     ctx->launches += 1;
     ctx->d_raw = ctx->raw_own.p;
     DTX_CUDA(cudaStreamSynchronize(st));   // host trace buffers may be released by the caller
-    dbuf.release(); dstats.release(); dseg.release(); doff.release(); dooff.release(); dlen.release(); dmin.release();
+    dbuf.release(); dbuf2.release(); dstats.release(); dseg.release(); doff.release(); doff2.release();
+    dooff.release(); dlen.release(); dlen2.release(); dmin.release();
     return DTX_OK;
+}
+
+int dtx_preprocess_chunks(dtx_ctx* ctx, int nchunks, int Nc, const void* const* chan_ptrs,
+                          const int64_t* chan_len, int dtype, const double* sos, int nsos, int zerophase,
+                          int detrend) {
+    return preprocess_impl(ctx, nchunks, Nc, chan_ptrs, chan_len, dtype, sos, nsos, zerophase, detrend, nullptr, 0, 1);
+}
+
+int dtx_preprocess_chunks_dec(dtx_ctx* ctx, int nchunks, int Nc, const void* const* chan_ptrs,
+                              const int64_t* chan_len, int dtype, const double* sos, int nsos, int zerophase,
+                              int detrend, const double* dec_sos, int ndec, int factor) {
+    return preprocess_impl(ctx, nchunks, Nc, chan_ptrs, chan_len, dtype, sos, nsos, zerophase, detrend, dec_sos, ndec,
+                           factor);
 }
 
 int dtx_get_chunk(dtx_ctx* ctx, int chunk, double* out, int64_t count, int64_t* L) {

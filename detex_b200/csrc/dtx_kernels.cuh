@@ -161,6 +161,8 @@ void launch_preproc(double* d_buf, const long long* d_off, const int* d_len, int
                     int nsos, int zerophase, int detrend, double* d_stats, double* d_segstate, cudaStream_t st);
 void launch_multiplex(const double* d_buf, const long long* d_off, const int* d_minlen, const long long* d_out_off,
                       int nchunks, int Nc, int maxlen, double* d_out, cudaStream_t st);
+void launch_decimate(const double* d_src, const long long* d_off, double* d_dst, const long long* d_off2,
+                     const int* d_len2, int ntr, int factor, cudaStream_t st);
 int preproc_seg();
 
 // k6_stalta.cu : classic STA/LTA screen of raw chunks (fas._checkSTALTA)

@@ -135,6 +135,19 @@ pp_biquad_pass2(double* __restrict__ buf, const long long* __restrict__ off, con
     }
 }
 
+// ------------------------------------------------------------------------------ decimate
+// data[::factor] of every trace (ObsPy Trace.decimate after its low-pass) into a second buffer
+__global__ void __launch_bounds__(256)
+pp_decimate(const double* __restrict__ src, const long long* __restrict__ off, double* __restrict__ dst,
+            const long long* __restrict__ off2, const int* __restrict__ len2, int factor) {
+    const int tr = blockIdx.y;
+    const int n = len2[tr];
+    const double* s = src + off[tr];
+    double* d = dst + off2[tr];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+        d[i] = s[static_cast<long long>(i) * factor];
+}
+
 // ------------------------------------------------------------------------------ multiplex
 __global__ void __launch_bounds__(256)
 pp_multiplex(const double* __restrict__ buf, const long long* __restrict__ off, const int* __restrict__ minlen,
@@ -177,6 +190,12 @@ void launch_multiplex(const double* d_buf, const long long* d_off, const int* d_
                       int nchunks, int Nc, int maxlen, double* d_out, cudaStream_t st) {
     const dim3 g(64, nchunks);
     pp_multiplex<<<g, 256, 0, st>>>(d_buf, d_off, d_minlen, d_out_off, Nc, d_out);
+}
+
+void launch_decimate(const double* d_src, const long long* d_off, double* d_dst, const long long* d_off2,
+                     const int* d_len2, int ntr, int factor, cudaStream_t st) {
+    const dim3 g(64, ntr);
+    pp_decimate<<<g, 256, 0, st>>>(d_src, d_off, d_dst, d_off2, d_len2, factor);
 }
 
 int preproc_seg() { return SEG; }

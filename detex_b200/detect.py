@@ -148,12 +148,14 @@ class SSDetex(object):
         Chunks the reference would skip (detect.py:262-274) are dropped with a warning."""
         return self._run(chunks, [len(c) for c in chunks], sr, starts, keep_ds, raw_filt=None)
 
-    def run_raw_chunks(self, traces, sr, starts, filt=(1, 10, 2, True), keep_ds=False):
+    def run_raw_chunks(self, traces, sr, starts, filt=(1, 10, 2, True), keep_ds=False, decimate=None):
         """As run_chunks, but from RAW per-channel traces (list of chunks, each a list of channel
-        arrays in sorted order): linear detrend + band-pass + multiplex run on the device too
-        (`_applyFilter` + `multiplex`, detect.py:231-241), so the samples cross PCIe once."""
-        lens = [min(len(t) for t in ch) * self.Nc for ch in traces]
-        return self._run(traces, lens, sr, starts, keep_ds, raw_filt=(filt,))
+        arrays in sorted order): decimation, linear detrend, band-pass and multiplex run on the device
+        too (`_applyFilter` + `multiplex`, detect.py:231-241), so the samples cross PCIe once.
+        `sr` is the rate of the raw traces; lags and trigger times use sr / decimate."""
+        f = int(decimate) if decimate else 1
+        lens = [min(-(-len(t) // f) for t in ch) * self.Nc for ch in traces]
+        return self._run(traces, lens, sr / float(f), starts, keep_ds, raw_filt=(filt, decimate, sr))
 
     def _run(self, chunks, lens, sr, starts, keep_ds, raw_filt):
         good = []
@@ -175,7 +177,8 @@ class SSDetex(object):
             eng.load_chunks([chunks[i] for i in good])
         else:
             from . import preprocess
-            preprocess.applyFilter([chunks[i] for i in good], sr, raw_filt[0], engine=eng)
+            preprocess.applyFilter([chunks[i] for i in good], raw_filt[2], raw_filt[0], decimate=raw_filt[1],
+                                   engine=eng)
         W = int(self.triggerLTATime * sr)
         eng.set_trigger_sta(int(self.triggerSTATime * sr))   # detect.py:285-287
         for n, names in sorted(self.groups.items()):

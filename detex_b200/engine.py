@@ -84,9 +84,10 @@ class Engine(object):
         self._keep = arrs  # async H2D: keep the host arrays alive until the next sync
         self.nchunks = len(arrs)
 
-    def preprocess_chunks(self, traces, sos, zerophase=True, detrend=True):
-        """traces: list (chunks) of lists (channels, ObsPy sort order) of 1-D host arrays.  Detrend,
-        SOS-filter and multiplex on the device; the result becomes the loaded batch."""
+    def preprocess_chunks(self, traces, sos, zerophase=True, detrend=True, dec_sos=None, factor=1):
+        """traces: list (chunks) of lists (channels, ObsPy sort order) of 1-D host arrays.  Optional
+        decimation (forward low-pass `dec_sos`, every factor-th sample), detrend, SOS filter and
+        multiplex on the device; the result becomes the loaded batch."""
         Nc = len(traces[0])
         f32 = all(np.asarray(t).dtype == np.float32 for ch in traces for t in ch)
         dt = np.float32 if f32 else np.float64
@@ -96,11 +97,18 @@ class Engine(object):
         ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
         lens = np.array([a.shape[0] for a in arrs], dtype=np.int64)
         sos = np.ascontiguousarray(np.atleast_2d(np.asarray(sos, dtype=np.float64)))
-        self._check(self._L.dtx_preprocess_chunks(self._h, len(traces), Nc, ptrs, _ptr(lens),
-                                                  _lib.DTX_F32 if f32 else _lib.DTX_F64, _ptr(sos), sos.shape[0],
-                                                  int(bool(zerophase)), int(bool(detrend))))
+        factor = int(factor)
+        if factor > 1:
+            dsos = np.ascontiguousarray(np.atleast_2d(np.asarray(dec_sos, dtype=np.float64)))
+            self._check(self._L.dtx_preprocess_chunks_dec(
+                self._h, len(traces), Nc, ptrs, _ptr(lens), _lib.DTX_F32 if f32 else _lib.DTX_F64, _ptr(sos),
+                sos.shape[0], int(bool(zerophase)), int(bool(detrend)), _ptr(dsos), dsos.shape[0], factor))
+        else:
+            self._check(self._L.dtx_preprocess_chunks(self._h, len(traces), Nc, ptrs, _ptr(lens),
+                                                      _lib.DTX_F32 if f32 else _lib.DTX_F64, _ptr(sos), sos.shape[0],
+                                                      int(bool(zerophase)), int(bool(detrend))))
         self.nchunks = len(traces)
-        return [int(min(len(t) for t in ch)) * Nc for ch in traces]
+        return [int(min(-(-len(t) // factor) for t in ch)) * Nc for ch in traces]
 
     def get_chunk(self, chunk):
         L = C.c_int64()

@@ -744,7 +744,8 @@ class SubSpace(object):
                 def flush():
                     if not raw:
                         return 0
-                    Sar, _, _ = det.run_raw_chunks(raw, self.cfetcher.sr, starts, filt=self.clusters.filt)
+                    Sar, _, _ = det.run_raw_chunks(raw, self.cfetcher.sr, starts, filt=self.clusters.filt,
+                                                   decimate=self.clusters.decimate)
                     if len(Sar):
                         results.saveSQLite(Sar, subspaceDB, 'ss_df' if issub else 'sg_df')
                     del raw[:], starts[:]

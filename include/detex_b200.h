@@ -101,6 +101,12 @@ int dtx_attach_device_chunks(dtx_ctx* ctx, int nchunks, const void* dev_base,
 int dtx_preprocess_chunks(dtx_ctx* ctx, int nchunks, int Nc, const void* const* chan_ptrs,
                           const int64_t* chan_len, int dtype, const double* sos, int nsos, int zerophase,
                           int detrend);
+/* As above with `st.decimate(factor)` first (construct.py:1014-1015; ObsPy 1.0.2 Trace.decimate:
+ * forward-only low-pass `dec_sos` [ndec][6] -- lowpass_cheby_2 designed by the caller -- then
+ * data[::factor]); detrend and band-pass then act on the decimated traces.  factor = 1 skips it. */
+int dtx_preprocess_chunks_dec(dtx_ctx* ctx, int nchunks, int Nc, const void* const* chan_ptrs,
+                              const int64_t* chan_len, int dtype, const double* sos, int nsos, int zerophase,
+                              int detrend, const double* dec_sos, int ndec, int factor);
 /* the multiplexed chunk as the device holds it (MPcon of detect.py:241), float64 chunks only */
 int dtx_get_chunk(dtx_ctx* ctx, int chunk, double* out, int64_t count, int64_t* L);
 

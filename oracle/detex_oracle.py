@@ -616,14 +616,29 @@ def est_mag(trigIndex, MPcon, Nc, U, ewf, mags, issubspace=True):
 # --------------------------------------------------------------------------
 
 
-def apply_filter(chans, sr, filt=(1, 10, 2, True)):
-    """chans: list of 1-D channel arrays (sorted order).  Returns the multiplexed chunk."""
+def apply_filter(chans, sr, filt=(1, 10, 2, True), decimate=None):
+    """chans: list of 1-D channel arrays (sorted order).  Returns the multiplexed chunk.
+    decimate: `st.decimate(factor)` first (construct.py:1014-1015) = ObsPy 1.0.2 Trace.decimate:
+    filter('lowpass_cheby_2', freq=0.5*sr/factor, maxorder=12) then data[::factor]
+    (obspy/core/trace.py, obspy/signal/filter.py::lowpass_cheby_2; restated, unpinned)."""
     import scipy.signal
     out = []
     for x in chans:
-        y = scipy.signal.detrend(np.asarray(x, dtype=np.float64), type="linear")
+        y = np.asarray(x, dtype=np.float64)
+        fs = sr
+        if decimate and int(decimate) > 1:
+            nyq = 0.5 * sr
+            ws = (0.5 * sr / float(decimate)) / nyq
+            wp, order = ws, 1e99
+            while order > 12:
+                wp = wp * 0.99
+                order, wn = scipy.signal.cheb2ord(wp, ws, 1, 96, analog=0)
+            z, p, k = scipy.signal.cheby2(order, 96, wn, btype="low", analog=0, output="zpk")
+            y = scipy.signal.sosfilt(scipy.signal.zpk2sos(z, p, k), y)[::int(decimate)]
+            fs = sr / float(decimate)
+        y = scipy.signal.detrend(y, type="linear")
         if filt is not None:
-            fe = 0.5 * sr
+            fe = 0.5 * fs
             z, p, k = scipy.signal.iirfilter(filt[2], [filt[0] / fe, filt[1] / fe], btype="band", ftype="butter",
                                              output="zpk")
             sos = scipy.signal.zpk2sos(z, p, k)

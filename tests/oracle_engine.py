@@ -33,12 +33,14 @@ class OracleEngine(object):
         self.chunks = [np.asarray(c, dtype=np.float64) for c in chunks]
         self.nchunks = len(chunks)
 
-    def preprocess_chunks(self, traces, sos, zerophase=True, detrend=True):
+    def preprocess_chunks(self, traces, sos, zerophase=True, detrend=True, dec_sos=None, factor=1):
         out = []
         for ch in traces:
             ys = []
             for x in ch:
                 y = np.asarray(x, dtype=np.float64)
+                if factor > 1:
+                    y = scipy.signal.sosfilt(dec_sos, y)[::factor]
                 if detrend:
                     y = scipy.signal.detrend(y, type="linear")
                 if len(sos):

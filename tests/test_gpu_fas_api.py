@@ -189,6 +189,13 @@ def test_preprocess_matches_scipy_restatement(engine):
             ref = orc.apply_filter(ch, sr, filt)
             assert g.shape == ref.shape
             assert np.abs(g - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+    # st.decimate(factor) first (ObsPy: Chebyshev-II low-pass, then every factor-th sample)
+    for factor, filt in ((2, [1, 10, 2, True]), (5, [1, 8, 4, False]), (4, None)):
+        got = preprocess.applyFilter_multiplex(traces, sr, filt, decimate=factor, engine=engine)
+        for g, ch in zip(got, traces):
+            ref = orc.apply_filter(ch, sr, filt, decimate=factor)
+            assert g.shape == ref.shape
+            assert np.abs(g - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
     # and straight into the detector: same triggers as filtering on the host first
     chunks, bases, _ = synth.detection_case(62, 2, 12000, 300, 3, [3, 4], planted=2)
     raw = [[c[k::3] + 25.0 + 1e-3 * np.arange(len(c) // 3) for k in range(3)] for c in chunks]

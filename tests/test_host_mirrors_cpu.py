@@ -106,6 +106,11 @@ def test_bandpass_design_matches_oracle_filter():
     tr = [[rng.standard_normal(900) + 3.0 for _ in range(3)]]
     got = preprocess.applyFilter_multiplex(tr, 40.0, (1, 10, 2, True), engine=OracleEngine())[0]
     assert np.abs(got - orc.apply_filter(tr[0], 40.0, (1, 10, 2, True))).max() < 1e-12
+    got = preprocess.applyFilter_multiplex(tr, 40.0, (1, 4, 2, False), decimate=4, engine=OracleEngine())[0]
+    ref = orc.apply_filter(tr[0], 40.0, (1, 4, 2, False), decimate=4)
+    assert got.shape == ref.shape == (225 * 3,) and np.abs(got - ref).max() < 1e-12
+    with pytest.raises(ArithmeticError):                           # ObsPy refuses automatic design above 16
+        preprocess.applyFilter(tr, 40.0, None, decimate=17, engine=OracleEngine())
     with pytest.warns(UserWarning):                                # ObsPy: high corner at Nyquist -> high-pass
         preprocess.bandpass_sos(1.0, 20.0, 40.0, 2)
     with pytest.raises(ValueError):

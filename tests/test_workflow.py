@@ -14,12 +14,12 @@ from oracle_engine import OracleEngine
 CCREQ = 0.55
 
 
-def _run(eng, tmp_path, seed=77):
+def _run(eng, tmp_path, seed=77, decimate=None, filt=(1, 10, 2, True)):
     case = synth.workflow_case(seed)
     fetcher = workflow.ArrayFetcher(case["events"], case["continuous"], sr=case["sr"], conDatDuration=280,
                                     conBuff=20, seed=5)
-    cl = workflow.createCluster(CCreq=CCREQ, fetch_arg=fetcher, filt=[1, 10, 2, True], stationKey=case["stakey"],
-                                templateKey=case["temkey"], trim=[2, 18], saveclust=True,
+    cl = workflow.createCluster(CCreq=CCREQ, fetch_arg=fetcher, filt=list(filt), stationKey=case["stakey"],
+                                templateKey=case["temkey"], trim=[2, 18], saveclust=True, decimate=decimate,
                                 fileName=str(tmp_path / "clust.pkl"), engine=eng)
     ss = workflow.createSubSpace(Pf=1e-10, clust=cl, engine=eng)
     ss.attachPickTimes(case["picks"], defaultDuration=8)
@@ -78,6 +78,24 @@ def test_workflow_host_logic_with_oracle_engine(tmp_path):
     case, cl, ss, db, found = _run(OracleEngine(), tmp_path)
     ssdf = _check_structure(case, cl, ss, db)
     assert sum(v for (sta, issub), v in found.items() if issub) == len(ssdf)
+
+
+def test_workflow_with_decimation(tmp_path):
+    """createCluster(decimate=2): 40 Hz traces are low-passed and decimated to 20 Hz before detrend /
+    band-pass (construct.py:1014-1015); lags, trims and trigger times then live on the 20 Hz grid."""
+    case, cl, ss, db, found = _run(OracleEngine(), tmp_path, decimate=2, filt=(1, 8, 2, True))
+    for sta in ("TA.M17A", "TA.M18A"):
+        assert sorted(len(x) for x in cl[sta].clusts) == [5, 5, 5]
+        row = cl.trdf[cl.trdf.Station == sta].iloc[0]
+        assert all(st["sampling_rate"] == 20.0 for st in row.Stats.values())
+        for _, r in ss.subspaces[sta].iterrows():
+            assert r.SampleTrims["Endtime"] - r.SampleTrims["Starttime"] == 8 * 20 * 3   # 8 s x 20 Hz x 3 ch
+    ssdf = results.loadSQLite(db, "ss_df")
+    t0 = float(case["stakey"].STARTTIME.iloc[0])
+    for sta, c, fam, tsec in case["planted"]:
+        hit = ssdf[(ssdf.Sta == sta.split(".")[1]) & (np.abs(ssdf.STMP - (t0 + c * case["chunk_seconds"] + tsec)) < 12)]
+        assert len(hit) >= 1 and hit.DS.max() > 0.3
+    assert np.allclose((ssdf.STMP.values - t0) * 20.0, np.round((ssdf.STMP.values - t0) * 20.0), atol=1e-5)
 
 
 def test_cluster_cut_matches_fcluster():
