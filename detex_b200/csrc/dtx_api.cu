@@ -11,6 +11,7 @@
 #include <functional>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/detex_b200.h"
@@ -446,8 +447,16 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     int group = std::max(1, (4 * ctx->num_sms + tiles_per_chunk - 1) / tiles_per_chunk);
     if (const char* g = std::getenv("DTX_K1_GROUP"))   // experiment knob (chunks per group)
         if (std::atoi(g) > 0) group = std::atoi(g);
+    // Superblocks: `super` consecutive basis blocks are run back to back on the same wave of
+    // num_sms tiles, so a tile's signal span and norm tile are re-read from L2 `super` times in a row
+    // and the whole group's signal only once per superblock pass instead of once per block pass
+    // (super = 1 is the plain (group, block, tile) order).  Pure reordering of the item list.
+    int super = 1;
+    if (const char* g = std::getenv("DTX_K1_SUPER"))
+        if (std::atoi(g) > 0) super = std::atoi(g);
+    const int wave = ctx->num_sms;
     // the list only depends on the batch's shape: reuse the device copy when it has not changed
-    std::vector<int> sig_key{nq, lay.nblocks, group, nchunks};
+    std::vector<int> sig_key{nq, lay.nblocks, group, nchunks, super, wave};
     for (int i = 0; i < nchunks; ++i) {
         sig_key.push_back(ctx->h_chunks[i].T);
         sig_key.push_back(ctx->h_chunks[i].blk_hi);
@@ -455,16 +464,26 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     const bool items_cached = sig_key == ctx->items_key && ctx->d_items.p != nullptr;
     std::vector<int4> items;
     if (!items_cached) items.reserve(static_cast<size_t>(nitems) * 2 * lay.nblocks);
+    std::vector<std::pair<int, int>> tl;   // (chunk, tile) of the current group
     for (int g0 = 0; g0 < nchunks && !items_cached; g0 += group) {
         const int g1 = std::min(nchunks, g0 + group);
         int max_blk = 0;
-        for (int i = g0; i < g1; ++i) max_blk = std::max(max_blk, ctx->h_chunks[i].blk_hi);
-        for (int b = 0; b < max_blk; ++b)
-            for (int i = g0; i < g1; ++i) {
-                if (b < ctx->h_chunks[i].blk_lo || b >= ctx->h_chunks[i].blk_hi) continue;
-                const int nt = (ctx->h_chunks[i].T + 8 * nq - 1) / (8 * nq);
-                for (int t = 0; t < nt; ++t) items.push_back(make_int4(i, t, b, 0));
-            }
+        tl.clear();
+        for (int i = g0; i < g1; ++i) {
+            max_blk = std::max(max_blk, ctx->h_chunks[i].blk_hi);
+            const int nt = (ctx->h_chunks[i].T + 8 * nq - 1) / (8 * nq);
+            for (int t = 0; t < nt; ++t) tl.emplace_back(i, t);
+        }
+        for (int sb = 0; sb < max_blk; sb += super)
+            for (size_t w0 = 0; w0 < tl.size(); w0 += (super > 1 ? wave : tl.size()))
+                for (int b = sb; b < std::min(sb + super, max_blk); ++b) {
+                    const size_t w1 = super > 1 ? std::min(tl.size(), w0 + wave) : tl.size();
+                    for (size_t k = w0; k < w1; ++k) {
+                        const ChunkDesc& cd = ctx->h_chunks[tl[k].first];
+                        if (b < cd.blk_lo || b >= cd.blk_hi) continue;
+                        items.push_back(make_int4(tl[k].first, tl[k].second, b, 0));
+                    }
+                }
     }
 
     DTX_CUDA(ctx->d_chunks.reserve(nchunks));
