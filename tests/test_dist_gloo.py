@@ -85,3 +85,61 @@ def test_two_rank_gather_equals_single_process():
     assert np.array_equal(hist, eh)
     assert np.all(fasst == 3.0)
     assert np.array_equal(full[:, 0], np.arange(8, dtype=np.float64))
+
+
+def _detect_worker(rank, world, port, q):
+    """One rank of a chunk-sharded detection run: the host path of bench.py / parallel.py with the
+    oracle-backed engine stand-in in place of the GPU (test infrastructure, tests/oracle_engine.py)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    from detex_b200 import synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        chunks, bases, _ = synth.detection_case(91, 5, 2500, 100, 3, [1, 3, 2], planted=2)
+        thr = [0.3, 0.3, 0.3]
+        S = len(bases)
+        lo, hi = parallel.shard_range(len(chunks), rank, world)
+        eng = OracleEngine()
+        eng.set_bases(0, bases, 3, thresholds=thr)
+        eng.load_chunks(chunks[lo:hi])
+        eng.detect_run(0, lta_window=50, want_fas=True)
+        c = eng.candidates()
+        c["row"] += lo * S                               # local chunk index -> global (bench.py)
+        mx, _ = eng.rowstats()
+        hist, fas = eng.hist(0), eng.fas(0)
+        if world > 1:
+            c = parallel.gather_records(c)
+            hist = parallel.allreduce_sum(hist)
+            fas = parallel.allreduce_sum(fas)
+            best = parallel.allreduce_max(mx.max(axis=0).astype(np.float64))
+        else:
+            best = mx.max(axis=0).astype(np.float64)
+        if rank == 0:
+            order = np.lexsort((c["t"], c["row"]))
+            q.put((c[order], hist, fas, best))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def test_sharded_detection_equals_single_process():
+    ctx = mp.get_context("spawn")
+    out = {}
+    for world in (1, 2):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_detect_worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        out[world] = q.get(timeout=300)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    (c1, h1, f1, b1), (c2, h2, f2, b2) = out[1], out[2]
+    assert len(c1) > 0 and np.array_equal(c1, c2)        # same triggers, bit for bit
+    assert np.array_equal(h1, h2) and h1.sum() == 5 * 3 * 2401
+    assert np.allclose(f1, f2, rtol=1e-12) and np.array_equal(b1, b2)
