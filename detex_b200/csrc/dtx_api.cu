@@ -438,20 +438,45 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     }
     // K1 tile: 2048 lags (N = 256), or 1024 (N = 128) when no chunk has more than 1024 lags
     const int nq = maxT <= TILE_T / 2 ? 128 : 256;
-    // work items (chunk, tile, basis block), ordered (chunk group, block, tile): all CTAs share
-    // the current A block in L2 and the group's split signal (<= ~40 MB) stays L2 resident
+    // Work items (chunk, tile, basis block).  Two orders, both keep the 148 CTAs on the same basis
+    // block at any time so that its image (lay.nchunks x 32 KB) is streamed from L2:
+    //   super = 1: (chunk group, block, tile)  -- a group's split signal + norm tiles are re-read once
+    //              per block pass and should survive it in L2; needs >= 4 waves of items per pass
+    //              (with 2.4 waves the CTAs spread over several blocks: 67 GB of DRAM reads);
+    //   super = S: (chunk group, superblock of S blocks, wave of num_sms tiles, block, tile) -- a tile's
+    //              signal is re-read S times in a row and the group's signal only once per SUPERBLOCK
+    //              pass, so the group can be the whole batch and the image is read from HBM once.
+    // Pure reordering of the list; which one reads less HBM depends on the shape.  Cost model fitted
+    // to the ncu sweep in profiles/r01_k1_traffic_ab.md (48 x 256-subspace detection chunks: group 4 /
+    // super 1 = 11.2 GB, whole batch / super 4 = 7.1 GB, super 8 thrashes the image; CCX, with
+    // 0.5 MB blocks and a 15 MB group signal, is best left at super 1):
+    //   image reads  = image bytes x number of groups
+    //   signal reads = signal bytes x (1 + miss x (passes - 1)),  passes = nblocks / super,
+    //   miss         = clamp((super x group signal + 2 super x block - 15 MB) / 120 MB, 0, 1)
     const int tiles_per_chunk = std::max(1, (maxT + 8 * nq - 1) / (8 * nq));
-    // (>= 4 waves of items per (group, block) pass.  Group size 8 vs 4 long chunks makes no measurable
-    // difference in time or DRAM traffic: ncu shows ~17-20 GB of L2 read misses per 48-chunk launch
-    // either way, see profiles/r01_k1_ncu_summary.md)
-    int group = std::max(1, (4 * ctx->num_sms + tiles_per_chunk - 1) / tiles_per_chunk);
-    if (const char* g = std::getenv("DTX_K1_GROUP"))   // experiment knob (chunks per group)
+    const int g4 = std::max(1, (4 * ctx->num_sms + tiles_per_chunk - 1) / tiles_per_chunk);
+    const double blk_bytes = 32768.0 * lay.nchunks, img_bytes = blk_bytes * lay.nblocks;
+    const double sig_bytes = 2.0 * sig + 8.0 * nrm;   // fp16 planes + mu / invE
+    auto dram_estimate = [&](int G, int S) {
+        const int ngroups = (nchunks + G - 1) / G;
+        const double miss = std::min(1.0, std::max(0.0, (S * sig_bytes / ngroups + 2.0 * S * blk_bytes - 15e6) / 120e6));
+        return img_bytes * ngroups + sig_bytes * (1.0 + miss * (static_cast<double>(lay.nblocks) / S - 1.0));
+    };
+    int group = std::min(g4, nchunks), super = 1;
+    {
+        double best = dram_estimate(group, 1);
+        const int cand_g[3] = {std::min(g4, nchunks), std::min(2 * g4, nchunks), nchunks};
+        for (int S : {1, 4}) {
+            if (S > 1 && (2.0 * S * blk_bytes > 40e6 || lay.nblocks < 2 * S)) continue;
+            for (int G : cand_g) {
+                if (S == 1 && G < std::min(g4, nchunks)) continue;
+                const double e = dram_estimate(G, S);
+                if (e < 0.8 * best) { best = e; group = G; super = S; }
+            }
+        }
+    }
+    if (const char* g = std::getenv("DTX_K1_GROUP"))   // experiment knobs: force the order
         if (std::atoi(g) > 0) group = std::atoi(g);
-    // Superblocks: `super` consecutive basis blocks are run back to back on the same wave of
-    // num_sms tiles, so a tile's signal span and norm tile are re-read from L2 `super` times in a row
-    // and the whole group's signal only once per superblock pass instead of once per block pass
-    // (super = 1 is the plain (group, block, tile) order).  Pure reordering of the item list.
-    int super = 1;
     if (const char* g = std::getenv("DTX_K1_SUPER"))
         if (std::atoi(g) > 0) super = std::atoi(g);
     const int wave = ctx->num_sms;

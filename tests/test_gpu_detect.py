@@ -270,3 +270,37 @@ def test_short_chunks_use_the_1024_lag_tile(engine):
             ref = orc.mpx_ds_direct(c, U, Nc)
             ds = engine.get_ds(ci, si)
             assert ds.shape == ref.shape and np.abs(ds - ref).max() < TOL
+
+
+def test_item_order_does_not_change_results(engine, monkeypatch):
+    """K1's work-item order (chunk groups x superblocks of basis blocks, chosen by a DRAM-traffic model
+    in project_run) is a pure reordering: every forced order gives bit-identical DS rows, histograms
+    and candidates."""
+    rng = np.random.default_rng(77)
+    Nc, ns = 2, 96
+    ranks = [16, 5, 11, 16, 3, 8, 8, 16, 1, 2, 13, 16, 7, 9, 16, 4]      # ~11 blocks of 16 slots
+    bases = [synth.random_basis(rng, ns * Nc, r) for r in ranks]
+    chunks = [synth.multiplex(synth.bandpassed_noise(rng, 5000 + 37 * i, nchan=Nc)) for i in range(5)]
+    thr = [0.2] * len(ranks)
+    engine.set_bases(31, bases, Nc, thresholds=thr)
+    ref = None
+    for group, sup in ((None, None), (1, 1), (5, 1), (2, 4), (5, 4), (5, 3)):
+        if group is None:
+            monkeypatch.delenv("DTX_K1_GROUP", raising=False)
+            monkeypatch.delenv("DTX_K1_SUPER", raising=False)
+        else:
+            monkeypatch.setenv("DTX_K1_GROUP", str(group))
+            monkeypatch.setenv("DTX_K1_SUPER", str(sup))
+        engine.hist(31, reset=True)
+        engine.load_chunks(chunks)
+        engine.detect_run(31, lta_window=50)
+        ds = [engine.get_ds(ci, si) for ci in range(len(chunks)) for si in (0, 3, 8, 15)]
+        cand = np.sort(engine.candidates(), order=["row", "t"])
+        out = (ds, engine.hist(31, reset=True), cand, engine.rowstats()[0])
+        if ref is None:
+            ref = out
+            assert np.abs(ds[0] - orc.mpx_ds_direct(chunks[0], bases[0], Nc)).max() < TOL
+        else:
+            assert all(np.array_equal(a, b) for a, b in zip(out[0], ref[0]))
+            assert np.array_equal(out[1], ref[1]) and np.array_equal(out[2], ref[2])
+            assert np.array_equal(out[3], ref[3])
