@@ -300,3 +300,134 @@ def associateDetections(ssdf, requiredNumStations, associateBuffer, temkey, exce
             rec[0] = _event_name(tmean[k])
             det_rows.append(rec)
     return [pd.DataFrame(det_rows, columns=EVENT_COLS), pd.DataFrame(auto_rows, columns=EVENT_COLS)]
+
+
+# ------------------------------------------------------------------ detResults
+def _approximateThreshold(beta_a, beta_b, target, numintervals=1000, numloops=3):
+    """results.py:209-229: forward grid search where `beta.isf` breaks down."""
+    import scipy.stats
+    startVal, stopVal = 0, 1
+    for _ in range(numloops):
+        Xs = np.linspace(startVal, stopVal, numintervals)
+        pfs = scipy.stats.beta.sf(Xs, beta_a, beta_b)
+        minind = int(np.abs(pfs - target).argmin())
+        bestPf, bestX = pfs[minind], Xs[minind]
+        if minind == 0 or minind == numintervals - 1:
+            raise ValueError('Grind search failing, set threshold manually')
+        startVal, stopVal = Xs[minind - 1], Xs[minind + 1]
+    return bestX, bestPf
+
+
+def makePfKey(info, Pf):
+    """`_makePfKey` for one info table (results.py:176-206): per (Sta, Name) the DS value whose
+    false-alarm probability under the fitted beta distribution is Pf."""
+    import scipy.stats
+    if not Pf or not isinstance(info, pd.DataFrame):
+        return None
+    rows = []
+    for _, row in info.iterrows():
+        TH = scipy.stats.beta.isf(Pf, row.beta1, row.beta2, 0, 1)
+        if TH > .94:
+            TH, _ = _approximateThreshold(row.beta1, row.beta2, Pf, 1000, 3)
+        rows.append([row.Sta, row.Name, TH, [row.beta1, row.beta2, 0, 1]])
+    return pd.DataFrame(rows, columns=['Sta', 'Name', 'DS', 'betadist'])
+
+
+def verifyEvents(Dets, Autos, veriFile, veriBuffer=1, includeAllVeriColumns=True):
+    """`_verifyEvents` (results.py:232-293): mark the detection (highest DSav) whose origin window
+    +- veriBuffer / 2 contains a known event; returns the frame of verified detections with the
+    Ver* columns.  veriFile: DataFrame or csv path with TIME, LAT, LON, MAG, DEPTH, NAME."""
+    if veriFile is None:
+        return None
+    ver = pd.read_csv(veriFile) if isinstance(veriFile, str) else veriFile.copy()
+    req = ['TIME', 'LAT', 'LON', 'MAG', 'DEPTH', 'NAME']
+    if not set(req).issubset(ver.columns):
+        raise Exception('veriFile does not have the required columns, it needs TIME,LAT,LON,MAG,DEPTH,NAME')
+    from .workflow import _timestamp
+    ver['STMP'] = [_timestamp(x) for x in ver['TIME']]
+    extra = [c for c in ver.columns if c not in ('TIME', 'LAT', 'LON', 'MAG', 'ProEnMag', 'DEPTH', 'NAME')]
+    out = []
+    for _, v in ver.iterrows():
+        for table in (Dets, Autos):
+            if table is None or len(table) == 0:
+                continue
+            m = ((table.MSTAMPmin - veriBuffer / 2.0 < v.STMP) & (table.MSTAMPmax + veriBuffer / 2.0 > v.STMP)
+                 & ~table.Verified.astype(bool))
+            tem = table[m]
+            if len(tem) == 0:
+                continue
+            tru = tem[tem.DSav == tem.DSav.max()].iloc[:1].copy()
+            table.loc[tru.index[0], 'Verified'] = True
+            if includeAllVeriColumns:
+                for col in extra:
+                    if col not in tru.columns:
+                        tru[col] = v[col]
+            tru['VerMag'], tru['VerLat'], tru['VerLon'] = v.MAG, v.LAT, v.LON
+            tru['VerDepth'], tru['VerName'] = v.DEPTH, v.NAME
+            out.append(tru)
+            break                                       # Autos are only searched when Dets had no match
+    if not out:
+        return pd.DataFrame()
+    return pd.concat(out, ignore_index=True).drop(columns=['Verified'])
+
+
+class SSResults(object):
+    """`detex.results.SSResults` (results.py:588-601) without `writeDetections` (it fetches and writes
+    ObsPy waveforms: out of scope)."""
+
+    def __init__(self, Dets, Autos, Vers, ss_info, ss_filt, temkey, stakey, templateKey=None, fetcher=None):
+        self.Autos, self.Dets, self.Vers = Autos, Dets, Vers
+        self.NumVerified = len(Vers) if isinstance(Vers, pd.DataFrame) else 'N/A'
+        self.info, self.filt = ss_info, ss_filt
+        self.StationKey, self.TemplateKey, self.TemKeyPath, self.fetcher = stakey, temkey, templateKey, fetcher
+
+    def __repr__(self):
+        return ('SSResults instance with %d autodections and %d new detections, %s are verified'
+                % (len(self.Autos), len(self.Dets), self.NumVerified))
+
+
+def detResults(trigCon=0, trigParameter=0, associateReq=0, ss_associateBuffer=1, sg_associateBuffer=2.5,
+               requiredNumStations=4, veriBuffer=1, ssDB='SubSpace.db', templateKey=None, stationKey=None,
+               veriFile=None, includeAllVeriColumns=True, reduceDets=True, Pf=False, stations=None,
+               starttime=None, endtime=None, fetch=None, exceptionalThreshold=None):
+    """`detex.results.detResults` (results.py:22-173): load the detections a run left in `ssDB`, drop
+    per-station duplicates, associate across stations, split off the auto-detections of the training
+    events, verify against a catalogue.  The keys are DataFrames (or csv paths)."""
+    import os
+    if not os.path.exists(ssDB):
+        raise Exception('%s does not exist' % ssDB)
+    if trigCon not in (0, 1):
+        raise Exception('trigCon must be 0 or 1')
+    if associateReq != 0:
+        raise Exception('associateReq values other than 0 not yet supported')     # results.py:120-122
+    temkey = pd.read_csv(templateKey) if isinstance(templateKey, str) else templateKey.copy()
+    stakey = pd.read_csv(stationKey) if isinstance(stationKey, str) else stationKey
+    from .workflow import _timestamp
+    temkey['STMP'] = [_timestamp(t) for t in temkey['TIME']]                      # results.py:421
+    ss_info, sg_info = loadSQLite(ssDB, 'ss_info'), loadSQLite(ssDB, 'sg_info')
+    filt = loadSQLite(ssDB, 'filt_params')
+    frames = []
+    for table, buf, info in (('ss_df', ss_associateBuffer, ss_info), ('sg_df', sg_associateBuffer, sg_info)):
+        if reduceDets:
+            df = select_detections(ssDB, table, trigCon, trigParameter, stations, starttime, endtime)
+            key = makePfKey(info, Pf)
+            if df is not None and key is not None:       # `_buildSQL` with a PfKey: per-detector DS floor
+                by_code = {(r.Sta, r.Name): r.DS for _, r in key.iterrows()}   # Sta = 'NET.STA' in both tables
+                floor = np.array([by_code.get((s, n), np.inf) for s, n in zip(df.Sta, df.Name)])
+                df = df[df.DS.to_numpy() >= floor]
+            df = deleteDetDups(df, buf)
+        else:
+            if Pf:
+                raise Exception('When using the Pf parameter reduceDets must be True')
+            df = loadSQLite(ssDB, table)
+        if df is not None and len(df):
+            frames.append(df)
+    if not frames:
+        raise Exception('No detections found that meet given criteria')
+    df = pd.concat(frames, ignore_index=True)
+    if isinstance(stations, (list, tuple)):
+        df = df[df.Sta.isin(stations)]
+    Dets, Autos = associateDetections(df, requiredNumStations, ss_associateBuffer, temkey, exceptionalThreshold)
+    Vers = verifyEvents(Dets, Autos, veriFile, veriBuffer, includeAllVeriColumns)
+    return SSResults(Dets, Autos, Vers, ss_info, filt, temkey, stakey, templateKey if isinstance(templateKey, str) else None,
+                     fetch)

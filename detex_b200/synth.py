@@ -141,6 +141,8 @@ def workflow_case(seed, stations=("TA.M17A", "TA.M18A"), nfam=3, per_fam=5, nsin
                            "STARTTIME": t0, "ENDTIME": t0 + nchunks * chunk_seconds,
                            "LAT": 40.5, "LON": -110.5, "ELEVATION": 1500.0, "CHANNELS": "BHE-BHN-BHZ"})
     events, continuous, picks, planted = {}, {}, [], []
+    # an event is seen by every station at (nearly) the same time: one origin per chunk, small moveout
+    plant_t = [int(rng.integers(int(20 * sr), Ls - int(40 * sr))) for _ in range(nchunks)]
 
     def raw_noise(nsamp, amp):
         x = amp * rng.standard_normal((Nc, nsamp))
@@ -173,7 +175,7 @@ def workflow_case(seed, stations=("TA.M17A", "TA.M18A"), nfam=3, per_fam=5, nsin
             x = raw_noise(Ls, 0.15)
             if c < nfam + 1:
                 fam = c % nfam
-                t = int(rng.integers(int(20 * sr), Ls - int(40 * sr)))
+                t = plant_t[c] + int(rng.integers(0, int(1.0 * sr)))
                 x[:, t:t + ns // 2] += float(rng.uniform(0.8, 1.2)) * fams[fam]
                 planted.append((sta, c, fam, t / sr))
             continuous[sta].append(([x[k].copy() for k in range(Nc)], t0 + c * chunk_seconds))

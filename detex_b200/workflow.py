@@ -732,7 +732,7 @@ class SubSpace(object):
                     continue
                 DF = frames[sta]
                 thr = {r.Name: float(r.Threshold) for _, r in DF.iterrows() if r.Name in ssTD}
-                det = SSDetex(ssTD, thr, offsets, Nc, sta=sta.split('.')[1], engine=self.engine,
+                det = SSDetex(ssTD, thr, offsets, Nc, sta=sta, engine=self.engine,   # 'NET.STA' (detect.py:82-86)
                               set_id=(40 if issub else 60) + si, triggerLTATime=triggerLTATime,
                               triggerSTATime=triggerSTATime, fillZeros=fillZeros, calcHist=calcHist,
                               ewf=ewf if estimateMags else None, mags=mags if estimateMags else None,

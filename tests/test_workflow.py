@@ -6,6 +6,7 @@ CPU (`-m "not gpu"`): the host logic driven by the oracle-backed engine stand-in
 GPU: the same sequence on the CUDA engine, compared with the stand-in's output row by row.
 """
 import numpy as np
+import pandas as pd
 import pytest
 
 from detex_b200 import results, synth, workflow
@@ -68,7 +69,7 @@ def _check_structure(case, cl, ss, db):
     # every planted family member is found by a subspace on its station, near where it was put
     t0 = float(case["stakey"].STARTTIME.iloc[0])
     for sta, c, fam, tsec in case["planted"]:
-        hit = ssdf[(ssdf.Sta == sta.split(".")[1]) & (np.abs(ssdf.STMP - (t0 + c * case["chunk_seconds"] + tsec)) < 12)]
+        hit = ssdf[(ssdf.Sta == sta) & (np.abs(ssdf.STMP - (t0 + c * case["chunk_seconds"] + tsec)) < 12)]
         assert len(hit) >= 1 and hit.DS.max() > 0.3, (sta, c, fam)
     assert np.isfinite(ssdf.Mag).all() and np.isfinite(ssdf.SNR).all()
     return ssdf
@@ -78,6 +79,28 @@ def test_workflow_host_logic_with_oracle_engine(tmp_path):
     case, cl, ss, db, found = _run(OracleEngine(), tmp_path)
     ssdf = _check_structure(case, cl, ss, db)
     assert sum(v for (sta, issub), v in found.items() if issub) == len(ssdf)
+    # ---- detResults (results.py:22-173): both stations must see an event; planted members become Dets
+    t0 = float(case["stakey"].STARTTIME.iloc[0])
+    veri = pd.DataFrame([{"TIME": t0 + c * case["chunk_seconds"] + tsec - 3.0, "LAT": 40.0, "LON": -110.0, "MAG": 1.0,
+                          "DEPTH": 5.0, "NAME": "known%d" % c}
+                         for sta, c, fam, tsec in case["planted"] if sta == "TA.M17A"][:2])
+    res = results.detResults(ssDB=db, templateKey=case["temkey"], stationKey=case["stakey"], requiredNumStations=2,
+                             ss_associateBuffer=8, sg_associateBuffer=8, veriFile=veri, veriBuffer=30)
+    assert "new detections" in repr(res) and len(res.Autos) == 0          # training events are a month earlier
+    assert len(res.Dets) >= 4 and (res.Dets.NumStations == 2).all()
+    for c in range(4):                                                      # chunks 0..3 hold a planted event per station
+        m = (res.Dets.MSTAMPmin < t0 + (c + 1) * case["chunk_seconds"]) & (res.Dets.MSTAMPmax > t0 + c * case["chunk_seconds"])
+        assert m.any()
+    assert res.NumVerified == 2 and set(res.Vers.VerName) == {"known0", "known1"}
+    assert res.Dets.Verified.sum() == 2
+    one = results.detResults(ssDB=db, templateKey=case["temkey"], stationKey=case["stakey"], requiredNumStations=3)
+    assert len(one.Dets) == 0 and one.NumVerified == 'N/A'
+    pf = results.detResults(ssDB=db, templateKey=case["temkey"], stationKey=case["stakey"], requiredNumStations=1,
+                            Pf=1e-4)
+    lo = results.detResults(ssDB=db, templateKey=case["temkey"], stationKey=case["stakey"], requiredNumStations=1)
+    assert 0 < len(pf.Dets) <= len(lo.Dets)
+    with pytest.raises(Exception):
+        results.detResults(ssDB=db, templateKey=case["temkey"], stationKey=case["stakey"], associateReq=1)
 
 
 def test_workflow_with_decimation(tmp_path):
@@ -93,7 +116,7 @@ def test_workflow_with_decimation(tmp_path):
     ssdf = results.loadSQLite(db, "ss_df")
     t0 = float(case["stakey"].STARTTIME.iloc[0])
     for sta, c, fam, tsec in case["planted"]:
-        hit = ssdf[(ssdf.Sta == sta.split(".")[1]) & (np.abs(ssdf.STMP - (t0 + c * case["chunk_seconds"] + tsec)) < 12)]
+        hit = ssdf[(ssdf.Sta == sta) & (np.abs(ssdf.STMP - (t0 + c * case["chunk_seconds"] + tsec)) < 12)]
         assert len(hit) >= 1 and hit.DS.max() > 0.3
     assert np.allclose((ssdf.STMP.values - t0) * 20.0, np.round((ssdf.STMP.values - t0) * 20.0), atol=1e-5)
 
