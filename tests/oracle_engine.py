@@ -165,7 +165,7 @@ class OracleEngine(object):
         out = np.eye(N)
         for i in range(N):
             for j in range(i + 1, N):
-                out[i, j] = out[j, i] = orc.fast_normcorr(X[i], X[j])
+                out[i, j] = out[j, i] = float(np.max(orc.fast_normcorr(X[i], X[j])))
         return out
 
     def ccx(self, X, Nc, row_begin=0, row_end=None, engine="fp64"):

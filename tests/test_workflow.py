@@ -103,6 +103,45 @@ def test_workflow_host_logic_with_oracle_engine(tmp_path):
         results.detResults(ssDB=db, templateKey=case["temkey"], stationKey=case["stakey"], associateReq=1)
 
 
+def test_subspace_options_without_fas(tmp_path):
+    """SVD with a fixed threshold / selectCriteria 3 and 4 (no FAS run), validateClusters, updateReqCC by
+    station, createSubSpace from the pickled ClusterStream (subspace.py:738-773, 1015-1054; construct.py:236-243)."""
+    case = synth.workflow_case(79, nchunks=2)
+    eng = OracleEngine()
+    f = workflow.ArrayFetcher(case["events"], case["continuous"], sr=case["sr"], seed=1)
+    path = str(tmp_path / "clust.pkl")
+    cl = workflow.createCluster(CCreq=CCREQ, fetch_arg=f, stationKey=case["stakey"], templateKey=case["temkey"],
+                                trim=[2, 18], fileName=path, engine=eng)
+    cl.updateReqCC({"M17A": 0.6, "TA.M18A": 0.5})
+    assert cl["M17A"].ccReq == 0.6 and cl[1].ccReq == 0.5
+    ss = workflow.createSubSpace(clust=path, engine=eng)             # un-pickles the ClusterStream
+    assert sorted(ss.subspaces) == ["TA.M17A", "TA.M18A"]
+    ss.attachPickTimes(case["picks"], defaultDuration=8, function="mean")
+    before = {sta: [list(r.Events) for _, r in ss.subspaces[sta].iterrows()] for sta in ss.subspaces}
+    ss.validateClusters()                                            # well-aligned families: nothing is dropped
+    assert before == {sta: [list(r.Events) for _, r in ss.subspaces[sta].iterrows()] for sta in ss.subspaces}
+    # a member replaced by noise fails the check against every later member and is removed
+    row = ss.subspaces["TA.M17A"].iloc[0]
+    ev0 = row.Events[0]
+    row.AlignedTD[ev0] = np.random.default_rng(0).standard_normal(len(row.AlignedTD[ev0]))
+    ss.validateClusters()
+    assert ev0 not in ss.subspaces["TA.M17A"].iloc[0].Events and len(ss.subspaces["TA.M17A"].iloc[0].Events) == 4
+    ss.SVD(selectCriteria=4, selectValue=1, threshold=0.33, useSingles=False)
+    for sta in ss.subspaces:
+        assert (ss.subspaces[sta].NumBasis == 2).all() and (ss.subspaces[sta].Threshold == 0.33).all()
+    ss.SVD(selectCriteria=3, selectValue=0.8, useSingles=False)
+    for sta in ss.subspaces:
+        for _, r in ss.subspaces[sta].iterrows():
+            assert abs(r.Threshold - 0.8 * r.FracEnergy["Minimum"][r.NumBasis]) < 1e-12
+            assert r.FracEnergy["Average"][r.NumBasis] >= 0.8
+    ss.SVD(selectCriteria=4, selectValue=0, threshold=0.4)           # singles get the manual threshold too
+    assert all((ss.singles[sta].Threshold == 0.4).all() for sta in ss.singles)
+    found = ss.detex(subspaceDB=str(tmp_path / "a.db"), useSingles=True, estimateMags=False, fillZeros=True)
+    df = results.loadSQLite(str(tmp_path / "a.db"), "ss_df")
+    assert len(df) == sum(v for (sta, sub), v in found.items() if sub)
+    assert (df.DS_STALTA == 0).all() and df.Mag.isna().all()          # fillZeros / estimateMags=False (detect.py:414-432)
+
+
 def test_workflow_with_decimation(tmp_path):
     """createCluster(decimate=2): 40 Hz traces are low-passed and decimated to 20 Hz before detrend /
     band-pass (construct.py:1014-1015); lags, trims and trigger times then live on the 20 Hz grid."""
