@@ -412,8 +412,8 @@ def detResults(trigCon=0, trigParameter=0, associateReq=0, ss_associateBuffer=1,
             df = select_detections(ssDB, table, trigCon, trigParameter, stations, starttime, endtime)
             key = makePfKey(info, Pf)
             if df is not None and key is not None:       # `_buildSQL` with a PfKey: per-detector DS floor
-                by_code = {(r.Sta, r.Name): r.DS for _, r in key.iterrows()}   # Sta = 'NET.STA' in both tables
-                floor = np.array([by_code.get((s, n), np.inf) for s, n in zip(df.Sta, df.Name)])
+                floor_of = {(r.Sta, r.Name): r.DS for _, r in key.iterrows()}   # Sta is NET.STA in both tables
+                floor = np.array([floor_of.get((s, n), np.inf) for s, n in zip(df.Sta, df.Name)])
                 df = df[df.DS.to_numpy() >= floor]
             df = deleteDetDups(df, buf)
         else:

@@ -349,6 +349,25 @@ def _sub_frames(DFcc, DFlag, all_events, events):
     return scc, slag
 
 
+def _ensureUnique(DFcc, seed=0):
+    """`_ensureUnique` (construct.py:814-835): the dendrogram walk looks lags up by coefficient, so equal
+    coefficients (duplicate catalogue entries, say) are nudged apart by < 1e-5 -- the reference lowers
+    the dissimilarity by `abs(.00001 * np.random.rand())`, unseeded; here the draw is seeded."""
+    cc = np.array(DFcc, dtype=np.float64)
+    iu = np.triu_indices(cc.shape[0])
+    rng = np.random.default_rng(seed)
+    for _ in range(11):
+        v = cc[iu]
+        _, first = np.unique(v, return_index=True)
+        dup = np.setdiff1d(np.arange(len(v)), first)
+        if len(dup) == 0:
+            return cc
+        log.warning('Duplicates found in correlation coefficients, perturbing slightly to get unique values')
+        v[dup] += np.abs(.00001 * rng.random(len(dup)))       # cx - d  <=>  cc + d
+        cc[iu] = v
+    _error('cannot make Coeficients unique, killing program')
+
+
 def createSubSpace(Pf=10 ** -12, clust=None, minEvents=2, dtype='double', conDatFetcher=None, engine=None):
     """`detex.createSubSpace` (construct.py:177-301): one row per (station, cluster) with the
     aligned waveforms, offsets and statistics the detector needs; singles per station."""
@@ -377,6 +396,7 @@ def createSubSpace(Pf=10 ** -12, clust=None, minEvents=2, dtype='double', conDat
             if len(evelist) < minEvents:                 # keep numbering, construct.py:596-598
                 continue
             DFcc, DFlag = _sub_frames(cll.CCs, cll.Lags, list(cll.Events), evelist)
+            DFcc = _ensureUnique(DFcc)                                          # construct.py:271
             link, delays = construct.get_delays(DFcc, DFlag)                    # construct.py:272-281
             aligned, sample_delays = construct.alignTD(delays, [row.MPtd[e] for e in evelist])
             stats = construct.update_start_times([row.Stats[e] for e in evelist], sample_delays,

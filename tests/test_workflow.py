@@ -142,6 +142,28 @@ def test_subspace_options_without_fas(tmp_path):
     assert (df.DS_STALTA == 0).all() and df.Mag.isna().all()          # fillZeros / estimateMags=False (detect.py:414-432)
 
 
+def test_duplicate_events_do_not_break_the_alignment(tmp_path):
+    """Two catalogue entries with identical waveforms give equal correlation coefficients; the reference
+    perturbs them (`_ensureUnique`, construct.py:814-835) instead of failing in the dendrogram walk."""
+    case = synth.workflow_case(80, stations=("TA.M17A",), nfam=1, per_fam=4, nsingles=0, nchunks=1)
+    ev = case["events"]["TA.M17A"]
+    names = list(case["temkey"].NAME)
+    ev[names[1]] = ([t.copy() for t in ev[names[0]][0]], ev[names[1]][1])       # event 1 := event 0
+    eng = OracleEngine()
+    f = workflow.ArrayFetcher(case["events"], case["continuous"], sr=case["sr"])
+    cl = workflow.createCluster(CCreq=0.4, fetch_arg=f, stationKey=case["stakey"], templateKey=case["temkey"],
+                                trim=[2, 18], saveclust=False, engine=eng)
+    row = cl.trdf.iloc[0]
+    cc = row.CCs.values.astype(float)
+    # cc(0,2) == cc(1,2): duplicate coefficients.  (cc(0,1) itself is round-off dependent in the reference:
+    # a lag-0 value of 1 + 2e-16 trips its |res| > 1 rule, construct.py:455-459, and the next-best lag wins.)
+    assert cc[0, 1] == cc[1, 1] and cc[0, 2] == cc[1, 2]
+    ss = workflow.createSubSpace(clust=cl, engine=eng)
+    r = ss.subspaces["TA.M17A"].iloc[0]
+    assert r.Events == names and len(set(len(v) for v in r.AlignedTD.values())) == 1
+    assert np.array_equal(r.AlignedTD[names[0]], r.AlignedTD[names[1]])
+
+
 def test_workflow_with_decimation(tmp_path):
     """createCluster(decimate=2): 40 Hz traces are low-passed and decimated to 20 Hz before detrend /
     band-pass (construct.py:1014-1015); lags, trims and trigger times then live on the 20 Hz grid."""
