@@ -24,7 +24,7 @@ EXPORTS = [
     "dtx_load_chunks", "dtx_attach_device_chunks", "dtx_preprocess_chunks", "dtx_get_chunk", "dtx_detect_run", "dtx_num_lags", "dtx_get_ds",
     "dtx_get_ds64", "dtx_get_stalta", "dtx_get_rowstats", "dtx_get_hist", "dtx_get_fas", "dtx_get_candidates",
     "dtx_sta_lta_max", "dtx_set_events", "dtx_est_mags", "dtx_last_k1_ms", "dtx_launch_count", "dtx_ccx", "dtx_corr_zero_lag",
-    "dtx_set_x8_tolerance", "dtx_get_chunk_modes", "dtx_set_trigger_sta", "dtx_preprocess_chunks_dec",
+    "dtx_set_x8_tolerance", "dtx_get_chunk_modes", "dtx_set_trigger_sta", "dtx_preprocess_chunks_dec", "dtx_set_hist_bins",
 ]
 
 
@@ -61,6 +61,7 @@ def load():
     L.dtx_set_x8_tolerance.argtypes = [p, C.c_double]
     L.dtx_get_chunk_modes.argtypes = [p, p]
     L.dtx_set_trigger_sta.argtypes = [p, C.c_int]
+    L.dtx_set_hist_bins.argtypes = [p, C.c_int]
     L.dtx_set_bases.argtypes = [p, C.c_int, p, p, C.c_int, C.c_int, C.c_int, p]
     L.dtx_load_chunks.argtypes = [p, C.c_int, p, p, C.c_int]
     L.dtx_attach_device_chunks.argtypes = [p, C.c_int, p, p, p, C.c_int]

@@ -106,6 +106,7 @@ struct dtx_ctx {
     DevBuf<double> d_DS64, d_sum;
     DevBuf<unsigned> d_maxbits, d_k4bits;
     DevBuf<int> d_chunk_mode;     // per chunk: 1 = 8-bit cross terms in the last run
+    int hist_bins = HIST_BINS;    // bins of the device histograms (numBins - 1 of fas._initFAS, fas.py:31)
     int sta_window = 0;           // triggerSTATime in samples (0 = reference default: STA = |DS|)
     double x8_eps = 2e-6;         // adaptive engine: admitted RMS error of a normalised projection
     DevBuf<int> d_rowflags, d_ncand;
@@ -319,7 +320,7 @@ static int set_bases_device(dtx_ctx* ctx, int set_id, const std::function<int(do
     DTX_CUDA(bs.d_slot_row.reserve(slot_row.size()));
     DTX_CUDA(bs.d_binfo.reserve(binfo.size()));
     DTX_CUDA(bs.d_thr.reserve(S));
-    DTX_CUDA(bs.d_hist.reserve(static_cast<size_t>(S) * HIST_BINS));
+    DTX_CUDA(bs.d_hist.reserve(static_cast<size_t>(S) * HIST_MAX_BINS));
     DTX_CUDA(bs.d_fas.reserve(static_cast<size_t>(S) * 5));
     const size_t img_bytes = static_cast<size_t>(lay.nblocks) * lay.nchunks * 32768;
     DTX_CUDA(bs.d_Aimg.reserve(img_bytes));
@@ -332,7 +333,7 @@ static int set_bases_device(dtx_ctx* ctx, int set_id, const std::function<int(do
     bs.has_thr = thresholds != nullptr;
     if (thresholds) for (int s = 0; s < S; ++s) thr[s] = static_cast<float>(thresholds[s]);
     DTX_CUDA(cudaMemcpy(bs.d_thr.p, thr.data(), sizeof(float) * S, cudaMemcpyHostToDevice));
-    DTX_CUDA(cudaMemset(bs.d_hist.p, 0, sizeof(unsigned long long) * S * HIST_BINS));
+    DTX_CUDA(cudaMemset(bs.d_hist.p, 0, sizeof(unsigned long long) * S * HIST_MAX_BINS));
     DTX_CUDA(cudaMemset(bs.d_fas.p, 0, sizeof(double) * S * 5));
     launch_basis_image(bs.d_U.p, bs.d_slot_row.p, lay, bs.d_Aimg.p, 0, ctx->stream);
     bs.have_img8 = false;
@@ -612,7 +613,7 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
     const int nchunks = ctx->nchunks, S = bs.lay.S;
     cudaStream_t st = ctx->stream;
     launch_k3(ctx->d_DS.p, ctx->d_chunks.p, nchunks, S, bs.d_thr.p, ctx->d_rowmax.p, ctx->d_rowflags.p,
-              bs.d_hist.p, hist_lo, hist_hi, ctx->d_cand.p, ctx->cand_cap, ctx->d_ncand.p,
+              bs.d_hist.p, hist_lo, hist_hi, ctx->hist_bins, ctx->d_cand.p, ctx->cand_cap, ctx->d_ncand.p,
               want_fas ? bs.d_fas.p : nullptr, st);
     DTX_CUDA(cudaGetLastError());
     ctx->launches += 2;  // k3_fast_kernel + k3_kernel (flagged rows only)
@@ -725,16 +726,28 @@ int dtx_get_rowstats(dtx_ctx* ctx, float* maxds, int32_t* flags, int64_t count) 
     return DTX_OK;
 }
 
+int dtx_set_hist_bins(dtx_ctx* ctx, int nbins) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (nbins < 1 || nbins > HIST_MAX_BINS) return fail(ctx, DTX_ERR_ARG, "dtx_set_hist_bins: 1 <= nbins <= 1024");
+    ctx->hist_bins = nbins;
+    return DTX_OK;
+}
+
 int dtx_get_hist(dtx_ctx* ctx, int set_id, uint64_t* hist, int64_t count, int reset) {
     if (!ctx) return DTX_ERR_ARG;
     auto it = ctx->sets.find(set_id);
     if (it == ctx->sets.end()) return fail(ctx, DTX_ERR_STATE, "dtx_get_hist: unknown basis set");
     BasisSet& bs = it->second;
-    const int64_t nel = static_cast<int64_t>(bs.lay.S) * HIST_BINS;
+    const int nb = ctx->hist_bins;
+    const int64_t nel = static_cast<int64_t>(bs.lay.S) * nb;
     if (hist && count < nel) return fail(ctx, DTX_ERR_CAPACITY, "dtx_get_hist: buffer too small");
     DTX_CUDA(cudaSetDevice(ctx->device));
-    if (hist) DTX_CUDA(cudaMemcpyAsync(hist, bs.d_hist.p, sizeof(uint64_t) * nel, cudaMemcpyDeviceToHost, ctx->stream));
-    if (reset) DTX_CUDA(cudaMemsetAsync(bs.d_hist.p, 0, sizeof(uint64_t) * nel, ctx->stream));
+    // device rows have a pitch of HIST_MAX_BINS; the caller gets [S][nbins] packed
+    if (hist)
+        DTX_CUDA(cudaMemcpy2DAsync(hist, sizeof(uint64_t) * nb, bs.d_hist.p, sizeof(uint64_t) * HIST_MAX_BINS,
+                                   sizeof(uint64_t) * nb, bs.lay.S, cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset)
+        DTX_CUDA(cudaMemsetAsync(bs.d_hist.p, 0, sizeof(uint64_t) * bs.lay.S * HIST_MAX_BINS, ctx->stream));
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));
     return DTX_OK;
 }

@@ -22,7 +22,8 @@ constexpr int CHUNK_TAPS = 64;      // taps per A stage
 constexpr int VEC_PER_BLOCK = 16;   // basis vectors per K1 basis block (x 8 phases = 128 rows)
 constexpr int MAX_SEG_TAPS = 3072;  // taps per K segment (bounded by the smem signal span)
 constexpr int MAX_SEGS = 48;
-constexpr int HIST_BINS = 400;
+constexpr int HIST_BINS = 400;        // default: np.linspace(lo, hi, 401) (detect.py:80, fas.py:31)
+constexpr int HIST_MAX_BINS = 1024;   // row pitch of the device histograms; numBins - 1 <= this
 // 8-bit cross-term engine: u_lo * 2^6 and u_hi * 2^-6 fit e4m3 (max|u * 2^eu| < 2^14), x_hi * 2^-6 and
 // x_lo * 2^6 fit e5m2 (max|x * 2^ex| < 2^15); the shifts cancel in each product.
 constexpr int X8_SHIFT = 6;
@@ -118,8 +119,8 @@ struct Candidate {
 };
 void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, const float* d_thr,
                float* d_rowmax, int* d_rowflags, unsigned long long* d_hist, double hist_lo,
-               double hist_hi, Candidate* d_cand, int cand_cap, int* d_ncand,
-               double* d_fas /*[S][4] or null*/, cudaStream_t st);
+               double hist_hi, int nbins, Candidate* d_cand, int cand_cap, int* d_ncand, double* d_fas,
+               cudaStream_t st);
 void launch_lta(const float* DS, const ChunkDesc* d_chunks, int S, const int* d_rowflags,
                 Candidate* d_cand, const int* d_ncand, int cand_cap, int W, int Wsta, cudaStream_t st);
 

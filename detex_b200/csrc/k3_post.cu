@@ -26,13 +26,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // np.histogram(x, bins=np.linspace(lo, hi, 401)): bin i holds edges[i] <= x < edges[i+1],
 // last bin closed; edges[i] = lo + i*step (float64), edges[400] = hi exactly.
-__device__ __forceinline__ int hist_bin(float xf, double lo, double hi, double step) {
+__device__ __forceinline__ int hist_bin(float xf, double lo, double hi, double step, int nb) {
     const double x = static_cast<double>(xf);
     if (!(x >= lo) || !(x <= hi)) return -1;
     int i = static_cast<int>((x - lo) / step);
-    if (i > HIST_BINS - 1) i = HIST_BINS - 1;
+    if (i > nb - 1) i = nb - 1;
     while (i > 0 && x < lo + i * step) --i;
-    while (i < HIST_BINS - 1 && x >= lo + (i + 1) * step) ++i;
+    while (i < nb - 1 && x >= lo + (i + 1) * step) ++i;
     return i;
 }
 
@@ -42,17 +42,18 @@ __device__ __forceinline__ int hist_bin(float xf, double lo, double hi, double s
 // float64 comparison against the same `lo + e*step` hist_bin uses -- no float64 division.  (Noise
 // DS of a rank-1 subspace is below 1e-3 of a bin 12 % of the time; with the generic fallback
 // nearly every warp took the division path.)
-__device__ __forceinline__ int hist_bin_fast(float x, float flo, float finv, double lo, double hi, double step) {
+__device__ __forceinline__ int hist_bin_fast(float x, float flo, float finv, double lo, double hi, double step,
+                                             int nb) {
     const float t = (x - flo) * finv;
     const float fl = floorf(t);
     const float fr = t - fl;
-    if (fr > 1e-3f && fr < 0.999f && t > 0.f && t < static_cast<float>(HIST_BINS)) return static_cast<int>(fl);
+    if (fr > 1e-3f && fr < 0.999f && t > 0.f && t < static_cast<float>(nb)) return static_cast<int>(fl);
     const float r = rintf(t);
-    if (!(r >= 0.f) || r > static_cast<float>(HIST_BINS)) return -1;   // outside by more than half a bin
+    if (!(r >= 0.f) || r > static_cast<float>(nb)) return -1;   // outside by more than half a bin
     const int e = static_cast<int>(r);
     const double xd = static_cast<double>(x);
     if (e == 0) return xd >= lo ? 0 : -1;
-    if (e == HIST_BINS) return xd <= hi ? HIST_BINS - 1 : -1;
+    if (e == nb) return xd <= hi ? nb - 1 : -1;
     return xd >= lo + e * step ? e : e - 1;
 }
 
@@ -63,7 +64,7 @@ k3_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, in
           const float* __restrict__ thr, float* __restrict__ rowmax, int* __restrict__ rowflags,
           unsigned long long* __restrict__ hist, double hlo, double hhi,
           Candidate* __restrict__ cand, int cand_cap, int* __restrict__ ncand,
-          double* __restrict__ fas, int only_flagged) {
+          double* __restrict__ fas, int only_flagged, int nb) {
     const ChunkDesc cd = chunks[blockIdx.y];
     const int s = blockIdx.x;
     const int row = blockIdx.y * S + s;
@@ -71,7 +72,7 @@ k3_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, in
     const float* x = DS + cd.ds_off + static_cast<long long>(s) * cd.Tpad;
     const int T = cd.T;
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
-    __shared__ int sh_hist[HIST_BINS];
+    __shared__ int sh_hist[HIST_MAX_BINS];
     __shared__ float sh_f[8][2];
     __shared__ int sh_i[8][2];
     __shared__ double sh_d[8][4];
@@ -103,7 +104,7 @@ k3_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, in
     ninf = __any_sync(0xffffffffu, ninf);
     npinf = __any_sync(0xffffffffu, npinf);
     if (l == 0) { sh_f[w][0] = mfin; sh_i[w][0] = nnan | (ninf << 1) | (npinf << 2); }
-    for (int i = tid; i < HIST_BINS; i += K3_THREADS) sh_hist[i] = 0;
+    for (int i = tid; i < nb; i += K3_THREADS) sh_hist[i] = 0;
     __syncthreads();
     if (tid == 0) {
         float m = -INFINITY; int f = 0;
@@ -125,14 +126,14 @@ k3_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, in
     if (has_nan) return;  // np.histogram raises -> chunk's histogram skipped; NaN max never triggers
 
     // ---- pass 2: histogram, candidates, FAS sums
-    const double step = (hhi - hlo) / HIST_BINS;
+    const double step = (hhi - hlo) / nb;
     const float th = thr ? thr[s] : INFINITY;
     const bool trig = eff_max > th;  // _evalTrigCon: strict >
     double f1 = 0, f2 = 0, f3 = 0, f4 = 0;
     for (int i = tid; i < T; i += K3_THREADS) {
         float a = x[i];
         if (zero_inf && isinf(a)) a = 0.f;
-        const int b = hist_bin(a, hlo, hhi, step);
+        const int b = hist_bin(a, hlo, hhi, step, nb);
         if (b >= 0) atomicAdd(&sh_hist[b], 1);
         if (trig && a >= th) {
             const int k = atomicAdd(ncand, 1);
@@ -150,9 +151,9 @@ k3_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, in
         }
     }
     __syncthreads();
-    for (int i = tid; i < HIST_BINS; i += K3_THREADS) {
+    for (int i = tid; i < nb; i += K3_THREADS) {
         const int c = sh_hist[i];
-        if (c) atomicAdd(&hist[static_cast<long long>(s) * HIST_BINS + i], static_cast<unsigned long long>(c));
+        if (c) atomicAdd(&hist[static_cast<long long>(s) * HIST_MAX_BINS + i], static_cast<unsigned long long>(c));
     }
     if (fas) {
         f1 = warp_sum(f1); f2 = warp_sum(f2); f3 = warp_sum(f3); f4 = warp_sum(f4);
@@ -179,23 +180,23 @@ k3_fast_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunk
                const float* __restrict__ thr, float* __restrict__ rowmax, int* __restrict__ rowflags,
                unsigned long long* __restrict__ hist, double hlo, double hhi,
                Candidate* __restrict__ cand, int cand_cap, int* __restrict__ ncand,
-               double* __restrict__ fas) {
+               double* __restrict__ fas, int nb) {
     const ChunkDesc cd = chunks[blockIdx.y];
     const int s = blockIdx.x;
     const int row = blockIdx.y * S + s;
     const float* x = DS + cd.ds_off + static_cast<long long>(s) * cd.Tpad;
     const int T = cd.T;
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
-    __shared__ int sh_hist[HIST_BINS];
+    __shared__ int sh_hist[HIST_MAX_BINS];
     __shared__ int2 sh_cand[K3_STAGE];
     __shared__ int sh_ncand, sh_bad, sh_base;
     __shared__ float sh_max[8];
     __shared__ double sh_d[8][4];
-    for (int i = tid; i < HIST_BINS; i += K3_THREADS) sh_hist[i] = 0;
+    for (int i = tid; i < nb; i += K3_THREADS) sh_hist[i] = 0;
     if (tid == 0) { sh_ncand = 0; sh_bad = 0; }
     __syncthreads();
-    const double step = (hhi - hlo) / HIST_BINS;
-    const float flo = static_cast<float>(hlo), finv = static_cast<float>(HIST_BINS / (hhi - hlo));
+    const double step = (hhi - hlo) / nb;
+    const float flo = static_cast<float>(hlo), finv = static_cast<float>(nb / (hhi - hlo));
     const float th = thr ? thr[s] : INFINITY;
     float mfin = -INFINITY;
     int bad = 0, cur = -1, cnt = 0;
@@ -210,7 +211,7 @@ k3_fast_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunk
     auto one = [&](float a, int i) {
         if (isnan(a) || isinf(a)) { bad = 1; return; }
         mfin = fmaxf(mfin, a);
-        const int b = hist_bin_fast(a, flo, finv, hlo, hhi, step);
+        const int b = hist_bin_fast(a, flo, finv, hlo, hhi, step, nb);
         if (b == cur) ++cnt;
         else {
             if (cnt > 0 && cur >= 0) atomicAdd(&sh_hist[cur], cnt);
@@ -293,9 +294,9 @@ k3_fast_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunk
         rowflags[row] = 0;
         sh_base = (trig && nc > 0) ? atomicAdd(ncand, nc) : 0;
     }
-    for (int i = tid; i < HIST_BINS; i += K3_THREADS) {
+    for (int i = tid; i < nb; i += K3_THREADS) {
         const int c = sh_hist[i];
-        if (c) atomicAdd(&hist[static_cast<long long>(s) * HIST_BINS + i], static_cast<unsigned long long>(c));
+        if (c) atomicAdd(&hist[static_cast<long long>(s) * HIST_MAX_BINS + i], static_cast<unsigned long long>(c));
     }
     if (fas) {
         if (tid < 4) {
@@ -420,17 +421,17 @@ ratio_kernel(const float* num, const float* den, int T, float* out) {  // out ma
 
 void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, const float* d_thr,
                float* d_rowmax, int* d_rowflags, unsigned long long* d_hist, double hist_lo,
-               double hist_hi, Candidate* d_cand, int cand_cap, int* d_ncand, double* d_fas,
+               double hist_hi, int nbins, Candidate* d_cand, int cand_cap, int* d_ncand, double* d_fas,
                cudaStream_t st) {
     const dim3 grid(S, nchunks);
     if (d_fas)
         k3_fast_kernel<true><<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist,
-                                                          hist_lo, hist_hi, d_cand, cand_cap, d_ncand, d_fas);
+                                                          hist_lo, hist_hi, d_cand, cand_cap, d_ncand, d_fas, nbins);
     else
         k3_fast_kernel<false><<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist,
-                                                           hist_lo, hist_hi, d_cand, cand_cap, d_ncand, nullptr);
+                                                           hist_lo, hist_hi, d_cand, cand_cap, d_ncand, nullptr, nbins);
     k3_kernel<<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist, hist_lo, hist_hi,
-                                           d_cand, cand_cap, d_ncand, d_fas, 1);
+                                           d_cand, cand_cap, d_ncand, d_fas, 1, nbins);
 }
 
 void launch_lta(const float* DS, const ChunkDesc* d_chunks, int S, const int* d_rowflags,

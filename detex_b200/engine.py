@@ -182,11 +182,17 @@ class Engine(object):
         self._check(self._L.dtx_get_rowstats(self._h, _ptr(mx), _ptr(fl), n))
         return mx.reshape(self.nchunks, self._run_S), fl.reshape(self.nchunks, self._run_S)
 
+    def set_hist_bins(self, nbins):
+        """Bins of the device histograms for later runs (numBins - 1 of fas._initFAS; default 400)."""
+        self._check(self._L.dtx_set_hist_bins(self._h, int(nbins)))
+        self._hist_bins = int(nbins)
+
     def hist(self, set_id, reset=False):
         S = self._S[set_id]
-        h = np.empty(S * HIST_BINS, dtype=np.uint64)
+        nb = getattr(self, "_hist_bins", HIST_BINS)
+        h = np.empty(S * nb, dtype=np.uint64)
         self._check(self._L.dtx_get_hist(self._h, int(set_id), _ptr(h), h.size, int(reset)))
-        return h.reshape(S, HIST_BINS).astype(np.int64)
+        return h.reshape(S, nb).astype(np.int64)
 
     def fas(self, set_id, reset=False):
         S = self._S[set_id]

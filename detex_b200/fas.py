@@ -94,17 +94,21 @@ def initFAS(bases, chunks, Nc, numBins=401, engine=None, set_id=900, kernel="tcg
     """Array part of `_initFAS` (fas.py:23-86).  bases: list of (r, n) arrays (one per
     subspace / single, same n); chunks: the null-space multiplexed chunks that passed the
     STA/LTA screen.  Returns a list of {'bins','hist','betadist','nnlf'} dicts."""
-    if numBins != 401:
-        raise NotImplementedError("the GPU histogram is fixed at 400 bins (reference default numBins=401)")
+    if not 2 <= int(numBins) <= 1025:
+        raise ValueError("numBins must be between 2 and 1025 (the device histogram holds up to 1024 bins)")
     eng = engine or default_engine()
     eng.set_bases(set_id, bases, Nc)
-    eng.hist(set_id, reset=True)
-    eng.fas(set_id, reset=True)
-    for i in range(0, len(chunks), batch):
-        eng.load_chunks(chunks[i:i + batch])
-        eng.detect_run(set_id, engine=kernel, hist_range=(-.01, 1.0), want_fas=True)
-    hist = eng.hist(set_id, reset=True)
-    st = eng.fas(set_id, reset=True)
+    eng.set_hist_bins(int(numBins) - 1)                    # np.linspace(-.01, 1, numBins) has numBins - 1 bins
+    try:
+        eng.hist(set_id, reset=True)
+        eng.fas(set_id, reset=True)
+        for i in range(0, len(chunks), batch):
+            eng.load_chunks(chunks[i:i + batch])
+            eng.detect_run(set_id, engine=kernel, hist_range=(-.01, 1.0), want_fas=True)
+        hist = eng.hist(set_id, reset=True)
+        st = eng.fas(set_id, reset=True)
+    finally:
+        eng.set_hist_bins(400)                             # detection histograms: 401 edges (detect.py:80)
     bins = np.linspace(-.01, 1, num=numBins)
     out = []
     for s in range(len(bases)):

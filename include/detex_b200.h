@@ -144,7 +144,11 @@ int dtx_set_trigger_sta(dtx_ctx* ctx, int sta_window);
 int dtx_get_stalta(dtx_ctx* ctx, int chunk, int subspace, int W, float* out, int64_t count);
 /* maxds[chunk*S+s] = CorDF.MaxDS (detect.py:275-281); flags bit0 = row has NaN, bit1 = infs zeroed */
 int dtx_get_rowstats(dtx_ctx* ctx, float* maxds, int32_t* flags, int64_t count);
-/* hist[s*400+b] accumulated over every run since the last reset (histdic, detect.py:146,181);
+/* Number of histogram bins of later dtx_detect_run calls = numBins - 1 of fas._initFAS (fas.py:31,79;
+ * `np.histogram(dss, bins=np.linspace(lo, hi, numBins))`), 1..1024.  Default 400 (detect.py:80 fixes
+ * 401 edges for detection).  Reset a set's histogram (dtx_get_hist with reset) before changing it. */
+int dtx_set_hist_bins(dtx_ctx* ctx, int nbins);
+/* hist[s*nbins+b] accumulated over every run since the last reset (histdic, detect.py:146,181);
  * reset before switching the histogram range of a set (detection [0,1] vs FAS [-.01,1]) */
 int dtx_get_hist(dtx_ctx* ctx, int set_id, uint64_t* hist, int64_t count, int reset);
 /* fas[s*5 + {0:N, 1:sum x, 2:sum x^2, 3:sum log x, 4:sum log1p(-x)}] */

@@ -18,6 +18,7 @@ class OracleEngine(object):
         self.sets = {}
         self.chunks = []
         self.sta_window = 0
+        self.hist_bins = 400
         self._events = {}
         self.nchunks = 0
 
@@ -26,7 +27,7 @@ class OracleEngine(object):
         bases = [np.atleast_2d(np.asarray(b, dtype=np.float64)) for b in bases]
         assert len(set(b.shape[1] for b in bases)) == 1
         self.sets[set_id] = dict(bases=bases, Nc=int(Nc), thr=None if thresholds is None else list(thresholds),
-                                 hist=np.zeros((len(bases), 400), dtype=np.int64),
+                                 hist=np.zeros((len(bases), 1024), dtype=np.int64),
                                  fas=np.zeros((len(bases), 5)))
 
     def load_chunks(self, chunks):
@@ -58,6 +59,9 @@ class OracleEngine(object):
     def set_trigger_sta(self, W):
         self.sta_window = int(W)
 
+    def set_hist_bins(self, nbins):
+        self.hist_bins = int(nbins)
+
     # ---- run
     def detect_run(self, set_id, engine="tcgen05", kblk=0, hist_range=(0.0, 1.0), lta_window=0, want_fas=False,
                    keep_ds64=False):
@@ -73,7 +77,7 @@ class OracleEngine(object):
         mx = np.zeros((len(self.chunks), S), dtype=np.float32)
         fl = np.zeros((len(self.chunks), S), dtype=np.int32)
         cands = []
-        bins = np.linspace(hist_range[0], hist_range[1], 401)
+        bins = np.linspace(hist_range[0], hist_range[1], self.hist_bins + 1)
         for ci, c in enumerate(self.chunks):
             for si, U in enumerate(st["bases"]):
                 ds = orc.mpx_ds_direct(c, U, Nc).astype(np.float32)
@@ -87,7 +91,7 @@ class OracleEngine(object):
                 if np.isnan(ds).any():
                     fl[ci, si] |= 1
                     continue
-                st["hist"][si] += np.histogram(ds.astype(np.float64), bins=bins)[0]
+                st["hist"][si, :self.hist_bins] += np.histogram(ds.astype(np.float64), bins=bins)[0]
                 if want_fas:
                     x = ds.astype(np.float64)
                     st["fas"][si] += [len(x), x.sum(), (x * x).sum(), np.log(x).sum(), np.log1p(-x).sum()]
@@ -127,7 +131,7 @@ class OracleEngine(object):
         return self._cand.copy()
 
     def hist(self, set_id, reset=False):
-        h = self.sets[set_id]["hist"].copy()
+        h = self.sets[set_id]["hist"][:, :self.hist_bins].copy()
         if reset:
             self.sets[set_id]["hist"][:] = 0
         return h

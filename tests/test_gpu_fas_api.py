@@ -24,6 +24,31 @@ def test_initFAS_matches_oracle(engine):
         assert abs(orc.threshold_from_beta(a, b) - orc.threshold_from_beta(ra, rb)) < 1e-5
 
 
+@pytest.mark.parametrize("numBins", [101, 257, 1001])
+def test_initFAS_numBins(engine, numBins):
+    """fas._initFAS(numBins=...) (fas.py:31, 79): the device histogram on np.linspace(-.01, 1, numBins)
+    equals np.histogram of the GPU's own DS values, for any bin count; detection stays at 400 bins."""
+    Nc, ns = 3, 150
+    rng = np.random.default_rng(71)
+    null = [synth.multiplex(synth.bandpassed_noise(rng, 6000 + 11 * i, nchan=Nc)) for i in range(3)]
+    bases = [synth.random_basis(rng, ns * Nc, r) for r in (1, 4, 2)]
+    res = fas.initFAS(bases, null, Nc, numBins=numBins, engine=engine, set_id=905)
+    ref = fas.initFAS(bases, null, Nc, engine=engine, set_id=905)
+    engine.set_bases(906, bases, Nc)
+    engine.load_chunks(null)
+    engine.detect_run(906)
+    edges = np.linspace(-.01, 1, numBins)
+    for si, r in enumerate(res):
+        ds = np.concatenate([engine.get_ds(ci, si).astype(np.float64) for ci in range(len(null))])
+        assert r["hist"].shape == (numBins - 1,) and np.array_equal(r["hist"], np.histogram(ds, bins=edges)[0])
+        assert np.array_equal(r["bins"], edges)
+        # the sums behind the beta fit are grouped differently (the quad fast path follows the bin runs)
+        assert np.allclose(r["betadist"][:2], ref[si]["betadist"][:2], rtol=1e-6) and ref[si]["hist"].shape == (400,)
+    assert engine.hist(906, reset=True).shape == (3, 400)
+    with pytest.raises(ValueError):
+        fas.initFAS(bases, null, Nc, numBins=1, engine=engine)
+
+
 def test_mpxds_dropins(engine):
     chunks, bases, _ = synth.detection_case(32, 1, 5000, 200, 3, [3])
     ref = orc.mpx_ds_fft(chunks[0], bases[0], 3)

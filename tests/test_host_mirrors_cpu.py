@@ -78,8 +78,15 @@ def test_initFAS_and_screen_with_stand_in():
         assert np.array_equal(r["hist"], ref["hist"])
         assert np.allclose(r["betadist"][:2], ref["betadist"][:2], rtol=1e-6)
         assert abs(r["nnlf"] - ref["nnlf"]) < 1e-6 * abs(ref["nnlf"])
-    with pytest.raises(NotImplementedError):
-        fas.initFAS(bases, null, Nc, numBins=101, engine=eng)
+    # numBins (fas.py:31): any bin count up to the device limit; the beta fit does not depend on it
+    r101 = fas.initFAS(bases, [null[i] for i in kept], Nc, numBins=101, engine=eng, batch=2)
+    for U, r, r0 in zip(bases, r101, res):
+        ds = np.concatenate([orc.mpx_ds_direct(null[i], U, Nc).astype(np.float32).astype(np.float64) for i in kept])
+        assert len(r["bins"]) == 101 and np.array_equal(r["hist"], np.histogram(ds, bins=np.linspace(-.01, 1, 101))[0])
+        assert r["betadist"] == r0["betadist"]
+    assert eng.hist_bins == 400                                     # restored for detection (detect.py:80)
+    with pytest.raises(ValueError):
+        fas.initFAS(bases, null, Nc, numBins=5000, engine=eng)
 
 
 def test_makeDFcclags_frames_and_errors():
