@@ -189,36 +189,42 @@ class SSDetex(object):
             cand = eng.candidates()
             S = len(names)
             for gi, ci in enumerate(good):
-                T = eng.num_lags(gi)
-                for si, name in enumerate(names):
-                    maxds[ci][name] = float(mx[gi, si])
-                    if keep_ds:
+                maxds[ci].update(zip(names, (float(v) for v in mx[gi, :S])))
+                if keep_ds:
+                    for si, name in enumerate(names):
                         dense[(ci, name)] = eng.get_ds(gi, si).astype(np.float64)
-                    if not _evalTrigCon(mx[gi, si], self.threshold[name]):
-                        continue
-                    sel = cand[cand["row"] == gi * S + si]
-                    sel = sel[np.argsort(sel["t"], kind="stable")]
-                    picks = greedy_pick(sel["t"], sel["ds"], T, sr)
-                    if len(picks) > 4000:  # kill switch, detect.py:433-436
-                        raise Exception('over 4000 events found in single data block on %s for %s'
-                                        % (self.sta, name))
-                    minof, maxof = np.min(self.offsets[name]), np.max(self.offsets[name])
-                    if self.estimateMags and len(picks):
-                        tt = np.asarray(sel["t"][picks], dtype=np.int32)
-                        mg = eng.est_mags(sid, np.full(len(tt), gi), np.full(len(tt), si), tt)
-                    for pi, k in enumerate(picks):
-                        coef = float(sel["ds"][k])
-                        times = float(sel["t"][k]) / sr + starts[ci]      # detect.py:413
-                        if self.fillZeros:
-                            sl = 0.0
-                        else:
-                            # |DS| / lta == STA / LTA at the trigger (detect.py:501-515); a chunk shorter
-                            # than a window has no STA/LTA array in the reference -> 0.0 (detect.py:416-419)
-                            den = float(sel["lta"][k])
-                            sl = abs(coef) / den if np.isfinite(den) else 0.0
-                        pe_mag, st_mag, snr = (mg[pi] if self.estimateMags else (np.nan, np.nan, np.nan))
-                        rows.append([coef, sl, times, name, self.sta, times - maxof, times - minof,
-                                     st_mag, snr, pe_mag])       # Mag = stMag, ProEnMag = peMag (detect.py:428,442)
+            # candidates grouped by (chunk, subspace) row once; only rows that triggered have any
+            cand = cand[np.lexsort((cand["t"], cand["row"]))]
+            urows, first = np.unique(cand["row"], return_index=True)
+            last = np.r_[first[1:], len(cand)]
+            for r, a, b in zip(urows, first, last):
+                gi, si = divmod(int(r), S)
+                ci, name = good[gi], names[si]
+                if not _evalTrigCon(mx[gi, si], self.threshold[name]):
+                    continue
+                T = eng.num_lags(gi)
+                sel = cand[a:b]
+                picks = greedy_pick(sel["t"], sel["ds"], T, sr)
+                if len(picks) > 4000:  # kill switch, detect.py:433-436
+                    raise Exception('over 4000 events found in single data block on %s for %s'
+                                    % (self.sta, name))
+                minof, maxof = np.min(self.offsets[name]), np.max(self.offsets[name])
+                if self.estimateMags and len(picks):
+                    tt = np.asarray(sel["t"][picks], dtype=np.int32)
+                    mg = eng.est_mags(sid, np.full(len(tt), gi), np.full(len(tt), si), tt)
+                for pi, k in enumerate(picks):
+                    coef = float(sel["ds"][k])
+                    times = float(sel["t"][k]) / sr + starts[ci]      # detect.py:413
+                    if self.fillZeros:
+                        sl = 0.0
+                    else:
+                        # |DS| / lta == STA / LTA at the trigger (detect.py:501-515); a chunk shorter
+                        # than a window has no STA/LTA array in the reference -> 0.0 (detect.py:416-419)
+                        den = float(sel["lta"][k])
+                        sl = abs(coef) / den if np.isfinite(den) else 0.0
+                    pe_mag, st_mag, snr = (mg[pi] if self.estimateMags else (np.nan, np.nan, np.nan))
+                    rows.append([coef, sl, times, name, self.sta, times - maxof, times - minof,
+                                 st_mag, snr, pe_mag])       # Mag = stMag, ProEnMag = peMag (detect.py:428,442)
             if self.calcHist:
                 h = eng.hist(sid, reset=True)
                 for si, name in enumerate(names):
