@@ -249,3 +249,23 @@ def test_workflow_on_gpu_matches_oracle_engine(engine, tmp_path):
     assert (gs.Name == ws.Name).all() and (gs.STMP == ws.STMP).all()
     assert np.abs(gs.DS - ws.DS).max() < 1e-5
     assert np.abs(gs.Mag - ws.Mag).max() < 1e-3 and np.abs(gs.SNR - ws.SNR).max() < 1e-3 * ws.SNR.abs().max()
+
+
+def test_array_fetcher_generators():
+    """getTemData / getConData stand-ins (getdata.py:351, 455): key order, time window, seeded sampling."""
+    case = synth.workflow_case(81, nfam=1, per_fam=3, nsingles=1, nchunks=5)
+    f = workflow.ArrayFetcher(case["events"], case["continuous"], sr=case["sr"], seed=3)
+    got = [name for _, _, name in f.getTemData(case["temkey"], case["stakey"].iloc[:1])]
+    assert got == list(case["temkey"].NAME)
+    sub = case["temkey"].iloc[[2, 0]]
+    assert [n for _, _, n in f.getTemData(sub, case["stakey"].iloc[:1])] == list(sub.NAME)
+    t0 = float(case["stakey"].STARTTIME.iloc[0])
+    sk = case["stakey"].iloc[1:2]
+    starts = [s for _, s in f.getConData(sk)]
+    assert starts == [t0 + 300.0 * i for i in range(5)]
+    assert [s for _, s in f.getConData(sk, utcstart=t0 + 300.0, utcend=t0 + 900.0)] == [t0 + 300.0, t0 + 600.0]
+    a = [s for _, s in f.getConData(sk, randSamps=3)]
+    b = [s for _, s in workflow.ArrayFetcher(case["events"], case["continuous"], sr=case["sr"], seed=3).getConData(sk, randSamps=3)]
+    assert len(a) == 3 and a == b and set(a) <= set(starts)
+    assert len([1 for _ in f.getConData(sk, randSamps=50)]) == 5            # asks for more than there is
+    assert workflow._timestamp("2010-01-01T00-00-00") == workflow._timestamp("2010-01-01 00:00:00") == 1262304000.0
