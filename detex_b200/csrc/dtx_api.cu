@@ -4,6 +4,7 @@
 // out the K segments, sizing / growing device buffers, building the work-item list and
 // launching K0 -> K1 -> K3 on the context's stream.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstdio>
@@ -21,10 +22,21 @@ using namespace dtx;
 
 namespace {
 
+// Owning device buffer: grows on demand, frees in the destructor (every early return of an entry
+// point releases its temporaries).
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;  // elements
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
@@ -46,12 +58,38 @@ struct DevBuf {
     }
 };
 
+// Pinned host staging buffer (async D2H target), same growth rule.
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    PinBuf() = default;
+    PinBuf(const PinBuf&) = delete;
+    PinBuf& operator=(const PinBuf&) = delete;
+    ~PinBuf() { release(); }
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 struct BasisSet {
     BasisLayout lay{};
     int R = 0;
     std::vector<int> rank_off;
     bool has_thr = false;
-    bool has_split = false;   // some subspace has rank > 16 (pieces accumulate into DS)
+    bool has_split = false;   // some subspace has rank > 16 (its pieces are summed after K1)
+    int ds_rows = 0;          // DS rows per chunk: S + scratch rows of the 2nd.. pieces of rank > 16 subspaces
+    std::vector<PieceSum> pieces;   // (subspace row, scratch row) in piece order
+    DevBuf<PieceSum> d_pieces;
     DevBuf<double> d_U;
     DevBuf<int> d_rank_off, d_slot_row;
     DevBuf<BlockInfo> d_binfo;
@@ -68,6 +106,7 @@ struct BasisSet {
     void release() {
         for (auto& kv : ev_blob) kv.second.release();
         ev_blob.clear(); ev_meta.clear();
+        d_pieces.release(); pieces.clear();
         d_U.release(); d_rank_off.release(); d_slot_row.release(); d_binfo.release();
         d_Aimg.release(); d_Aimg8.release(); have_img8 = false; d_thr.release(); d_hist.release(); d_fas.release();
     }
@@ -109,12 +148,29 @@ struct dtx_ctx {
     int hist_bins = HIST_BINS;    // bins of the device histograms (numBins - 1 of fas._initFAS, fas.py:31)
     int sta_window = 0;           // triggerSTATime in samples (0 = reference default: STA = |DS|)
     double x8_eps = 2e-6;         // adaptive engine: admitted RMS error of a normalised projection
-    DevBuf<int> d_rowflags, d_ncand;
+    DevBuf<int> d_rowflags, d_ncand, d_zeroE;
     DevBuf<Candidate> d_cand;
     int cand_cap = 1 << 20;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // K1 timing: one CUDA event pair per run, kept until dtx_k1_ms_history collects them
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> k1_events;   // pool
+    size_t k1_used = 0;          // pairs recorded since the last collection
     bool k1_timed = false;
     long long launches = 0;
+
+    // results accumulating over the batches of a station (dtx_accumulate_begin): candidate rows and
+    // rowmax / rowflags entries are indexed by the chunk's position in the whole sequence
+    bool accumulate = false;
+    long long acc_chunks = 0;    // chunks of the batches run so far
+    long long acc_capacity = 0;  // chunks the row buffers were sized for
+
+    // CCX: persistent workspace (no allocation per call once warm) and its own basis set
+    BasisSet ccx_set;
+    DevBuf<uint8_t> cx_X;
+    DevBuf<double> cx_wa, cx_wb, cx_es, cx_ed, cx_pad, cx_cc, cx_sub, cx_tcc, cx_tsub, cx_pcc, cx_psub;
+    DevBuf<int> cx_lag, cx_tlag, cx_plag, cx_rows, cx_nflag, cx_slot;
+    DevBuf<int2> cx_flag;
+    int ccx_max_batch = 512;     // signals per K1 launch (dtx_set_ccx_batch lowers it for tests)
+    long long ccx_ds_bytes = 4LL << 30;   // DS budget of one CCX batch
 };
 
 namespace {
@@ -164,8 +220,6 @@ int dtx_create(int device, void* stream, dtx_ctx** out) {
         }
         ctx->own_stream = true;
     }
-    cudaEventCreate(&ctx->ev0);
-    cudaEventCreate(&ctx->ev1);
     *out = ctx;
     return DTX_OK;
 }
@@ -174,16 +228,13 @@ void dtx_destroy(dtx_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& kv : ctx->sets) kv.second.release();
-    ctx->raw_own.release(); ctx->d_chunks.release(); ctx->d_items.release(); ctx->d_xsplit.release();
-    ctx->d_mu.release(); ctx->d_invE.release(); ctx->d_DS.release(); ctx->d_scale.release();
-    ctx->d_rowmax.release(); ctx->d_DS64.release(); ctx->d_sum.release(); ctx->d_maxbits.release();
-    ctx->d_k4bits.release(); ctx->d_chunk_mode.release();
-    ctx->d_rowflags.release(); ctx->d_ncand.release(); ctx->d_cand.release();
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    for (auto& ev : ctx->k1_events) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    cudaStream_t st = ctx->own_stream ? ctx->stream : nullptr;
+    delete ctx;   // every device / pinned buffer is released by its destructor
+    if (st) cudaStreamDestroy(st);
 }
 
 const char* dtx_last_error(const dtx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -198,7 +249,7 @@ int dtx_sync(dtx_ctx* ctx) {
 // Basis set from vectors already in bs.d_U ([R][n] float64 on the device; `fill_U`, if given, is
 // called once the buffer exists and puts them there).  All per-vector statistics come from one
 // reduction kernel, so nothing here is O(R*n) on the host.
-static int set_bases_device(dtx_ctx* ctx, int set_id, const std::function<int(double*)>& fill_U,
+static int set_bases_device(dtx_ctx* ctx, BasisSet& bs, int set_id, const std::function<int(double*)>& fill_U,
                             const int32_t* rank_off, int S, int n, int Nc, const double* thresholds) {
     const int R = rank_off[S];
     for (int s = 0; s < S; ++s) {
@@ -210,7 +261,6 @@ static int set_bases_device(dtx_ctx* ctx, int set_id, const std::function<int(do
         if (Nc * ((kc + MAX_SEG_TAPS - 1) / MAX_SEG_TAPS) > MAX_SEGS)
             return fail(ctx, DTX_ERR_ARG, "dtx_set_bases: template too long");
     }
-    BasisSet& bs = ctx->sets[set_id];
     DTX_CUDA(bs.d_U.reserve(static_cast<size_t>(R) * n));
     {
         const int rc = fill_U(bs.d_U.p);
@@ -225,7 +275,6 @@ static int set_bases_device(dtx_ctx* ctx, int set_id, const std::function<int(do
     std::vector<double> stats(static_cast<size_t>(R) * 4);
     DTX_CUDA(cudaMemcpyAsync(stats.data(), d_stats.p, sizeof(double) * R * 4, cudaMemcpyDeviceToHost, ctx->stream));
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));
-    d_stats.release();
     for (auto& kv : bs.ev_blob) kv.second.release();   // events belong to the previous bases
     bs.ev_blob.clear();
     bs.ev_meta.clear();
@@ -256,17 +305,25 @@ static int set_bases_device(dtx_ctx* ctx, int set_id, const std::function<int(do
     lay.nchunks = chunk0;
 
     // pack subspaces into blocks of 16 vector slots, first-fit decreasing by rank.  A subspace
-    // of rank > 16 is cut into pieces of <= 16 vectors; DS is additive over the pieces
-    // (sum of squared projections), so their epilogues accumulate into the same DS row.
-    struct Piece { int s, row0, r; bool split; };
+    // of rank > 16 is cut into pieces of <= 16 vectors; DS is additive over the pieces (sum of
+    // squared projections): the first piece writes the subspace's DS row, every further piece a
+    // scratch row behind the S subspace rows, and launch_sum_pieces adds them up in piece order
+    // (bit-reproducible, unlike atomics in the epilogue).
+    struct Piece { int s, row0, r, out_row; };
     std::vector<Piece> pieces;
     bs.has_split = false;
+    bs.pieces.clear();
+    int nscratch = 0;
     for (int s = 0; s < S; ++s) {
         const int r = rank_off[s + 1] - rank_off[s];
-        for (int k0 = 0; k0 < r; k0 += VEC_PER_BLOCK)
-            pieces.push_back(Piece{s, rank_off[s] + k0, std::min(VEC_PER_BLOCK, r - k0), r > VEC_PER_BLOCK});
+        for (int k0 = 0; k0 < r; k0 += VEC_PER_BLOCK) {
+            const int out_row = k0 == 0 ? s : S + nscratch++;
+            pieces.push_back(Piece{s, rank_off[s] + k0, std::min(VEC_PER_BLOCK, r - k0), out_row});
+            if (k0 > 0) bs.pieces.push_back(PieceSum{s, out_row});
+        }
         if (r > VEC_PER_BLOCK) bs.has_split = true;
     }
+    bs.ds_rows = S + nscratch;
     std::vector<int> order(pieces.size());
     for (size_t i = 0; i < pieces.size(); ++i) order[i] = static_cast<int>(i);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pieces[a].r > pieces[b].r; });
@@ -310,9 +367,10 @@ static int set_bases_device(dtx_ctx* ctx, int set_id, const std::function<int(do
                 slot_row[static_cast<size_t>(b) * VEC_PER_BLOCK + slot] = row;
                 BlockInfo& bi = binfo[static_cast<size_t>(b) * VEC_PER_BLOCK + slot];
                 bi.sumU = static_cast<float>(stats[static_cast<size_t>(row) * 4]);   // float64 block reduction
-                bi.out_row = s;
-                bi.nrows = (k == 0) ? (pc.split ? -r : r) : 0;   // negative: accumulate into the row
+                bi.out_row = pc.out_row;
+                bi.nrows = (k == 0) ? r : 0;
                 bi.seg_end = slot - k + r;
+                (void)s;
             }
         }
     }
@@ -329,6 +387,10 @@ static int set_bases_device(dtx_ctx* ctx, int set_id, const std::function<int(do
     DTX_CUDA(cudaMemcpy(bs.d_rank_off.p, rank_off, sizeof(int) * (S + 1), cudaMemcpyHostToDevice));
     DTX_CUDA(cudaMemcpy(bs.d_slot_row.p, slot_row.data(), sizeof(int) * slot_row.size(), cudaMemcpyHostToDevice));
     DTX_CUDA(cudaMemcpy(bs.d_binfo.p, binfo.data(), sizeof(BlockInfo) * binfo.size(), cudaMemcpyHostToDevice));
+    if (!bs.pieces.empty()) {
+        DTX_CUDA(bs.d_pieces.reserve(bs.pieces.size()));
+        DTX_CUDA(cudaMemcpy(bs.d_pieces.p, bs.pieces.data(), sizeof(PieceSum) * bs.pieces.size(), cudaMemcpyHostToDevice));
+    }
     std::vector<float> thr(S, INFINITY);
     bs.has_thr = thresholds != nullptr;
     if (thresholds) for (int s = 0; s < S; ++s) thr[s] = static_cast<float>(thresholds[s]);
@@ -356,7 +418,7 @@ int dtx_set_bases(dtx_ctx* ctx, int set_id, const double* U, const int32_t* rank
         DTX_CUDA(cudaMemcpy(d_U, U, sizeof(double) * count, cudaMemcpyHostToDevice));
         return DTX_OK;
     };
-    return set_bases_device(ctx, set_id, fill, rank_off, S, n, Nc, thresholds);
+    return set_bases_device(ctx, ctx->sets[set_id], set_id, fill, rank_off, S, n, Nc, thresholds);
 }
 
 static int set_chunk_table(dtx_ctx* ctx, int nchunks, const int64_t* L, const int64_t* offs, int dtype) {
@@ -431,7 +493,7 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         cd.blk_hi = blk_hi ? blk_hi[i] : lay.nblocks;
         sig += 2LL * Nc * cd.Lpad;
         nrm += cd.Tpad;
-        ds += static_cast<long long>(S) * cd.Tpad;
+        ds += static_cast<long long>(bs.ds_rows) * cd.Tpad;
         max_Lpad = std::max(max_Lpad, cd.Lpad);
         max_ntiles = std::max(max_ntiles, cd.ntiles);
         maxT = std::max(maxT, cd.T);
@@ -528,9 +590,12 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     DTX_CUDA(ctx->d_maxbits.reserve(nchunks));
     DTX_CUDA(ctx->d_k4bits.reserve(nchunks));
     DTX_CUDA(ctx->d_chunk_mode.reserve(nchunks));
-    DTX_CUDA(ctx->d_rowmax.reserve(static_cast<size_t>(nchunks) * S));
-    DTX_CUDA(ctx->d_rowflags.reserve(static_cast<size_t>(nchunks) * S));
-    DTX_CUDA(ctx->d_ncand.reserve(1));
+    DTX_CUDA(ctx->d_zeroE.reserve(nchunks));
+    if (!ctx->accumulate) {
+        DTX_CUDA(ctx->d_rowmax.reserve(static_cast<size_t>(nchunks) * S));
+        DTX_CUDA(ctx->d_rowflags.reserve(static_cast<size_t>(nchunks) * S));
+    }
+    DTX_CUDA(ctx->d_ncand.reserve(2));   // [0] = candidates so far, [1] = count before the current batch
     DTX_CUDA(ctx->d_cand.reserve(ctx->cand_cap));
     cudaStream_t st = ctx->stream;
     DTX_CUDA(cudaMemcpyAsync(ctx->d_chunks.p, ctx->h_chunks.data(), sizeof(ChunkDesc) * nchunks,
@@ -538,7 +603,8 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     if (!items_cached)
         DTX_CUDA(cudaMemcpyAsync(ctx->d_items.p, items.data(), sizeof(int4) * items.size(),
                                  cudaMemcpyHostToDevice, st));
-    DTX_CUDA(cudaMemsetAsync(ctx->d_ncand.p, 0, sizeof(int), st));
+    if (!ctx->accumulate) DTX_CUDA(cudaMemsetAsync(ctx->d_ncand.p, 0, 2 * sizeof(int), st));
+    else DTX_CUDA(cudaMemcpyAsync(ctx->d_ncand.p + 1, ctx->d_ncand.p, sizeof(int), cudaMemcpyDeviceToDevice, st));
 
     const int f32 = ctx->dtype == DTX_F32;
     // 8-bit cross terms: forced, or per chunk where the random-rounding model
@@ -558,7 +624,7 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     }
     launch_k0(ctx->d_raw, f32, ctx->d_chunks.p, nchunks, Nc, n, max_Lpad, max_ntiles, ctx->d_sum.p,
               ctx->d_maxbits.p, ctx->d_scale.p, ctx->d_xsplit.p, ctx->d_mu.p, ctx->d_invE.p, x8, k4_limit,
-              ctx->d_k4bits.p, ctx->d_chunk_mode.p, st);
+              ctx->d_k4bits.p, ctx->d_chunk_mode.p, mode == 0 ? ctx->d_zeroE.p : nullptr, st);
     DTX_CUDA(cudaGetLastError());
     ctx->launches += 3;  // k0_stats, k0_split, k0_norm
     ctx->have_ds64 = false;
@@ -572,13 +638,28 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         a.chunk_scale = ctx->d_scale.p; a.chunks = ctx->d_chunks.p; a.items = ctx->d_items.p;
         a.binfo = bs.d_binfo.p; a.DS = ctx->d_DS.p; a.nitems = ctx->n_items;
         a.kblk = kblk; a.num_sms = ctx->num_sms; a.nq = nq; a.mode = mode;
-        if (bs.has_split) DTX_CUDA(cudaMemsetAsync(ctx->d_DS.p, 0, sizeof(float) * ds, st));
-        DTX_CUDA(cudaEventRecord(ctx->ev0, st));
+        if (!ctx->accumulate) ctx->k1_used = 0;            // only the last run's pair is kept
+        if (ctx->k1_used >= ctx->k1_events.size()) {
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            DTX_CUDA(cudaEventCreate(&e0));
+            DTX_CUDA(cudaEventCreate(&e1));
+            ctx->k1_events.emplace_back(e0, e1);
+        }
+        DTX_CUDA(cudaEventRecord(ctx->k1_events[ctx->k1_used].first, st));
         launch_k1(a, lay, st);
-        DTX_CUDA(cudaEventRecord(ctx->ev1, st));
+        DTX_CUDA(cudaEventRecord(ctx->k1_events[ctx->k1_used].second, st));
+        ctx->k1_used += 1;
         ctx->k1_timed = true;
         ctx->launches += 1 + (keep_ds64 ? 1 : 0);
         DTX_CUDA(cudaGetLastError());
+        if (bs.has_split) {
+            int max_Tpad = 0;
+            for (int i = 0; i < nchunks; ++i) max_Tpad = std::max(max_Tpad, ctx->h_chunks[i].Tpad);
+            launch_sum_pieces(ctx->d_chunks.p, nchunks, max_Tpad, bs.d_pieces.p, static_cast<int>(bs.pieces.size()),
+                              ctx->d_DS.p, st);
+            ctx->launches += 1;
+            DTX_CUDA(cudaGetLastError());
+        }
         if (keep_ds64) {
             launch_direct(ctx->d_raw, f32, ctx->d_chunks.p, nchunks, bs.d_U.p, bs.d_rank_off.p, S, n, Nc,
                           maxT, ctx->d_sum.p, nullptr, ctx->d_DS64.p, st);
@@ -591,6 +672,12 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         ctx->launches += 1;
     }
     DTX_CUDA(cudaGetLastError());
+    if (mode == 0) {   // zero-energy windows: DS = +inf in every subspace row (reference: x/0, detect.py:577)
+        launch_zero_energy_fix(ctx->d_chunks.p, nchunks, max_ntiles, S, ctx->d_invE.p, ctx->d_zeroE.p, ctx->d_DS.p,
+                               ctx->have_ds64 ? ctx->d_DS64.p : nullptr, st);
+        ctx->launches += 1;
+        DTX_CUDA(cudaGetLastError());
+    }
     ctx->run_S = bs.lay.S;
     return DTX_OK;
 }
@@ -608,24 +695,61 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
     if (kblk == 0) kblk = 2;  // default: drain every 128 taps (bias <= ~2e-6 at DS = 1)
     if (kblk < 1 || kblk > 64) return fail(ctx, DTX_ERR_ARG, "kblk out of range");
     BasisSet& bs = it->second;
+    const int S = bs.lay.S;
+    if (ctx->accumulate) {
+        if (ctx->acc_chunks + ctx->nchunks > ctx->acc_capacity)
+            return fail(ctx, DTX_ERR_CAPACITY, "dtx_detect_run: more chunks than dtx_accumulate_begin announced");
+        if (ctx->acc_chunks > 0 && (ctx->run_set != set_id || ctx->run_S != S))
+            return fail(ctx, DTX_ERR_STATE, "dtx_detect_run: the basis set changed inside an accumulation");
+        DTX_CUDA(ctx->d_rowmax.reserve(static_cast<size_t>(ctx->acc_capacity) * S));   // no-ops once sized
+        DTX_CUDA(ctx->d_rowflags.reserve(static_cast<size_t>(ctx->acc_capacity) * S));
+    }
     const int rc = project_run(ctx, bs, engine, kblk, 0, keep_ds64, nullptr);
     if (rc != DTX_OK) return rc;
-    const int nchunks = ctx->nchunks, S = bs.lay.S;
+    const int nchunks = ctx->nchunks;
+    const int row_base = ctx->accumulate ? static_cast<int>(ctx->acc_chunks * S) : 0;
     cudaStream_t st = ctx->stream;
     launch_k3(ctx->d_DS.p, ctx->d_chunks.p, nchunks, S, bs.d_thr.p, ctx->d_rowmax.p, ctx->d_rowflags.p,
               bs.d_hist.p, hist_lo, hist_hi, ctx->hist_bins, ctx->d_cand.p, ctx->cand_cap, ctx->d_ncand.p,
-              want_fas ? bs.d_fas.p : nullptr, st);
+              want_fas ? bs.d_fas.p : nullptr, row_base, st);
     DTX_CUDA(cudaGetLastError());
     ctx->launches += 2;  // k3_fast_kernel + k3_kernel (flagged rows only)
     if (bs.has_thr && lta_window > 0) {
         launch_lta(ctx->d_DS.p, ctx->d_chunks.p, S, ctx->d_rowflags.p, ctx->d_cand.p, ctx->d_ncand.p,
-                   ctx->cand_cap, lta_window, ctx->sta_window, st);
+                   ctx->d_ncand.p + 1, ctx->cand_cap, row_base, lta_window, ctx->sta_window, st);
         DTX_CUDA(cudaGetLastError());
         ctx->launches += 1;
     }
+    if (ctx->accumulate) ctx->acc_chunks += nchunks;
     ctx->run_set = set_id;
     ctx->run_S = S;
     ctx->ran = true;
+    return DTX_OK;
+}
+
+/* Results of several dtx_detect_run calls (the batches of one station) accumulate on the device:
+ * candidate rows and rowmax / rowflags entries are numbered by the chunk's position in the whole
+ * sequence, and nothing has to be fetched (no host synchronisation) between the batches. */
+int dtx_accumulate_begin(dtx_ctx* ctx, int64_t total_chunks) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (total_chunks < 1 || total_chunks > (1LL << 24)) return fail(ctx, DTX_ERR_ARG, "dtx_accumulate_begin: bad chunk count");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    DTX_CUDA(ctx->d_ncand.reserve(2));
+    DTX_CUDA(cudaMemsetAsync(ctx->d_ncand.p, 0, 2 * sizeof(int), ctx->stream));
+    ctx->accumulate = true;
+    ctx->acc_chunks = 0;
+    ctx->acc_capacity = total_chunks;
+    ctx->k1_used = 0;
+    ctx->ran = false;
+    return DTX_OK;
+}
+
+int dtx_accumulate_end(dtx_ctx* ctx) {
+    if (!ctx) return DTX_ERR_ARG;
+    ctx->accumulate = false;
+    ctx->acc_chunks = 0;
+    ctx->acc_capacity = 0;
+    ctx->ran = false;
     return DTX_OK;
 }
 
@@ -695,12 +819,15 @@ int dtx_get_stalta(dtx_ctx* ctx, int chunk, int subspace, int W, float* out, int
     if (count < cd.T) return fail(ctx, DTX_ERR_CAPACITY, "dtx_get_stalta: buffer smaller than T");
     DTX_CUDA(cudaSetDevice(ctx->device));
     const int Wsta = ctx->sta_window;
+    if (W > stalta_dense_max_window() || Wsta > stalta_dense_max_window())
+        return fail(ctx, DTX_ERR_ARG, "dtx_get_stalta: rolling window does not fit in shared memory (max ~13800 samples)");
     if (cd.T < W || cd.T < Wsta) {
         for (int i = 0; i < cd.T; ++i) out[i] = NAN;
         return DTX_OK;
     }
     int flags = 0;
-    DTX_CUDA(cudaMemcpyAsync(&flags, ctx->d_rowflags.p + static_cast<long long>(chunk) * ctx->run_S + subspace,
+    const long long batch0 = ctx->accumulate ? ctx->acc_chunks - ctx->nchunks : 0;   // first chunk of the last batch
+    DTX_CUDA(cudaMemcpyAsync(&flags, ctx->d_rowflags.p + (batch0 + chunk) * ctx->run_S + subspace,
                              sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));
     DevBuf<float> tmp;
@@ -710,14 +837,13 @@ int dtx_get_stalta(dtx_ctx* ctx, int chunk, int subspace, int W, float* out, int
     DTX_CUDA(cudaGetLastError());
     DTX_CUDA(cudaMemcpyAsync(out, tmp.p, sizeof(float) * cd.T, cudaMemcpyDeviceToHost, ctx->stream));
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));
-    tmp.release();
     return DTX_OK;
 }
 
 int dtx_get_rowstats(dtx_ctx* ctx, float* maxds, int32_t* flags, int64_t count) {
     if (!ctx) return DTX_ERR_ARG;
     if (!ctx->ran) return fail(ctx, DTX_ERR_STATE, "dtx_get_rowstats: no run");
-    const int64_t rows = static_cast<int64_t>(ctx->nchunks) * ctx->run_S;
+    const int64_t rows = (ctx->accumulate ? ctx->acc_chunks : static_cast<int64_t>(ctx->nchunks)) * ctx->run_S;
     if (count < rows) return fail(ctx, DTX_ERR_CAPACITY, "dtx_get_rowstats: buffer too small");
     DTX_CUDA(cudaSetDevice(ctx->device));
     if (maxds) DTX_CUDA(cudaMemcpyAsync(maxds, ctx->d_rowmax.p, sizeof(float) * rows, cudaMemcpyDeviceToHost, ctx->stream));
@@ -774,6 +900,10 @@ int dtx_get_candidates(dtx_ctx* ctx, dtx_cand* out, int64_t cap, int64_t* n) {
     DTX_CUDA(cudaMemcpyAsync(&nc, ctx->d_ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));
     *n = nc;
+    if (!out) {   // count query
+        if (nc > ctx->cand_cap) return fail(ctx, DTX_ERR_CAPACITY, "candidate list truncated on the device");
+        return DTX_OK;
+    }
     int64_t ncopy = std::min<int64_t>(std::min<int64_t>(nc, ctx->cand_cap), cap);
     if (out && ncopy > 0) {
         static_assert(sizeof(dtx_cand) == sizeof(Candidate), "candidate layout");
@@ -786,10 +916,25 @@ int dtx_get_candidates(dtx_ctx* ctx, dtx_cand* out, int64_t cap, int64_t* n) {
 
 int dtx_last_k1_ms(dtx_ctx* ctx, float* ms) {
     if (!ctx || !ms) return DTX_ERR_ARG;
-    if (!ctx->ran || !ctx->k1_timed) return fail(ctx, DTX_ERR_STATE, "no tcgen05 run to time");
+    if (!ctx->k1_timed || ctx->k1_used == 0) return fail(ctx, DTX_ERR_STATE, "no tcgen05 run to time");
     DTX_CUDA(cudaSetDevice(ctx->device));
-    DTX_CUDA(cudaEventSynchronize(ctx->ev1));
-    DTX_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    const auto& ev = ctx->k1_events[ctx->k1_used - 1];
+    DTX_CUDA(cudaEventSynchronize(ev.second));
+    DTX_CUDA(cudaEventElapsedTime(ms, ev.first, ev.second));
+    return DTX_OK;
+}
+
+int dtx_k1_ms_history(dtx_ctx* ctx, float* ms, int64_t cap, int64_t* n) {
+    if (!ctx || !n) return DTX_ERR_ARG;
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    *n = static_cast<int64_t>(ctx->k1_used);
+    if (!ms) return DTX_OK;
+    if (cap < *n) return fail(ctx, DTX_ERR_CAPACITY, "dtx_k1_ms_history: buffer too small");
+    for (size_t i = 0; i < ctx->k1_used; ++i) {
+        DTX_CUDA(cudaEventSynchronize(ctx->k1_events[i].second));
+        DTX_CUDA(cudaEventElapsedTime(ms + i, ctx->k1_events[i].first, ctx->k1_events[i].second));
+    }
+    ctx->k1_used = 0;
     return DTX_OK;
 }
 
@@ -855,9 +1000,17 @@ static int preprocess_impl(dtx_ctx* ctx, int nchunks, int Nc, const void* const*
     DTX_CUDA(cudaMemcpyAsync(dlen.p, len.data(), sizeof(int) * ntr, cudaMemcpyHostToDevice, st));
     DTX_CUDA(cudaMemcpyAsync(dmin.p, minlen.data(), sizeof(int) * nchunks, cudaMemcpyHostToDevice, st));
     DTX_CUDA(cudaMemcpyAsync(dooff.p, out_off.data(), sizeof(long long) * nchunks, cudaMemcpyHostToDevice, st));
+    // the channels of a chunk are trimmed to their common window BEFORE detrend and filter
+    // (st.trim(startTrim, endTrim), construct.py:1019-1024; channels share a start time here, so
+    // that is the first min-length samples of each, taken after the optional decimation)
+    std::vector<int> lenw(ntr);
+    for (int t = 0; t < ntr; ++t) lenw[t] = minlen[t / Nc];
+    DevBuf<int> dlenw;
+    DTX_CUDA(dlenw.reserve(ntr));
+    DTX_CUDA(cudaMemcpyAsync(dlenw.p, lenw.data(), sizeof(int) * ntr, cudaMemcpyHostToDevice, st));
     double* work = dbuf.p;
     const long long* work_off = doff.p;
-    const int* work_len = dlen.p;
+    const int* work_len = dlenw.p;
     int work_maxlen = maxlen;
     if (factor > 1) {
         // anti-alias low-pass (forward only, no detrend), then keep every factor-th sample
@@ -869,7 +1022,7 @@ static int preprocess_impl(dtx_ctx* ctx, int nchunks, int Nc, const void* const*
         launch_decimate(dbuf.p, doff.p, dbuf2.p, doff2.p, dlen2.p, ntr, factor, st);
         DTX_CUDA(cudaGetLastError());
         ctx->launches += 3 * ndec + 1;
-        work = dbuf2.p; work_off = doff2.p; work_len = dlen2.p; work_maxlen = maxlen2;
+        work = dbuf2.p; work_off = doff2.p; work_maxlen = maxlen2;
     }
     launch_preproc(work, work_off, work_len, ntr, work_maxlen, sos, nsos, zerophase, detrend, dstats.p, dseg.p, st);
     DTX_CUDA(cudaGetLastError());
@@ -1062,151 +1215,255 @@ int dtx_corr_zero_lag(dtx_ctx* ctx, const double* X, int N, int n, double* out) 
     return DTX_OK;
 }
 
-static const int CCX_SET_ID = -77;
+// ------------------------------------------------------------------------------------ CCX
+// The loaded-chunk table and the basis sets of the detection path survive a CCX call; only the
+// results of the last dtx_detect_run are invalidated (CCX shares the DS / split-signal workspace).
+namespace {
+struct BatchTable {
+    int nchunks, dtype;
+    std::vector<long long> raw_off, rawL;
+    const void* d_raw;
+};
+BatchTable save_table(dtx_ctx* ctx) {
+    return BatchTable{ctx->nchunks, ctx->dtype, ctx->raw_off, ctx->rawL, ctx->d_raw};
+}
+void restore_table(dtx_ctx* ctx, BatchTable& t) {
+    ctx->nchunks = t.nchunks; ctx->dtype = t.dtype; ctx->raw_off.swap(t.raw_off); ctx->rawL.swap(t.rawL);
+    ctx->d_raw = t.d_raw;
+    ctx->ran = false;
+    ctx->items_key.clear();
+}
+}  // namespace
 
-// Tensor-core CCX: events [row_begin,row_end) as rank-1 templates, padded events as chunks.
-static int ccx_tcgen05(dtx_ctx* ctx, const void* X, int dtype, const void* dX, int N, int n, int Nc, int row_begin,
-                       int row_end, const double* wa, const double* wb, const double* es, const double* ed,
+// Tensor-core CCX: events rows[0..nrows) as rank-1 templates, padded events as chunks.
+static int ccx_tcgen05(dtx_ctx* ctx, int dtype, const void* dX, int N, int n, int Nc, const int* h_rows, int nrows,
                        double* dcc, int* dlag, double* dsub, std::vector<int2>& flagged) {
     const int ns = n / Nc, trunc = n / (2 * Nc) - 1, nl = 2 * ns - 1 - 2 * trunc;
-    const int rows = row_end - row_begin;
     cudaStream_t st = ctx->stream;
     // templates: x / ||x - mean||  (zero rows for zeroed-out waveforms), built on the device
-    std::vector<int32_t> roff(rows + 1);
-    for (int r = 0; r <= rows; ++r) roff[r] = r;
+    std::vector<int32_t> roff(nrows + 1);
+    for (int r = 0; r <= nrows; ++r) roff[r] = r;
     auto fill = [&](double* d_U) -> int {
-        launch_ccx_templates(dX, dtype == DTX_F32, n, row_begin, rows, d_U, st);
+        launch_ccx_templates(dX, dtype == DTX_F32, n, ctx->cx_rows.p, nrows, d_U, st);
         ctx->launches += 1;
         DTX_CUDA(cudaGetLastError());
         return DTX_OK;
     };
-    int rc = set_bases_device(ctx, CCX_SET_ID, fill, roff.data(), rows, n, Nc, nullptr);
+    int rc = set_bases_device(ctx, ctx->ccx_set, INT32_MIN, fill, roff.data(), nrows, n, Nc, nullptr);
     if (rc != DTX_OK) return rc;
-    BasisSet& bs = ctx->sets[CCX_SET_ID];
+    BasisSet& bs = ctx->ccx_set;
     const int P = ns - trunc - 1;
     const int Lc = nl + ns - 1;
     const long long Lm = static_cast<long long>(Lc) * Nc;
     // batch of signals bounded by the DS buffer (rows x Tpad floats per signal)
-    const long long per_sig = static_cast<long long>(rows) * ((nl + TILE_T - 1) / TILE_T * TILE_T) * 4;
-    int batch = static_cast<int>(std::max<long long>(1, std::min<long long>(512, (4LL << 30) / per_sig)));
-    DevBuf<double> dpad;
-    DevBuf<int> dnflag;
-    DevBuf<int2> dflag;
+    const long long per_sig = static_cast<long long>(nrows) * ((nl + TILE_T - 1) / TILE_T * TILE_T) * 4;
+    const int batch = static_cast<int>(std::max<long long>(
+        1, std::min<long long>(ctx->ccx_max_batch, ctx->ccx_ds_bytes / std::max<long long>(1, per_sig))));
     const int flag_cap = 1 << 20;
-    DTX_CUDA(dpad.reserve(static_cast<size_t>(batch) * Lm));
-    DTX_CUDA(dnflag.reserve(1));
-    DTX_CUDA(dflag.reserve(flag_cap));
-    DTX_CUDA(cudaMemsetAsync(dnflag.p, 0, sizeof(int), st));
+    DTX_CUDA(ctx->cx_pad.reserve(static_cast<size_t>(batch) * Lm));
+    DTX_CUDA(ctx->cx_nflag.reserve(1));
+    DTX_CUDA(ctx->cx_flag.reserve(flag_cap));
+    DTX_CUDA(cudaMemsetAsync(ctx->cx_nflag.p, 0, sizeof(int), st));
     std::vector<int64_t> offs, lens;
     std::vector<int> blk_hi;
-    for (int c0 = row_begin + 1; c0 < N; c0 += batch) {
+    const int c_first = h_rows[0] + 1;   // signals c <= rows[0] have no template b < c
+    for (int c0 = c_first; c0 < N; c0 += batch) {
         const int nsig = std::min(batch, N - c0);
-        launch_ccx_pad(dX, dtype == DTX_F32, n, Nc, c0, nsig, P, Lc, dpad.p, st);
+        launch_ccx_pad(dX, dtype == DTX_F32, n, Nc, c0, nsig, P, Lc, ctx->cx_pad.p, st);
         DTX_CUDA(cudaGetLastError());
         offs.resize(nsig); lens.resize(nsig); blk_hi.resize(nsig);
         for (int i = 0; i < nsig; ++i) {
             offs[i] = static_cast<int64_t>(i) * Lm;
             lens[i] = Lm;
-            const int nrow = std::min(c0 + i, row_end) - row_begin;   // templates b < c
+            // templates b < c are a prefix of the (ascending) row list
+            const int nrow = static_cast<int>(std::lower_bound(h_rows, h_rows + nrows, c0 + i) - h_rows);
             blk_hi[i] = (nrow + VEC_PER_BLOCK - 1) / VEC_PER_BLOCK;
         }
-        rc = dtx_attach_device_chunks(ctx, nsig, dpad.p, offs.data(), lens.data(), DTX_F64);
+        rc = dtx_attach_device_chunks(ctx, nsig, ctx->cx_pad.p, offs.data(), lens.data(), DTX_F64);
         if (rc != DTX_OK) return rc;
         rc = project_run(ctx, bs, DTX_ENGINE_TCGEN05, 2, 1, 0, blk_hi.data());
         if (rc != DTX_OK) return rc;
-        launch_ccx_post(ctx->d_DS.p, ctx->d_chunks.p, c0, nsig, dX, dtype == DTX_F32, N, n, Nc, row_begin, row_end,
-                        wa, wb, es, ed, dcc, dlag, dsub, dnflag.p, dflag.p, flag_cap, st);
+        launch_ccx_post(ctx->d_DS.p, ctx->d_chunks.p, c0, nsig, dX, dtype == DTX_F32, N, n, Nc, ctx->cx_rows.p, nrows,
+                        ctx->cx_wa.p, ctx->cx_wb.p, ctx->cx_es.p, ctx->cx_ed.p, dcc, dlag, dsub, ctx->cx_nflag.p,
+                        ctx->cx_flag.p, flag_cap, st);
         DTX_CUDA(cudaGetLastError());
         ctx->launches += 2;
     }
     int nflag = 0;
-    DTX_CUDA(cudaMemcpyAsync(&nflag, dnflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaMemcpyAsync(&nflag, ctx->cx_nflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     DTX_CUDA(cudaStreamSynchronize(st));
     if (nflag > flag_cap) return fail(ctx, DTX_ERR_CAPACITY, "dtx_ccx: too many degenerate pairs");
     flagged.resize(nflag);
-    if (nflag) DTX_CUDA(cudaMemcpy(flagged.data(), dflag.p, sizeof(int2) * nflag, cudaMemcpyDeviceToHost));
-    dpad.release(); dnflag.release(); dflag.release();
-    // the detection state of this context was overwritten and the padded chunks are gone
-    ctx->ran = false;
-    ctx->d_raw = nullptr;
-    ctx->nchunks = 0;
+    if (nflag) DTX_CUDA(cudaMemcpy(flagged.data(), ctx->cx_flag.p, sizeof(int2) * nflag, cudaMemcpyDeviceToHost));
     return DTX_OK;
+}
+
+// Shared body: X on the host (x_on_device = 0, copied H2D) or already on the device; results into
+// the device arrays d_cc / d_lag / d_sub, dense [nrows][N] (slot r = event rows[r]).
+static int ccx_run(dtx_ctx* ctx, const void* X, int x_on_device, int dtype, int N, int n, int Nc, const int32_t* rows,
+                   int nrows, int engine, double* d_cc, int* d_lag, double* d_sub) {
+    if (N < 2 || Nc < 1 || n % Nc != 0 || n / Nc < 4)
+        return fail(ctx, DTX_ERR_ARG, "dtx_ccx: lengths not equal / not a multiple of Nc (construct.py:430-436)");
+    if (!rows || nrows < 1) return fail(ctx, DTX_ERR_ARG, "dtx_ccx: empty row list");
+    for (int r = 0; r < nrows; ++r)
+        if (rows[r] < 0 || rows[r] >= N || (r > 0 && rows[r] <= rows[r - 1]))
+            return fail(ctx, DTX_ERR_ARG, "dtx_ccx: rows must be ascending, unique and inside [0, N)");
+    if (dtype != DTX_F64 && dtype != DTX_F32) return fail(ctx, DTX_ERR_ARG, "dtx_ccx: bad dtype");
+    if (engine != DTX_ENGINE_TCGEN05 && engine != DTX_ENGINE_FP64) return fail(ctx, DTX_ERR_ARG, "dtx_ccx: bad engine");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    const int ns = n / Nc, trunc = n / (2 * Nc) - 1, nl = 2 * ns - 1 - 2 * trunc;
+    const size_t esz = dtype == DTX_F32 ? 4 : 8;
+    cudaStream_t st = ctx->stream;
+    const void* dX = X;
+    if (!x_on_device) {
+        DTX_CUDA(ctx->cx_X.reserve(static_cast<size_t>(N) * n * esz));
+        DTX_CUDA(cudaMemcpyAsync(ctx->cx_X.p, X, static_cast<size_t>(N) * n * esz, cudaMemcpyHostToDevice, st));
+        dX = ctx->cx_X.p;
+    }
+    DTX_CUDA(ctx->cx_wa.reserve(static_cast<size_t>(N) * nl));
+    DTX_CUDA(ctx->cx_wb.reserve(static_cast<size_t>(N) * nl));
+    DTX_CUDA(ctx->cx_es.reserve(N));
+    DTX_CUDA(ctx->cx_ed.reserve(N));
+    DTX_CUDA(ctx->cx_rows.reserve(nrows));
+    DTX_CUDA(cudaMemcpyAsync(ctx->cx_rows.p, rows, sizeof(int) * nrows, cudaMemcpyHostToDevice, st));
+    const size_t cells = static_cast<size_t>(nrows) * N;
+    DTX_CUDA(cudaMemsetAsync(d_cc, 0, cells * sizeof(double), st));
+    DTX_CUDA(cudaMemsetAsync(d_sub, 0, cells * sizeof(double), st));
+    DTX_CUDA(cudaMemsetAsync(d_lag, 0, cells * sizeof(int), st));
+    launch_ccx_stats(dX, dtype == DTX_F32, N, n, Nc, ctx->cx_wa.p, ctx->cx_wb.p, ctx->cx_es.p, ctx->cx_ed.p, st);
+    DTX_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    if (engine == DTX_ENGINE_FP64 || nl < 16) {  // tiny templates: not worth a GEMM
+        launch_ccx_fp64(dX, dtype == DTX_F32, N, n, Nc, 0, nrows, ctx->cx_rows.p, ctx->cx_wa.p, ctx->cx_wb.p,
+                        ctx->cx_es.p, ctx->cx_ed.p, d_cc, d_lag, d_sub, ctx->num_sms, st);
+        DTX_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+        return DTX_OK;
+    }
+    BatchTable saved = save_table(ctx);
+    std::vector<int2> flagged;
+    const int rc = ccx_tcgen05(ctx, dtype, dX, N, n, Nc, rows, nrows, d_cc, d_lag, d_sub, flagged);
+    restore_table(ctx, saved);
+    if (rc != DTX_OK) return rc;
+    if (!flagged.empty()) {
+        // degenerate pairs (|res| > 1 from zero-variance windows, or a crowded maximum): the
+        // float64 kernel re-does their rows; only the flagged entries are taken from it
+        std::vector<int> frows;
+        for (const int2& f : flagged) frows.push_back(f.x);
+        std::sort(frows.begin(), frows.end());
+        frows.erase(std::unique(frows.begin(), frows.end()), frows.end());
+        DTX_CUDA(ctx->cx_tcc.reserve(N)); DTX_CUDA(ctx->cx_tsub.reserve(N)); DTX_CUDA(ctx->cx_tlag.reserve(N));
+        for (int b : frows) {
+            launch_ccx_fp64(dX, dtype == DTX_F32, N, n, Nc, b, 1, nullptr, ctx->cx_wa.p, ctx->cx_wb.p, ctx->cx_es.p,
+                            ctx->cx_ed.p, ctx->cx_tcc.p, ctx->cx_tlag.p, ctx->cx_tsub.p, ctx->num_sms, st);
+            DTX_CUDA(cudaGetLastError());
+            ctx->launches += 1;
+            const size_t slot = static_cast<size_t>(std::lower_bound(rows, rows + nrows, b) - rows);
+            for (const int2& f : flagged)
+                if (f.x == b) {
+                    const size_t o = slot * N + f.y;
+                    DTX_CUDA(cudaMemcpyAsync(d_cc + o, ctx->cx_tcc.p + f.y, sizeof(double), cudaMemcpyDeviceToDevice, st));
+                    DTX_CUDA(cudaMemcpyAsync(d_sub + o, ctx->cx_tsub.p + f.y, sizeof(double), cudaMemcpyDeviceToDevice, st));
+                    DTX_CUDA(cudaMemcpyAsync(d_lag + o, ctx->cx_tlag.p + f.y, sizeof(int), cudaMemcpyDeviceToDevice, st));
+                }
+        }
+    }
+    return DTX_OK;
+}
+
+int dtx_ccx_device(dtx_ctx* ctx, const void* X, int x_on_device, int dtype, int N, int n, int Nc,
+                   const int32_t* rows, int nrows, int engine, double* d_cc, int32_t* d_lag, double* d_sub) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (!X || !d_cc || !d_lag || !d_sub) return fail(ctx, DTX_ERR_ARG, "dtx_ccx_device: null pointer");
+    return ccx_run(ctx, X, x_on_device, dtype, N, n, Nc, rows, nrows, engine, d_cc, d_lag, d_sub);
 }
 
 int dtx_ccx(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int row_begin, int row_end,
             int engine, double* cc, int32_t* lag, double* subsamp) {
     if (!ctx) return DTX_ERR_ARG;
     if (!X || !cc || !lag || !subsamp) return fail(ctx, DTX_ERR_ARG, "dtx_ccx: null pointer");
-    if (N < 2 || Nc < 1 || n % Nc != 0 || n / Nc < 4)
-        return fail(ctx, DTX_ERR_ARG, "dtx_ccx: lengths not equal / not a multiple of Nc (construct.py:430-436)");
     if (row_begin < 0 || row_end > N || row_begin >= row_end) return fail(ctx, DTX_ERR_ARG, "dtx_ccx: bad row range");
-    if (dtype != DTX_F64 && dtype != DTX_F32) return fail(ctx, DTX_ERR_ARG, "dtx_ccx: bad dtype");
-    if (engine != DTX_ENGINE_TCGEN05 && engine != DTX_ENGINE_FP64) return fail(ctx, DTX_ERR_ARG, "dtx_ccx: bad engine");
     DTX_CUDA(cudaSetDevice(ctx->device));
-    const int ns = n / Nc, trunc = n / (2 * Nc) - 1, nl = 2 * ns - 1 - 2 * trunc;
-    const size_t esz = dtype == DTX_F32 ? 4 : 8;
-    const size_t rows = static_cast<size_t>(row_end - row_begin);
-    DevBuf<uint8_t> dX;
-    DevBuf<double> dcc, dsub, wa, wb, es, ed;
-    DevBuf<int> dlag;
-    DTX_CUDA(dX.reserve(static_cast<size_t>(N) * n * esz));
-    DTX_CUDA(dcc.reserve(rows * N));
-    DTX_CUDA(dsub.reserve(rows * N));
-    DTX_CUDA(dlag.reserve(rows * N));
-    DTX_CUDA(wa.reserve(static_cast<size_t>(N) * nl));
-    DTX_CUDA(wb.reserve(static_cast<size_t>(N) * nl));
-    DTX_CUDA(es.reserve(N));
-    DTX_CUDA(ed.reserve(N));
+    const size_t nrows = static_cast<size_t>(row_end - row_begin);
+    std::vector<int32_t> rows(nrows);
+    for (size_t r = 0; r < nrows; ++r) rows[r] = row_begin + static_cast<int>(r);
+    DTX_CUDA(ctx->cx_cc.reserve(nrows * N));
+    DTX_CUDA(ctx->cx_sub.reserve(nrows * N));
+    DTX_CUDA(ctx->cx_lag.reserve(nrows * N));
+    const int rc = ccx_run(ctx, X, 0, dtype, N, n, Nc, rows.data(), static_cast<int>(nrows), engine, ctx->cx_cc.p,
+                           ctx->cx_lag.p, ctx->cx_sub.p);
+    if (rc != DTX_OK) return rc;
     cudaStream_t st = ctx->stream;
-    DTX_CUDA(cudaMemcpyAsync(dX.p, X, static_cast<size_t>(N) * n * esz, cudaMemcpyHostToDevice, st));
-    DTX_CUDA(cudaMemsetAsync(dcc.p, 0, rows * N * sizeof(double), st));
-    DTX_CUDA(cudaMemsetAsync(dsub.p, 0, rows * N * sizeof(double), st));
-    DTX_CUDA(cudaMemsetAsync(dlag.p, 0, rows * N * sizeof(int), st));
-    launch_ccx_stats(dX.p, dtype == DTX_F32, N, n, Nc, wa.p, wb.p, es.p, ed.p, st);
+    DTX_CUDA(cudaMemcpyAsync(cc, ctx->cx_cc.p, nrows * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaMemcpyAsync(lag, ctx->cx_lag.p, nrows * N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaMemcpyAsync(subsamp, ctx->cx_sub.p, nrows * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaStreamSynchronize(st));
+    return DTX_OK;
+}
+
+int dtx_ccx_pack(dtx_ctx* ctx, const double* d_cc, const int32_t* d_lag, const double* d_sub,
+                 const int32_t* slot_rows, int nslots, int N, double* cc, int32_t* lag, double* subsamp) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (!d_cc || !d_lag || !d_sub || !slot_rows || !cc || !lag || !subsamp || N < 2 || nslots < N - 1)
+        return fail(ctx, DTX_ERR_ARG, "dtx_ccx_pack: bad arguments");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    std::vector<int> slot_of_row(N, -1);
+    for (int s = 0; s < nslots; ++s)
+        if (slot_rows[s] >= 0) {
+            if (slot_rows[s] >= N) return fail(ctx, DTX_ERR_ARG, "dtx_ccx_pack: slot row out of range");
+            slot_of_row[slot_rows[s]] = s;
+        }
+    for (int b = 0; b < N - 1; ++b)
+        if (slot_of_row[b] < 0) return fail(ctx, DTX_ERR_ARG, "dtx_ccx_pack: a row is missing from the slots");
+    const size_t np = static_cast<size_t>(N) * (N - 1) / 2;
+    DTX_CUDA(ctx->cx_slot.reserve(N));
+    DTX_CUDA(ctx->cx_pcc.reserve(np)); DTX_CUDA(ctx->cx_psub.reserve(np)); DTX_CUDA(ctx->cx_plag.reserve(np));
+    cudaStream_t st = ctx->stream;
+    DTX_CUDA(cudaMemcpyAsync(ctx->cx_slot.p, slot_of_row.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+    launch_ccx_pack(d_cc, d_lag, d_sub, ctx->cx_slot.p, N, ctx->cx_pcc.p, ctx->cx_plag.p, ctx->cx_psub.p, st);
     DTX_CUDA(cudaGetLastError());
     ctx->launches += 1;
-    if (engine == DTX_ENGINE_FP64 || nl < 16) {  // tiny templates: not worth a GEMM
-        launch_ccx_fp64(dX.p, dtype == DTX_F32, N, n, Nc, row_begin, row_end, wa.p, wb.p, es.p, ed.p, dcc.p, dlag.p,
-                        dsub.p, ctx->num_sms, st);
-        DTX_CUDA(cudaGetLastError());
-        ctx->launches += 1;
-    } else {
-        std::vector<int2> flagged;
-        const int rc = ccx_tcgen05(ctx, X, dtype, dX.p, N, n, Nc, row_begin, row_end, wa.p, wb.p, es.p, ed.p, dcc.p,
-                                   dlag.p, dsub.p, flagged);
-        if (rc != DTX_OK) return rc;
-        if (!flagged.empty()) {
-            // degenerate pairs (|res| > 1 from zero-variance windows, or a crowded maximum): the
-            // float64 kernel re-does their rows; only the flagged entries are taken from it
-            std::vector<int> frows;
-            for (const int2& f : flagged) frows.push_back(f.x);
-            std::sort(frows.begin(), frows.end());
-            frows.erase(std::unique(frows.begin(), frows.end()), frows.end());
-            DevBuf<double> tcc, tsub;
-            DevBuf<int> tlag;
-            DTX_CUDA(tcc.reserve(N)); DTX_CUDA(tsub.reserve(N)); DTX_CUDA(tlag.reserve(N));
-            for (int b : frows) {
-                launch_ccx_fp64(dX.p, dtype == DTX_F32, N, n, Nc, b, b + 1, wa.p, wb.p, es.p, ed.p, tcc.p, tlag.p,
-                                tsub.p, ctx->num_sms, st);
-                DTX_CUDA(cudaGetLastError());
-                for (const int2& f : flagged)
-                    if (f.x == b) {
-                        const size_t o = static_cast<size_t>(b - row_begin) * N + f.y;
-                        DTX_CUDA(cudaMemcpyAsync(dcc.p + o, tcc.p + f.y, sizeof(double), cudaMemcpyDeviceToDevice, st));
-                        DTX_CUDA(cudaMemcpyAsync(dsub.p + o, tsub.p + f.y, sizeof(double), cudaMemcpyDeviceToDevice, st));
-                        DTX_CUDA(cudaMemcpyAsync(dlag.p + o, tlag.p + f.y, sizeof(int), cudaMemcpyDeviceToDevice, st));
-                    }
-            }
-            DTX_CUDA(cudaStreamSynchronize(st));
-            tcc.release(); tsub.release(); tlag.release();
-        }
-    }
-    DTX_CUDA(cudaMemcpyAsync(cc, dcc.p, rows * N * sizeof(double), cudaMemcpyDeviceToHost, st));
-    DTX_CUDA(cudaMemcpyAsync(lag, dlag.p, rows * N * sizeof(int), cudaMemcpyDeviceToHost, st));
-    DTX_CUDA(cudaMemcpyAsync(subsamp, dsub.p, rows * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaMemcpyAsync(cc, ctx->cx_pcc.p, np * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaMemcpyAsync(lag, ctx->cx_plag.p, np * sizeof(int), cudaMemcpyDeviceToHost, st));
+    DTX_CUDA(cudaMemcpyAsync(subsamp, ctx->cx_psub.p, np * sizeof(double), cudaMemcpyDeviceToHost, st));
     DTX_CUDA(cudaStreamSynchronize(st));
-    dX.release(); dcc.release(); dsub.release(); dlag.release(); wa.release(); wb.release(); es.release(); ed.release();
     return DTX_OK;
+}
+
+int dtx_ccx_condensed(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int engine, double* cc,
+                      int32_t* lag, double* subsamp) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (!X || !cc || !lag || !subsamp || N < 2) return fail(ctx, DTX_ERR_ARG, "dtx_ccx_condensed: bad arguments");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    const size_t nrows = static_cast<size_t>(N - 1);
+    std::vector<int32_t> rows(nrows);
+    for (size_t r = 0; r < nrows; ++r) rows[r] = static_cast<int>(r);
+    DTX_CUDA(ctx->cx_cc.reserve(nrows * N));
+    DTX_CUDA(ctx->cx_sub.reserve(nrows * N));
+    DTX_CUDA(ctx->cx_lag.reserve(nrows * N));
+    const int rc = ccx_run(ctx, X, 0, dtype, N, n, Nc, rows.data(), static_cast<int>(nrows), engine, ctx->cx_cc.p,
+                           ctx->cx_lag.p, ctx->cx_sub.p);
+    if (rc != DTX_OK) return rc;
+    return dtx_ccx_pack(ctx, ctx->cx_cc.p, ctx->cx_lag.p, ctx->cx_sub.p, rows.data(), static_cast<int>(nrows), N, cc,
+                        lag, subsamp);
+}
+
+int dtx_set_ccx_batch(dtx_ctx* ctx, int max_signals, int64_t ds_bytes) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (max_signals < 1 || ds_bytes < (1 << 20)) return fail(ctx, DTX_ERR_ARG, "dtx_set_ccx_batch: bad limits");
+    ctx->ccx_max_batch = max_signals;
+    ctx->ccx_ds_bytes = ds_bytes;
+    return DTX_OK;
+}
+
+int dtx_host_alloc(void** out, int64_t bytes) {
+    if (!out || bytes < 1) return DTX_ERR_ARG;
+    return cudaMallocHost(out, static_cast<size_t>(bytes)) == cudaSuccess ? DTX_OK : DTX_ERR_CUDA;
+}
+
+int dtx_host_free(void* p) {
+    if (!p) return DTX_OK;
+    return cudaFreeHost(p) == cudaSuccess ? DTX_OK : DTX_ERR_CUDA;
 }
 
 }  // extern "C"

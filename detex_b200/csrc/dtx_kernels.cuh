@@ -52,9 +52,10 @@ struct Seg {
 
 struct BlockInfo {   // one per (basis block, vector slot)
     float sumU;      // sum of the basis vector's entries (true units)
-    int out_row;     // DS row of the subspace this vector belongs to, -1 = padding
-    int nrows;       // rank of the piece if this slot is its first vector, else 0; negative =
-                     // piece of a rank > 16 subspace (epilogue accumulates into the DS row)
+    int out_row;     // DS row this vector's piece is written to, -1 = padding: the subspace's own row,
+                     // or for the 2nd, 3rd, .. 16-vector piece of a rank > 16 subspace a scratch row >= S
+                     // (launch_sum_pieces adds those to the subspace row afterwards)
+    int nrows;       // rank of the piece if this slot is its first vector, else 0
     int seg_end;     // slot index one past the last vector of this slot's subspace
 };
 
@@ -71,10 +72,23 @@ struct BasisLayout {
 
 // ------------------------------------------------------------------ launchers
 // k0_prep.cu
+// d_zeroE (may be null): per chunk, set to 1 when a window's energy is zero within round-off; such
+// windows get invE = +inf (the reference's x/0, detect.py:577) and launch_zero_energy_fix then makes
+// their DS +inf for every subspace instead of the 0*inf = NaN of an exactly-zero projection.
 void launch_k0(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nchunks, int Nc, int n,
                int max_Lpad, int max_ntiles, double* d_sum, unsigned* d_maxbits, float* d_scale,
                __half* d_xsplit, float* d_mu, float* d_invE, int x8_policy, float k4_limit,
-               unsigned* d_k4bits, int* d_chunk_mode, cudaStream_t st);
+               unsigned* d_k4bits, int* d_chunk_mode, int* d_zeroE, cudaStream_t st);
+// DS[s][t] = +inf for every subspace row at the lags whose window energy is zero (invE = +inf), for
+// the chunks k0_norm flagged.  nrows = DS rows per chunk.  DS64 may be null.
+void launch_zero_energy_fix(const ChunkDesc* d_chunks, int nchunks, int max_ntiles, int nrows, const float* d_invE,
+                            const int* d_zeroE, float* d_DS, double* d_DS64, cudaStream_t st);
+// Rank > 16 subspaces: their 16-vector pieces land in separate DS rows (the first in the subspace's
+// own row, the others in scratch rows behind the S subspace rows); this adds the scratch rows to the
+// subspace row in piece order, so the result does not depend on the order the CTAs finished in.
+struct PieceSum { int dst_row, src_row; };
+void launch_sum_pieces(const ChunkDesc* d_chunks, int nchunks, int max_Tpad, const PieceSum* d_pieces, int npieces,
+                       float* d_DS, cudaStream_t st);
 
 // basis image (k1_project.cu)
 // per row of U: {sum, max |u|, sum u^2, sum u^4} (float64)
@@ -117,28 +131,38 @@ struct Candidate {
     float ds;    // detection statistic
     float lta;   // denominator of DS_STALTA: |ds| / lta = STA / LTA at t (filled by launch_lta)
 };
+// row_base: candidate rows and the rowmax / rowflags entries of this batch start at row_base
+// (= chunks of earlier batches * S when results accumulate over the batches of a station)
 void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, const float* d_thr,
                float* d_rowmax, int* d_rowflags, unsigned long long* d_hist, double hist_lo,
                double hist_hi, int nbins, Candidate* d_cand, int cand_cap, int* d_ncand, double* d_fas,
-               cudaStream_t st);
+               int row_base, cudaStream_t st);
+// candidates [*d_ncand_before, *d_ncand) belong to the current batch (d_ncand_before may be null = 0)
 void launch_lta(const float* DS, const ChunkDesc* d_chunks, int S, const int* d_rowflags,
-                Candidate* d_cand, const int* d_ncand, int cand_cap, int W, int Wsta, cudaStream_t st);
+                Candidate* d_cand, const int* d_ncand, const int* d_ncand_before, int cand_cap, int row_base, int W,
+                int Wsta, cudaStream_t st);
 
 // k4_ccx.cu : pairwise CCX
 void launch_ccx_stats(const void* d_X, int dtype_f32, int N, int n, int Nc, double* wa, double* wb, double* es,
                       double* ed, cudaStream_t st);
-void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int row_begin, int row_end,
+// template rows: d_rows[0..nrows) if given, else row_begin .. row_begin + nrows - 1
+void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int row_begin, int nrows, const int* d_rows,
                      const double* wa, const double* wb, const double* es, const double* ed, double* d_cc,
                      int* d_lag, double* d_sub, int num_sms, cudaStream_t st);
 void launch_corr0(const double* d_X, int N, int n, double* d_out, cudaStream_t st);
-void launch_ccx_templates(const void* d_X, int dtype_f32, int n, int row_begin, int rows, double* d_U,
+// d_rows[r] = event index of template row r (sorted ascending)
+void launch_ccx_templates(const void* d_X, int dtype_f32, int n, const int* d_rows, int rows, double* d_U,
                           cudaStream_t st);
 void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int nsig, int P, int Lc, double* out,
                     cudaStream_t st);
 void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsig, const void* d_X, int dtype_f32,
-                     int N, int n, int Nc, int row_begin, int row_end, const double* wa, const double* wb,
+                     int N, int n, int Nc, const int* d_rows, int nrows, const double* wa, const double* wb,
                      const double* es, const double* ed, double* d_cc, int* d_lag, double* d_sub, int* d_nflag,
                      int2* d_flagged, int flag_cap, cudaStream_t st);
+// dense per-slot rows [nslots][N] -> SciPy condensed order (pair (b, c), b < c, at b*N - b(b+1)/2 + c-b-1);
+// d_slot_of_row[b] = slot holding event b's row
+void launch_ccx_pack(const double* d_cc, const int* d_lag, const double* d_sub, const int* d_slot_of_row, int N,
+                     double* o_cc, int* o_lag, double* o_sub, cudaStream_t st);
 
 // k7_mag.cu : per-detection magnitude / SNR estimates (_estMag)
 constexpr int MAG_MAX_RANK = 64;
@@ -172,5 +196,6 @@ void launch_stalta_max(const void* raw, int dtype_f32, const long long* d_raw_of
 
 void launch_stalta_dense(const float* row, int T, int W, int Wsta, int zero_inf, float* out, float* tmp,
                          cudaStream_t st);
+int stalta_dense_max_window();
 
 }  // namespace dtx

@@ -106,10 +106,20 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k0_norm(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
         const double* __restrict__ sum, float* __restrict__ mu, float* __restrict__ invE, int Nc,
-        int n, unsigned* __restrict__ k4bits) {
+        int n, unsigned* __restrict__ k4bits, const unsigned* __restrict__ maxbits, int* __restrict__ zeroE) {
     const ChunkDesc cd = chunks[blockIdx.y];
     if (blockIdx.x >= cd.ntiles) return;
     const double mean = sum[blockIdx.y] / static_cast<double>(cd.L);
+    // A window of constant data (a zero-filled gap, fillZeros=True) has zero energy, but S2 - S1^2/n of
+    // the centred samples only cancels to ~1e-16 n max^2.  Below 1e-13 n max^2 (dead data: a window
+    // standard deviation under 3e-7 of the chunk's largest sample) the window counts as constant and
+    // gets invE = +inf, the reference's sum(if1^2)/0 (detect.py:577; the infs are zeroed at :278-281).
+    double etol = 0.0;
+    if (zeroE) {
+        const double mc = static_cast<double>(__uint_as_float(maxbits[blockIdx.y])) + fabs(mean);
+        etol = 1e-13 * static_cast<double>(n) * mc * mc;
+    }
+    bool any_zero = false;
     const T* x = raw + cd.raw_off;
     const int t0 = blockIdx.x * TILE_T;
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
@@ -218,6 +228,7 @@ k0_norm(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
             const double s2 = base2 + o2 + d2[k];
             double E = s2 - s1 * s1 / nn;
             if (E < 0.0) E = 0.0;
+            if (zeroE && E <= etol) { E = 0.0; any_zero = true; }
             fm = static_cast<float>(s1 / nn);
             fe = static_cast<float>(cn / E);  // E == 0 -> +inf, as the reference's x/0
             if (want4) {
@@ -230,6 +241,7 @@ k0_norm(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
         pm[(i & ~1023) + (i & 7) * 128 + ((i & 1023) >> 3)] = fm;
         pe[i] = fe;
     }
+    if (zeroE && __any_sync(0xffffffffu, any_zero) && l == 0) atomicOr(&zeroE[blockIdx.y], 1);
     if (want4) {
         for (int s = 16; s > 0; s >>= 1) k4 = fmaxf(k4, __shfl_xor_sync(0xffffffffu, k4, s));
         if (l == 0) atomicMax(&k4bits[blockIdx.y], __float_as_uint(k4));  // k4 >= 0: uint order == float order
@@ -239,8 +251,9 @@ k0_norm(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
 void launch_k0(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nchunks, int Nc, int n,
                int max_Lpad, int max_ntiles, double* d_sum, unsigned* d_maxbits, float* d_scale,
                __half* d_xsplit, float* d_mu, float* d_invE, int x8_policy, float k4_limit,
-               unsigned* d_k4bits, int* d_chunk_mode, cudaStream_t st) {
+               unsigned* d_k4bits, int* d_chunk_mode, int* d_zeroE, cudaStream_t st) {
     cudaMemsetAsync(d_sum, 0, sizeof(double) * nchunks, st);
+    if (d_zeroE) cudaMemsetAsync(d_zeroE, 0, sizeof(int) * nchunks, st);
     cudaMemsetAsync(d_maxbits, 0, sizeof(unsigned) * nchunks, st);
     cudaMemsetAsync(d_k4bits, 0, sizeof(unsigned) * nchunks, st);
     unsigned* k4 = x8_policy == X8_AUTO ? d_k4bits : nullptr;   // k0_norm runs before k0_split reads it
@@ -253,16 +266,64 @@ void launch_k0(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nc
     if (dtype_f32) {
         const float* r = static_cast<const float*>(raw);
         k0_stats<float><<<g1, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits);
-        k0_norm<float><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n, k4);
+        k0_norm<float><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n, k4, d_maxbits, d_zeroE);
         k0_split<float><<<g2, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits, d_scale, d_xsplit, Nc, x8_policy,
                                             k4_limit, d_k4bits, d_chunk_mode);
     } else {
         const double* r = static_cast<const double*>(raw);
         k0_stats<double><<<g1, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits);
-        k0_norm<double><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n, k4);
+        k0_norm<double><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n, k4, d_maxbits, d_zeroE);
         k0_split<double><<<g2, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits, d_scale, d_xsplit, Nc, x8_policy,
                                              k4_limit, d_k4bits, d_chunk_mode);
     }
+}
+
+// DS = +inf at the zero-energy lags of the flagged chunks (one block per K1 tile of TILE_T lags).
+__global__ void __launch_bounds__(256)
+zero_energy_fix_kernel(const ChunkDesc* __restrict__ chunks, int nrows, const float* __restrict__ invE,
+                       const int* __restrict__ zeroE, float* __restrict__ DS, double* __restrict__ DS64) {
+    if (!zeroE[blockIdx.y]) return;
+    const ChunkDesc cd = chunks[blockIdx.y];
+    if (blockIdx.x >= cd.ntiles) return;
+    const int t0 = blockIdx.x * TILE_T;
+    for (int i = threadIdx.x; i < TILE_T; i += 256) {
+        const int t = t0 + i;
+        if (t >= cd.T || !isinf(invE[cd.norm_off + t])) continue;
+        for (int s = 0; s < nrows; ++s) {
+            const long long o = cd.ds_off + static_cast<long long>(s) * cd.Tpad + t;
+            if (DS) DS[o] = INFINITY;
+            if (DS64) DS64[o] = static_cast<double>(INFINITY);
+        }
+    }
+}
+
+void launch_zero_energy_fix(const ChunkDesc* d_chunks, int nchunks, int max_ntiles, int nrows, const float* d_invE,
+                            const int* d_zeroE, float* d_DS, double* d_DS64, cudaStream_t st) {
+    const dim3 g(max_ntiles, nchunks);
+    zero_energy_fix_kernel<<<g, 256, 0, st>>>(d_chunks, nrows, d_invE, d_zeroE, d_DS, d_DS64);
+}
+
+// dst row += src row, in the order of the list (pieces of a rank > 16 subspace, see launch_sum_pieces)
+__global__ void __launch_bounds__(256)
+sum_pieces_kernel(const ChunkDesc* __restrict__ chunks, const PieceSum* __restrict__ pieces, int npieces,
+                  float* __restrict__ DS) {
+    const ChunkDesc cd = chunks[blockIdx.y];
+    const int i = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i >= cd.Tpad) return;
+    // pieces are grouped by dst_row; a thread owns 4 lags of every row, so the order is fixed
+    for (int k = 0; k < npieces; ++k) {
+        float4* d = reinterpret_cast<float4*>(DS + cd.ds_off + static_cast<long long>(pieces[k].dst_row) * cd.Tpad + i);
+        const float4 a = *d;
+        const float4 b = *reinterpret_cast<const float4*>(DS + cd.ds_off +
+                                                           static_cast<long long>(pieces[k].src_row) * cd.Tpad + i);
+        *d = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+}
+
+void launch_sum_pieces(const ChunkDesc* d_chunks, int nchunks, int max_Tpad, const PieceSum* d_pieces, int npieces,
+                       float* d_DS, cudaStream_t st) {
+    const dim3 g((max_Tpad / 4 + 255) / 256, nchunks);
+    sum_pieces_kernel<<<g, 256, 0, st>>>(d_chunks, d_pieces, npieces, d_DS);
 }
 
 }  // namespace dtx

@@ -290,13 +290,6 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
 }
 
 // ------------------------------------------------- drain + epilogue (8 warps, 256 threads)
-// Rare path of the epilogue read-out, kept out of the unrolled code: a piece of a rank > 16
-// subspace accumulates into its DS row.
-__device__ __noinline__ void epi_accumulate(float* dst, float4 acc) {
-    atomicAdd(dst, acc.x); atomicAdd(dst + 1, acc.y);
-    atomicAdd(dst + 2, acc.z); atomicAdd(dst + 3, acc.w);
-}
-
 // DS rows are written with the streaming (evict-first) hint so that the 18 GB DS stream of a launch
 // does not evict the L2-resident inputs; -DDTX_DS_STREAM=0 uses plain stores.
 #ifndef DTX_DS_STREAM
@@ -408,15 +401,9 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
                     }
                     acc.x *= ie.x; acc.y *= ie.y; acc.z *= ie.z; acc.w *= ie.w;
                     float* dst = dsbase + static_cast<long long>(hb[k].out_row) * cd.Tpad + c * EPI_LAGS;
-#ifdef DTX_EPI_INLINE_ATOMICS
-                    if (hb[k].nrows < 0) {
-                        atomicAdd(dst, acc.x); atomicAdd(dst + 1, acc.y);
-                        atomicAdd(dst + 2, acc.z); atomicAdd(dst + 3, acc.w);
-                    } else store_ds_row(dst, acc);
-#else
-                    if (hb[k].nrows < 0) epi_accumulate(dst, acc);
-                    else store_ds_row(dst, acc);
-#endif
+                    // (pieces of a rank > 16 subspace have rows of their own: launch_sum_pieces adds them
+                    // up in a fixed order afterwards, so DS does not depend on CTA timing)
+                    store_ds_row(dst, acc);
                 }
                 named_bar_sync(1 + colhalf, 128);
             }

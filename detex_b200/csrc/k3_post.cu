@@ -64,10 +64,10 @@ k3_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, in
           const float* __restrict__ thr, float* __restrict__ rowmax, int* __restrict__ rowflags,
           unsigned long long* __restrict__ hist, double hlo, double hhi,
           Candidate* __restrict__ cand, int cand_cap, int* __restrict__ ncand,
-          double* __restrict__ fas, int only_flagged, int nb) {
+          double* __restrict__ fas, int only_flagged, int nb, int row_base) {
     const ChunkDesc cd = chunks[blockIdx.y];
     const int s = blockIdx.x;
-    const int row = blockIdx.y * S + s;
+    const int row = row_base + blockIdx.y * S + s;
     if (only_flagged && !(rowflags[row] & 4)) return;  // the single-pass kernel already did this row
     const float* x = DS + cd.ds_off + static_cast<long long>(s) * cd.Tpad;
     const int T = cd.T;
@@ -180,10 +180,10 @@ k3_fast_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunk
                const float* __restrict__ thr, float* __restrict__ rowmax, int* __restrict__ rowflags,
                unsigned long long* __restrict__ hist, double hlo, double hhi,
                Candidate* __restrict__ cand, int cand_cap, int* __restrict__ ncand,
-               double* __restrict__ fas, int nb) {
+               double* __restrict__ fas, int nb, int row_base) {
     const ChunkDesc cd = chunks[blockIdx.y];
     const int s = blockIdx.x;
-    const int row = blockIdx.y * S + s;
+    const int row = row_base + blockIdx.y * S + s;
     const float* x = DS + cd.ds_off + static_cast<long long>(s) * cd.Tpad;
     const int T = cd.T;
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
@@ -343,13 +343,16 @@ __device__ __forceinline__ float centred_abs_mean(const float* __restrict__ x, i
 __global__ void __launch_bounds__(256)
 lta_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, int S,
            const int* __restrict__ rowflags, Candidate* __restrict__ cand,
-           const int* __restrict__ ncand, int cand_cap, int W, int Wsta) {
+           const int* __restrict__ ncand, const int* __restrict__ ncand_before, int cand_cap, int row_base, int W,
+           int Wsta) {
     const int n = min(*ncand, cand_cap);
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+    const int wid = (ncand_before ? *ncand_before : 0) + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int l = threadIdx.x & 31;
     if (wid >= n) return;
     Candidate c = cand[wid];
-    const ChunkDesc cd = chunks[c.row / S];
-    const float* x = DS + cd.ds_off + static_cast<long long>(c.row % S) * cd.Tpad;
+    const int lrow = c.row - row_base;          // row inside the current batch
+    const ChunkDesc cd = chunks[lrow / S];
+    const float* x = DS + cd.ds_off + static_cast<long long>(lrow % S) * cd.Tpad;
     const bool zero_inf = (rowflags[c.row] & 2) != 0;
     float out = centred_abs_mean(x, cd.T, W, c.t, zero_inf, l);
     if (Wsta > 0) {
@@ -395,8 +398,29 @@ stalta_dense_kernel(const float* __restrict__ x, int T, int W, int zero_inf, int
     }
     if (threadIdx.x == 0) pre[0] = 0.0;
     __syncthreads();
-    if (threadIdx.x == 0)
-        for (int j = 1; j <= cnt; ++j) pre[j] += pre[j - 1];
+    {   // inclusive prefix sum of pre[1..cnt]: serial inside a thread's segment, block scan of the totals
+        __shared__ double seg_tot[256];
+        const int per = (cnt + 255) / 256;
+        const int j0 = 1 + threadIdx.x * per, j1 = min(cnt + 1, j0 + per);
+        double run = 0.0;
+        for (int j = j0; j < j1; ++j) { run += pre[j]; pre[j] = run; }
+        seg_tot[threadIdx.x] = run;
+        __syncthreads();
+        if (threadIdx.x < 32) {   // one warp scans the 256 totals, 8 per lane
+            double t[8], acc = 0.0;
+            for (int k = 0; k < 8; ++k) { acc += seg_tot[threadIdx.x * 8 + k]; t[k] = acc; }
+            double incl = acc;
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (threadIdx.x >= o) incl += v;
+            }
+            const double excl = incl - acc;
+            for (int k = 0; k < 8; ++k) seg_tot[threadIdx.x * 8 + k] = excl + t[k];
+        }
+        __syncthreads();
+        const double off = threadIdx.x ? seg_tot[threadIdx.x - 1] : 0.0;
+        for (int j = j0; j < j1; ++j) pre[j] += off;
+    }
     __syncthreads();
     for (int k = threadIdx.x; k < SL_TILE; k += 256) {
         const int i = i0 + k;
@@ -422,24 +446,26 @@ ratio_kernel(const float* num, const float* den, int T, float* out) {  // out ma
 void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, const float* d_thr,
                float* d_rowmax, int* d_rowflags, unsigned long long* d_hist, double hist_lo,
                double hist_hi, int nbins, Candidate* d_cand, int cand_cap, int* d_ncand, double* d_fas,
-               cudaStream_t st) {
+               int row_base, cudaStream_t st) {
     const dim3 grid(S, nchunks);
     if (d_fas)
         k3_fast_kernel<true><<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist,
-                                                          hist_lo, hist_hi, d_cand, cand_cap, d_ncand, d_fas, nbins);
+                                                          hist_lo, hist_hi, d_cand, cand_cap, d_ncand, d_fas, nbins, row_base);
     else
         k3_fast_kernel<false><<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist,
-                                                           hist_lo, hist_hi, d_cand, cand_cap, d_ncand, nullptr, nbins);
+                                                           hist_lo, hist_hi, d_cand, cand_cap, d_ncand, nullptr, nbins, row_base);
     k3_kernel<<<grid, K3_THREADS, 0, st>>>(DS, d_chunks, S, d_thr, d_rowmax, d_rowflags, d_hist, hist_lo, hist_hi,
-                                           d_cand, cand_cap, d_ncand, d_fas, 1, nbins);
+                                           d_cand, cand_cap, d_ncand, d_fas, 1, nbins, row_base);
 }
 
 void launch_lta(const float* DS, const ChunkDesc* d_chunks, int S, const int* d_rowflags,
-                Candidate* d_cand, const int* d_ncand, int cand_cap, int W, int Wsta, cudaStream_t st) {
+                Candidate* d_cand, const int* d_ncand, const int* d_ncand_before, int cand_cap, int row_base, int W,
+                int Wsta, cudaStream_t st) {
     // grid sized for the capacity; warps beyond *ncand exit immediately
     const int warps = cand_cap;
     const int grid = (warps * 32 + 255) / 256;
-    lta_kernel<<<grid, 256, 0, st>>>(DS, d_chunks, S, d_rowflags, d_cand, d_ncand, cand_cap, W, Wsta);
+    lta_kernel<<<grid, 256, 0, st>>>(DS, d_chunks, S, d_rowflags, d_cand, d_ncand, d_ncand_before, cand_cap, row_base,
+                                     W, Wsta);
 }
 
 static void launch_rolling(const float* row, int T, int W, int zero_inf, int mean_only, float* out,
@@ -449,6 +475,9 @@ static void launch_rolling(const float* row, int T, int W, int zero_inf, int mea
     cudaFuncSetAttribute(stalta_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
     stalta_dense_kernel<<<grid, 256, sm, st>>>(row, T, W, zero_inf, mean_only, out);
 }
+
+// largest rolling window (samples) the dense STA/LTA kernel can stage in shared memory
+int stalta_dense_max_window() { return (227 * 1024 / static_cast<int>(sizeof(double)) - SL_TILE - 2) / 2; }
 
 // Wsta == 0: out = |DS| / LTA.  Wsta > 0: out = STA / LTA, `tmp` (T floats) holds the STA means.
 void launch_stalta_dense(const float* row, int T, int W, int Wsta, int zero_inf, float* out, float* tmp,

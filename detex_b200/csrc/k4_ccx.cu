@@ -129,14 +129,14 @@ __device__ MaxLoc block_maxloc(const double* res, int nl, MaxLoc* sh) {
 template <typename T>
 __global__ void __launch_bounds__(CT)
 ccx_kernel(const T* __restrict__ X, int N, int n, int Nc, int trunc, int nl, int row_begin,
-           const double* __restrict__ wa, const double* __restrict__ wb,
+           const int* __restrict__ rows, const double* __restrict__ wa, const double* __restrict__ wb,
            const double* __restrict__ evsum, const double* __restrict__ evstd,
            double* __restrict__ cc, int* __restrict__ lag, double* __restrict__ sub) {
     extern __shared__ double res[];  // [nl]
     __shared__ double x1t[JT];
     __shared__ double x2t[4][X2ROW];
     __shared__ MaxLoc shml[CT / 32];
-    const int b = row_begin + blockIdx.y;
+    const int b = rows ? rows[blockIdx.y] : row_begin + blockIdx.y;
     const int ns = n / Nc;
     const int tid = threadIdx.x;
     const T* x1 = X + static_cast<long long>(b) * n;
@@ -288,7 +288,7 @@ constexpr float CCX_CAND_BAND = 3e-5f;   // float32 series is within ~2e-6 of fl
 template <typename T>
 __global__ void __launch_bounds__(256)
 ccx_post_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, int c0, const T* __restrict__ X,
-                int N, int n, int Nc, int trunc, int nl, int row_begin, int row_end,
+                int N, int n, int Nc, int trunc, int nl, const int* __restrict__ rows, int nrows,
                 const double* __restrict__ wa, const double* __restrict__ wb, const double* __restrict__ evsum,
                 const double* __restrict__ evstd, double* __restrict__ cc, int* __restrict__ lag,
                 double* __restrict__ sub, int* __restrict__ nflag, int2* __restrict__ flagged, int flag_cap) {
@@ -296,8 +296,9 @@ ccx_post_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
     const int c = c0 + ci;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    const int b = row_begin + r;
-    if (b >= row_end || b >= c) return;
+    if (r >= nrows) return;
+    const int b = rows[r];
+    if (b >= c) return;
     const ChunkDesc cd = chunks[ci];
     const float* row = DS + cd.ds_off + static_cast<long long>(r) * cd.Tpad;
     const long long o = static_cast<long long>(r) * N + c;
@@ -414,14 +415,14 @@ void launch_ccx_stats(const void* d_X, int dtype_f32, int N, int n, int Nc, doub
     }
 }
 
-void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int row_begin, int row_end,
+void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int row_begin, int nrows, const int* d_rows,
                      const double* wa, const double* wb, const double* es, const double* ed, double* d_cc,
                      int* d_lag, double* d_sub, int num_sms, cudaStream_t st) {
     const int ns = n / Nc;
     const int trunc = n / (2 * Nc) - 1;
     const int nl = 2 * ns - 1 - 2 * trunc;
     const size_t sm_res = sizeof(double) * nl;
-    const int rows = row_end - row_begin;
+    const int rows = nrows;
     int gx = (2 * num_sms + rows - 1) / rows;
     if (gx < 1) gx = 1;
     if (gx > N) gx = N;
@@ -429,11 +430,11 @@ void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int r
     if (dtype_f32) {
         cudaFuncSetAttribute(ccx_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_res));
         ccx_kernel<float><<<grid, CT, sm_res, st>>>(static_cast<const float*>(d_X), N, n, Nc, trunc, nl, row_begin,
-                                                    wa, wb, es, ed, d_cc, d_lag, d_sub);
+                                                    d_rows, wa, wb, es, ed, d_cc, d_lag, d_sub);
     } else {
         cudaFuncSetAttribute(ccx_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_res));
         ccx_kernel<double><<<grid, CT, sm_res, st>>>(static_cast<const double*>(d_X), N, n, Nc, trunc, nl, row_begin,
-                                                     wa, wb, es, ed, d_cc, d_lag, d_sub);
+                                                     d_rows, wa, wb, es, ed, d_cc, d_lag, d_sub);
     }
 }
 
@@ -441,8 +442,8 @@ void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int r
 // x / ||x - mean|| in float64 (zero rows for zeroed-out waveforms).  One block per event.
 template <typename T>
 __global__ void __launch_bounds__(256)
-ccx_templates_kernel(const T* __restrict__ X, int n, int row_begin, double* __restrict__ U) {
-    const T* x = X + static_cast<long long>(row_begin + blockIdx.x) * n;
+ccx_templates_kernel(const T* __restrict__ X, int n, const int* __restrict__ rows, double* __restrict__ U) {
+    const T* x = X + static_cast<long long>(rows[blockIdx.x]) * n;
     double* u = U + static_cast<long long>(blockIdx.x) * n;
     __shared__ double sh[8];
     __shared__ double bc;
@@ -472,12 +473,12 @@ ccx_templates_kernel(const T* __restrict__ X, int n, int row_begin, double* __re
     for (int i = threadIdx.x; i < n; i += 256) u[i] = nrm > 0 ? static_cast<double>(x[i]) / nrm : 0.0;
 }
 
-void launch_ccx_templates(const void* d_X, int dtype_f32, int n, int row_begin, int rows, double* d_U,
+void launch_ccx_templates(const void* d_X, int dtype_f32, int n, const int* d_rows, int rows, double* d_U,
                           cudaStream_t st) {
     if (dtype_f32)
-        ccx_templates_kernel<float><<<rows, 256, 0, st>>>(static_cast<const float*>(d_X), n, row_begin, d_U);
+        ccx_templates_kernel<float><<<rows, 256, 0, st>>>(static_cast<const float*>(d_X), n, d_rows, d_U);
     else
-        ccx_templates_kernel<double><<<rows, 256, 0, st>>>(static_cast<const double*>(d_X), n, row_begin, d_U);
+        ccx_templates_kernel<double><<<rows, 256, 0, st>>>(static_cast<const double*>(d_X), n, d_rows, d_U);
 }
 
 void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int nsig, int P, int Lc, double* out,
@@ -490,22 +491,43 @@ void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int n
 }
 
 void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsig, const void* d_X, int dtype_f32,
-                     int N, int n, int Nc, int row_begin, int row_end, const double* wa, const double* wb,
+                     int N, int n, int Nc, const int* d_rows, int nrows, const double* wa, const double* wb,
                      const double* es, const double* ed, double* d_cc, int* d_lag, double* d_sub, int* d_nflag,
                      int2* d_flagged, int flag_cap, cudaStream_t st) {
     const int ns = n / Nc;
     const int trunc = n / (2 * Nc) - 1;
     const int nl = 2 * ns - 1 - 2 * trunc;
-    const int rows = row_end - row_begin;
+    const int rows = nrows;
     const dim3 grid((rows + 7) / 8, nsig);
     if (dtype_f32)
         ccx_post_kernel<float><<<grid, 256, 0, st>>>(DS, d_chunks, c0, static_cast<const float*>(d_X), N, n, Nc, trunc,
-                                                     nl, row_begin, row_end, wa, wb, es, ed, d_cc, d_lag, d_sub,
+                                                     nl, d_rows, nrows, wa, wb, es, ed, d_cc, d_lag, d_sub,
                                                      d_nflag, d_flagged, flag_cap);
     else
         ccx_post_kernel<double><<<grid, 256, 0, st>>>(DS, d_chunks, c0, static_cast<const double*>(d_X), N, n, Nc,
-                                                      trunc, nl, row_begin, row_end, wa, wb, es, ed, d_cc, d_lag,
+                                                      trunc, nl, d_rows, nrows, wa, wb, es, ed, d_cc, d_lag,
                                                       d_sub, d_nflag, d_flagged, flag_cap);
+}
+
+// dense [nslots][N] rows -> SciPy condensed order; one block row per event b, threads over c > b
+__global__ void __launch_bounds__(256)
+ccx_pack_kernel(const double* __restrict__ cc, const int* __restrict__ lag, const double* __restrict__ sub,
+                const int* __restrict__ slot_of_row, int N, double* __restrict__ o_cc, int* __restrict__ o_lag,
+                double* __restrict__ o_sub) {
+    const int b = blockIdx.y;
+    const int c = b + 1 + blockIdx.x * 256 + threadIdx.x;
+    if (c >= N) return;
+    const long long src = static_cast<long long>(slot_of_row[b]) * N + c;
+    const long long dst = static_cast<long long>(b) * N - static_cast<long long>(b) * (b + 1) / 2 + (c - b - 1);
+    o_cc[dst] = cc[src];
+    o_lag[dst] = lag[src];
+    o_sub[dst] = sub[src];
+}
+
+void launch_ccx_pack(const double* d_cc, const int* d_lag, const double* d_sub, const int* d_slot_of_row, int N,
+                     double* o_cc, int* o_lag, double* o_sub, cudaStream_t st) {
+    const dim3 grid((N - 1 + 255) / 256, N - 1);
+    ccx_pack_kernel<<<grid, 256, 0, st>>>(d_cc, d_lag, d_sub, d_slot_of_row, N, o_cc, o_lag, o_sub);
 }
 
 }  // namespace dtx

@@ -220,8 +220,9 @@ class SSDetex(object):
                     else:
                         # |DS| / lta == STA / LTA at the trigger (detect.py:501-515); a chunk shorter
                         # than a window has no STA/LTA array in the reference -> 0.0 (detect.py:416-419)
+                        # (a window of less than one sample -- triggerLTATime * sr < 1 -- has none either)
                         den = float(sel["lta"][k])
-                        sl = abs(coef) / den if np.isfinite(den) else 0.0
+                        sl = abs(coef) / den if (np.isfinite(den) and den > 0.0) else 0.0
                     pe_mag, st_mag, snr = (mg[pi] if self.estimateMags else (np.nan, np.nan, np.nan))
                     rows.append([coef, sl, times, name, self.sta, times - maxof, times - minof,
                                  st_mag, snr, pe_mag])       # Mag = stMag, ProEnMag = peMag (detect.py:428,442)

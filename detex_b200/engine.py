@@ -38,6 +38,9 @@ class Engine(object):
         if getattr(self, "_h", None):
             self._L.dtx_destroy(self._h)
             self._h = None
+            for ptr in getattr(self, "_pinned", []):
+                self._L.dtx_host_free(ptr)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -137,6 +140,8 @@ class Engine(object):
                                            float(hist_range[1]), int(lta_window), int(bool(want_fas)),
                                            int(bool(keep_ds64))))
         self._run_S = self._S[set_id]
+        if getattr(self, "_accumulating", False):
+            self._acc_total += self.nchunks
 
     def sync(self):
         self._check(self._L.dtx_sync(self._h))
@@ -176,11 +181,12 @@ class Engine(object):
         return m
 
     def rowstats(self):
-        n = self.nchunks * self._run_S
+        nch = self._acc_total if getattr(self, "_accumulating", False) else self.nchunks
+        n = nch * self._run_S
         mx = np.empty(n, dtype=np.float32)
         fl = np.empty(n, dtype=np.int32)
         self._check(self._L.dtx_get_rowstats(self._h, _ptr(mx), _ptr(fl), n))
-        return mx.reshape(self.nchunks, self._run_S), fl.reshape(self.nchunks, self._run_S)
+        return mx.reshape(nch, self._run_S), fl.reshape(nch, self._run_S)
 
     def set_hist_bins(self, nbins):
         """Bins of the device histograms for later runs (numBins - 1 of fas._initFAS; default 400)."""
@@ -201,19 +207,42 @@ class Engine(object):
         return f.reshape(S, 5)
 
     def candidates(self, cap=1 << 20):
-        out = np.empty(cap, dtype=CAND_DTYPE)
         n = C.c_int64()
-        rc = self._L.dtx_get_candidates(self._h, _ptr(out), cap, C.byref(n))
-        if rc == _lib.DTX_ERR_CAPACITY:
+        rc = self._L.dtx_get_candidates(self._h, None, 0, C.byref(n))      # count only
+        if rc == _lib.DTX_ERR_CAPACITY or n.value > cap:
             # mirrors the reference's kill switch for runaway trigger counts (detect.py:433-436)
-            raise DtxError(rc, "more than %d candidate lags above threshold" % cap)
+            raise DtxError(_lib.DTX_ERR_CAPACITY, "more than %d candidate lags above threshold" % cap)
         self._check(rc)
-        return out[:n.value].copy()
+        out = np.empty(n.value, dtype=CAND_DTYPE)
+        if n.value:
+            self._check(self._L.dtx_get_candidates(self._h, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def accumulate_begin(self, total_chunks):
+        """Results of the following detect_run calls (the batches of one station) accumulate on the
+        device; candidates() / rowstats() then return everything since this call, with rows numbered
+        by the chunk's position in the whole sequence.  No host synchronisation between batches."""
+        self._check(self._L.dtx_accumulate_begin(self._h, int(total_chunks)))
+        self._acc_total = 0
+        self._accumulating = True
+
+    def accumulate_end(self):
+        self._check(self._L.dtx_accumulate_end(self._h))
+        self._accumulating = False
 
     def k1_ms(self):
         ms = C.c_float()
         self._check(self._L.dtx_last_k1_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def k1_ms_history(self):
+        """K1 durations (ms) of every run since accumulate_begin / the last call; waits for them."""
+        n = C.c_int64()
+        self._check(self._L.dtx_k1_ms_history(self._h, None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=np.float32)
+        if n.value:
+            self._check(self._L.dtx_k1_ms_history(self._h, _ptr(out), out.size, C.byref(n)))
+        return out
 
     def sta_lta_max(self, Nc, chan, nsta, nlta):
         """max of ObsPy's classic STA/LTA of channel `chan` for every loaded chunk (fas.py:175-205)."""
@@ -251,6 +280,8 @@ class Engine(object):
 
     # -------------------------------------------------------------------- ccx
     def ccx(self, X, Nc, row_begin=0, row_end=None, engine="fp64"):
+        """Dense rows [row_begin, row_end) of the pair matrix: cc, lag, subsamp as (rows, N) arrays
+        (entries with c <= b are zero)."""
         X = np.asarray(X)
         dt = np.float32 if X.dtype == np.float32 else np.float64
         X = np.ascontiguousarray(X, dtype=dt)
@@ -264,4 +295,70 @@ class Engine(object):
         self._check(self._L.dtx_ccx(self._h, _ptr(X), _lib.DTX_F32 if dt == np.float32 else _lib.DTX_F64,
                                     N, n, int(Nc), int(row_begin), int(row_end), eng, _ptr(cc), _ptr(lag),
                                     _ptr(sub)))
+        return cc, lag, sub
+
+    def set_ccx_batch(self, max_signals=512, ds_bytes=4 << 30):
+        """Limits of one tensor-core CCX batch (tests lower them to force several batches)."""
+        self._check(self._L.dtx_set_ccx_batch(self._h, int(max_signals), int(ds_bytes)))
+
+    def pinned_empty(self, shape, dtype):
+        """NumPy array in page-locked host memory (staging buffer of the end-to-end paths); it stays
+        valid until the engine is closed."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        ptr = C.c_void_p()
+        if self._L.dtx_host_alloc(C.byref(ptr), max(1, nbytes)) != 0:
+            raise DtxError(1, "dtx_host_alloc failed")
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        buf = (C.c_char * max(1, nbytes)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def ccx_condensed(self, X, Nc, engine="tcgen05", out=None):
+        """All pairs b < c in SciPy's condensed order: (cc float64, lag int32, subsamp float64), each
+        N (N-1)/2 long.  `out` = three preallocated (e.g. pinned) arrays to fill."""
+        X = np.asarray(X)
+        dt = np.float32 if X.dtype == np.float32 else np.float64
+        X = np.ascontiguousarray(X, dtype=dt)
+        N, n = X.shape
+        npair = N * (N - 1) // 2
+        if out is None:
+            out = (np.empty(npair, np.float64), np.empty(npair, np.int32), np.empty(npair, np.float64))
+        cc, lag, sub = out
+        assert cc.size == npair and lag.size == npair and sub.size == npair
+        eng = ENGINE_TCGEN05 if engine == "tcgen05" else ENGINE_FP64
+        self._check(self._L.dtx_ccx_condensed(self._h, _ptr(X), _lib.DTX_F32 if dt == np.float32 else _lib.DTX_F64,
+                                              N, n, int(Nc), eng, _ptr(cc), _ptr(lag), _ptr(sub)))
+        return cc, lag, sub
+
+    def ccx_device(self, X, Nc, rows, d_cc, d_lag, d_sub, engine="tcgen05", x_device_ptr=None, shape=None):
+        """Template rows `rows` (ascending event indices) of the pair matrix, results left in the
+        caller's device arrays (addresses; dense [len(rows)][N] float64 / int32 / float64).  X is a
+        host array, or (x_device_ptr, shape) for waveforms already in HBM."""
+        rows = np.ascontiguousarray(np.asarray(rows, dtype=np.int32))
+        eng = ENGINE_TCGEN05 if engine == "tcgen05" else ENGINE_FP64
+        if x_device_ptr is not None:
+            N, n = shape
+            dt = np.dtype(X) if X is not None else np.dtype(np.float64)
+            xp, ondev = C.c_void_p(int(x_device_ptr)), 1
+        else:
+            X = np.asarray(X)
+            dt = np.dtype(np.float32) if X.dtype == np.float32 else np.dtype(np.float64)
+            X = np.ascontiguousarray(X, dtype=dt)
+            N, n = X.shape
+            xp, ondev = _ptr(X), 0
+        self._check(self._L.dtx_ccx_device(self._h, xp, ondev, _lib.DTX_F32 if dt == np.float32 else _lib.DTX_F64,
+                                           N, n, int(Nc), _ptr(rows), len(rows), eng, C.c_void_p(int(d_cc)),
+                                           C.c_void_p(int(d_lag)), C.c_void_p(int(d_sub))))
+        self._keep = X
+
+    def ccx_pack(self, d_cc, d_lag, d_sub, slot_rows, N, out=None):
+        """Dense device slots (slot s = event slot_rows[s], -1 = padding) -> condensed host arrays."""
+        slot_rows = np.ascontiguousarray(np.asarray(slot_rows, dtype=np.int32))
+        npair = N * (N - 1) // 2
+        if out is None:
+            out = (np.empty(npair, np.float64), np.empty(npair, np.int32), np.empty(npair, np.float64))
+        cc, lag, sub = out
+        self._check(self._L.dtx_ccx_pack(self._h, C.c_void_p(int(d_cc)), C.c_void_p(int(d_lag)), C.c_void_p(int(d_sub)),
+                                         _ptr(slot_rows), len(slot_rows), int(N), _ptr(cc), _ptr(lag), _ptr(sub)))
         return cc, lag, sub

@@ -34,6 +34,73 @@ def ccx_row_blocks(N, world):
     return [(bounds[i], bounds[i + 1]) for i in range(world)]
 
 
+def ccx_deal_rows(N, world):
+    """Template rows b = 0..N-2 of the upper-triangular pair matrix dealt to `world` ranks back and
+    forth (rank k gets the rows with b mod 2W in {k, 2W-1-k}): row b owns N-1-b pairs, so each such
+    couple owns the same number and every rank ends up with the same number of rows (within 2) AND
+    of pairs (within ~2N/W), whatever N.  Returns a list of ascending int32 arrays."""
+    b = np.arange(N - 1, dtype=np.int64)
+    j = b % (2 * world)
+    owner = np.where(j < world, j, 2 * world - 1 - j)
+    return [b[owner == k].astype(np.int32) for k in range(world)]
+
+
+def ccx_slot_rows(N, world):
+    """Row held by every slot of the all-gathered dense buffer: ranks' row lists padded with -1 to
+    the longest one, back to back.  Returns (slot_rows int32 [world * nmax], nmax)."""
+    deal = ccx_deal_rows(N, world)
+    nmax = max(len(r) for r in deal)
+    slots = np.full((world, nmax), -1, dtype=np.int32)
+    for k, r in enumerate(deal):
+        slots[k, :len(r)] = r
+    return slots.reshape(-1), nmax
+
+
+def pack_condensed(cc, lag, sub, slot_rows, N):
+    """Host statement of dtx_ccx_pack (tests / CPU plumbing): dense slots [nslots][N] -> condensed."""
+    slot_of = np.full(N, -1, dtype=np.int64)
+    for s, b in enumerate(slot_rows):
+        if b >= 0:
+            slot_of[b] = s
+    iu = np.triu_indices(N, 1)
+    src = slot_of[iu[0]]
+    return cc[src, iu[1]], lag[src, iu[1]], sub[src, iu[1]]
+
+
+def ccx_sharded(eng, X, Nc, engine="tcgen05", out=None):
+    """The whole CCX matrix of one station over all ranks (BASELINE configs[2]): every
+    rank computes its dealt rows with the results left in HBM, ONE all-gather of the equal-sized dense
+    blocks over NCCL / NVLink, then every rank packs the upper triangle into SciPy's condensed order
+    and copies it to the host.  Returns (cc, lag, subsamp) condensed; identical on every rank and to
+    the single-GPU result."""
+    world = _world()
+    if world == 1:
+        return eng.ccx_condensed(X, Nc, engine=engine, out=out)
+    X = np.asarray(X)
+    N = X.shape[0]
+    rank = dist.get_rank()
+    dev = _dev()
+    slot_rows, nmax = ccx_slot_rows(N, world)
+    mine = slot_rows.reshape(world, nmax)[rank]
+    mine = mine[mine >= 0]
+    d_cc = torch.zeros((nmax, N), dtype=torch.float64, device=dev)
+    d_lag = torch.zeros((nmax, N), dtype=torch.int32, device=dev)
+    d_sub = torch.zeros((nmax, N), dtype=torch.float64, device=dev)
+    if len(mine):
+        eng.ccx_device(X, Nc, mine, d_cc.data_ptr(), d_lag.data_ptr(), d_sub.data_ptr(), engine=engine)
+    g_cc = torch.empty((world * nmax, N), dtype=torch.float64, device=dev)
+    g_lag = torch.empty((world * nmax, N), dtype=torch.int32, device=dev)
+    g_sub = torch.empty((world * nmax, N), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(g_cc, d_cc)
+    dist.all_gather_into_tensor(g_lag, d_lag)
+    dist.all_gather_into_tensor(g_sub, d_sub)
+    if dev.type == "cuda":
+        torch.cuda.current_stream().synchronize()      # the engine may run on another stream
+    res = eng.ccx_pack(g_cc.data_ptr(), g_lag.data_ptr(), g_sub.data_ptr(), slot_rows, N, out=out)
+    del g_cc, g_lag, g_sub
+    return res
+
+
 def _dev():
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 

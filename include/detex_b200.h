@@ -122,6 +122,19 @@ int dtx_get_chunk(dtx_ctx* ctx, int chunk, double* out, int64_t count, int64_t* 
 int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_lo, double hist_hi,
                    int lta_window, int want_fas, int keep_ds64);
 
+/* Accumulating the batches of one station ------------------------------------------------
+ * _corDat (detect.py:154-212) walks the chunks of a station one after the other and only looks at
+ * the results at the end of each chunk; nothing there needs the host between chunks.  Between
+ * dtx_accumulate_begin(total_chunks) and dtx_accumulate_end, every dtx_detect_run APPENDS: candidate
+ * rows and the rowmax / rowflags entries are numbered by the chunk's position in the whole sequence
+ * (row = chunk_index * S + subspace, chunk_index counted over all runs since begin), histograms and
+ * FAS sums keep accumulating as always, and no call synchronises the stream until the caller
+ * fetches (dtx_get_candidates / dtx_get_rowstats return everything since begin).  All runs must use
+ * the same basis set; total_chunks bounds the sum of the batch sizes.  dtx_get_ds / dtx_get_stalta
+ * / dtx_est_mags keep addressing the chunks of the LAST run by their index inside that run. */
+int dtx_accumulate_begin(dtx_ctx* ctx, int64_t total_chunks);
+int dtx_accumulate_end(dtx_ctx* ctx);
+
 /* DTX_ENGINE_TCGEN05_AUTO: admitted rms error of a normalised projection (u.w)/(|u||w|) under the
  * random-rounding model (default 2e-6: the 8-bit terms then add 2 sqrt(DS) eps <= 4e-6 per model
  * standard deviation; measured maxima are 0.2-0.6 of that, profiles/r01_x8_engine.md);
@@ -153,7 +166,8 @@ int dtx_set_hist_bins(dtx_ctx* ctx, int nbins);
 int dtx_get_hist(dtx_ctx* ctx, int set_id, uint64_t* hist, int64_t count, int reset);
 /* fas[s*5 + {0:N, 1:sum x, 2:sum x^2, 3:sum log x, 4:sum log1p(-x)}] */
 int dtx_get_fas(dtx_ctx* ctx, int set_id, double* fas, int64_t count, int reset);
-/* candidates of the last run; *n receives the number produced (may exceed cap: truncated) */
+/* candidates of the last run (or of every run since dtx_accumulate_begin); *n receives the number
+ * produced (may exceed cap: truncated, DTX_ERR_CAPACITY).  out == NULL only queries the count. */
 int dtx_get_candidates(dtx_ctx* ctx, dtx_cand* out, int64_t cap, int64_t* n);
 
 /* STA/LTA screen of the loaded chunks -----------------------------------------------------
@@ -178,6 +192,9 @@ int dtx_est_mags(dtx_ctx* ctx, int set_id, int ntrig, const int32_t* chunk, cons
 /* Timing aid for bench.py: device milliseconds of the dominant kernel (K1) in the last
  * dtx_detect_run, measured with CUDA events on the context's stream. */
 int dtx_last_k1_ms(dtx_ctx* ctx, float* ms);
+/* The K1 durations of every run since dtx_accumulate_begin (or the last call of this function), in
+ * run order; ms == NULL only queries the count.  Waits for those runs to finish. */
+int dtx_k1_ms_history(dtx_ctx* ctx, float* ms, int64_t cap, int64_t* n);
 /* Number of CUDA kernels this context has launched since creation (bench.py's gpu_launches). */
 int dtx_launch_count(dtx_ctx* ctx, int64_t* n);
 
@@ -189,6 +206,32 @@ int dtx_launch_count(dtx_ctx* ctx, int64_t* n);
  * [(row_end-row_begin)][N] arrays (entries with c <= b untouched). */
 int dtx_ccx(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int row_begin, int row_end,
             int engine, double* cc, int32_t* lag, double* subsamp);
+/* The same for an arbitrary ascending list of template rows b (the share of one GPU when the
+ * matrix is dealt over several) with the results LEFT ON THE DEVICE: d_cc / d_lag /
+ * d_sub are caller-owned device arrays, dense [nrows][N], slot r holding event rows[r] (entries
+ * with c <= rows[r] are zero).  X is a host array, or a device array if x_on_device != 0.  The
+ * call is asynchronous on the context's stream except for one small read-back (the list of
+ * degenerate pairs the float64 kernel re-does).  No device memory is allocated once the context's
+ * CCX workspace has reached the problem size. */
+int dtx_ccx_device(dtx_ctx* ctx, const void* X, int x_on_device, int dtype, int N, int n, int Nc,
+                   const int32_t* rows, int nrows, int engine, double* d_cc, int32_t* d_lag, double* d_sub);
+/* Dense device slots (e.g. the all-gathered shares of several GPUs, [nslots][N], slot s holding event
+ * slot_rows[s], -1 = padding; every b in [0, N-1) must appear) -> host arrays in SciPy's condensed
+ * order: pair (b, c), b < c, at index b*N - b*(b+1)/2 + (c-b-1), N*(N-1)/2 entries each.  That is
+ * the order `_flatNoNan(1.0000001 - DFcc)` feeds to linkage (construct.py:152-156). */
+int dtx_ccx_pack(dtx_ctx* ctx, const double* d_cc, const int32_t* d_lag, const double* d_sub,
+                 const int32_t* slot_rows, int nslots, int N, double* cc, int32_t* lag, double* subsamp);
+/* dtx_ccx_device over all rows + dtx_ccx_pack: host X in, condensed host cc / lag / subsamp out. */
+int dtx_ccx_condensed(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int engine, double* cc,
+                      int32_t* lag, double* subsamp);
+/* Limits of one tensor-core CCX batch: at most max_signals padded events per K1 launch and at most
+ * ds_bytes of correlation series (defaults 512 and 4 GiB; tests lower them to force several batches). */
+int dtx_set_ccx_batch(dtx_ctx* ctx, int max_signals, int64_t ds_bytes);
+
+/* Page-locked host memory for the staging buffers of the end-to-end paths (H2D / D2H at PCIe rate
+ * instead of through the driver's bounce buffer). */
+int dtx_host_alloc(void** out, int64_t bytes);
+int dtx_host_free(void* p);
 
 /* Zero-lag Pearson matrix of N equal-length waveforms (next row N3, validateClusters,
  * subspace.py:738-773: fast_normcorr of every pair of aligned, trimmed cluster members).

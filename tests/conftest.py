@@ -58,3 +58,8 @@ def ccx_golden():
 @pytest.fixture(scope="session")
 def align_golden():
     return np.load(os.path.join(GOLDEN, "align_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def gap_golden():
+    return np.load(os.path.join(GOLDEN, "gap_golden.npz"))

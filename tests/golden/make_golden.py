@@ -19,8 +19,26 @@ from oracle import ref_shim  # noqa: E402
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
+def gap_case(R):
+    """A zero-filled gap longer than the template (fillZeros=True merges, construct.py:1004-1005):
+    the reference's own FFT path gives +inf on the windows inside the gap (sum(if1^2)/0,
+    detect.py:577), which _getRA zeroes when MaxDS > 1.1 (detect.py:275-281)."""
+    chunks, bases, _ = synth.detection_case(seed=105, nchunks=1, Ls=6000, ns=300, Nc=3, ranks=[2, 4], planted=2)
+    x = chunks[0].copy()
+    x[3000 * 3:3000 * 3 + 3 * 700] = 0.0
+    out = dict(gap_chunk=x, gap_Nc=3, gap_U0=bases[0], gap_U1=bases[1])
+    for si, U in enumerate(bases):
+        ds = R.MPXDS(x, U, 3)
+        assert np.isinf(ds).sum() == 401 and not np.isnan(ds).any()
+        out["gap_DS%d" % si] = ds
+    np.savez_compressed(os.path.join(OUT, "gap_golden.npz"), **out)
+
+
 def main():
     R = ref_shim.RefFunctions()
+    gap_case(R)
+    if len(sys.argv) > 1 and sys.argv[1] == "gap":
+        return
     # ---- detection statistic (_MPXDS, detect.py:559-578; _MPXSSCorr, fas.py:120-134)
     cases = {}
     specs = [

@@ -184,5 +184,32 @@ class OracleEngine(object):
                 cc[b - row_begin, c], lag[b - row_begin, c], sub[b - row_begin, c] = orc.ccx2(X[b], X[c], Nc)
         return cc, lag, sub
 
+    # the device-resident CCX calls of parallel.ccx_sharded; "device" addresses are CPU tensors here
+    @staticmethod
+    def _view(ptr, shape, dtype):
+        import ctypes
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        return np.frombuffer((ctypes.c_char * n).from_address(int(ptr)), dtype=dtype).reshape(shape)
+
+    def ccx_device(self, X, Nc, rows, d_cc, d_lag, d_sub, engine="tcgen05"):
+        X = np.asarray(X, dtype=np.float64)
+        N = len(X)
+        cc, lag, sub = (self._view(d_cc, (len(rows), N), np.float64), self._view(d_lag, (len(rows), N), np.int32),
+                        self._view(d_sub, (len(rows), N), np.float64))
+        for r, b in enumerate(rows):
+            for c in range(int(b) + 1, N):
+                cc[r, c], lag[r, c], sub[r, c] = orc.ccx2(X[int(b)], X[c], Nc)
+
+    def ccx_pack(self, d_cc, d_lag, d_sub, slot_rows, N, out=None):
+        from detex_b200 import parallel
+        ns = len(slot_rows)
+        return parallel.pack_condensed(self._view(d_cc, (ns, N), np.float64), self._view(d_lag, (ns, N), np.int32),
+                                       self._view(d_sub, (ns, N), np.float64), slot_rows, N)
+
+    def ccx_condensed(self, X, Nc, engine="tcgen05", out=None):
+        cc, lag, sub = self.ccx(X, Nc, 0, len(X) - 1)
+        iu = np.triu_indices(len(X), 1)
+        return cc[iu], lag[iu], sub[iu]
+
     def close(self):
         pass

@@ -143,3 +143,59 @@ def test_sharded_detection_equals_single_process():
     assert len(c1) > 0 and np.array_equal(c1, c2)        # same triggers, bit for bit
     assert np.array_equal(h1, h2) and h1.sum() == 5 * 3 * 2401
     assert np.allclose(f1, f2, rtol=1e-12) and np.array_equal(b1, b2)
+
+
+def _ccx_worker(rank, world, port, q):
+    """One rank of the dealt-row CCX (parallel.ccx_sharded) with the oracle-backed engine stand-in."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    from detex_b200 import synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        X = synth.event_families(77, 3, 6, 40, 3, max_shift=8)        # 18 events, n = 120
+        res = parallel.ccx_sharded(OracleEngine(), X, 3)
+        if rank == world - 1:
+            q.put(res)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dealt_rows_are_balanced_and_complete():
+    for N in (9, 50, 600, 4096, 16384):
+        for world in (2, 4, 8):
+            deal = parallel.ccx_deal_rows(N, world)
+            assert sorted(np.concatenate(deal).tolist()) == list(range(N - 1))
+            assert all(np.all(np.diff(r) > 0) for r in deal if len(r) > 1)
+            rows = [len(r) for r in deal]
+            pairs = [int((N - 1 - r.astype(np.int64)).sum()) for r in deal]
+            assert max(rows) - min(rows) <= 2
+            assert max(pairs) - min(pairs) <= 2 * N
+            slots, nmax = parallel.ccx_slot_rows(N, world)
+            assert len(slots) == world * nmax and sorted(slots[slots >= 0].tolist()) == list(range(N - 1))
+
+
+def test_eight_rank_dealt_ccx_equals_single_process():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from detex_b200 import synth
+    from oracle import detex_oracle as orc
+    world = 8
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ccx_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    cc, lag, sub = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    X = synth.event_families(77, 3, 6, 40, 3, max_shift=8)
+    rcc, rlag, rsub = orc.make_cclags(X, 3)
+    iu = np.triu_indices(len(X), 1)
+    assert np.array_equal(cc, rcc[iu[0], iu[1] - 1])
+    assert np.array_equal(lag.astype(float), rlag[iu[0], iu[1] - 1])
+    assert np.array_equal(sub, rsub[iu[0], iu[1] - 1])

@@ -120,13 +120,14 @@ def test_large_dynamic_range_spike(engine):
         assert np.abs(engine.get_ds(0, si) - orc.mpx_ds_direct(x, U, Nc)).max() < TOL
 
 
-def test_constant_run_gives_nan_row(engine):
-    """A window of constant data is 0/0: the row carries NaN, MaxDS is NaN, nothing triggers
-    and the chunk's histogram is skipped (np.histogram raises -> detect.py:182-185)."""
+def test_constant_run_gives_inf_that_is_zeroed(engine):
+    """A window of constant data has zero energy: the reference's statistic there is sum(if1^2)/0 =
+    +inf (detect.py:577), MaxDS = inf > 1.1 so the infs are zeroed (detect.py:275-281) and the rest of
+    the chunk is used as usual.  (Before round 2 the exactly-zero projection made these windows NaN
+    and the whole row was lost.)  Reference golden: tests/test_gpu_scale.py::test_zero_filled_gap..."""
     Nc, ns, Ls = 1, 100, 3000
     _, bases, _ = synth.detection_case(25, 1, Ls, ns, Nc, [2])
-    # integer-valued samples with an exactly-zero sum: centring is exact in every
-    # implementation, so the all-zero run below is exactly 0/0 everywhere
+    # integer-valued samples with an exactly-zero sum: centring is exact in every implementation
     x = np.random.default_rng(25).integers(-50, 51, size=Ls).astype(np.float64)
     x[1000:1400] = 0.0
     x[0] -= x.sum()
@@ -136,15 +137,16 @@ def test_constant_run_gives_nan_row(engine):
     engine.load_chunks([x])
     engine.detect_run(18, lta_window=50)
     mx, fl = engine.rowstats()
-    ref = orc.mpx_ds_direct(x, bases[0], Nc)
-    assert np.isnan(ref).any()
-    assert fl[0, 0] & 1 and np.isnan(mx[0, 0])
-    assert len(engine.candidates()) == 0
-    assert engine.hist(18, reset=True).sum() == 0
+    ref = orc.mpx_ds_fft(x, bases[0], Nc)                 # the reference's algorithm: inf in the run
+    bad = ~np.isfinite(ref)
+    assert bad.sum() == 301          # (+inf, or NaN where the FFT round-off happens to be exactly 0)
     ds = engine.get_ds(0, 0)
-    ok = ~np.isnan(ref)
-    assert np.array_equal(np.isnan(ds), ~ok)
-    assert np.abs(ds[ok] - ref[ok]).max() < TOL
+    assert np.array_equal(np.isinf(ds), bad) and not np.isnan(ds).any()
+    assert np.abs(ds[~bad] - ref[~bad]).max() < TOL
+    assert fl[0, 0] == 2 and abs(mx[0, 0] - ref[~bad].max()) < TOL
+    assert engine.hist(18, reset=True).sum() == len(ds)
+    cand = engine.candidates()
+    assert np.isfinite(cand["ds"]).all() and not bad[cand["t"]].any()
 
 
 def test_rowstats_histogram_candidates_lta(engine):
