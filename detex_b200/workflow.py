@@ -66,6 +66,9 @@ class ArrayFetcher(object):
                  channel-name order (what `st.sort()` gives, construct.py:998)
     continuous : {'NET.STA': [(list of channel arrays, starttime epoch s), ...]} chronological chunks
                  of conDatDuration + conBuff seconds (getdata.py:299, 517-518)
+    The channels of one entry share ONE start time (a single epoch per chunk is carried): the
+    common-window trim of `_applyFilter` (construct.py:1019-1024) then reduces to cutting every
+    channel to the shortest one, which the device pre-processing does before detrend and filter.
     """
     method = 'array'
 

@@ -623,6 +623,11 @@ def apply_filter(chans, sr, filt=(1, 10, 2, True), decimate=None):
     (obspy/core/trace.py, obspy/signal/filter.py::lowpass_cheby_2; restated, unpinned)."""
     import scipy.signal
     out = []
+    # channels are trimmed to their common window AFTER the optional decimation and BEFORE detrend /
+    # filter (st.trim(startTrim, endTrim), construct.py:1019-1024); with a shared start time that is
+    # the first min-length samples of every channel
+    fac = int(decimate) if decimate and int(decimate) > 1 else 1
+    common = min(-(-len(x) // fac) for x in chans)
     for x in chans:
         y = np.asarray(x, dtype=np.float64)
         fs = sr
@@ -636,6 +641,7 @@ def apply_filter(chans, sr, filt=(1, 10, 2, True), decimate=None):
             z, p, k = scipy.signal.cheby2(order, 96, wn, btype="low", analog=0, output="zpk")
             y = scipy.signal.sosfilt(scipy.signal.zpk2sos(z, p, k), y)[::int(decimate)]
             fs = sr / float(decimate)
+        y = y[:common]
         y = scipy.signal.detrend(y, type="linear")
         if filt is not None:
             fe = 0.5 * fs

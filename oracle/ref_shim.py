@@ -23,7 +23,12 @@ import pandas as pd
 import scipy
 import scipy.fftpack
 
+# the reference tree itself (build container), else the unmodified copy oracle/make_ref.py put under
+# oracle/_ref (git-ignored; it travels to the GPU box so that bench.py can time the real reference)
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = os.environ.get("DETEX_REFERENCE", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "detex")) and os.path.isdir(os.path.join(_HERE, "_ref", "detex")):
+    REF_ROOT = os.path.join(_HERE, "_ref")
 
 
 def available():

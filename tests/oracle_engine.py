@@ -38,10 +38,12 @@ class OracleEngine(object):
         out = []
         for ch in traces:
             ys = []
+            common = min(-(-len(x) // factor) for x in ch)   # common window before detrend / filter
             for x in ch:
                 y = np.asarray(x, dtype=np.float64)
                 if factor > 1:
                     y = scipy.signal.sosfilt(dec_sos, y)[::factor]
+                y = y[:common]
                 if detrend:
                     y = scipy.signal.detrend(y, type="linear")
                 if len(sos):
