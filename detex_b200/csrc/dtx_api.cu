@@ -638,7 +638,7 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         a.chunk_scale = ctx->d_scale.p; a.chunks = ctx->d_chunks.p; a.items = ctx->d_items.p;
         a.binfo = bs.d_binfo.p; a.DS = ctx->d_DS.p; a.nitems = ctx->n_items;
         a.kblk = kblk; a.num_sms = ctx->num_sms; a.nq = nq; a.mode = mode;
-        if (!ctx->accumulate) ctx->k1_used = 0;            // only the last run's pair is kept
+        if (!ctx->accumulate && mode == 0) ctx->k1_used = 0;   // only the last run's pair is kept (CCX keeps its batches')
         if (ctx->k1_used >= ctx->k1_events.size()) {
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             DTX_CUDA(cudaEventCreate(&e0));
@@ -1240,6 +1240,7 @@ static int ccx_tcgen05(dtx_ctx* ctx, int dtype, const void* dX, int N, int n, in
                        double* dcc, int* dlag, double* dsub, std::vector<int2>& flagged) {
     const int ns = n / Nc, trunc = n / (2 * Nc) - 1, nl = 2 * ns - 1 - 2 * trunc;
     cudaStream_t st = ctx->stream;
+    ctx->k1_used = 0;   // dtx_k1_ms_history after the call returns the K1 time of every signal batch
     // templates: x / ||x - mean||  (zero rows for zeroed-out waveforms), built on the device
     std::vector<int32_t> roff(nrows + 1);
     for (int r = 0; r <= nrows; ++r) roff[r] = r;

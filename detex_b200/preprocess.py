@@ -18,7 +18,31 @@ from .detect import default_engine
 
 def bandpass_sos(freqmin, freqmax, df, corners=4):
     """Second-order sections of ObsPy's `bandpass` (falls back to a high-pass when freqmax is
-    at or above Nyquist, as ObsPy does)."""
+    at or above Nyquist, as ObsPy does).
+
+    ObsPy itself cannot be installed here, so this is pinned on the text of the function it restates
+    -- obspy 1.0.2 (the version `environment.txt` of the reference pins), obspy/signal/filter.py::bandpass:
+
+        fe = 0.5 * df
+        low = freqmin / fe
+        high = freqmax / fe
+        # raise for some bad scenarios
+        if high - 1.0 > -1e-6:
+            ... warnings.warn(msg)
+            return highpass(data, freq=freqmin, df=df, corners=corners, zerophase=zerophase)
+        if low > 1:
+            raise ValueError("Selected low corner frequency is above Nyquist.")
+        z, p, k = iirfilter(corners, [low, high], btype='band', ftype='butter', output='zpk')
+        sos = zpk2sos(z, p, k)
+        if zerophase:
+            firstpass = sosfilt(sos, data)
+            return sosfilt(sos, firstpass[::-1])[::-1]
+        else:
+            return sosfilt(sos, data)
+
+    and on known answers that do not come from SciPy (tests/test_host_logic.py::test_bandpass_design_kat):
+    the closed-form bilinear-transform coefficients of the first-order band-pass and the -3 dB points
+    of every order sitting exactly on freqmin / freqmax."""
     fe = 0.5 * df
     low = freqmin / fe
     high = freqmax / fe

@@ -213,6 +213,37 @@ class RefFunctions(object):
         return s._estMag(trigIndex, cs, MPcon, np.asarray(mags, dtype=float), evs, WFU, UtU, np.atleast_2d(ewf), 0.0,
                          0.0, "SS0", "STA")
 
+    # detex/subspace.py:875-905 (the body of SubSpace.SVD for one subspace row): `_trimGroups` :921-943,
+    # scipy.linalg.svd :890, svdDict :892-893, `_getFracEnergy` :968-997, `_getUsedBasis` :999-1013 --
+    # the reference's own methods, unmodified.  They never touch `self`; the only Python-2 idiom in
+    # them is `d.keys().sort()`, which the inputs satisfy with a dict whose keys() is a list.
+    def svdSelect(self, aligned, start, end, selectCriteria, selectValue, normalize=False):
+        import detex.subspace as subspace
+        import scipy.linalg
+
+        class Py2Dict(dict):
+            def keys(self):
+                return list(dict.keys(self))
+
+        SS = subspace.SubSpace
+        evs = ["ev%03d" % i for i in range(len(aligned))]
+        row = types.SimpleNamespace(Events=list(evs), Name="SS0",
+                                    AlignedTD={e: np.asarray(aligned[i], dtype=float) for i, e in enumerate(evs)},
+                                    SampleTrims=Py2Dict(Starttime=int(start), Endtime=int(end)))
+        keys = sorted(row.Events)
+        arr, basisLength = SS._trimGroups(None, 0, row, keys, "STA")          # subspace.py:879
+        if normalize:
+            arr = np.array([x / np.linalg.norm(x) for x in arr])               # :887-888
+        U, s, Vh = scipy.linalg.svd(np.transpose(arr), full_matrices=False)   # :889-890
+        svdDict = Py2Dict()
+        for einum, eival in enumerate(s):                                      # :892-893
+            svdDict[eival] = U[:, einum]
+        frac = SS._getFracEnergy(None, 0, row, svdDict, U)                     # :896
+        used = SS._getUsedBasis(None, 0, row, svdDict, frac, selectCriteria, selectValue)   # :898-899
+        return dict(basisLength=basisLength, s=s, Ufull=U, frac_avg=np.asarray(frac['Average'], dtype=float),
+                    frac_min=np.asarray(frac['Minimum'], dtype=float), used_keys=np.asarray(used, dtype=float),
+                    U=np.array([svdDict[k] for k in used]).reshape(len(used), basisLength))
+
     # detex/construct.py:928-987
     def multiplex(self, chans):
         st = [types.SimpleNamespace(data=np.asarray(c)) for c in chans]

@@ -34,10 +34,28 @@ def gap_case(R):
     np.savez_compressed(os.path.join(OUT, "gap_golden.npz"), **out)
 
 
+def svd_case(R):
+    """SubSpace.SVD's per-subspace body (subspace.py:875-905, 921-943, 968-1013) run by the reference
+    itself: aligned waveforms -> trimmed, demeaned stack -> SVD -> fractional energy -> used basis, for
+    every selectCriteria."""
+    X = synth.event_families(301, 1, 7, 260, 3, max_shift=6, noise=0.8) + 0.05     # one cluster, n = 780
+    out = dict(svd_X=X, svd_start=30, svd_end=750)
+    cases = [(1, 0.5, False), (2, 0.9, False), (2, 0.6, True), (3, 0.95, False), (4, 2, False), (2, 1.0, False),
+             (2, 0.0, False)]
+    out["svd_cases"] = np.array([[c, v, float(nm)] for c, v, nm in cases])
+    for k, (crit, val, nm) in enumerate(cases):
+        r = R.svdSelect(X, 30, 750, crit, val, normalize=nm)
+        assert r["basisLength"] == 720
+        for name in ("s", "frac_avg", "frac_min", "used_keys", "U"):
+            out["svd%d_%s" % (k, name)] = r[name]
+    np.savez_compressed(os.path.join(OUT, "svd_golden.npz"), **out)
+
+
 def main():
     R = ref_shim.RefFunctions()
     gap_case(R)
-    if len(sys.argv) > 1 and sys.argv[1] == "gap":
+    svd_case(R)
+    if len(sys.argv) > 1 and sys.argv[1] in ("gap", "svd"):
         return
     # ---- detection statistic (_MPXDS, detect.py:559-578; _MPXSSCorr, fas.py:120-134)
     cases = {}

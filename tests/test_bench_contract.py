@@ -19,12 +19,18 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["metric"] == "subspace_detector_template_samples_per_sec"
     assert d["unit"] == "template*samples/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
     assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1 and d["vs_baseline"] is None
-    assert d["value"] > 1e5 and abs(d["ms_per_step"] * d["value"] / 1e3 - d["config"]["lags_per_chunk"] *
-                                    int(d["cpu_baseline"]["sample"].split(" x ")[-1].split()[0])) < 1e-3 * d["value"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    cfg = d["config"]
+    assert d["value"] > 1e5 and abs(d["ms_per_step"] * d["value"] / 1e3 - cfg["lags_per_chunk"] *
+                                    cfg["subspaces_per_step"] * cfg["chunks_per_step"]) < 1e-3 * d["value"]
+    # the unmodified reference where it is available (oracle/_ref or /root/reference), else the oracle port
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shim
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_shim.available() else "port")
+    assert 1 <= d["cpu_baseline"]["cores"] <= (os.cpu_count() or 1)
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert 0 < d["cpu_baseline"]["one_process_value"] <= d["value"] * 1.5
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert d["config"]["subspaces"] == 256 and d["config"]["n"] == 9000 and "workload" in d["config"]
+    assert cfg["subspaces"] == 256 and cfg["n"] == 9000 and "workload" in cfg and "tcgen05" not in json.dumps(cfg)
 
 
 def test_other_ranks_of_the_reference_arm_do_nothing():

@@ -155,3 +155,30 @@ def test_update_start_times():
     assert out[1]["starttime"] == 2000.0 + 30 / 300.0 and out[1]["magnitude"] == 2.0
     assert abs(out[1]["offset"] - (5.0 + 0.1)) < 1e-12
     assert st[1]["starttime"] == 2000.0          # inputs untouched
+
+
+def test_bandpass_design_kat():
+    """N2: known answers for the Butterworth band-pass design `preprocess.bandpass_sos` hands to the
+    device filter (ObsPy 1.0.2 `bandpass`: iirfilter(corners, [low, high], 'band', 'butter') -> zpk2sos).
+    (i) corners = 1 has a closed form: with W1 = tan(pi f1 / fs), W2 = tan(pi f2 / fs), BW = W2 - W1,
+    W0^2 = W1 W2, the bilinear transform of BW s / (s^2 + BW s + W0^2) is
+        b = [BW, 0, -BW] / D,  a = [1, 2 (W0^2 - 1) / D, (1 - BW + W0^2) / D],  D = 1 + BW + W0^2.
+    (ii) a Butterworth band-pass of any order is exactly -3 dB (|H|^2 = 1/2) at both corner frequencies
+    and 0 dB at the (pre-warped) geometric centre; zero-phase = two passes squares the response."""
+    import scipy.signal
+    from detex_b200 import preprocess
+    f1, f2, fs = 1.0, 10.0, 100.0
+    sos = preprocess.bandpass_sos(f1, f2, fs, corners=1)
+    W1, W2 = np.tan(np.pi * f1 / fs), np.tan(np.pi * f2 / fs)
+    BW, W02 = W2 - W1, W1 * W2
+    D = 1 + BW + W02
+    assert sos.shape == (1, 6)
+    assert np.allclose(sos[0], [BW / D, 0.0, -BW / D, 1.0, 2 * (W02 - 1) / D, (1 - BW + W02) / D], rtol=0, atol=1e-14)
+    for corners, (lo, hi, rate) in ((2, (1.0, 10.0, 100.0)), (4, (2.0, 8.0, 40.0)), (3, (0.5, 4.0, 20.0))):
+        sos = preprocess.bandpass_sos(lo, hi, rate, corners=corners)
+        assert sos.shape == (corners, 6)
+        fc = rate / np.pi * np.arctan(np.sqrt(np.tan(np.pi * lo / rate) * np.tan(np.pi * hi / rate)))
+        w, h = scipy.signal.sosfreqz(sos, worN=np.array([lo, hi, fc]) * 2 * np.pi / rate)
+        assert np.allclose(np.abs(h[:2]) ** 2, 0.5, atol=1e-12) and abs(abs(h[2]) - 1.0) < 1e-12
+    with pytest.raises(ValueError):
+        preprocess.bandpass_sos(30.0, 35.0, 40.0, 2)

@@ -134,3 +134,33 @@ def test_alignment_delays_match_reference(align_golden, case):
     assert np.array_equal(link, g[case + "_link"])
     assert np.array_equal(delays, g[case + "_delays"])
     assert np.array_equal(orc.align_td(delays, g[case + "_X"]), g[case + "_aligned"])
+
+
+def _same_basis(U, ref):
+    """Singular vectors are defined up to sign: rows agree up to a factor of +-1."""
+    assert U.shape == ref.shape
+    for a, b in zip(U, ref):
+        assert min(np.abs(a - b).max(), np.abs(a + b).max()) < 1e-10
+
+
+def test_svd_selection_matches_reference():
+    """a16: SubSpace.SVD's per-subspace body run by the REFERENCE (`_trimGroups`, scipy.linalg.svd,
+    `_getFracEnergy`, `_getUsedBasis`, subspace.py:875-1013; golden from make_golden.svd_case) against
+    the oracle restatement and the product's `subspace.svd_basis`, every selectCriteria."""
+    from detex_b200 import subspace
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "svd_golden.npz"))
+    W = g["svd_X"][:, int(g["svd_start"]):int(g["svd_end"])]              # the trimmed aligned waveforms
+    for k, (crit, val, nm) in enumerate(g["svd_cases"]):
+        crit, nm = int(crit), bool(nm)
+        val = int(val) if crit == 4 else float(val)
+        o = orc.svd_basis(W, select_criteria=crit, select_value=val, normalize=nm)
+        p = subspace.svd_basis(W, selectCriteria=crit, selectValue=val, normalize=nm)
+        ref_U, ref_s = g["svd%d_U" % k], g["svd%d_s" % k]
+        assert o["ndim"] == p["NumBasis"] == len(ref_U) == len(g["svd%d_used_keys" % k])
+        assert np.allclose(o["s"], ref_s, rtol=1e-12) and np.allclose(p["s"], ref_s, rtol=1e-12)
+        assert np.array_equal(g["svd%d_used_keys" % k], ref_s[:len(ref_U)])   # UsedSVDKeys = top singular values
+        for got_avg, got_min in ((o["frac_avg"], o["frac_min"]), (p["FracEnergy"]["Average"], p["FracEnergy"]["Minimum"])):
+            assert np.abs(got_avg - g["svd%d_frac_avg" % k]).max() < 1e-12
+            assert np.abs(got_min - g["svd%d_frac_min" % k]).max() < 1e-12
+        _same_basis(o["U"], ref_U)
+        _same_basis(p["U"], ref_U)

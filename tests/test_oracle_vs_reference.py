@@ -82,3 +82,20 @@ def test_alignment_delays(R, seed, N):
     assert np.array_equal(link, l2) and np.array_equal(delays, d2)
     X = rng.standard_normal((N, 1500))
     assert np.array_equal(R.alignTD(delays, X), orc.align_td(d2, X))
+
+
+@pytest.mark.parametrize("crit,val,nm", [(1, 0.7, False), (2, 0.9, True), (3, 0.8, False), (4, 1, False)])
+def test_svd_selection_live(R, crit, val, nm):
+    """a16 against the live reference: `_trimGroups` / svd / `_getFracEnergy` / `_getUsedBasis`
+    (subspace.py:875-1013), unmodified, on a fresh cluster."""
+    from detex_b200 import subspace
+    X = synth.event_families(900 + crit, 1, 5, 150, 3, max_shift=5, noise=0.6) - 0.02
+    ref = R.svdSelect(X, 12, 432, crit, val, normalize=nm)
+    W = X[:, 12:432]
+    for got in (orc.svd_basis(W, select_criteria=crit, select_value=val, normalize=nm),
+                subspace.svd_basis(W, selectCriteria=crit, selectValue=val, normalize=nm)):
+        U = got["U"]
+        assert U.shape == ref["U"].shape and np.allclose(got["s"], ref["s"], rtol=1e-12)
+        for a, b in zip(U, ref["U"]):
+            assert min(np.abs(a - b).max(), np.abs(a + b).max()) < 1e-10
+    assert np.abs(orc.svd_basis(W, crit, val, nm)["frac_avg"] - ref["frac_avg"]).max() < 1e-12
