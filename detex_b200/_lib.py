@@ -26,7 +26,7 @@ EXPORTS = [
     "dtx_sta_lta_max", "dtx_set_events", "dtx_est_mags", "dtx_last_k1_ms", "dtx_launch_count", "dtx_ccx", "dtx_corr_zero_lag",
     "dtx_set_x8_tolerance", "dtx_get_chunk_modes", "dtx_set_trigger_sta", "dtx_preprocess_chunks_dec", "dtx_set_hist_bins",
     "dtx_accumulate_begin", "dtx_accumulate_end", "dtx_k1_ms_history", "dtx_ccx_device", "dtx_ccx_pack",
-    "dtx_ccx_condensed", "dtx_set_ccx_batch", "dtx_host_alloc", "dtx_host_free",
+    "dtx_ccx_condensed", "dtx_set_ccx_batch", "dtx_host_alloc", "dtx_host_free", "dtx_set_core_lags",
 ]
 
 
@@ -88,6 +88,7 @@ def load():
     L.dtx_launch_count.argtypes = [p, C.POINTER(C.c_int64)]
     L.dtx_corr_zero_lag.argtypes = [p, p, C.c_int, C.c_int, p]
     L.dtx_ccx.argtypes = [p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p, p, p]
+    L.dtx_set_core_lags.argtypes = [p, p, p]
     L.dtx_accumulate_begin.argtypes = [p, C.c_int64]
     L.dtx_accumulate_end.argtypes = [p]
     L.dtx_k1_ms_history.argtypes = [p, p, C.c_int64, C.POINTER(C.c_int64)]

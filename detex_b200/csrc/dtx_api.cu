@@ -127,8 +127,15 @@ struct dtx_ctx {
     int dtype = DTX_F64;
     std::vector<long long> raw_off;  // element offsets in raw buffer
     std::vector<long long> rawL;
+    std::vector<long long> core_lo, core_hi;   // per chunk core lag range (dtx_set_core_lags), empty = all lags
     const void* d_raw = nullptr;     // points into raw_own or caller memory
     DevBuf<uint8_t> raw_own;
+    // H2D of the next batch overlaps the projection of the current one: the copies run on a second
+    // stream, ordered behind the last kernel that READS the raw chunks (K0 of the previous batch)
+    // and in front of everything the main stream does next
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_raw_read = nullptr, ev_copy_done = nullptr;
+    bool raw_read_pending = false, copy_pending = false;
 
     // last run
     int run_set = -1;
@@ -167,7 +174,7 @@ struct dtx_ctx {
     BasisSet ccx_set;
     DevBuf<uint8_t> cx_X;
     DevBuf<double> cx_wa, cx_wb, cx_es, cx_ed, cx_pad, cx_cc, cx_sub, cx_tcc, cx_tsub, cx_pcc, cx_psub;
-    DevBuf<int> cx_lag, cx_tlag, cx_plag, cx_rows, cx_nflag, cx_slot;
+    DevBuf<int> cx_lag, cx_tlag, cx_plag, cx_rows, cx_nflag, cx_slot, cx_karg;
     DevBuf<int2> cx_flag;
     int ccx_max_batch = 512;     // signals per K1 launch (dtx_set_ccx_batch lowers it for tests)
     long long ccx_ds_bytes = 4LL << 30;   // DS budget of one CCX batch
@@ -192,6 +199,12 @@ int fail(dtx_ctx* c, int code, const std::string& msg) {
     } while (0)
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Called after enqueuing a kernel that reads (or writes) the raw chunk buffer on the main stream.
+void mark_raw_access(dtx_ctx* ctx) {
+    if (!ctx->ev_raw_read) cudaEventCreateWithFlags(&ctx->ev_raw_read, cudaEventDisableTiming);
+    if (ctx->ev_raw_read && cudaEventRecord(ctx->ev_raw_read, ctx->stream) == cudaSuccess) ctx->raw_read_pending = true;
+}
 
 }  // namespace
 
@@ -232,6 +245,12 @@ void dtx_destroy(dtx_ctx* ctx) {
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
     }
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
+    if (ctx->ev_raw_read) cudaEventDestroy(ctx->ev_raw_read);
+    if (ctx->ev_copy_done) cudaEventDestroy(ctx->ev_copy_done);
     cudaStream_t st = ctx->own_stream ? ctx->stream : nullptr;
     delete ctx;   // every device / pinned buffer is released by its destructor
     if (st) cudaStreamDestroy(st);
@@ -428,6 +447,8 @@ static int set_chunk_table(dtx_ctx* ctx, int nchunks, const int64_t* L, const in
     ctx->dtype = dtype;
     ctx->raw_off.resize(nchunks);
     ctx->rawL.resize(nchunks);
+    ctx->core_lo.clear();
+    ctx->core_hi.clear();
     long long off = 0;
     for (int i = 0; i < nchunks; ++i) {
         if (L[i] < 1 || L[i] > (1LL << 30)) return fail(ctx, DTX_ERR_ARG, "chunk length out of range");
@@ -446,12 +467,37 @@ int dtx_load_chunks(dtx_ctx* ctx, int nchunks, const void* const* host_ptrs, con
     if (rc) return rc;
     const size_t esz = dtype == DTX_F32 ? 4 : 8;
     const long long total = ctx->raw_off.back() + ((ctx->rawL.back() + 1) & ~1LL);
-    // the previous batch may still be in flight on the stream: order the overwrite behind it
+    if (!ctx->copy_stream) {
+        DTX_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        DTX_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming));
+    }
+    // the host arrays of the previous dtx_load_chunks may be released by the caller once this call
+    // has started: wait for their copy (long finished unless nothing ran in between)
+    if (ctx->copy_pending) DTX_CUDA(cudaEventSynchronize(ctx->ev_copy_done));
     DTX_CUDA(ctx->raw_own.reserve(static_cast<size_t>(total) * esz));
+    // the previous batch may still be in flight: overwrite its chunks only behind the last kernel that
+    // reads them (K0 / the float64 engine / magnitudes), not behind the whole projection
+    if (ctx->raw_read_pending) DTX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_raw_read, 0));
     for (int i = 0; i < nchunks; ++i)
         DTX_CUDA(cudaMemcpyAsync(ctx->raw_own.p + ctx->raw_off[i] * esz, host_ptrs[i],
-                                 static_cast<size_t>(L[i]) * esz, cudaMemcpyHostToDevice, ctx->stream));
+                                 static_cast<size_t>(L[i]) * esz, cudaMemcpyHostToDevice, ctx->copy_stream));
+    DTX_CUDA(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
+    ctx->copy_pending = true;
+    DTX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
     ctx->d_raw = ctx->raw_own.p;
+    return DTX_OK;
+}
+
+int dtx_set_core_lags(dtx_ctx* ctx, const int64_t* lo, const int64_t* hi) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (ctx->nchunks < 1) return fail(ctx, DTX_ERR_STATE, "dtx_set_core_lags: no chunks loaded");
+    if (!lo || !hi) {
+        ctx->core_lo.clear();
+        ctx->core_hi.clear();
+        return DTX_OK;
+    }
+    ctx->core_lo.assign(lo, lo + ctx->nchunks);
+    ctx->core_hi.assign(hi, hi + ctx->nchunks);
     return DTX_OK;
 }
 
@@ -491,6 +537,14 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         cd.sig_off = sig; cd.norm_off = nrm; cd.ds_off = ds;
         cd.blk_lo = 0;
         cd.blk_hi = blk_hi ? blk_hi[i] : lay.nblocks;
+        cd.t_lo = 0;
+        cd.t_hi = cd.T;
+        if (mode == 0 && !ctx->core_lo.empty()) {
+            if (ctx->core_lo[i] < 0 || ctx->core_lo[i] >= ctx->core_hi[i] || ctx->core_hi[i] > cd.T || ctx->core_lo[i] % 4)
+                return fail(ctx, DTX_ERR_ARG, "dtx_set_core_lags: need 0 <= lo < hi <= T and lo % 4 == 0 for every chunk");
+            cd.t_lo = static_cast<int>(ctx->core_lo[i]);
+            cd.t_hi = static_cast<int>(ctx->core_hi[i]);
+        }
         sig += 2LL * Nc * cd.Lpad;
         nrm += cd.Tpad;
         ds += static_cast<long long>(bs.ds_rows) * cd.Tpad;
@@ -626,6 +680,7 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
               ctx->d_maxbits.p, ctx->d_scale.p, ctx->d_xsplit.p, ctx->d_mu.p, ctx->d_invE.p, x8, k4_limit,
               ctx->d_k4bits.p, ctx->d_chunk_mode.p, mode == 0 ? ctx->d_zeroE.p : nullptr, st);
     DTX_CUDA(cudaGetLastError());
+    if (engine != DTX_ENGINE_FP64 && !keep_ds64) mark_raw_access(ctx);   // K1 works on the split planes only
     ctx->launches += 3;  // k0_stats, k0_split, k0_norm
     ctx->have_ds64 = false;
     ctx->k1_timed = false;
@@ -672,6 +727,7 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         ctx->launches += 1;
     }
     DTX_CUDA(cudaGetLastError());
+    if (engine == DTX_ENGINE_FP64 || keep_ds64) mark_raw_access(ctx);    // the float64 kernel reads the raw chunks
     if (mode == 0) {   // zero-energy windows: DS = +inf in every subspace row (reference: x/0, detect.py:577)
         launch_zero_energy_fix(ctx->d_chunks.p, nchunks, max_ntiles, S, ctx->d_invE.p, ctx->d_zeroE.p, ctx->d_DS.p,
                                ctx->have_ds64 ? ctx->d_DS64.p : nullptr, st);
@@ -1035,6 +1091,7 @@ static int preprocess_impl(dtx_ctx* ctx, int nchunks, int Nc, const void* const*
     DTX_CUDA(ctx->raw_own.reserve(static_cast<size_t>(otot) * 8));
     launch_multiplex(work, work_off, dmin.p, dooff.p, nchunks, Nc, work_maxlen, reinterpret_cast<double*>(ctx->raw_own.p), st);
     DTX_CUDA(cudaGetLastError());
+    mark_raw_access(ctx);
     ctx->launches += 1;
     ctx->d_raw = ctx->raw_own.p;
     DTX_CUDA(cudaStreamSynchronize(st));   // host trace buffers may be released by the caller
@@ -1094,6 +1151,7 @@ int dtx_sta_lta_max(dtx_ctx* ctx, int Nc, int chan, int nsta, int nlta, float* o
     DTX_CUDA(cudaMemcpyAsync(dLs.p, Ls.data(), sizeof(int) * nch, cudaMemcpyHostToDevice, st));
     launch_stalta_max(ctx->d_raw, ctx->dtype == DTX_F32, doff.p, dLs.p, nch, maxLs, Nc, chan, nsta, nlta, dout.p, st);
     DTX_CUDA(cudaGetLastError());
+    mark_raw_access(ctx);
     ctx->launches += 1;
     static_assert(sizeof(float) == sizeof(unsigned), "bit copy");
     DTX_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(float) * nch, cudaMemcpyDeviceToHost, st));
@@ -1184,6 +1242,7 @@ int dtx_est_mags(dtx_ctx* ctx, int set_id, int ntrig, const int32_t* chunk, cons
     launch_mag(ctx->d_raw, ctx->dtype == DTX_F32, ctx->d_chunks.p, ctx->d_sum.p, dtrig.p, ntrig, dsubs.p, bs.d_U.p, n,
                bs.lay.Nc, dscr.p, stride, dout.p, st);
     DTX_CUDA(cudaGetLastError());
+    mark_raw_access(ctx);
     ctx->launches += 1;
     DTX_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * 3 * ntrig, cudaMemcpyDeviceToHost, st));
     DTX_CUDA(cudaStreamSynchronize(st));
@@ -1262,6 +1321,7 @@ static int ccx_tcgen05(dtx_ctx* ctx, int dtype, const void* dX, int N, int n, in
         1, std::min<long long>(ctx->ccx_max_batch, ctx->ccx_ds_bytes / std::max<long long>(1, per_sig))));
     const int flag_cap = 1 << 20;
     DTX_CUDA(ctx->cx_pad.reserve(static_cast<size_t>(batch) * Lm));
+    DTX_CUDA(ctx->cx_karg.reserve(static_cast<size_t>(batch) * nrows));
     DTX_CUDA(ctx->cx_nflag.reserve(1));
     DTX_CUDA(ctx->cx_flag.reserve(flag_cap));
     DTX_CUDA(cudaMemsetAsync(ctx->cx_nflag.p, 0, sizeof(int), st));
@@ -1286,9 +1346,9 @@ static int ccx_tcgen05(dtx_ctx* ctx, int dtype, const void* dX, int N, int n, in
         if (rc != DTX_OK) return rc;
         launch_ccx_post(ctx->d_DS.p, ctx->d_chunks.p, c0, nsig, dX, dtype == DTX_F32, N, n, Nc, ctx->cx_rows.p, nrows,
                         ctx->cx_wa.p, ctx->cx_wb.p, ctx->cx_es.p, ctx->cx_ed.p, dcc, dlag, dsub, ctx->cx_nflag.p,
-                        ctx->cx_flag.p, flag_cap, st);
+                        ctx->cx_flag.p, flag_cap, ctx->cx_karg.p, st);
         DTX_CUDA(cudaGetLastError());
-        ctx->launches += 2;
+        ctx->launches += 4;   // pad, scan, tiled re-scoring, leftover pairs
     }
     int nflag = 0;
     DTX_CUDA(cudaMemcpyAsync(&nflag, ctx->cx_nflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -41,6 +41,8 @@ struct ChunkDesc {
     int Lpad;            // padded per-channel length of the split arrays
     int Tpad;            // ntiles * TILE_T
     int blk_lo, blk_hi;  // basis blocks K1 runs for this chunk: [blk_lo, blk_hi)
+    int t_lo, t_hi;      // core lags [t_lo, t_hi) that K3 counts (max, histogram, candidates, FAS sums); the
+                         // lags outside are a halo that only the LTA windows read (time-segment sharding)
 };
 
 struct Seg {
@@ -158,7 +160,7 @@ void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int n
 void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsig, const void* d_X, int dtype_f32,
                      int N, int n, int Nc, const int* d_rows, int nrows, const double* wa, const double* wb,
                      const double* es, const double* ed, double* d_cc, int* d_lag, double* d_sub, int* d_nflag,
-                     int2* d_flagged, int flag_cap, cudaStream_t st);
+                     int2* d_flagged, int flag_cap, int* d_karg, cudaStream_t st);   // d_karg: [nsig][nrows] scratch
 // dense per-slot rows [nslots][N] -> SciPy condensed order (pair (b, c), b < c, at b*N - b(b+1)/2 + c-b-1);
 // d_slot_of_row[b] = slot holding event b's row
 void launch_ccx_pack(const double* d_cc, const int* d_lag, const double* d_sub, const int* d_slot_of_row, int N,

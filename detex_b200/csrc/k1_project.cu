@@ -67,6 +67,10 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * SIG_BUF_BYTES + 2 * NORM_B
 // UBLKCP in an ELECT loop, ~128 cycles per MMA, i.e. the issuer paces the tensor pipe).  Same-box
 // A/B (experiments/gpu_round1k.sh, profiles/r01_issue_ab.md): converged is +0.8 % with 3 MMAs per
 // K step and +2.2 % with the 8-bit cross terms, where the pipe is not saturated.
+// A-operand collector reuse between the hi*hi and hi*lo MMAs of a K step (1 = on).
+#ifndef DTX_COLLECTOR_A
+#define DTX_COLLECTOR_A 1
+#endif
 #ifndef DTX_SINGLE_LANE_ISSUE
 #define ISSUE_LANE elect_one()
 #define ISSUE_SYNC() __syncwarp()
@@ -264,8 +268,15 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
                                 const uint64_t dal = a_base | ((al + kk * 256) >> 4);
                                 const uint64_t dbh = b_base | ((sh + bo + kk * 32) >> 4);
                                 const uint64_t dbl = b_base | ((sl + bo + kk * 32) >> 4);
+#if DTX_COLLECTOR_A
+                                // hi*hi and hi*lo share the A tile: the second takes it from the operand
+                                // collector instead of reading its 4 KB from shared memory again
+                                umma_f16_a_fill(d, dah, dbh, idesc, (cib | kk) ? 1u : 0u);
+                                umma_f16_a_lastuse(d, dah, dbl, idesc, 1u);
+#else
                                 umma_f16(d, dah, dbh, idesc, (cib | kk) ? 1u : 0u);
                                 umma_f16(d, dah, dbl, idesc, 1u);
+#endif
                                 umma_f16(d, dal, dbh, idesc, 1u);
                             }
                         }

@@ -69,8 +69,8 @@ k3_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, in
     const int s = blockIdx.x;
     const int row = row_base + blockIdx.y * S + s;
     if (only_flagged && !(rowflags[row] & 4)) return;  // the single-pass kernel already did this row
-    const float* x = DS + cd.ds_off + static_cast<long long>(s) * cd.Tpad;
-    const int T = cd.T;
+    const float* x = DS + cd.ds_off + static_cast<long long>(s) * cd.Tpad + cd.t_lo;   // core lags only
+    const int T = cd.t_hi - cd.t_lo;
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     __shared__ int sh_hist[HIST_MAX_BINS];
     __shared__ float sh_f[8][2];
@@ -138,7 +138,7 @@ k3_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, in
         if (trig && a >= th) {
             const int k = atomicAdd(ncand, 1);
             if (k < cand_cap) {
-                Candidate c; c.row = row; c.t = i; c.ds = a; c.lta = 0.f;
+                Candidate c; c.row = row; c.t = cd.t_lo + i; c.ds = a; c.lta = 0.f;
                 cand[k] = c;
             }
         }
@@ -184,8 +184,8 @@ k3_fast_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunk
     const ChunkDesc cd = chunks[blockIdx.y];
     const int s = blockIdx.x;
     const int row = row_base + blockIdx.y * S + s;
-    const float* x = DS + cd.ds_off + static_cast<long long>(s) * cd.Tpad;
-    const int T = cd.T;
+    const float* x = DS + cd.ds_off + static_cast<long long>(s) * cd.Tpad + cd.t_lo;   // core lags only (t_lo % 4 == 0)
+    const int T = cd.t_hi - cd.t_lo;
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     __shared__ int sh_hist[HIST_MAX_BINS];
     __shared__ int2 sh_cand[K3_STAGE];
@@ -311,7 +311,7 @@ k3_fast_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunk
         for (int i = tid; i < nc; i += K3_THREADS) {
             const int k = sh_base + i;
             if (k < cand_cap) {
-                Candidate c; c.row = row; c.t = sh_cand[i].x; c.ds = __int_as_float(sh_cand[i].y); c.lta = 0.f;
+                Candidate c; c.row = row; c.t = cd.t_lo + sh_cand[i].x; c.ds = __int_as_float(sh_cand[i].y); c.lta = 0.f;
                 cand[k] = c;
             }
         }
@@ -353,7 +353,11 @@ lta_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, i
     const int lrow = c.row - row_base;          // row inside the current batch
     const ChunkDesc cd = chunks[lrow / S];
     const float* x = DS + cd.ds_off + static_cast<long long>(lrow % S) * cd.Tpad;
-    const bool zero_inf = (rowflags[c.row] & 2) != 0;
+    // An inf anywhere in a row makes its MaxDS inf > 1.1, so the reference has zeroed every inf of the
+    // row before it forms the LTA (detect.py:275-288): infs count as 0 here whether they sit in this
+    // segment's core (rowflags bit 1) or only in its halo.
+    const bool zero_inf = true;
+    (void)rowflags;
     float out = centred_abs_mean(x, cd.T, W, c.t, zero_inf, l);
     if (Wsta > 0) {
         const float sta = centred_abs_mean(x, cd.T, Wsta, c.t, zero_inf, l);

@@ -13,6 +13,9 @@
 // This first engine evaluates the correlations in float64 on the FP64 pipe (register
 // window over 4 lags per thread, de-interleaved smem so the sliding read is conflict
 // free).  The per-event window statistics are computed once per event by ccx_stats.
+#include <algorithm>
+#include <cstdlib>
+
 #include "dtx_kernels.cuh"
 
 namespace dtx {
@@ -291,7 +294,8 @@ ccx_post_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
                 int N, int n, int Nc, int trunc, int nl, const int* __restrict__ rows, int nrows,
                 const double* __restrict__ wa, const double* __restrict__ wb, const double* __restrict__ evsum,
                 const double* __restrict__ evstd, double* __restrict__ cc, int* __restrict__ lag,
-                double* __restrict__ sub, int* __restrict__ nflag, int2* __restrict__ flagged, int flag_cap) {
+                double* __restrict__ sub, int* __restrict__ nflag, int2* __restrict__ flagged, int flag_cap,
+                const int* __restrict__ karg) {
     const int ci = blockIdx.y;
     const int c = c0 + ci;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -299,6 +303,9 @@ ccx_post_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
     if (r >= nrows) return;
     const int b = rows[r];
     if (b >= c) return;
+    // with the tiled re-scoring this kernel only takes the pairs the scan left for it (several
+    // near-maxima, a maximum at either end of the lag range, an out-of-range series)
+    if (karg && karg[static_cast<long long>(ci) * nrows + r] != -1) return;
     const ChunkDesc cd = chunks[ci];
     const float* row = DS + cd.ds_off + static_cast<long long>(r) * cd.Tpad;
     const long long o = static_cast<long long>(r) * N + c;
@@ -398,6 +405,234 @@ ccx_post_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
     }
 }
 
+
+// Scan of the float32 correlation series of every pair (one warp per pair, many warps per SM: the
+// 4 KB rows stream from HBM / L2): karg[ci][r] = the arg-max lag when it is the only lag within the
+// band of the maximum and not at either end of the lag range -- the tiled kernel then re-scores it and
+// its two neighbours in float64 --, -1 when ccx_post_kernel has to look at the pair (several
+// near-maxima, end of range, out-of-range values), -2 when there is nothing to do (b >= c, or a
+// zeroed-out waveform, whose result (0, 0, 0) is written here).
+__global__ void __launch_bounds__(256)
+ccx_scan_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, int c0, int N, int nl,
+                const int* __restrict__ rows, int nrows, const double* __restrict__ evstd,
+                double* __restrict__ cc, int* __restrict__ lag, double* __restrict__ sub, int* __restrict__ karg) {
+    const int ci = blockIdx.y;
+    const int c = c0 + ci;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= nrows) return;
+    const int b = rows[r];
+    int* out = karg + static_cast<long long>(ci) * nrows + r;
+    if (b >= c) {
+        if (lane == 0) *out = -2;
+        return;
+    }
+    const long long o = static_cast<long long>(r) * N + c;
+    if (!(evstd[b] > 0.0) || !(evstd[c] > 0.0)) {        // zeroed-out waveform: the reference's all-NaN branch
+        if (lane == 0) { cc[o] = 0.0; lag[o] = 0; sub[o] = 0.0; *out = -2; }
+        return;
+    }
+    const ChunkDesc cd = chunks[ci];
+    const float* row = DS + cd.ds_off + static_cast<long long>(r) * cd.Tpad;
+    float mx = -INFINITY, mn = INFINITY;
+    int amax = -1, cnt = 0;
+    for (int k = lane; k < nl; k += 32) {
+        const float v = __ldcs(row + k);
+        if (!isnan(v)) {
+            if (v > mx) { mx = v; amax = k; }
+            mn = fminf(mn, v);
+            ++cnt;
+        }
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+        const float omx = __shfl_xor_sync(0xffffffffu, mx, s);
+        const int oam = __shfl_xor_sync(0xffffffffu, amax, s);
+        if (omx > mx || (omx == mx && oam >= 0 && (amax < 0 || oam < amax))) { mx = omx; amax = oam; }
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+    }
+    if (cnt == 0) {
+        if (lane == 0) { cc[o] = 0.0; lag[o] = 0; sub[o] = 0.0; *out = -2; }
+        return;
+    }
+    int res = amax;
+    if (mx > 1.001f || mn < -1.001f || amax <= 0 || amax >= nl - 1) res = -1;
+    else {
+        // any other lag within the band of the maximum?
+        const float thr = mx - CCX_CAND_BAND;
+        int others = 0;
+        for (int k = lane; k < nl; k += 32) others += (k != amax && row[k] >= thr) ? 1 : 0;
+        if (__any_sync(0xffffffffu, others)) res = -1;
+    }
+    if (lane == 0) *out = res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiled re-scoring.  ccx_post_kernel above streams both float64 waveforms of every pair from L2
+// (48 KB per pair at n = 3000; 8.4 M pairs of configs[2] = 73 ms, L2-bandwidth bound).  Here a CTA
+// keeps TC signals (events c) de-multiplexed in shared memory and walks over a group of template rows
+// b: row b's waveform is staged once per CTA and shared by the 8 warps, warp w scores the pair
+// (b, signal w).  L2 traffic per pair drops to n*8/TC bytes + the pair's float32 series.
+// Lane l owns the samples [l*m, (l+1)*m) of every channel, m odd (conflict-free 64-bit shared loads),
+// and rolls a three-sample window of the signal, so the arg-max lag and its two neighbours cost one
+// shared load per tap each.
+constexpr int POST_WARPS = 8;
+
+__device__ __forceinline__ double sm_at(const double* s, int idx, int ns) {
+    return (static_cast<unsigned>(idx) < static_cast<unsigned>(ns)) ? s[idx] : 0.0;
+}
+
+// acc[j] = sum_c sum_i x1_c[i] * x2_c[i + kappa - 1 + j], j = 0..2 (x2 zero outside [0, ns))
+__device__ __forceinline__ void sm_dot3(const double* __restrict__ s1, const double* __restrict__ s2, int ns, int Nc,
+                                        int m, int kappa, int lane, double acc[3]) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    const int j0 = lane * m, j1 = min(ns, j0 + m);
+    for (int c = 0; c < Nc; ++c) {
+        const double* x1 = s1 + c * ns;
+        const double* x2 = s2 + c * ns;
+        if (j0 < j1) {
+            double w0 = sm_at(x2, j0 + kappa - 1, ns), w1 = sm_at(x2, j0 + kappa, ns);
+            for (int j = j0; j < j1; ++j) {
+                const double w2 = sm_at(x2, j + kappa + 1, ns);
+                const double v = x1[j];
+                a0 = fma(v, w0, a0);
+                a1 = fma(v, w1, a1);
+                a2 = fma(v, w2, a2);
+                w0 = w1;
+                w1 = w2;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    acc[0] = a0; acc[1] = a1; acc[2] = a2;
+}
+
+__device__ __forceinline__ double sm_exact(const double* __restrict__ s1, const double* __restrict__ s2, int ns, int Nc,
+                                           int m, int kappa, int lane) {
+    double a = 0.0;
+    const int j0 = lane * m, j1 = min(ns, j0 + m);
+    for (int c = 0; c < Nc; ++c)
+        for (int j = j0; j < j1; ++j) a = fma(s1[c * ns + j], sm_at(s2 + c * ns, j + kappa, ns), a);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    return a;
+}
+
+template <typename T>
+__device__ __forceinline__ void stage_demux(const T* __restrict__ x, double* __restrict__ dst, int n, int Nc, int ns,
+                                            int tid, int nthreads) {
+    for (int i = tid; i < n; i += nthreads) dst[(i % Nc) * ns + i / Nc] = static_cast<double>(x[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(POST_WARPS * 32)
+ccx_post_tiled_kernel(const int* __restrict__ karg, int c0, int nsig,
+                      const T* __restrict__ X, int N, int n, int Nc, int trunc, int nl,
+                      const int* __restrict__ rows, int nrows, int TC, int RG,
+                      const double* __restrict__ wa, const double* __restrict__ wb,
+                      const double* __restrict__ evsum, const double* __restrict__ evstd,
+                      double* __restrict__ cc, int* __restrict__ lag, double* __restrict__ sub,
+                      int* __restrict__ nflag, int2* __restrict__ flagged, int flag_cap) {
+    extern __shared__ double sm[];   // [TC] signals, then the current template row; each [Nc][ns]
+    const int ns = n / Nc;
+    const int m = ((ns + 31) / 32) | 1;                  // samples per lane and channel, odd
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sig0 = blockIdx.y * TC;
+    const int nmine = min(TC, nsig - sig0);              // signals of this CTA
+    const int r0 = blockIdx.x * RG, r1 = min(nrows, r0 + RG);
+    const int c_last = c0 + sig0 + nmine - 1;
+    if (r0 >= nrows || rows[r0] >= c_last) return;       // nothing with b < c in this tile
+    for (int s = 0; s < nmine; ++s)
+        stage_demux(X + static_cast<long long>(c0 + sig0 + s) * n, sm + static_cast<size_t>(s) * n, n, Nc, ns, tid,
+                    POST_WARPS * 32);
+    double* s1 = sm + static_cast<size_t>(TC) * n;
+    const int ci = sig0 + warp;                          // this warp's signal (index inside the batch)
+    const int c = c0 + ci;
+    const bool have_sig = warp < nmine;
+    const double* s2 = sm + static_cast<size_t>(warp) * n;
+    const double* wac = wa + static_cast<long long>(have_sig ? c : 0) * nl;
+    const double* wbc = wb + static_cast<long long>(have_sig ? c : 0) * nl;
+    const double dn = static_cast<double>(n);
+    // the next template row is fetched into registers while the current one is scored (n <= 4096;
+    // longer waveforms are staged directly)
+    constexpr int PF = 16;
+    const bool use_pf = n <= PF * POST_WARPS * 32;
+    double pf[PF];
+    int k_nx = -2;              // the next row's arg-max lag, per-event scalars (fetched a row ahead)
+    double std_nx = 0.0, sum_nx = 0.0;
+    auto prefetch = [&](int r) {
+        const int bb = rows[r];
+        if (use_pf) {
+            const T* x = X + static_cast<long long>(bb) * n;
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int i = tid + k * POST_WARPS * 32;
+                pf[k] = i < n ? static_cast<double>(x[i]) : 0.0;
+            }
+        }
+        k_nx = (have_sig && bb < c) ? karg[static_cast<long long>(ci) * nrows + r] : -2;
+        std_nx = evstd[bb];
+        sum_nx = evsum[bb];
+    };
+    prefetch(r0);
+    for (int r = r0; r < r1; ++r) {
+        const int b = rows[r];
+        if (b >= c_last) break;                          // rows ascend: no later row has a pair here
+        __syncthreads();                                 // previous row's readers are done with s1
+        if (use_pf) {
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int i = tid + k * POST_WARPS * 32;
+                if (i < n) s1[(i % Nc) * ns + i / Nc] = pf[k];
+            }
+        } else {
+            stage_demux(X + static_cast<long long>(b) * n, s1, n, Nc, ns, tid, POST_WARPS * 32);
+        }
+        __syncthreads();
+        const int k = k_nx;                               // arg-max lag of the float32 series
+        const double std1 = std_nx, sum1 = sum_nx;
+        if (r + 1 < r1) prefetch(r + 1);
+        if (k < 0) continue;                              // b >= c, or not a single interior maximum (ccx_post_kernel)
+        const long long o = static_cast<long long>(r) * N + c;
+        double best = 0.0, cb4 = 0.0, caf = 0.0;
+        int ind = -1;
+        bool fallback = false;
+        {
+            double acc[3];
+            sm_dot3(s1, s2, ns, Nc, m, k + trunc + 1 - ns, lane, acc);
+            const double v = (acc[1] - sum1 * wac[k]) / (dn * wbc[k] * std1);
+            if (!isnan(v)) {
+                best = v; ind = k;
+                cb4 = (acc[0] - sum1 * wac[k - 1]) / (dn * wbc[k - 1] * std1);
+                caf = (acc[2] - sum1 * wac[k + 1]) / (dn * wbc[k + 1] * std1);
+            }
+            if (ind < 0 || best > 1.0 + CC_GUARD) fallback = true;
+        }
+        if (fallback) {
+            if (lane == 0) {
+                const int q = atomicAdd(nflag, 1);
+                if (q < flag_cap) flagged[q] = make_int2(b, c);
+            }
+            continue;
+        }
+        double ss = 0.0;
+        {
+            const double alpha = acos((cb4 + caf) / (2 * best));
+            const double alsi = sin(alpha);
+            const double tau = -(atan((cb4 - caf) / (2 * best * alsi)) / alpha);
+            ss = (fabs(tau) > 0.5) ? static_cast<double>(ind) : tau;
+        }
+        if (lane == 0) {
+            cc[o] = best;
+            lag[o] = (ind + 1 + trunc) * Nc - n;
+            sub[o] = ss;
+        }
+    }
+}
+
 }  // namespace
 
 void launch_ccx_stats(const void* d_X, int dtype_f32, int N, int n, int Nc, double* wa, double* wb, double* es,
@@ -493,20 +728,45 @@ void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int n
 void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsig, const void* d_X, int dtype_f32,
                      int N, int n, int Nc, const int* d_rows, int nrows, const double* wa, const double* wb,
                      const double* es, const double* ed, double* d_cc, int* d_lag, double* d_sub, int* d_nflag,
-                     int2* d_flagged, int flag_cap, cudaStream_t st) {
+                     int2* d_flagged, int flag_cap, int* d_karg, cudaStream_t st) {
     const int ns = n / Nc;
     const int trunc = n / (2 * Nc) - 1;
     const int nl = 2 * ns - 1 - 2 * trunc;
     const int rows = nrows;
+    // tiled variant: TC signals + 1 template row, float64, in shared memory
+    const long long per_wave = static_cast<long long>(n) * 8;
+    const int TC = static_cast<int>(std::min<long long>(POST_WARPS, (220 * 1024) / per_wave - 1));
+    const int* karg = nullptr;
+    if (TC >= 1 && d_karg && !std::getenv("DTX_CCX_POST_UNTILED")) {
+        const dim3 sg((rows + 7) / 8, nsig);
+        ccx_scan_kernel<<<sg, 256, 0, st>>>(DS, d_chunks, c0, N, nl, d_rows, nrows, ed, d_cc, d_lag, d_sub, d_karg);
+        const int RG = 64;
+        const size_t smem = static_cast<size_t>(TC + 1) * per_wave;
+        const dim3 tg((rows + RG - 1) / RG, (nsig + TC - 1) / TC);
+        if (dtype_f32) {
+            cudaFuncSetAttribute(ccx_post_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem));
+            ccx_post_tiled_kernel<float><<<tg, POST_WARPS * 32, smem, st>>>(
+                d_karg, c0, nsig, static_cast<const float*>(d_X), N, n, Nc, trunc, nl, d_rows, nrows, TC, RG, wa,
+                wb, es, ed, d_cc, d_lag, d_sub, d_nflag, d_flagged, flag_cap);
+        } else {
+            cudaFuncSetAttribute(ccx_post_tiled_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem));
+            ccx_post_tiled_kernel<double><<<tg, POST_WARPS * 32, smem, st>>>(
+                d_karg, c0, nsig, static_cast<const double*>(d_X), N, n, Nc, trunc, nl, d_rows, nrows, TC, RG, wa,
+                wb, es, ed, d_cc, d_lag, d_sub, d_nflag, d_flagged, flag_cap);
+        }
+        karg = d_karg;   // ccx_post_kernel below: only the pairs the scan left for it
+    }
     const dim3 grid((rows + 7) / 8, nsig);
     if (dtype_f32)
         ccx_post_kernel<float><<<grid, 256, 0, st>>>(DS, d_chunks, c0, static_cast<const float*>(d_X), N, n, Nc, trunc,
                                                      nl, d_rows, nrows, wa, wb, es, ed, d_cc, d_lag, d_sub,
-                                                     d_nflag, d_flagged, flag_cap);
+                                                     d_nflag, d_flagged, flag_cap, karg);
     else
         ccx_post_kernel<double><<<grid, 256, 0, st>>>(DS, d_chunks, c0, static_cast<const double*>(d_X), N, n, Nc,
                                                       trunc, nl, d_rows, nrows, wa, wb, es, ed, d_cc, d_lag,
-                                                      d_sub, d_nflag, d_flagged, flag_cap);
+                                                      d_sub, d_nflag, d_flagged, flag_cap, karg);
 }
 
 // dense [nslots][N] rows -> SciPy condensed order; one block row per event b, threads over c > b

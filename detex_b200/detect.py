@@ -86,6 +86,10 @@ def _evalTrigCon(maxDS, threshold):
     return bool(maxDS > threshold)
 
 
+# candidate records with 64-bit lags (a month of 100 Hz data has 2.6e8 lags; segment lags are int32)
+LONG_CAND_DTYPE = np.dtype([("row", np.int64), ("t", np.int64), ("ds", np.float32), ("lta", np.float32)])
+
+
 class SSDetex(object):
     """Batched detector for the subspaces (or singles) of one station.
 
@@ -235,6 +239,106 @@ class SSDetex(object):
             log.warning("DS values above 1 found in sar on %s, removing values above 1", self.sta)
             Sar = Sar[Sar.DS <= 1.05].reset_index(drop=True)
         return Sar, maxds, dense
+
+    # ------------------------------------------------------- time-segment sharding with a halo
+    @staticmethod
+    def long_array_segments(Ls, ns, seg_lags, halo):
+        """Cut the T = Ls - ns + 1 lags of a long array (Ls samples per channel) into segments of
+        `seg_lags` core lags plus `halo` lags on either inner side (both multiples of 4).  Returns a list
+        of (first lag, number of lags incl. halos, core lo, core hi) -- lo / hi relative to the segment."""
+        if seg_lags % 4 or halo % 4 or seg_lags < 4:
+            raise ValueError("seg_lags and halo must be multiples of 4")
+        T = Ls - ns + 1
+        segs = []
+        for g0 in range(0, T, seg_lags):
+            g1 = min(T, g0 + seg_lags)
+            a = max(0, g0 - halo)
+            b = min(T, g1 + halo)
+            segs.append((a, b - a, g0 - a, g1 - a))
+        return segs
+
+    def run_long_array(self, x, sr, start, seg_lags=1 << 18, batch=16, shard=None):
+        """Detection on ONE long pre-processed multiplexed array, sharded by time segment with a halo
+        ("long-array mode"; BASELINE.json north_star: "Continuous data shards naturally by
+        time segment, with a template-length halo").  Every segment is a chunk of `seg_lags` core lags
+        whose samples extend ns - 1 further (the template-length halo a lag needs) and whose lags extend
+        an LTA window further on both inner sides (so triggers next to a cut see the LTA of the uncut
+        array); only core lags are counted, so histograms, MaxDS and the candidate set are those of the
+        whole array processed as a single chunk, and the greedy +-20 s pick runs once over the merged
+        list.  shard = (rank, world) runs a contiguous range of the segments on this rank and merges the
+        candidate lists / histograms / maxima over the ranks (one gather at the end, no data-path
+        collective).  Returns (Sar DataFrame, {name: MaxDS}, histograms are added to self.histdic)."""
+        if self.estimateMags:
+            raise ValueError("run_long_array: magnitude estimates work per chunk; use run_chunks")
+        if len(self.groups) != 1:
+            raise ValueError("run_long_array: all subspaces must share one basis length")
+        n, names = next(iter(self.groups.items()))
+        Nc, ns = self.Nc, n // self.Nc
+        x = np.asarray(x)
+        Ls = len(x) // Nc
+        T = Ls - ns + 1
+        if T < 10:
+            return pd.DataFrame(columns=SAR_COLS), {}
+        W = int(self.triggerLTATime * sr)
+        Wsta = int(self.triggerSTATime * sr)
+        halo = -(-max(W, Wsta, 4) // 4) * 4
+        segs = self.long_array_segments(Ls, ns, int(seg_lags), halo)
+        lo_s, hi_s = 0, len(segs)
+        if shard is not None:
+            from . import parallel
+            lo_s, hi_s = parallel.shard_range(len(segs), shard[0], shard[1])
+        mine = segs[lo_s:hi_s]
+        eng, sid, S = self.engine, self.set_ids[n], len(names)
+        eng.set_trigger_sta(Wsta)
+        cands, mx = [], np.full(S, -np.inf)
+        nanrow = np.zeros(S, dtype=bool)
+        for b0 in range(0, len(mine), batch):
+            part = mine[b0:b0 + batch]
+            eng.load_chunks([x[a * Nc:(a + nl + ns - 1) * Nc] for a, nl, _, _ in part])
+            eng.set_core_lags([p[2] for p in part], [p[3] for p in part])
+            eng.detect_run(sid, engine=self.kernel, kblk=self.kblk, hist_range=(0.0, 1.0),
+                           lta_window=0 if self.fillZeros else W)
+            m, fl = eng.rowstats()
+            c = eng.candidates()
+            c = c.astype(LONG_CAND_DTYPE)
+            c["t"] += np.array([p[0] for p in part], dtype=np.int64)[c["row"] // S]   # segment lag -> array lag
+            c["row"] %= S
+            cands.append(c)
+            nanrow |= (fl & 1).any(axis=0)
+            mx = np.fmax(mx, np.where(np.isnan(m), -np.inf, m).max(axis=0))
+        cand = np.concatenate(cands) if cands else np.zeros(0, dtype=LONG_CAND_DTYPE)
+        hist = eng.hist(sid, reset=True)
+        if shard is not None and shard[1] > 1:
+            from . import parallel
+            cand = parallel.gather_records(cand)
+            hist = parallel.allreduce_sum(hist)
+            mx = parallel.allreduce_max(mx)
+            nanrow = parallel.allreduce_max(nanrow.astype(np.float64)) > 0
+        if self.calcHist:
+            for si, name in enumerate(names):
+                if not nanrow[si]:                      # np.histogram raises on NaN: row skipped (detect.py:182-185)
+                    self.histdic[name] = self.histdic[name] + hist[si]
+        maxds = {name: (float("nan") if nanrow[si] else float(mx[si])) for si, name in enumerate(names)}
+        rows = []
+        cand = cand[np.lexsort((cand["t"], cand["row"]))]
+        for si, name in enumerate(names):
+            sel = cand[cand["row"] == si]
+            if nanrow[si] or not len(sel) or not _evalTrigCon(mx[si], self.threshold[name]):
+                continue
+            picks = greedy_pick(sel["t"], sel["ds"], T, sr)
+            if len(picks) > 4000:  # kill switch, detect.py:433-436
+                raise Exception('over 4000 events found in single data block on %s for %s' % (self.sta, name))
+            minof, maxof = np.min(self.offsets[name]), np.max(self.offsets[name])
+            for k in picks:
+                coef = float(sel["ds"][k])
+                times = float(sel["t"][k]) / sr + start
+                den = float(sel["lta"][k])
+                sl = 0.0 if self.fillZeros else (abs(coef) / den if (np.isfinite(den) and den > 0.0) else 0.0)
+                rows.append([coef, sl, times, name, self.sta, times - maxof, times - minof, np.nan, np.nan, np.nan])
+        Sar = pd.DataFrame(rows, columns=SAR_COLS)
+        if len(Sar) and (Sar.DS > 1.05).any():  # detect.py:199-204
+            Sar = Sar[Sar.DS <= 1.05].reset_index(drop=True)
+        return Sar, maxds
 
     def getRA(self, chunk, sr, start, File=None):
         """CorDF of one chunk (array part of `_getRA`, detect.py:225-296): index = sorted

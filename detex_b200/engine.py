@@ -130,6 +130,17 @@ class Engine(object):
                                                      _ptr(L), _lib.DTX_F32 if f32 else _lib.DTX_F64))
         self.nchunks = len(L)
 
+    def set_core_lags(self, lo=None, hi=None):
+        """Core lag range [lo[i], hi[i]) of every loaded chunk (time-segment sharding with a halo): only
+        these lags count for MaxDS / histograms / candidates / FAS sums of later runs.  None = all lags."""
+        if lo is None:
+            self._check(self._L.dtx_set_core_lags(self._h, None, None))
+            return
+        lo = np.ascontiguousarray(np.asarray(lo, dtype=np.int64))
+        hi = np.ascontiguousarray(np.asarray(hi, dtype=np.int64))
+        assert len(lo) == len(hi) == self.nchunks
+        self._check(self._L.dtx_set_core_lags(self._h, _ptr(lo), _ptr(hi)))
+
     # -------------------------------------------------------------------- run
     def detect_run(self, set_id, engine="tcgen05", kblk=0, hist_range=(0.0, 1.0), lta_window=0,
                    want_fas=False, keep_ds64=False):

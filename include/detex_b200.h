@@ -89,6 +89,18 @@ int dtx_load_chunks(dtx_ctx* ctx, int nchunks, const void* const* host_ptrs, con
 int dtx_attach_device_chunks(dtx_ctx* ctx, int nchunks, const void* dev_base,
                              const int64_t* elem_offsets, const int64_t* L, int dtype);
 
+/* Time-segment sharding with a halo ("long-array mode") -------------------------------
+ * A long pre-processed array can be cut into segments that overlap: each segment carries, besides the
+ * template-length tail every chunk needs, a halo of extra lags on either side so that the LTA windows
+ * of triggers near a cut see the same samples as in the uncut array.  lo[i] / hi[i] (lags of chunk i,
+ * lo % 4 == 0) delimit the CORE of each loaded chunk: MaxDS, histograms, candidates and FAS sums of
+ * later runs only count lags lo <= t < hi, while candidate lags stay relative to the chunk start and the
+ * LTA / STA windows read the halo.  With cores that partition the lags of the long array the results are
+ * those of the uncut array.  NULL pointers (or loading new chunks) restore "every lag counts".  The
+ * reference analogue is the conBuff overlap of consecutive chunks (getdata.py:509-518), whose duplicate
+ * detections results._deleteDetDups (results.py:393-397) removes afterwards. */
+int dtx_set_core_lags(dtx_ctx* ctx, const int64_t* lo, const int64_t* hi);
+
 /* On-device pre-processing (next row N2) ----------------------------------------------------
  * Replaces the array part of construct._applyFilter (construct.py:1017-1029) + multiplex
  * (construct.py:928-987): every trace is linearly detrended (scipy.signal.detrend, which is what

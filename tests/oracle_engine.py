@@ -33,6 +33,10 @@ class OracleEngine(object):
     def load_chunks(self, chunks):
         self.chunks = [np.asarray(c, dtype=np.float64) for c in chunks]
         self.nchunks = len(chunks)
+        self._core = None
+
+    def set_core_lags(self, lo=None, hi=None):
+        self._core = None if lo is None else (list(lo), list(hi))
 
     def preprocess_chunks(self, traces, sos, zerophase=True, detrend=True, dec_sos=None, factor=1):
         out = []
@@ -83,22 +87,25 @@ class OracleEngine(object):
         for ci, c in enumerate(self.chunks):
             for si, U in enumerate(st["bases"]):
                 ds = orc.mpx_ds_direct(c, U, Nc).astype(np.float32)
-                m = np.nanmax(ds) if not np.isnan(ds).any() else np.nan
+                # core lags (time-segment sharding): only these count; the LTA reads the whole row
+                c_lo, c_hi = (0, len(ds)) if getattr(self, "_core", None) is None else (self._core[0][ci], self._core[1][ci])
+                core = ds[c_lo:c_hi]
+                m = np.nanmax(core) if not np.isnan(core).any() else np.nan
                 if m > 1.1:                                  # detect.py:275-281
                     ds[np.isinf(ds)] = 0
-                    m = ds.max()
+                    m = core.max()
                     fl[ci, si] |= 2
                 self._ds[(ci, si)] = ds
                 mx[ci, si] = m
-                if np.isnan(ds).any():
+                if np.isnan(core).any():
                     fl[ci, si] |= 1
                     continue
-                st["hist"][si, :self.hist_bins] += np.histogram(ds.astype(np.float64), bins=bins)[0]
+                st["hist"][si, :self.hist_bins] += np.histogram(core.astype(np.float64), bins=bins)[0]
                 if want_fas:
-                    x = ds.astype(np.float64)
+                    x = core.astype(np.float64)
                     st["fas"][si] += [len(x), x.sum(), (x * x).sum(), np.log(x).sum(), np.log1p(-x).sum()]
                 if st["thr"] is not None and m > np.float32(st["thr"][si]):
-                    idx = np.nonzero(ds >= np.float32(st["thr"][si]))[0]
+                    idx = c_lo + np.nonzero(core >= np.float32(st["thr"][si]))[0]
                     lta = np.zeros(len(idx), dtype=np.float32)
                     if lta_window > 0 and len(ds) >= lta_window:
                         sl = orc.sta_lta(ds.astype(np.float64), lta_window, self.sta_window)

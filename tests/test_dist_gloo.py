@@ -199,3 +199,47 @@ def test_eight_rank_dealt_ccx_equals_single_process():
     assert np.array_equal(cc, rcc[iu[0], iu[1] - 1])
     assert np.array_equal(lag.astype(float), rlag[iu[0], iu[1] - 1])
     assert np.array_equal(sub, rsub[iu[0], iu[1] - 1])
+
+
+def _long_worker(rank, world, port, q):
+    """One rank of a time-segment-sharded detection on a long array (SSDetex.run_long_array)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    from detex_b200 import detect, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        chunks, bases, _ = synth.detection_case(95, 1, 7000, 100, 3, [2, 3], planted=3)
+        names = ["SS0", "SS1"]
+        det = detect.SSDetex(dict(zip(names, bases)), {n: 0.3 for n in names}, {n: [0.0, 1.0] for n in names}, 3,
+                             engine=OracleEngine(), triggerLTATime=0.5)
+        df, mx = det.run_long_array(chunks[0], 100.0, 50.0, seg_lags=1000, batch=2,
+                                    shard=(rank, world) if world > 1 else None)
+        if rank == 0:
+            q.put((df.STMP.values, df.DS.values, df.DS_STALTA.values, list(df.Name), mx,
+                   {k: v.copy() for k, v in det.histdic.items()}))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def test_time_segment_sharding_two_ranks_equals_one():
+    ctx = mp.get_context("spawn")
+    out = {}
+    for world in (1, 2):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_long_worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        out[world] = q.get(timeout=300)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    a, b = out[1], out[2]
+    assert len(a[0]) > 0 and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[3] == b[3]
+    assert np.array_equal(a[2], b[2]) and a[4] == b[4]
+    assert all(np.array_equal(a[5][k], b[5][k]) for k in a[5])

@@ -225,3 +225,34 @@ def test_zero_filled_gap_matches_reference_golden(engine, gap_golden):
     cand = engine.candidates()
     assert len(cand) > 0 and set(cand["row"].tolist()) == {1}   # the planted event of subspace 1 survives
     assert np.isfinite(cand["ds"]).all() and np.isfinite(cand["lta"]).all()
+
+
+def test_long_array_time_segments_with_halo(engine):
+    """Time-segment sharding with a halo on the GPU: a 3-hour array cut into 7 overlapping segments
+    gives the triggers (bit-exact times), maxima and histograms of the same array run as ONE chunk."""
+    from detex_b200 import detect
+    Nc, ns, Ls, sr = 3, 300, 160000, 100.0
+    chunks, bases, _ = synth.detection_case(94, 1, Ls, ns, Nc, [2, 4, 7], planted=6)
+    x = chunks[0]
+    names = ["SS0", "SS1", "SS2"]
+    mk = lambda sid: detect.SSDetex(dict(zip(names, bases)), {n: 0.3 for n in names}, {n: [0.0, 2.0] for n in names},
+                                    Nc, engine=engine, set_id=sid)
+    one = mk(21)
+    ref, mref, _ = one.run_chunks([x], sr, [5.0e8])
+    det = mk(22)
+    got, mx = det.run_long_array(x, sr, 5.0e8, seg_lags=24576, batch=3)
+    assert len(det.long_array_segments(Ls, ns, 24576, 500)) == 7
+    assert len(ref) >= 6 and len(got) == len(ref)
+    assert np.array_equal(got.STMP.values, ref.STMP.values) and list(got.Name) == list(ref.Name)
+    assert np.abs(got.DS.values - ref.DS.values).max() < 2e-6     # per-segment centring / scaling of the fp16 split
+    assert np.abs(got.DS_STALTA.values / ref.DS_STALTA.values - 1).max() < 1e-4
+    for name in names:
+        assert abs(mx[name] - mref[0][name]) < 2e-6
+        assert det.histdic[name].sum() == one.histdic[name].sum() == Ls - ns + 1
+        assert np.abs(det.histdic[name] - one.histdic[name]).sum() <= 8
+    # and against the oracle on the uncut array
+    for si, name in enumerate(names):
+        ds = orc.mpx_ds_direct(x, bases[si], Nc)
+        sel = got[got.Name == name]
+        t = np.rint((sel.STMP.values - 5.0e8) * sr).astype(int)
+        assert np.abs(sel.DS.values - ds[t]).max() < TOL

@@ -122,3 +122,31 @@ def test_bandpass_design_matches_oracle_filter():
         preprocess.bandpass_sos(1.0, 20.0, 40.0, 2)
     with pytest.raises(ValueError):
         preprocess.bandpass_sos(30.0, 35.0, 40.0, 2)
+
+
+def test_long_array_segments_equal_single_chunk():
+    """Time-segment sharding with a halo (`SSDetex.run_long_array`): cutting a long array into
+    overlapping segments whose core lags partition the array gives the triggers, MaxDS and histograms
+    of the uncut array processed as one chunk (host logic on the oracle-backed engine)."""
+    Nc, ns, Ls, sr = 3, 100, 9000, 100.0
+    chunks, bases, _ = synth.detection_case(93, 1, Ls, ns, Nc, [2, 3], planted=4)
+    x = chunks[0]
+    names = ["SS0", "SS1"]
+    mk = lambda: detect.SSDetex(dict(zip(names, bases)), {n: 0.3 for n in names}, {n: [0.0, 1.5] for n in names}, Nc,
+                                engine=OracleEngine(), triggerLTATime=0.5)
+    one = mk()
+    ref, mref, _ = one.run_chunks([x], sr, [1000.0])
+    for seg in (2000, 4096, 1 << 18):
+        det = mk()
+        got, mx = det.run_long_array(x, sr, 1000.0, seg_lags=seg, batch=2)
+        segs = det.long_array_segments(Ls, ns, seg, 52)
+        assert sum(hi - lo for _, _, lo, hi in segs) == Ls - ns + 1
+        assert len(got) == len(ref) > 0
+        assert np.array_equal(got.STMP.values, ref.STMP.values) and list(got.Name) == list(ref.Name)
+        assert np.abs(got.DS.values - ref.DS.values).max() < 1e-6
+        assert np.abs(got.DS_STALTA.values - ref.DS_STALTA.values).max() < 1e-4 * ref.DS_STALTA.values.max()
+        for name in names:
+            assert abs(mx[name] - mref[0][name]) < 1e-6
+            assert np.abs(det.histdic[name] - one.histdic[name]).sum() <= 4
+    with pytest.raises(ValueError):
+        mk().long_array_segments(Ls, ns, 1001, 52)
