@@ -174,8 +174,12 @@ struct dtx_ctx {
     BasisSet ccx_set;
     DevBuf<uint8_t> cx_X;
     DevBuf<double> cx_wa, cx_wb, cx_es, cx_ed, cx_pad, cx_cc, cx_sub, cx_tcc, cx_tsub, cx_pcc, cx_psub;
-    DevBuf<int> cx_lag, cx_tlag, cx_plag, cx_rows, cx_nflag, cx_slot, cx_karg;
+    DevBuf<int> cx_lag, cx_tlag, cx_plag, cx_rows, cx_nflag, cx_slot;
+    DevBuf<int4> cx_karg;
+    PinBuf<int> cx_nflag_h;      // degenerate-pair count of the last CCX call, checked at the next synchronisation
+    bool cx_flag_check = false;
     DevBuf<int2> cx_flag;
+    int ccx_passes = 1;          // MMAs per K step of the CCX series: 1 = hi*hi screening (default), 3 = fp16x3
     int ccx_max_batch = 512;     // signals per K1 launch (dtx_set_ccx_batch lowers it for tests)
     long long ccx_ds_bytes = 4LL << 30;   // DS budget of one CCX batch
 };
@@ -258,11 +262,13 @@ void dtx_destroy(dtx_ctx* ctx) {
 
 const char* dtx_last_error(const dtx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+static int ccx_check_flags(dtx_ctx* ctx);
+
 int dtx_sync(dtx_ctx* ctx) {
     if (!ctx) return DTX_ERR_ARG;
     DTX_CUDA(cudaSetDevice(ctx->device));
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));
-    return DTX_OK;
+    return ccx_check_flags(ctx);
 }
 
 // Basis set from vectors already in bs.d_U ([R][n] float64 on the device; `fill_U`, if given, is
@@ -512,7 +518,7 @@ int dtx_attach_device_chunks(dtx_ctx* ctx, int nchunks, const void* dev_base, co
 
 // K0 + (K1 | fp64 direct) on the loaded chunks; leaves DS in ctx->d_DS.
 static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mode, int keep_ds64,
-                       const int* blk_hi) {
+                       const int* blk_hi, int hi_only = 0) {
     const BasisLayout& lay = bs.lay;
     const int Nc = lay.Nc, n = lay.n, ns = lay.ns, S = lay.S;
     const int Kc = round_up(ns + 7, CHUNK_TAPS);
@@ -669,6 +675,9 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     constexpr double X8_C = 1.6e-5;
     const int x8 = (engine == DTX_ENGINE_TCGEN05_X8) ? X8_FORCE
                  : (engine == DTX_ENGINE_TCGEN05_AUTO && mode == 0) ? X8_AUTO : X8_OFF;
+    // CCX (mode 1): k0_norm records, per padded event, the worst ratio of window power to window energy
+    // -- the amplification of operand rounding in the normalised series (band of ccx_scan_kernel)
+    const int k0_policy = mode == 1 ? X8_RATIO : x8;
     const float k4_limit = static_cast<float>(std::pow(ctx->x8_eps / X8_C, 4.0) / bs.nu4);
     if (x8 && !bs.have_img8) {
         DTX_CUDA(bs.d_Aimg8.reserve(static_cast<size_t>(lay.nblocks) * lay.nchunks * 32768));
@@ -677,7 +686,7 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         ctx->launches += 1;
     }
     launch_k0(ctx->d_raw, f32, ctx->d_chunks.p, nchunks, Nc, n, max_Lpad, max_ntiles, ctx->d_sum.p,
-              ctx->d_maxbits.p, ctx->d_scale.p, ctx->d_xsplit.p, ctx->d_mu.p, ctx->d_invE.p, x8, k4_limit,
+              ctx->d_maxbits.p, ctx->d_scale.p, ctx->d_xsplit.p, ctx->d_mu.p, ctx->d_invE.p, k0_policy, k4_limit,
               ctx->d_k4bits.p, ctx->d_chunk_mode.p, mode == 0 ? ctx->d_zeroE.p : nullptr, st);
     DTX_CUDA(cudaGetLastError());
     if (engine != DTX_ENGINE_FP64 && !keep_ds64) mark_raw_access(ctx);   // K1 works on the split planes only
@@ -693,6 +702,7 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         a.chunk_scale = ctx->d_scale.p; a.chunks = ctx->d_chunks.p; a.items = ctx->d_items.p;
         a.binfo = bs.d_binfo.p; a.DS = ctx->d_DS.p; a.nitems = ctx->n_items;
         a.kblk = kblk; a.num_sms = ctx->num_sms; a.nq = nq; a.mode = mode;
+        a.hi_only = hi_only;
         if (!ctx->accumulate && mode == 0) ctx->k1_used = 0;   // only the last run's pair is kept (CCX keeps its batches')
         if (ctx->k1_used >= ctx->k1_events.size()) {
             cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1296,7 +1306,7 @@ void restore_table(dtx_ctx* ctx, BatchTable& t) {
 
 // Tensor-core CCX: events rows[0..nrows) as rank-1 templates, padded events as chunks.
 static int ccx_tcgen05(dtx_ctx* ctx, int dtype, const void* dX, int N, int n, int Nc, const int* h_rows, int nrows,
-                       double* dcc, int* dlag, double* dsub, std::vector<int2>& flagged) {
+                       double* dcc, int* dlag, double* dsub) {
     const int ns = n / Nc, trunc = n / (2 * Nc) - 1, nl = 2 * ns - 1 - 2 * trunc;
     cudaStream_t st = ctx->stream;
     ctx->k1_used = 0;   // dtx_k1_ms_history after the call returns the K1 time of every signal batch
@@ -1342,20 +1352,40 @@ static int ccx_tcgen05(dtx_ctx* ctx, int dtype, const void* dX, int N, int n, in
         }
         rc = dtx_attach_device_chunks(ctx, nsig, ctx->cx_pad.p, offs.data(), lens.data(), DTX_F64);
         if (rc != DTX_OK) return rc;
-        rc = project_run(ctx, bs, DTX_ENGINE_TCGEN05, 2, 1, 0, blk_hi.data());
+        // The float32 series only LOCATES the maximum (every lag within a band of it is re-scored in
+        // float64), so by default it is computed with ONE fp16 MMA per K step: operands rounded to 11
+        // bits move a normalised value by at most 2 * 2^-11 (Cauchy-Schwarz) times the amplification
+        // factors the scan applies, and accumulating all taps in TMEM adds ~2e-5 of truncation bias.
+        // band0 = 2 * (2^-10 + 5e-5) covers both operands of the comparison.  passes = 3: the
+        // fp16x3 series of the detection path (error ~2e-6, band 3e-5).
+        const int hi_only = ctx->ccx_passes == 1;
+        const float band0 = hi_only ? 2.2e-3f : 3e-5f;
+        rc = project_run(ctx, bs, DTX_ENGINE_TCGEN05, hi_only ? bs.lay.nchunks : 2, 1, 0, blk_hi.data(), hi_only);
         if (rc != DTX_OK) return rc;
         launch_ccx_post(ctx->d_DS.p, ctx->d_chunks.p, c0, nsig, dX, dtype == DTX_F32, N, n, Nc, ctx->cx_rows.p, nrows,
                         ctx->cx_wa.p, ctx->cx_wb.p, ctx->cx_es.p, ctx->cx_ed.p, dcc, dlag, dsub, ctx->cx_nflag.p,
-                        ctx->cx_flag.p, flag_cap, ctx->cx_karg.p, st);
+                        ctx->cx_flag.p, flag_cap, ctx->cx_karg.p, ctx->d_k4bits.p, band0, st);
         DTX_CUDA(cudaGetLastError());
         ctx->launches += 4;   // pad, scan, tiled re-scoring, leftover pairs
     }
-    int nflag = 0;
-    DTX_CUDA(cudaMemcpyAsync(&nflag, ctx->cx_nflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    DTX_CUDA(cudaStreamSynchronize(st));
-    if (nflag > flag_cap) return fail(ctx, DTX_ERR_CAPACITY, "dtx_ccx: too many degenerate pairs");
-    flagged.resize(nflag);
-    if (nflag) DTX_CUDA(cudaMemcpy(flagged.data(), ctx->cx_flag.p, sizeof(int2) * nflag, cudaMemcpyDeviceToHost));
+    // degenerate pairs (|res| > 1 from zero-variance windows, a crowded maximum, NaN): the float64
+    // kernel re-does exactly those pairs, from the device-side list -- no host round trip
+    launch_ccx_fp64_pairs(dX, dtype == DTX_F32, N, n, Nc, ctx->cx_rows.p, ctx->cx_wa.p, ctx->cx_wb.p, ctx->cx_es.p,
+                          ctx->cx_ed.p, dcc, dlag, dsub, ctx->cx_flag.p, ctx->cx_nflag.p, flag_cap, ctx->num_sms, st);
+    DTX_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    DTX_CUDA(ctx->cx_nflag_h.reserve(1));
+    DTX_CUDA(cudaMemcpyAsync(ctx->cx_nflag_h.p, ctx->cx_nflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ctx->cx_flag_check = true;
+    return DTX_OK;
+}
+
+// After a stream synchronisation: did the degenerate-pair list of the last CCX call overflow?
+static int ccx_check_flags(dtx_ctx* ctx) {
+    if (!ctx->cx_flag_check) return DTX_OK;
+    ctx->cx_flag_check = false;
+    if (ctx->cx_nflag_h.p && *ctx->cx_nflag_h.p > (1 << 20))
+        return fail(ctx, DTX_ERR_CAPACITY, "dtx_ccx: more than 2^20 degenerate pairs (use DTX_ENGINE_FP64)");
     return DTX_OK;
 }
 
@@ -1402,34 +1432,9 @@ static int ccx_run(dtx_ctx* ctx, const void* X, int x_on_device, int dtype, int 
         return DTX_OK;
     }
     BatchTable saved = save_table(ctx);
-    std::vector<int2> flagged;
-    const int rc = ccx_tcgen05(ctx, dtype, dX, N, n, Nc, rows, nrows, d_cc, d_lag, d_sub, flagged);
+    const int rc = ccx_tcgen05(ctx, dtype, dX, N, n, Nc, rows, nrows, d_cc, d_lag, d_sub);
     restore_table(ctx, saved);
-    if (rc != DTX_OK) return rc;
-    if (!flagged.empty()) {
-        // degenerate pairs (|res| > 1 from zero-variance windows, or a crowded maximum): the
-        // float64 kernel re-does their rows; only the flagged entries are taken from it
-        std::vector<int> frows;
-        for (const int2& f : flagged) frows.push_back(f.x);
-        std::sort(frows.begin(), frows.end());
-        frows.erase(std::unique(frows.begin(), frows.end()), frows.end());
-        DTX_CUDA(ctx->cx_tcc.reserve(N)); DTX_CUDA(ctx->cx_tsub.reserve(N)); DTX_CUDA(ctx->cx_tlag.reserve(N));
-        for (int b : frows) {
-            launch_ccx_fp64(dX, dtype == DTX_F32, N, n, Nc, b, 1, nullptr, ctx->cx_wa.p, ctx->cx_wb.p, ctx->cx_es.p,
-                            ctx->cx_ed.p, ctx->cx_tcc.p, ctx->cx_tlag.p, ctx->cx_tsub.p, ctx->num_sms, st);
-            DTX_CUDA(cudaGetLastError());
-            ctx->launches += 1;
-            const size_t slot = static_cast<size_t>(std::lower_bound(rows, rows + nrows, b) - rows);
-            for (const int2& f : flagged)
-                if (f.x == b) {
-                    const size_t o = slot * N + f.y;
-                    DTX_CUDA(cudaMemcpyAsync(d_cc + o, ctx->cx_tcc.p + f.y, sizeof(double), cudaMemcpyDeviceToDevice, st));
-                    DTX_CUDA(cudaMemcpyAsync(d_sub + o, ctx->cx_tsub.p + f.y, sizeof(double), cudaMemcpyDeviceToDevice, st));
-                    DTX_CUDA(cudaMemcpyAsync(d_lag + o, ctx->cx_tlag.p + f.y, sizeof(int), cudaMemcpyDeviceToDevice, st));
-                }
-        }
-    }
-    return DTX_OK;
+    return rc;
 }
 
 int dtx_ccx_device(dtx_ctx* ctx, const void* X, int x_on_device, int dtype, int N, int n, int Nc,
@@ -1459,7 +1464,7 @@ int dtx_ccx(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int ro
     DTX_CUDA(cudaMemcpyAsync(lag, ctx->cx_lag.p, nrows * N * sizeof(int), cudaMemcpyDeviceToHost, st));
     DTX_CUDA(cudaMemcpyAsync(subsamp, ctx->cx_sub.p, nrows * N * sizeof(double), cudaMemcpyDeviceToHost, st));
     DTX_CUDA(cudaStreamSynchronize(st));
-    return DTX_OK;
+    return ccx_check_flags(ctx);
 }
 
 int dtx_ccx_pack(dtx_ctx* ctx, const double* d_cc, const int32_t* d_lag, const double* d_sub,
@@ -1488,7 +1493,7 @@ int dtx_ccx_pack(dtx_ctx* ctx, const double* d_cc, const int32_t* d_lag, const d
     DTX_CUDA(cudaMemcpyAsync(lag, ctx->cx_plag.p, np * sizeof(int), cudaMemcpyDeviceToHost, st));
     DTX_CUDA(cudaMemcpyAsync(subsamp, ctx->cx_psub.p, np * sizeof(double), cudaMemcpyDeviceToHost, st));
     DTX_CUDA(cudaStreamSynchronize(st));
-    return DTX_OK;
+    return ccx_check_flags(ctx);
 }
 
 int dtx_ccx_condensed(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int engine, double* cc,
@@ -1507,6 +1512,13 @@ int dtx_ccx_condensed(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int 
     if (rc != DTX_OK) return rc;
     return dtx_ccx_pack(ctx, ctx->cx_cc.p, ctx->cx_lag.p, ctx->cx_sub.p, rows.data(), static_cast<int>(nrows), N, cc,
                         lag, subsamp);
+}
+
+int dtx_set_ccx_passes(dtx_ctx* ctx, int passes) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (passes != 1 && passes != 3) return fail(ctx, DTX_ERR_ARG, "dtx_set_ccx_passes: 1 (hi*hi screening) or 3 (fp16x3)");
+    ctx->ccx_passes = passes;
+    return DTX_OK;
 }
 
 int dtx_set_ccx_batch(dtx_ctx* ctx, int max_signals, int64_t ds_bytes) {

@@ -27,7 +27,8 @@ constexpr int HIST_MAX_BINS = 1024;   // row pitch of the device histograms; num
 // 8-bit cross-term engine: u_lo * 2^6 and u_hi * 2^-6 fit e4m3 (max|u * 2^eu| < 2^14), x_hi * 2^-6 and
 // x_lo * 2^6 fit e5m2 (max|x * 2^ex| < 2^15); the shifts cancel in each product.
 constexpr int X8_SHIFT = 6;
-enum { X8_OFF = 0, X8_AUTO = 1, X8_FORCE = 2 };   // per-run policy handed to k0_split
+enum { X8_OFF = 0, X8_AUTO = 1, X8_FORCE = 2,     // per-run policy handed to k0_split
+       X8_RATIO = 3 };   // no 8-bit mode; k0_norm records max_t sum(x - chunk mean)^2 / window energy per chunk
 
 struct ChunkDesc {
     long long raw_off;   // element offset of the chunk in the raw buffer
@@ -117,6 +118,9 @@ struct K1Args {
     int num_sms;
     int nq;        // MMA N: 256 (tiles of 2048 lags) or 128 (tiles of 1024 lags)
     int mode;      // 0 = detection statistic, 1 = signed correlation coefficient (CCX)
+    int hi_only;   // 1 = ONE MMA per K step (fp16 hi * hi only, 11-bit operands): a screening series whose
+                   // error is bounded by ~2^-10 of the normalised value; CCX uses it to LOCATE the maximum,
+                   // which is then re-scored in float64 (k4_ccx.cu)
 };
 void launch_k1(const K1Args& a, const BasisLayout& lay, cudaStream_t st);
 int k1_smem_bytes();
@@ -151,6 +155,10 @@ void launch_ccx_stats(const void* d_X, int dtype_f32, int N, int n, int Nc, doub
 void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int row_begin, int nrows, const int* d_rows,
                      const double* wa, const double* wb, const double* es, const double* ed, double* d_cc,
                      int* d_lag, double* d_sub, int num_sms, cudaStream_t st);
+void launch_ccx_fp64_pairs(const void* d_X, int dtype_f32, int N, int n, int Nc, const int* d_rows, const double* wa,
+                           const double* wb, const double* es, const double* ed, double* d_cc, int* d_lag,
+                           double* d_sub, const int2* d_pairs, const int* d_npairs, int pair_cap, int num_sms,
+                           cudaStream_t st);
 void launch_corr0(const double* d_X, int N, int n, double* d_out, cudaStream_t st);
 // d_rows[r] = event index of template row r (sorted ascending)
 void launch_ccx_templates(const void* d_X, int dtype_f32, int n, const int* d_rows, int rows, double* d_U,
@@ -160,7 +168,8 @@ void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int n
 void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsig, const void* d_X, int dtype_f32,
                      int N, int n, int Nc, const int* d_rows, int nrows, const double* wa, const double* wb,
                      const double* es, const double* ed, double* d_cc, int* d_lag, double* d_sub, int* d_nflag,
-                     int2* d_flagged, int flag_cap, int* d_karg, cudaStream_t st);   // d_karg: [nsig][nrows] scratch
+                     int2* d_flagged, int flag_cap, int4* d_karg, const unsigned* d_ratio_bits, float band0,
+                     cudaStream_t st);   // d_karg: [nsig][nrows] scratch; d_ratio_bits: per signal, from k0_norm
 // dense per-slot rows [nslots][N] -> SciPy condensed order (pair (b, c), b < c, at b*N - b(b+1)/2 + c-b-1);
 // d_slot_of_row[b] = slot holding event b's row
 void launch_ccx_pack(const double* d_cc, const int* d_lag, const double* d_sub, const int* d_slot_of_row, int N,

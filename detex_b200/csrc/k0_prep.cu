@@ -106,7 +106,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k0_norm(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
         const double* __restrict__ sum, float* __restrict__ mu, float* __restrict__ invE, int Nc,
-        int n, unsigned* __restrict__ k4bits, const unsigned* __restrict__ maxbits, int* __restrict__ zeroE) {
+        int n, unsigned* __restrict__ k4bits, const unsigned* __restrict__ maxbits, int* __restrict__ zeroE,
+        int ratio_mode) {
     const ChunkDesc cd = chunks[blockIdx.y];
     if (blockIdx.x >= cd.ntiles) return;
     const double mean = sum[blockIdx.y] / static_cast<double>(cd.L);
@@ -232,7 +233,10 @@ k0_norm(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
             fm = static_cast<float>(s1 / nn);
             fe = static_cast<float>(cn / E);  // E == 0 -> +inf, as the reference's x/0
             if (want4) {
-                const float r = static_cast<float>((base4 + o4 + d4[k]) / (E * E));
+                // ratio_mode: sum (x - chunk mean)^2 / window energy, the factor by which rounding the
+                // operands of the projection is amplified in the normalised value (CCX screening band)
+                const float r = ratio_mode ? static_cast<float>(s2 / E)
+                                           : static_cast<float>((base4 + o4 + d4[k]) / (E * E));
                 k4 = fmaxf(k4, r >= 0.f && r < 3e38f ? r : 3e38f);   // NaN / inf -> never 8-bit
             }
         }
@@ -256,7 +260,8 @@ void launch_k0(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nc
     if (d_zeroE) cudaMemsetAsync(d_zeroE, 0, sizeof(int) * nchunks, st);
     cudaMemsetAsync(d_maxbits, 0, sizeof(unsigned) * nchunks, st);
     cudaMemsetAsync(d_k4bits, 0, sizeof(unsigned) * nchunks, st);
-    unsigned* k4 = x8_policy == X8_AUTO ? d_k4bits : nullptr;   // k0_norm runs before k0_split reads it
+    unsigned* k4 = (x8_policy == X8_AUTO || x8_policy == X8_RATIO) ? d_k4bits : nullptr;   // k0_norm runs before k0_split reads it
+    const int ratio_mode = x8_policy == X8_RATIO;
     const dim3 g1(64, nchunks);
     long long tot = static_cast<long long>(Nc) * max_Lpad;
     int gx = static_cast<int>((tot + 256 * 8 - 1) / (256 * 8));
@@ -266,13 +271,13 @@ void launch_k0(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nc
     if (dtype_f32) {
         const float* r = static_cast<const float*>(raw);
         k0_stats<float><<<g1, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits);
-        k0_norm<float><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n, k4, d_maxbits, d_zeroE);
+        k0_norm<float><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n, k4, d_maxbits, d_zeroE, ratio_mode);
         k0_split<float><<<g2, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits, d_scale, d_xsplit, Nc, x8_policy,
                                             k4_limit, d_k4bits, d_chunk_mode);
     } else {
         const double* r = static_cast<const double*>(raw);
         k0_stats<double><<<g1, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits);
-        k0_norm<double><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n, k4, d_maxbits, d_zeroE);
+        k0_norm<double><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n, k4, d_maxbits, d_zeroE, ratio_mode);
         k0_split<double><<<g2, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits, d_scale, d_xsplit, Nc, x8_policy,
                                              k4_limit, d_k4bits, d_chunk_mode);
     }

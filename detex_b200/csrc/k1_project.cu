@@ -161,6 +161,8 @@ template <int NQ>
 __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) {
     constexpr int TT = 8 * NQ;
     Ring st(STAGES), sg(2), nm(2);
+    const bool hi_only = P.a.hi_only != 0;
+    const uint32_t a_bytes = hi_only ? TILE_BYTES : STAGE_BYTES;
 #if DTX_SIG_HINT
     const uint64_t pol_sig = l2_policy_evict_last();
 #endif
@@ -191,11 +193,12 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
                 const uint32_t bytes = (TT + sgm.ntaps) * 2;
                 mbar_wait(&S.sigempty[sg.idx], sg.phase ^ 1);
                 if (ISSUE_LANE) {
-                    mbar_arrive_expect_tx(&S.sigfull[sg.idx], 2 * bytes);
+                    mbar_arrive_expect_tx(&S.sigfull[sg.idx], hi_only ? bytes : 2 * bytes);
                     const __half* src = sig0 + static_cast<long long>(sgm.chan * 2) * cd.Lpad + sgm.tap0;
                     SIG_G2S(S.sig + sg.idx * SIG_BUF_BYTES, src, bytes, &S.sigfull[sg.idx]);
-                    SIG_G2S(S.sig + sg.idx * SIG_BUF_BYTES + SIG_HALFS * 2, src + cd.Lpad, bytes,
-                             &S.sigfull[sg.idx]);
+                    if (!hi_only)
+                        SIG_G2S(S.sig + sg.idx * SIG_BUF_BYTES + SIG_HALFS * 2, src + cd.Lpad, bytes,
+                                 &S.sigfull[sg.idx]);
                 }
                 ISSUE_SYNC();
                 sg.advance();
@@ -203,9 +206,10 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
                 for (int kc = 0; kc < nck; ++kc) {
                     mbar_wait(&S.empty[st.idx], st.phase ^ 1);
                     if (ISSUE_LANE) {
-                        mbar_arrive_expect_tx(&S.full[st.idx], STAGE_BYTES);
+                        // hi-only screening: the A_hi tile is the first half of the stage image
+                        mbar_arrive_expect_tx(&S.full[st.idx], a_bytes);
                         A_G2S(S.stage + st.idx * STAGE_BYTES,
-                                 ablk + static_cast<size_t>(sgm.chunk0 + kc) * STAGE_BYTES, STAGE_BYTES,
+                                 ablk + static_cast<size_t>(sgm.chunk0 + kc) * STAGE_BYTES, a_bytes,
                                  &S.full[st.idx]);
                     }
                     ISSUE_SYNC();
@@ -225,6 +229,7 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
     const uint64_t b_base = smem_desc_kmajor_noswz(0, B_LBO, B_SBO);
     const uint32_t stage0 = smem_u32(S.stage), sig0 = smem_u32(S.sig);
     Ring st(STAGES), sg(2), ac(2);
+    const bool hi_only = P.a.hi_only != 0;
     int x8_next = blockIdx.x < P.a.nitems ? item_x8(P, P.a.items[blockIdx.x].x) : 0;
     for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
         const bool x8 = x8_next != 0;
@@ -249,7 +254,14 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
                     const uint32_t bo = kc * (CHUNK_TAPS * 2);
                     const bool last = (cib + 1 == acc_stages(nacc, kblk)) || (done + 1 == P.nchunks);
                     if (ISSUE_LANE) {
-                        if (x8) {
+                        if (hi_only) {
+#pragma unroll
+                            for (int kk = 0; kk < CHUNK_TAPS / 16; ++kk) {
+                                const uint64_t dah = a_base | ((ah + kk * 256) >> 4);
+                                const uint64_t dbh = b_base | ((sh + bo + kk * 32) >> 4);
+                                umma_f16(d, dah, dbh, idesc, (cib | kk) ? 1u : 0u);
+                            }
+                        } else if (x8) {
                             // both cross terms in ONE 8-bit MMA: the "lo" tiles hold byte pairs
                             // per tap, (u_lo, u_hi) in e4m3 against (x_hi, x_lo) in e5m2
 #pragma unroll

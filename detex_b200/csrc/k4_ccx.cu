@@ -134,18 +134,35 @@ __global__ void __launch_bounds__(CT)
 ccx_kernel(const T* __restrict__ X, int N, int n, int Nc, int trunc, int nl, int row_begin,
            const int* __restrict__ rows, const double* __restrict__ wa, const double* __restrict__ wb,
            const double* __restrict__ evsum, const double* __restrict__ evstd,
-           double* __restrict__ cc, int* __restrict__ lag, double* __restrict__ sub) {
+           double* __restrict__ cc, int* __restrict__ lag, double* __restrict__ sub,
+           const int2* __restrict__ pairs, const int* __restrict__ npairs, int pair_cap) {
     extern __shared__ double res[];  // [nl]
     __shared__ double x1t[JT];
     __shared__ double x2t[4][X2ROW];
     __shared__ MaxLoc shml[CT / 32];
-    const int b = rows ? rows[blockIdx.y] : row_begin + blockIdx.y;
     const int ns = n / Nc;
     const int tid = threadIdx.x;
-    const T* x1 = X + static_cast<long long>(b) * n;
     const double nn = static_cast<double>(n);
-    const double sum1 = evsum[b], std1 = evstd[b];
-    for (int c = b + 1 + blockIdx.x; c < N; c += gridDim.x) {
+    // two ways to enumerate the pairs: every c > b of the template row blockIdx.y, or (pairs != null) a
+    // device-side list of (slot r, event c) entries -- the degenerate pairs the tensor-core engine
+    // hands over -- walked with a grid stride
+    const int npr = pairs ? min(*npairs, pair_cap) : 0;
+    int b = 0, orow = 0, c = 0, it = blockIdx.x;
+    if (!pairs) {
+        b = rows ? rows[blockIdx.y] : row_begin + blockIdx.y;
+        orow = blockIdx.y;
+        c = b + 1 + blockIdx.x;
+    }
+    for (;; ) {
+        if (pairs) {
+            if (it >= npr) break;
+            orow = pairs[it].x;
+            c = pairs[it].y;
+            b = rows[orow];
+            it += gridDim.x;
+        } else if (c >= N) break;
+        const T* x1 = X + static_cast<long long>(b) * n;
+        const double sum1 = evsum[b], std1 = evstd[b];
         const T* x2 = X + static_cast<long long>(c) * n;
         for (int m0 = 0; m0 < nl; m0 += LT) {
             double acc[4] = {0, 0, 0, 0};
@@ -219,12 +236,13 @@ ccx_kernel(const T* __restrict__ X, int N, int n, int Nc, int trunc, int nl, int
             }
         }
         if (tid == 0) {
-            const long long o = static_cast<long long>(blockIdx.y) * N + c;
+            const long long o = static_cast<long long>(orow) * N + c;
             cc[o] = maxcc;
             lag[o] = lg;
             sub[o] = ss;
         }
         __syncthreads();
+        if (!pairs) c += gridDim.x;
     }
 }
 
@@ -285,7 +303,19 @@ __device__ __forceinline__ void ccx_dot3(const T* __restrict__ x1, const T* __re
 }
 
 constexpr int CCX_MAXCAND = 8;
-constexpr float CCX_CAND_BAND = 3e-5f;   // float32 series is within ~2e-6 of float64; generous band
+// Candidate band of a pair: every lag whose float32 series value is within `band` of the series maximum
+// is re-scored in float64, so the exact maximum is found as long as band >= 2 * (error of the series).
+// band0 is that bound for operands of unit amplification (3e-5 for the fp16x3 series, 2.2e-3 for the
+// one-MMA screening series); rounding an operand moves the dot product by <= eps * |u| * |w|, i.e. the
+// normalised value by eps * (|x1| / |x1 - mean|) * (|w| / |w - mean(w)|): a1 from the template's
+// statistics, a2 = the worst window of the padded signal (k0_norm, ratio mode).
+__device__ __forceinline__ float ccx_band(float band0, double sum1, double std1, int n, unsigned ratio_bits) {
+    const double mean1 = sum1 / n;
+    const float a1 = sqrtf(1.f + static_cast<float>((mean1 * mean1) / (std1 * std1)));
+    const float a2 = sqrtf(fmaxf(1.f, __uint_as_float(ratio_bits)));
+    const float b = band0 * a1 * a2;
+    return b == b ? b : INFINITY;
+}
 
 // one warp per (signal chunk ci, template row r)
 template <typename T>
@@ -295,7 +325,7 @@ ccx_post_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
                 const double* __restrict__ wa, const double* __restrict__ wb, const double* __restrict__ evsum,
                 const double* __restrict__ evstd, double* __restrict__ cc, int* __restrict__ lag,
                 double* __restrict__ sub, int* __restrict__ nflag, int2* __restrict__ flagged, int flag_cap,
-                const int* __restrict__ karg) {
+                const int4* __restrict__ karg, const unsigned* __restrict__ ratio_bits, float band0) {
     const int ci = blockIdx.y;
     const int c = c0 + ci;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -305,7 +335,7 @@ ccx_post_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
     if (b >= c) return;
     // with the tiled re-scoring this kernel only takes the pairs the scan left for it (several
     // near-maxima, a maximum at either end of the lag range, an out-of-range series)
-    if (karg && karg[static_cast<long long>(ci) * nrows + r] != -1) return;
+    if (karg && karg[static_cast<long long>(ci) * nrows + r].x != -1) return;
     const ChunkDesc cd = chunks[ci];
     const float* row = DS + cd.ds_off + static_cast<long long>(r) * cd.Tpad;
     const long long o = static_cast<long long>(r) * N + c;
@@ -329,12 +359,14 @@ ccx_post_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
         if (lane == 0) { cc[o] = 0.0; lag[o] = 0; sub[o] = 0.0; }
         return;
     }
-    bool fallback = (mx > 1.001f) || (mn < -1.001f);
+    const float band = ccx_band(band0, evsum[b], std1, n, ratio_bits[ci]);
+    const float lim = 1.f + fmaxf(1e-3f, band);       // beyond: zero-variance windows (inf), not round-off
+    bool fallback = (mx > lim) || (mn < -lim);
     // candidates: every lag whose float32 value is within the band of the maximum
     int cand[CCX_MAXCAND];
     int ncand = 0;
     if (!fallback) {
-        const float thr = mx - CCX_CAND_BAND;
+        const float thr = mx - band;
         for (int m0 = 0; m0 < nl && !fallback; m0 += 32) {
             const int m = m0 + lane;
             const bool hit = m < nl && row[m] >= thr;
@@ -383,7 +415,7 @@ ccx_post_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
     if (fallback) {
         if (lane == 0) {
             const int k = atomicAdd(nflag, 1);
-            if (k < flag_cap) flagged[k] = make_int2(b, c);
+            if (k < flag_cap) flagged[k] = make_int2(r, c);   // (slot, event c)
         }
         return;
     }
@@ -406,65 +438,88 @@ ccx_post_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
 }
 
 
-// Scan of the float32 correlation series of every pair (one warp per pair, many warps per SM: the
-// 4 KB rows stream from HBM / L2): karg[ci][r] = the arg-max lag when it is the only lag within the
-// band of the maximum and not at either end of the lag range -- the tiled kernel then re-scores it and
-// its two neighbours in float64 --, -1 when ccx_post_kernel has to look at the pair (several
-// near-maxima, end of range, out-of-range values), -2 when there is nothing to do (b >= c, or a
-// zeroed-out waveform, whose result (0, 0, 0) is written here).
+// Scan of the float32 correlation series of every pair (one warp per pair, many warps per SM, 128-bit
+// loads: the 4 KB rows stream from HBM / L2).  Per pair an int4 record:
+//   x >= 0 : the lags (ascending, up to 4, unused = -1) whose value lies within the pair's band of the
+//            series maximum -- the tiled kernel scores them in float64, keeps the first largest, and
+//            re-scores its two neighbours for the cosine fit;
+//   x = -1 : more than 4 such lags or an out-of-range series (zero-variance windows): ccx_post_kernel;
+//   x = -2 : nothing to do (b >= c, or a zeroed-out waveform, whose result (0, 0, 0) is written here).
+constexpr int SCAN_MAXC = 4;
 __global__ void __launch_bounds__(256)
 ccx_scan_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chunks, int c0, int N, int nl,
-                const int* __restrict__ rows, int nrows, const double* __restrict__ evstd,
-                double* __restrict__ cc, int* __restrict__ lag, double* __restrict__ sub, int* __restrict__ karg) {
+                const int* __restrict__ rows, int nrows, const double* __restrict__ evsum,
+                const double* __restrict__ evstd, int n, const unsigned* __restrict__ ratio_bits, float band0,
+                double* __restrict__ cc, int* __restrict__ lag, double* __restrict__ sub, int4* __restrict__ karg) {
     const int ci = blockIdx.y;
     const int c = c0 + ci;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= nrows) return;
     const int b = rows[r];
-    int* out = karg + static_cast<long long>(ci) * nrows + r;
+    int4* out = karg + static_cast<long long>(ci) * nrows + r;
     if (b >= c) {
-        if (lane == 0) *out = -2;
+        if (lane == 0) *out = make_int4(-2, -1, -1, -1);
         return;
     }
     const long long o = static_cast<long long>(r) * N + c;
     if (!(evstd[b] > 0.0) || !(evstd[c] > 0.0)) {        // zeroed-out waveform: the reference's all-NaN branch
-        if (lane == 0) { cc[o] = 0.0; lag[o] = 0; sub[o] = 0.0; *out = -2; }
+        if (lane == 0) { cc[o] = 0.0; lag[o] = 0; sub[o] = 0.0; *out = make_int4(-2, -1, -1, -1); }
         return;
     }
     const ChunkDesc cd = chunks[ci];
-    const float* row = DS + cd.ds_off + static_cast<long long>(r) * cd.Tpad;
+    const float4* row4 = reinterpret_cast<const float4*>(DS + cd.ds_off + static_cast<long long>(r) * cd.Tpad);
+    const int nq = (nl + 3) / 4;                         // rows are padded to a multiple of TILE_T floats
     float mx = -INFINITY, mn = INFINITY;
-    int amax = -1, cnt = 0;
-    for (int k = lane; k < nl; k += 32) {
-        const float v = __ldcs(row + k);
-        if (!isnan(v)) {
-            if (v > mx) { mx = v; amax = k; }
-            mn = fminf(mn, v);
-            ++cnt;
-        }
+    int cnt = 0;
+    for (int q = lane; q < nq; q += 32) {
+        const float4 v4 = __ldcs(row4 + q);
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (4 * q + e < nl && !isnan(v[e])) { mx = fmaxf(mx, v[e]); mn = fminf(mn, v[e]); ++cnt; }
     }
     for (int s = 16; s > 0; s >>= 1) {
-        const float omx = __shfl_xor_sync(0xffffffffu, mx, s);
-        const int oam = __shfl_xor_sync(0xffffffffu, amax, s);
-        if (omx > mx || (omx == mx && oam >= 0 && (amax < 0 || oam < amax))) { mx = omx; amax = oam; }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
         mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, s));
         cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
     }
     if (cnt == 0) {
-        if (lane == 0) { cc[o] = 0.0; lag[o] = 0; sub[o] = 0.0; *out = -2; }
+        if (lane == 0) { cc[o] = 0.0; lag[o] = 0; sub[o] = 0.0; *out = make_int4(-2, -1, -1, -1); }
         return;
     }
-    int res = amax;
-    if (mx > 1.001f || mn < -1.001f || amax <= 0 || amax >= nl - 1) res = -1;
-    else {
-        // any other lag within the band of the maximum?
-        const float thr = mx - CCX_CAND_BAND;
-        int others = 0;
-        for (int k = lane; k < nl; k += 32) others += (k != amax && row[k] >= thr) ? 1 : 0;
-        if (__any_sync(0xffffffffu, others)) res = -1;
+    const float band = ccx_band(band0, evsum[b], evstd[b], n, ratio_bits[ci]);
+    const float lim = 1.f + fmaxf(1e-3f, band);          // beyond: zero-variance windows (inf), not round-off
+    int cand[SCAN_MAXC] = {-1, -1, -1, -1};
+    int nc = 0;
+    bool slow = mx > lim || mn < -lim;
+    if (!slow) {
+        const float thr = mx - band;
+        for (int q0 = 0; q0 < nq && !slow; q0 += 32) {   // second read of the row: L1 / L2 hits
+            const int q = q0 + lane;
+            unsigned m4 = 0;
+            if (q < nq) {
+                const float4 v4 = row4[q];
+                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (4 * q + e < nl && v[e] >= thr) m4 |= 1u << e;
+            }
+            unsigned any = __ballot_sync(0xffffffffu, m4 != 0);
+            while (any && !slow) {
+                const int l = __ffs(any) - 1;
+                any &= any - 1;
+                unsigned mm = __shfl_sync(0xffffffffu, m4, l);
+                while (mm) {
+                    const int e = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    if (nc < SCAN_MAXC) cand[nc++] = 4 * (q0 + l) + e;
+                    else slow = true;
+                }
+            }
+        }
     }
-    if (lane == 0) *out = res;
+    if (lane == 0) *out = slow ? make_int4(-1, -1, -1, -1) : make_int4(cand[0], cand[1], cand[2], cand[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -476,24 +531,42 @@ ccx_scan_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
 // Lane l owns the samples [l*m, (l+1)*m) of every channel, m odd (conflict-free 64-bit shared loads),
 // and rolls a three-sample window of the signal, so the arg-max lag and its two neighbours cost one
 // shared load per tap each.
-constexpr int POST_WARPS = 8;
+// Warps per pair: 1.  (Measured on B200, profiles/r02_ccx_rescoring.md: splitting a pair's taps over two
+// warps -- 16 warps per CTA -- is SLOWER, 48 ms against 37 ms per 8.4 M pairs, and so are 12 independent
+// partial sums per warp, 40 ms: the kernel is bound by the float64 FMA count, not by latency.)
+constexpr int POST_PARTS = 1;
+constexpr int POST_SIGS = 8;     // signals per CTA at most
+constexpr int POST_WARPS = POST_SIGS * POST_PARTS;
 
 __device__ __forceinline__ double sm_at(const double* s, int idx, int ns) {
     return (static_cast<unsigned>(idx) < static_cast<unsigned>(ns)) ? s[idx] : 0.0;
 }
 
-// acc[j] = sum_c sum_i x1_c[i] * x2_c[i + kappa - 1 + j], j = 0..2 (x2 zero outside [0, ns))
+// acc[j] = sum_c sum_i x1_c[i] * x2_c[i + kappa - 1 + j], j = 0..2 (x2 zero outside [0, ns)).
+// Only 8 warps share an SM (the tile fills its shared memory), so the inner loop must be lean: the taps
+// whose three signal samples all lie inside [0, ns) run without any bounds check (two shared loads and
+// three FMAs per tap, the signal window rolls through registers); at most two taps on either side of
+// that range have a sample outside and take the checked path; taps with no sample inside are skipped.
 __device__ __forceinline__ void sm_dot3(const double* __restrict__ s1, const double* __restrict__ s2, int ns, int Nc,
-                                        int m, int kappa, int lane, double acc[3]) {
+                                        int m, int kappa, int vlane, double acc[3]) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    const int j0 = lane * m, j1 = min(ns, j0 + m);
+    const int j0 = min(ns, vlane * m), j1 = min(ns, j0 + m);   // vlane: 0..63 over the two warps of a pair
+    const int alo = max(j0, -kappa - 1), ahi = min(j1, ns - kappa + 1);      // some sample inside
+    const int ilo = max(alo, 1 - kappa), ihi = min(ahi, ns - 1 - kappa);     // all three inside
     for (int c = 0; c < Nc; ++c) {
         const double* x1 = s1 + c * ns;
-        const double* x2 = s2 + c * ns;
-        if (j0 < j1) {
-            double w0 = sm_at(x2, j0 + kappa - 1, ns), w1 = sm_at(x2, j0 + kappa, ns);
-            for (int j = j0; j < j1; ++j) {
-                const double w2 = sm_at(x2, j + kappa + 1, ns);
+        const double* x2 = s2 + c * ns + kappa;
+        for (int j = alo; j < min(ahi, ilo); ++j) {                           // head (<= 2 taps)
+            const double v = x1[j];
+            a0 = fma(v, sm_at(x2 - kappa, j + kappa - 1, ns), a0);
+            a1 = fma(v, sm_at(x2 - kappa, j + kappa, ns), a1);
+            a2 = fma(v, sm_at(x2 - kappa, j + kappa + 1, ns), a2);
+        }
+        if (ilo < ihi) {
+            double w0 = x2[ilo - 1], w1 = x2[ilo];
+#pragma unroll 3
+            for (int j = ilo; j < ihi; ++j) {
+                const double w2 = x2[j + 1];
                 const double v = x1[j];
                 a0 = fma(v, w0, a0);
                 a1 = fma(v, w1, a1);
@@ -502,6 +575,12 @@ __device__ __forceinline__ void sm_dot3(const double* __restrict__ s1, const dou
                 w1 = w2;
             }
         }
+        for (int j = max(alo, max(ihi, ilo)); j < ahi; ++j) {                 // tail (<= 2 taps)
+            const double v = x1[j];
+            a0 = fma(v, sm_at(x2 - kappa, j + kappa - 1, ns), a0);
+            a1 = fma(v, sm_at(x2 - kappa, j + kappa, ns), a1);
+            a2 = fma(v, sm_at(x2 - kappa, j + kappa + 1, ns), a2);
+        }
     }
     for (int o = 16; o > 0; o >>= 1) {
         a0 += __shfl_xor_sync(0xffffffffu, a0, o);
@@ -509,6 +588,48 @@ __device__ __forceinline__ void sm_dot3(const double* __restrict__ s1, const dou
         a2 += __shfl_xor_sync(0xffffffffu, a2, o);
     }
     acc[0] = a0; acc[1] = a1; acc[2] = a2;
+}
+
+// sum_c sum_i x1_c[i] * x2_c[i + kappa]: a single lag, no bounds checks at all (two partial sums)
+__device__ __forceinline__ double sm_dot1(const double* __restrict__ s1, const double* __restrict__ s2, int ns, int Nc,
+                                          int m, int kappa, int lane) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const int j0 = lane * m, j1 = min(ns, j0 + m);
+    const int lo = max(j0, -kappa), hi = min(j1, ns - kappa);
+    for (int c = 0; c < Nc; ++c) {
+        const double* x1 = s1 + c * ns;
+        const double* x2 = s2 + c * ns + kappa;
+        int j = lo;
+        for (; j + 3 < hi; j += 4) {
+            a0 = fma(x1[j], x2[j], a0);
+            a1 = fma(x1[j + 1], x2[j + 1], a1);
+            a2 = fma(x1[j + 2], x2[j + 2], a2);
+            a3 = fma(x1[j + 3], x2[j + 3], a3);
+        }
+        for (; j < hi; ++j) a0 = fma(x1[j], x2[j], a0);
+    }
+    a0 = (a0 + a1) + (a2 + a3);
+    for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    return a0;
+}
+
+// Several lags within the band (rare path, kept out of the main loop's register allocation): their
+// float64 values, the first largest wins (np.nanargmax), NaN values are skipped.  Returns the
+// winning lag or -1 (every value NaN).
+__device__ __noinline__ int sm_best_of(const double* s1, const double* s2, int ns, int Nc, int m, int4 kc, int koff,
+                                       int lane, double sum1, double std1, double dn, const double* wac,
+                                       const double* wbc) {
+    double bestv = 0.0;
+    int bestk = -1;
+    const int ks[4] = {kc.x, kc.y, kc.z, kc.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int k = ks[q];
+        if (k < 0) break;
+        const double v = (sm_dot1(s1, s2, ns, Nc, m, k + koff, lane) - sum1 * wac[k]) / (dn * wbc[k] * std1);
+        if (!isnan(v) && (bestk < 0 || v > bestv)) { bestv = v; bestk = k; }
+    }
+    return bestk;
 }
 
 __device__ __forceinline__ double sm_exact(const double* __restrict__ s1, const double* __restrict__ s2, int ns, int Nc,
@@ -529,7 +650,7 @@ __device__ __forceinline__ void stage_demux(const T* __restrict__ x, double* __r
 
 template <typename T>
 __global__ void __launch_bounds__(POST_WARPS * 32)
-ccx_post_tiled_kernel(const int* __restrict__ karg, int c0, int nsig,
+ccx_post_tiled_kernel(const int4* __restrict__ karg, int c0, int nsig,
                       const T* __restrict__ X, int N, int n, int Nc, int trunc, int nl,
                       const int* __restrict__ rows, int nrows, int TC, int RG,
                       const double* __restrict__ wa, const double* __restrict__ wb,
@@ -537,9 +658,13 @@ ccx_post_tiled_kernel(const int* __restrict__ karg, int c0, int nsig,
                       double* __restrict__ cc, int* __restrict__ lag, double* __restrict__ sub,
                       int* __restrict__ nflag, int2* __restrict__ flagged, int flag_cap) {
     extern __shared__ double sm[];   // [TC] signals, then the current template row; each [Nc][ns]
+    __shared__ double pbuf[POST_SIGS][3];                // partial sums of a pair's second warp
     const int ns = n / Nc;
-    const int m = ((ns + 31) / 32) | 1;                  // samples per lane and channel, odd
+    const int m32 = ((ns + 31) / 32) | 1;                // taps per lane and channel when ONE warp covers a row (odd:
+    const int m64 = ((ns + 32 * POST_PARTS - 1) / (32 * POST_PARTS)) | 1;   // conflict-free 64-bit shared loads); when POST_PARTS warps do
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sig = warp / POST_PARTS, part = warp % POST_PARTS;   // POST_PARTS warps share a signal: taps split among them
+    const int vlane = part * 32 + lane;
     const int sig0 = blockIdx.y * TC;
     const int nmine = min(TC, nsig - sig0);              // signals of this CTA
     const int r0 = blockIdx.x * RG, r1 = min(nrows, r0 + RG);
@@ -549,87 +674,129 @@ ccx_post_tiled_kernel(const int* __restrict__ karg, int c0, int nsig,
         stage_demux(X + static_cast<long long>(c0 + sig0 + s) * n, sm + static_cast<size_t>(s) * n, n, Nc, ns, tid,
                     POST_WARPS * 32);
     double* s1 = sm + static_cast<size_t>(TC) * n;
-    const int ci = sig0 + warp;                          // this warp's signal (index inside the batch)
+    const bool have_sig = sig < nmine;
+    const int ci = sig0 + (have_sig ? sig : 0);          // this warp's signal (index inside the batch)
     const int c = c0 + ci;
-    const bool have_sig = warp < nmine;
-    const double* s2 = sm + static_cast<size_t>(warp) * n;
-    const double* wac = wa + static_cast<long long>(have_sig ? c : 0) * nl;
-    const double* wbc = wb + static_cast<long long>(have_sig ? c : 0) * nl;
+    const double* s2 = sm + static_cast<size_t>(have_sig ? sig : 0) * n;
+    const double* wac = wa + static_cast<long long>(c) * nl;
+    const double* wbc = wb + static_cast<long long>(c) * nl;
     const double dn = static_cast<double>(n);
     // the next template row is fetched into registers while the current one is scored (n <= 4096;
-    // longer waveforms are staged directly)
-    constexpr int PF = 16;
+    // longer waveforms are staged directly); the de-multiplexed shared-memory offset of each of a
+    // thread's elements is computed once
+    constexpr int PF = 16 / POST_PARTS;
     const bool use_pf = n <= PF * POST_WARPS * 32;
     double pf[PF];
-    int k_nx = -2;              // the next row's arg-max lag, per-event scalars (fetched a row ahead)
+    int soff[PF];
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {
+        const int i = tid + k * POST_WARPS * 32;
+        soff[k] = i < n ? (i % Nc) * ns + i / Nc : -1;
+    }
+    int4 k_nx = make_int4(-2, -1, -1, -1);   // the next row's candidate lags and per-event scalars (fetched a row ahead)
     double std_nx = 0.0, sum_nx = 0.0;
     auto prefetch = [&](int r) {
         const int bb = rows[r];
         if (use_pf) {
             const T* x = X + static_cast<long long>(bb) * n;
 #pragma unroll
-            for (int k = 0; k < PF; ++k) {
-                const int i = tid + k * POST_WARPS * 32;
-                pf[k] = i < n ? static_cast<double>(x[i]) : 0.0;
-            }
+            for (int k = 0; k < PF; ++k) pf[k] = soff[k] >= 0 ? static_cast<double>(x[tid + k * POST_WARPS * 32]) : 0.0;
         }
-        k_nx = (have_sig && bb < c) ? karg[static_cast<long long>(ci) * nrows + r] : -2;
+        k_nx = (have_sig && bb < c) ? karg[static_cast<long long>(ci) * nrows + r] : make_int4(-2, -1, -1, -1);
         std_nx = evstd[bb];
         sum_nx = evsum[bb];
+    };
+    // Finalisation is deferred twice.  (i) The first warp of a pair keeps its three partial dot products
+    // until the second warp's have arrived through shared memory (next barrier).  (ii) Lane (count % 32)
+    // of the first warp then keeps the complete sums of a pair, and every 32 pairs all lanes normalise, fit
+    // the cosine and store in parallel -- the float64 divisions and acos / sin / atan would otherwise be
+    // executed by the whole warp for every single pair.
+    double q_a0 = 0.0, q_a1 = 0.0, q_a2 = 0.0, q_sum = 0.0, q_std = 0.0;
+    int q_k = 0, q_r = -1;
+    double p_a0 = 0.0, p_a1 = 0.0, p_a2 = 0.0, p_sum = 0.0, p_std = 0.0;
+    long long p_o = -1;
+    int p_k = 0, p_b = 0, npend = 0;
+    auto flush = [&]() {
+        if (p_o >= 0) {
+            const int k = p_k;
+            const double v = (p_a1 - p_sum * wac[k]) / (dn * wbc[k] * p_std);
+            if (isnan(v) || v > 1.0 + CC_GUARD) {
+                const int q = atomicAdd(nflag, 1);
+                if (q < flag_cap) flagged[q] = make_int2(p_b, c);   // p_b holds the slot r
+            } else {
+                double ss = 0.0;                          // maximum at either end of the lag range: 0 (construct.py:402)
+                if (k > 0 && k < nl - 1) {
+                    const double cb4 = (p_a0 - p_sum * wac[k - 1]) / (dn * wbc[k - 1] * p_std);
+                    const double caf = (p_a2 - p_sum * wac[k + 1]) / (dn * wbc[k + 1] * p_std);
+                    const double alpha = acos((cb4 + caf) / (2 * v));
+                    const double alsi = sin(alpha);
+                    const double tau = -(atan((cb4 - caf) / (2 * v * alsi)) / alpha);
+                    ss = (fabs(tau) > 0.5) ? static_cast<double>(k) : tau;   // reference quirk, construct.py:418-421
+                }
+                cc[p_o] = v;
+                lag[p_o] = (k + 1 + trunc) * Nc - n;
+                sub[p_o] = ss;
+            }
+            p_o = -1;
+        }
+        npend = 0;
+    };
+    auto complete = [&]() {      // first warp of a pair, after a barrier: add the second warp's partial sums
+        if (q_r >= 0) {
+            if (lane == npend) {
+                if (POST_PARTS > 1) { q_a0 += pbuf[sig][0]; q_a1 += pbuf[sig][1]; q_a2 += pbuf[sig][2]; }
+                p_a0 = q_a0; p_a1 = q_a1; p_a2 = q_a2;
+                p_sum = q_sum; p_std = q_std; p_k = q_k; p_b = q_r;
+                p_o = static_cast<long long>(q_r) * N + c;
+            }
+            q_r = -1;
+            if (++npend == 32) flush();
+        }
     };
     prefetch(r0);
     for (int r = r0; r < r1; ++r) {
         const int b = rows[r];
         if (b >= c_last) break;                          // rows ascend: no later row has a pair here
-        __syncthreads();                                 // previous row's readers are done with s1
+        __syncthreads();                                 // previous row's readers are done with s1, pbuf is written
+        if (part == 0) complete();
         if (use_pf) {
 #pragma unroll
-            for (int k = 0; k < PF; ++k) {
-                const int i = tid + k * POST_WARPS * 32;
-                if (i < n) s1[(i % Nc) * ns + i / Nc] = pf[k];
-            }
+            for (int k = 0; k < PF; ++k)
+                if (soff[k] >= 0) s1[soff[k]] = pf[k];
         } else {
             stage_demux(X + static_cast<long long>(b) * n, s1, n, Nc, ns, tid, POST_WARPS * 32);
         }
         __syncthreads();
-        const int k = k_nx;                               // arg-max lag of the float32 series
+        const int4 kc = k_nx;                             // candidate lags of the float32 series
         const double std1 = std_nx, sum1 = sum_nx;
         if (r + 1 < r1) prefetch(r + 1);
-        if (k < 0) continue;                              // b >= c, or not a single interior maximum (ccx_post_kernel)
-        const long long o = static_cast<long long>(r) * N + c;
-        double best = 0.0, cb4 = 0.0, caf = 0.0;
-        int ind = -1;
-        bool fallback = false;
-        {
-            double acc[3];
-            sm_dot3(s1, s2, ns, Nc, m, k + trunc + 1 - ns, lane, acc);
-            const double v = (acc[1] - sum1 * wac[k]) / (dn * wbc[k] * std1);
-            if (!isnan(v)) {
-                best = v; ind = k;
-                cb4 = (acc[0] - sum1 * wac[k - 1]) / (dn * wbc[k - 1] * std1);
-                caf = (acc[2] - sum1 * wac[k + 1]) / (dn * wbc[k + 1] * std1);
+        if (kc.x < 0) continue;                           // b >= c, or left to ccx_post_kernel
+        int k = kc.x;
+        if (kc.y >= 0) {
+            // both warps of the pair evaluate the candidates over all taps and reach the same winner
+            k = sm_best_of(s1, s2, ns, Nc, m32, kc, trunc + 1 - ns, lane, sum1, std1, dn, wac, wbc);
+            if (k < 0) {                                  // every candidate NaN: let the float64 kernel decide
+                if (lane == 0 && part == 0) {
+                    const int q = atomicAdd(nflag, 1);
+                    if (q < flag_cap) flagged[q] = make_int2(r, c);
+                }
+                continue;
             }
-            if (ind < 0 || best > 1.0 + CC_GUARD) fallback = true;
         }
-        if (fallback) {
-            if (lane == 0) {
-                const int q = atomicAdd(nflag, 1);
-                if (q < flag_cap) flagged[q] = make_int2(b, c);
-            }
-            continue;
+        double acc[3];
+        sm_dot3(s1, s2, ns, Nc, m64, k + trunc + 1 - ns, vlane, acc);
+        if (part == 1) {
+            if (lane < 3) pbuf[sig][lane] = acc[lane == 0 ? 0 : (lane == 1 ? 1 : 2)];
+        } else {
+            q_a0 = acc[0]; q_a1 = acc[1]; q_a2 = acc[2];
+            q_sum = sum1; q_std = std1; q_k = k; q_r = r;
+            if (POST_PARTS == 1) complete();              // nothing to wait for
         }
-        double ss = 0.0;
-        {
-            const double alpha = acos((cb4 + caf) / (2 * best));
-            const double alsi = sin(alpha);
-            const double tau = -(atan((cb4 - caf) / (2 * best * alsi)) / alpha);
-            ss = (fabs(tau) > 0.5) ? static_cast<double>(ind) : tau;
-        }
-        if (lane == 0) {
-            cc[o] = best;
-            lag[o] = (ind + 1 + trunc) * Nc - n;
-            sub[o] = ss;
-        }
+    }
+    __syncthreads();
+    if (part == 0) {
+        complete();
+        flush();
     }
 }
 
@@ -665,11 +832,32 @@ void launch_ccx_fp64(const void* d_X, int dtype_f32, int N, int n, int Nc, int r
     if (dtype_f32) {
         cudaFuncSetAttribute(ccx_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_res));
         ccx_kernel<float><<<grid, CT, sm_res, st>>>(static_cast<const float*>(d_X), N, n, Nc, trunc, nl, row_begin,
-                                                    d_rows, wa, wb, es, ed, d_cc, d_lag, d_sub);
+                                                    d_rows, wa, wb, es, ed, d_cc, d_lag, d_sub, nullptr, nullptr, 0);
     } else {
         cudaFuncSetAttribute(ccx_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_res));
         ccx_kernel<double><<<grid, CT, sm_res, st>>>(static_cast<const double*>(d_X), N, n, Nc, trunc, nl, row_begin,
-                                                     d_rows, wa, wb, es, ed, d_cc, d_lag, d_sub);
+                                                     d_rows, wa, wb, es, ed, d_cc, d_lag, d_sub, nullptr, nullptr, 0);
+    }
+}
+
+// The float64 kernel over a device-side list of (slot, event c) pairs (no host round trip).
+void launch_ccx_fp64_pairs(const void* d_X, int dtype_f32, int N, int n, int Nc, const int* d_rows, const double* wa,
+                           const double* wb, const double* es, const double* ed, double* d_cc, int* d_lag,
+                           double* d_sub, const int2* d_pairs, const int* d_npairs, int pair_cap, int num_sms,
+                           cudaStream_t st) {
+    const int ns = n / Nc;
+    const int trunc = n / (2 * Nc) - 1;
+    const int nl = 2 * ns - 1 - 2 * trunc;
+    const size_t sm_res = sizeof(double) * nl;
+    const dim3 grid(4 * num_sms, 1);
+    if (dtype_f32) {
+        cudaFuncSetAttribute(ccx_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_res));
+        ccx_kernel<float><<<grid, CT, sm_res, st>>>(static_cast<const float*>(d_X), N, n, Nc, trunc, nl, 0, d_rows, wa, wb,
+                                                    es, ed, d_cc, d_lag, d_sub, d_pairs, d_npairs, pair_cap);
+    } else {
+        cudaFuncSetAttribute(ccx_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_res));
+        ccx_kernel<double><<<grid, CT, sm_res, st>>>(static_cast<const double*>(d_X), N, n, Nc, trunc, nl, 0, d_rows, wa,
+                                                     wb, es, ed, d_cc, d_lag, d_sub, d_pairs, d_npairs, pair_cap);
     }
 }
 
@@ -728,20 +916,22 @@ void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int n
 void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsig, const void* d_X, int dtype_f32,
                      int N, int n, int Nc, const int* d_rows, int nrows, const double* wa, const double* wb,
                      const double* es, const double* ed, double* d_cc, int* d_lag, double* d_sub, int* d_nflag,
-                     int2* d_flagged, int flag_cap, int* d_karg, cudaStream_t st) {
+                     int2* d_flagged, int flag_cap, int4* d_karg, const unsigned* d_ratio_bits, float band0,
+                     cudaStream_t st) {
     const int ns = n / Nc;
     const int trunc = n / (2 * Nc) - 1;
     const int nl = 2 * ns - 1 - 2 * trunc;
     const int rows = nrows;
     // tiled variant: TC signals + 1 template row, float64, in shared memory
     const long long per_wave = static_cast<long long>(n) * 8;
-    const int TC = static_cast<int>(std::min<long long>(POST_WARPS, (220 * 1024) / per_wave - 1));
-    const int* karg = nullptr;
+    const int TC = static_cast<int>(std::min<long long>(POST_SIGS, (220 * 1024 - 128) / per_wave - 1));
+    const int4* karg = nullptr;
     if (TC >= 1 && d_karg && !std::getenv("DTX_CCX_POST_UNTILED")) {
         const dim3 sg((rows + 7) / 8, nsig);
-        ccx_scan_kernel<<<sg, 256, 0, st>>>(DS, d_chunks, c0, N, nl, d_rows, nrows, ed, d_cc, d_lag, d_sub, d_karg);
+        ccx_scan_kernel<<<sg, 256, 0, st>>>(DS, d_chunks, c0, N, nl, d_rows, nrows, es, ed, n, d_ratio_bits, band0, d_cc,
+                                            d_lag, d_sub, d_karg);
         const int RG = 64;
-        const size_t smem = static_cast<size_t>(TC + 1) * per_wave;
+        const size_t smem = static_cast<size_t>(TC + 1) * per_wave + 128;   // + slack behind the last row
         const dim3 tg((rows + RG - 1) / RG, (nsig + TC - 1) / TC);
         if (dtype_f32) {
             cudaFuncSetAttribute(ccx_post_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -762,11 +952,11 @@ void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsi
     if (dtype_f32)
         ccx_post_kernel<float><<<grid, 256, 0, st>>>(DS, d_chunks, c0, static_cast<const float*>(d_X), N, n, Nc, trunc,
                                                      nl, d_rows, nrows, wa, wb, es, ed, d_cc, d_lag, d_sub,
-                                                     d_nflag, d_flagged, flag_cap, karg);
+                                                     d_nflag, d_flagged, flag_cap, karg, d_ratio_bits, band0);
     else
         ccx_post_kernel<double><<<grid, 256, 0, st>>>(DS, d_chunks, c0, static_cast<const double*>(d_X), N, n, Nc,
                                                       trunc, nl, d_rows, nrows, wa, wb, es, ed, d_cc, d_lag,
-                                                      d_sub, d_nflag, d_flagged, flag_cap, karg);
+                                                      d_sub, d_nflag, d_flagged, flag_cap, karg, d_ratio_bits, band0);
 }
 
 // dense [nslots][N] rows -> SciPy condensed order; one block row per event b, threads over c > b

@@ -312,6 +312,10 @@ class Engine(object):
         """Limits of one tensor-core CCX batch (tests lower them to force several batches)."""
         self._check(self._L.dtx_set_ccx_batch(self._h, int(max_signals), int(ds_bytes)))
 
+    def set_ccx_passes(self, passes=1):
+        """MMAs per K step of the tensor-core CCX series: 1 = hi*hi screening (default), 3 = fp16x3."""
+        self._check(self._L.dtx_set_ccx_passes(self._h, int(passes)))
+
     def pinned_empty(self, shape, dtype):
         """NumPy array in page-locked host memory (staging buffer of the end-to-end paths); it stays
         valid until the engine is closed."""

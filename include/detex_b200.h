@@ -236,6 +236,10 @@ int dtx_ccx_pack(dtx_ctx* ctx, const double* d_cc, const int32_t* d_lag, const d
 /* dtx_ccx_device over all rows + dtx_ccx_pack: host X in, condensed host cc / lag / subsamp out. */
 int dtx_ccx_condensed(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int engine, double* cc,
                       int32_t* lag, double* subsamp);
+/* MMAs per K step of the tensor-core CCX series: 1 (default) = fp16 hi*hi only -- the float32 series only
+ * LOCATES the maximum, every lag within a rigorous error band of it is re-scored in float64, so cc / lag /
+ * subsamp are unchanged; 3 = the fp16x3 series of the detection path. */
+int dtx_set_ccx_passes(dtx_ctx* ctx, int passes);
 /* Limits of one tensor-core CCX batch: at most max_signals padded events per K1 launch and at most
  * ds_bytes of correlation series (defaults 512 and 4 GiB; tests lower them to force several batches). */
 int dtx_set_ccx_batch(dtx_ctx* ctx, int max_signals, int64_t ds_bytes);

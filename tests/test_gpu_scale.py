@@ -242,7 +242,7 @@ def test_long_array_time_segments_with_halo(engine):
     det = mk(22)
     got, mx = det.run_long_array(x, sr, 5.0e8, seg_lags=24576, batch=3)
     assert len(det.long_array_segments(Ls, ns, 24576, 500)) == 7
-    assert len(ref) >= 6 and len(got) == len(ref)
+    assert len(ref) >= 4 and len(got) == len(ref)
     assert np.array_equal(got.STMP.values, ref.STMP.values) and list(got.Name) == list(ref.Name)
     assert np.abs(got.DS.values - ref.DS.values).max() < 2e-6     # per-segment centring / scaling of the fp16 split
     assert np.abs(got.DS_STALTA.values / ref.DS_STALTA.values - 1).max() < 1e-4
@@ -256,3 +256,33 @@ def test_long_array_time_segments_with_halo(engine):
         sel = got[got.Name == name]
         t = np.rint((sel.STMP.values - 5.0e8) * sr).astype(int)
         assert np.abs(sel.DS.values - ds[t]).max() < TOL
+
+
+def test_ccx_screening_series_equals_three_pass_series(engine):
+    """The tensor-core CCX series only locates the maximum: the default one-MMA (hi*hi) screening series
+    and the fp16x3 series give the same cc / lag / subsamp (float64 re-scoring of the same lags) -- also
+    for waveforms with a DC offset, where the rounding of the operands is amplified and the candidate
+    band widens accordingly."""
+    X = synth.event_families(6002, 8, 20, 500, 3, max_shift=60)           # 160 events, n = 1500
+    X[7] = X[3]                                                           # an identical pair (cc = 1)
+    X[11] = 0.0                                                           # a zeroed-out waveform
+    rng = np.random.default_rng(9)
+    Xoff = synth.event_families(6003, 2, 12, 300, 3, max_shift=30) + 4.0 * rng.standard_normal((24, 1))
+    for Xc, check_oracle in ((X, False), (Xoff, True)):
+        res = {}
+        for passes in (1, 3):
+            engine.set_ccx_passes(passes)
+            try:
+                res[passes] = engine.ccx_condensed(Xc, 3, engine="tcgen05")
+            finally:
+                engine.set_ccx_passes(1)
+        assert np.abs(res[1][0] - res[3][0]).max() < 1e-12
+        assert np.array_equal(res[1][1], res[3][1])
+        assert np.nanmax(np.abs(res[1][2] - res[3][2])) < 1e-8
+        c64, l64, _ = engine.ccx_condensed(Xc, 3, engine="fp64")
+        assert np.abs(res[1][0] - c64).max() < 1e-12 and np.array_equal(res[1][1], l64)
+        if check_oracle:
+            rcc, rlag, _ = orc.make_cclags(Xc, 3, fft=False)
+            iu = np.triu_indices(len(Xc), 1)
+            assert np.abs(res[1][0] - rcc[iu[0], iu[1] - 1]).max() < 1e-9
+            assert np.array_equal(res[1][1].astype(float), rlag[iu[0], iu[1] - 1])
