@@ -351,6 +351,7 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream()
     eng = Engine(local, stream=stream.cuda_stream)
+    eng.set_fused(args.fused)
     sections = set(args.sections.split(","))
     peaks = measured_peaks()
 
@@ -811,7 +812,7 @@ def workload_config(args):
         "chunks_per_gpu": args.chunks, "subspaces": args.nsub, "basis_vectors": sum(ranks_list(args.nsub)),
         "n": N_MUX, "lags_per_chunk": T_PER_CHUNK, "batch_chunks": args.batch,
         "l2": "inputs (%.1f GB/GPU) larger than L2" % (args.chunks * LS * NC * 8 / 1e9),
-        "input_dtype": "f64", "kblk": args.kblk, "engine": args.engine,
+        "input_dtype": "f64", "kblk": args.kblk or 3, "engine": args.engine, "fused_epilogue": bool(args.fused),
     }
 
 
@@ -824,7 +825,8 @@ def main():
     ap.add_argument("--chunks", type=int, default=CHUNKS_PER_STATION, help="chunks per GPU (720 = 30 days)")
     ap.add_argument("--nsub", type=int, default=NSUB)
     ap.add_argument("--batch", type=int, default=48, help="chunks per detect_run (DS buffer = batch*S*T*4 B)")
-    ap.add_argument("--kblk", type=int, default=2)
+    ap.add_argument("--kblk", type=int, default=0, help="64-tap stages per TMEM accumulation (0 = library default 3)")
+    ap.add_argument("--fused", action="store_true", help="fused mode: K1 does the row reductions, DS is never written")
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "tcgen05_x8", "tcgen05_auto"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the extra pass with the adaptive-precision engine")

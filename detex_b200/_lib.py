@@ -26,7 +26,7 @@ EXPORTS = [
     "dtx_sta_lta_max", "dtx_set_events", "dtx_est_mags", "dtx_last_k1_ms", "dtx_launch_count", "dtx_ccx", "dtx_corr_zero_lag",
     "dtx_set_x8_tolerance", "dtx_get_chunk_modes", "dtx_set_trigger_sta", "dtx_preprocess_chunks_dec", "dtx_set_hist_bins",
     "dtx_accumulate_begin", "dtx_accumulate_end", "dtx_k1_ms_history", "dtx_ccx_device", "dtx_ccx_pack",
-    "dtx_ccx_condensed", "dtx_set_ccx_batch", "dtx_host_alloc", "dtx_host_free", "dtx_set_core_lags", "dtx_set_ccx_passes",
+    "dtx_ccx_condensed", "dtx_set_ccx_batch", "dtx_host_alloc", "dtx_host_free", "dtx_set_core_lags", "dtx_set_ccx_passes", "dtx_set_fused",
 ]
 
 
@@ -97,6 +97,7 @@ def load():
     L.dtx_ccx_condensed.argtypes = [p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p, p, p]
     L.dtx_set_ccx_batch.argtypes = [p, C.c_int, C.c_int64]
     L.dtx_set_ccx_passes.argtypes = [p, C.c_int]
+    L.dtx_set_fused.argtypes = [p, C.c_int]
     L.dtx_host_alloc.argtypes = [C.POINTER(p), C.c_int64]
     L.dtx_host_free.argtypes = [p]
     for name in EXPORTS:

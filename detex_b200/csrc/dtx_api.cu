@@ -155,7 +155,11 @@ struct dtx_ctx {
     int hist_bins = HIST_BINS;    // bins of the device histograms (numBins - 1 of fas._initFAS, fas.py:31)
     int sta_window = 0;           // triggerSTATime in samples (0 = reference default: STA = |DS|)
     double x8_eps = 2e-6;         // adaptive engine: admitted RMS error of a normalised projection
-    DevBuf<int> d_rowflags, d_ncand, d_zeroE;
+    DevBuf<int> d_rowflags, d_ncand, d_zeroE, d_chunk_bad;
+    DevBuf<double> d_lta_acc;     // fused mode: window sums of |DS| per candidate (kept zero between uses)
+    bool fused = false;           // dtx_set_fused: K1 does the row reductions itself, DS is never written
+    bool last_fused = false;      // the last run had no dense DS
+    bool d_lta_acc_zeroed = false;
     DevBuf<Candidate> d_cand;
     int cand_cap = 1 << 20;
     // K1 timing: one CUDA event pair per run, kept until dtx_k1_ms_history collects them
@@ -516,9 +520,16 @@ int dtx_attach_device_chunks(dtx_ctx* ctx, int nchunks, const void* dev_base, co
     return DTX_OK;
 }
 
-// K0 + (K1 | fp64 direct) on the loaded chunks; leaves DS in ctx->d_DS.
+// what K1's fused epilogue (MODE 2) needs from dtx_detect_run
+struct FusedArgs {
+    double hist_lo, hist_hi;
+    int want_fas, row_base;
+};
+
+// K0 + (K1 | fp64 direct) on the loaded chunks; leaves DS in ctx->d_DS (unless `fused`: then K1 itself
+// produces rowmax / flags / histograms / candidates / FAS sums and no DS exists).
 static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mode, int keep_ds64,
-                       const int* blk_hi, int hi_only = 0) {
+                       const int* blk_hi, int hi_only = 0, const FusedArgs* fused = nullptr) {
     const BasisLayout& lay = bs.lay;
     const int Nc = lay.Nc, n = lay.n, ns = lay.ns, S = lay.S;
     const int Kc = round_up(ns + 7, CHUNK_TAPS);
@@ -643,8 +654,9 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     DTX_CUDA(ctx->d_xsplit.reserve(sig));
     DTX_CUDA(ctx->d_mu.reserve(nrm));
     DTX_CUDA(ctx->d_invE.reserve(nrm));
-    DTX_CUDA(ctx->d_DS.reserve(ds));
+    if (!fused) DTX_CUDA(ctx->d_DS.reserve(ds));
     if (keep_ds64) DTX_CUDA(ctx->d_DS64.reserve(ds));
+    DTX_CUDA(ctx->d_chunk_bad.reserve(nchunks));
     DTX_CUDA(ctx->d_scale.reserve(nchunks));
     DTX_CUDA(ctx->d_sum.reserve(nchunks));
     DTX_CUDA(ctx->d_maxbits.reserve(nchunks));
@@ -687,7 +699,7 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     }
     launch_k0(ctx->d_raw, f32, ctx->d_chunks.p, nchunks, Nc, n, max_Lpad, max_ntiles, ctx->d_sum.p,
               ctx->d_maxbits.p, ctx->d_scale.p, ctx->d_xsplit.p, ctx->d_mu.p, ctx->d_invE.p, k0_policy, k4_limit,
-              ctx->d_k4bits.p, ctx->d_chunk_mode.p, mode == 0 ? ctx->d_zeroE.p : nullptr, st);
+              ctx->d_k4bits.p, ctx->d_chunk_mode.p, mode == 0 ? ctx->d_zeroE.p : nullptr, ctx->d_chunk_bad.p, st);
     DTX_CUDA(cudaGetLastError());
     if (engine != DTX_ENGINE_FP64 && !keep_ds64) mark_raw_access(ctx);   // K1 works on the split planes only
     ctx->launches += 3;  // k0_stats, k0_split, k0_norm
@@ -703,6 +715,20 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         a.binfo = bs.d_binfo.p; a.DS = ctx->d_DS.p; a.nitems = ctx->n_items;
         a.kblk = kblk; a.num_sms = ctx->num_sms; a.nq = nq; a.mode = mode;
         a.hi_only = hi_only;
+        a.fused = fused ? 1 : 0;
+        a.thr = bs.d_thr.p; a.rowmax_bits = reinterpret_cast<unsigned*>(ctx->d_rowmax.p); a.rowflags = ctx->d_rowflags.p;
+        a.hist = bs.d_hist.p; a.nbins = ctx->hist_bins; a.cand = ctx->d_cand.p; a.cand_cap = ctx->cand_cap;
+        a.ncand = ctx->d_ncand.p; a.chunk_bad = ctx->d_chunk_bad.p; a.S = S;
+        a.hist_lo = 0.0; a.hist_hi = 1.0; a.fas = nullptr; a.row_base = 0;
+        if (fused) {
+            a.DS = nullptr;
+            a.hist_lo = fused->hist_lo; a.hist_hi = fused->hist_hi; a.row_base = fused->row_base;
+            a.fas = fused->want_fas ? bs.d_fas.p : nullptr;
+            // the epilogue raises maxima / flags with atomics: start the rows of this batch from zero
+            const size_t rows = static_cast<size_t>(nchunks) * S;
+            DTX_CUDA(cudaMemsetAsync(ctx->d_rowmax.p + fused->row_base, 0, sizeof(float) * rows, st));
+            DTX_CUDA(cudaMemsetAsync(ctx->d_rowflags.p + fused->row_base, 0, sizeof(int) * rows, st));
+        }
         if (!ctx->accumulate && mode == 0) ctx->k1_used = 0;   // only the last run's pair is kept (CCX keeps its batches')
         if (ctx->k1_used >= ctx->k1_events.size()) {
             cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -738,7 +764,12 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     }
     DTX_CUDA(cudaGetLastError());
     if (engine == DTX_ENGINE_FP64 || keep_ds64) mark_raw_access(ctx);    // the float64 kernel reads the raw chunks
-    if (mode == 0) {   // zero-energy windows: DS = +inf in every subspace row (reference: x/0, detect.py:577)
+    if (fused) {       // rows of chunks with non-finite samples: MaxDS = NaN, flag bit 0
+        launch_fused_bad_rows(ctx->d_chunk_bad.p, nchunks, S, fused->row_base, reinterpret_cast<unsigned*>(ctx->d_rowmax.p),
+                              ctx->d_rowflags.p, st);
+        ctx->launches += 1;
+        DTX_CUDA(cudaGetLastError());
+    } else if (mode == 0) {   // zero-energy windows: DS = +inf in every subspace row (reference: x/0, detect.py:577)
         launch_zero_energy_fix(ctx->d_chunks.p, nchunks, max_ntiles, S, ctx->d_invE.p, ctx->d_zeroE.p, ctx->d_DS.p,
                                ctx->have_ds64 ? ctx->d_DS64.p : nullptr, st);
         ctx->launches += 1;
@@ -758,7 +789,10 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
     if (engine != DTX_ENGINE_TCGEN05 && engine != DTX_ENGINE_FP64 && engine != DTX_ENGINE_TCGEN05_X8 &&
         engine != DTX_ENGINE_TCGEN05_AUTO)
         return fail(ctx, DTX_ERR_ARG, "bad engine");
-    if (kblk == 0) kblk = 2;  // default: drain every 128 taps (bias <= ~2e-6 at DS = 1)
+    // default: drain every 192 taps (36 MMAs per TMEM accumulation).  Same-box A/B (profiles/r02_kblk_ab.md):
+    // kblk 2 / 3 / 4 = 5.995e9 / 6.118e9 / 6.151e9 ts/s with max |DS - float64| 1.5e-6 / 2.4e-6 / 3.4e-6 on
+    // a planted chunk (DS = 0.97); 3 keeps a 4x margin to the 1e-5 tolerance.
+    if (kblk == 0) kblk = 3;
     if (kblk < 1 || kblk > 64) return fail(ctx, DTX_ERR_ARG, "kblk out of range");
     BasisSet& bs = it->second;
     const int S = bs.lay.S;
@@ -770,11 +804,42 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
         DTX_CUDA(ctx->d_rowmax.reserve(static_cast<size_t>(ctx->acc_capacity) * S));   // no-ops once sized
         DTX_CUDA(ctx->d_rowflags.reserve(static_cast<size_t>(ctx->acc_capacity) * S));
     }
-    const int rc = project_run(ctx, bs, engine, kblk, 0, keep_ds64, nullptr);
+    const int row_base = ctx->accumulate ? static_cast<int>(ctx->acc_chunks * S) : 0;
+    // fused mode: tensor-core engines, subspaces of rank <= 16 (the pieces of larger ones must be summed
+    // before anything can be counted), no float64 copy requested
+    const bool fused = ctx->fused && engine != DTX_ENGINE_FP64 && !keep_ds64 && !bs.has_split;
+    FusedArgs fa{hist_lo, hist_hi, want_fas, row_base};
+    if (fused && !ctx->accumulate) {
+        DTX_CUDA(ctx->d_rowmax.reserve(static_cast<size_t>(ctx->nchunks) * S));
+        DTX_CUDA(ctx->d_rowflags.reserve(static_cast<size_t>(ctx->nchunks) * S));
+    }
+    const int rc = project_run(ctx, bs, engine, kblk, 0, keep_ds64, nullptr, 0, fused ? &fa : nullptr);
     if (rc != DTX_OK) return rc;
     const int nchunks = ctx->nchunks;
-    const int row_base = ctx->accumulate ? static_cast<int>(ctx->acc_chunks * S) : 0;
     cudaStream_t st = ctx->stream;
+    ctx->last_fused = fused;
+    if (fused) {
+        if (bs.has_thr && lta_window > 0) {
+            // DS_STALTA of the candidates: the statistic around each from the float64 closed form
+            if (lta_window > 65536) return fail(ctx, DTX_ERR_ARG, "dtx_detect_run: LTA window too long for the fused mode");
+            DTX_CUDA(ctx->d_lta_acc.reserve(2 * static_cast<size_t>(ctx->cand_cap)));
+            if (!ctx->d_lta_acc_zeroed) {
+                DTX_CUDA(cudaMemsetAsync(ctx->d_lta_acc.p, 0, sizeof(double) * 2 * ctx->cand_cap, st));
+                ctx->d_lta_acc_zeroed = true;
+            }
+            launch_lta_direct(ctx->d_raw, ctx->dtype == DTX_F32, ctx->d_chunks.p, ctx->d_sum.p, bs.d_U.p, bs.d_rank_off.p,
+                              bs.lay.n, bs.lay.Nc, S, ctx->d_cand.p, ctx->d_ncand.p, ctx->d_ncand.p + 1, ctx->cand_cap,
+                              row_base, lta_window, ctx->sta_window, ctx->d_lta_acc.p, st);
+            DTX_CUDA(cudaGetLastError());
+            mark_raw_access(ctx);       // reads the raw chunks
+            ctx->launches += 2;
+        }
+        if (ctx->accumulate) ctx->acc_chunks += nchunks;
+        ctx->run_set = set_id;
+        ctx->run_S = S;
+        ctx->ran = true;
+        return DTX_OK;
+    }
     launch_k3(ctx->d_DS.p, ctx->d_chunks.p, nchunks, S, bs.d_thr.p, ctx->d_rowmax.p, ctx->d_rowflags.p,
               bs.d_hist.p, hist_lo, hist_hi, ctx->hist_bins, ctx->d_cand.p, ctx->cand_cap, ctx->d_ncand.p,
               want_fas ? bs.d_fas.p : nullptr, row_base, st);
@@ -819,6 +884,12 @@ int dtx_accumulate_end(dtx_ctx* ctx) {
     return DTX_OK;
 }
 
+int dtx_set_fused(dtx_ctx* ctx, int on) {
+    if (!ctx) return DTX_ERR_ARG;
+    ctx->fused = on != 0;
+    return DTX_OK;
+}
+
 int dtx_set_x8_tolerance(dtx_ctx* ctx, double eps) {
     if (!ctx) return DTX_ERR_ARG;
     if (!(eps >= 0.0) || !std::isfinite(eps)) return fail(ctx, DTX_ERR_ARG, "dtx_set_x8_tolerance: eps must be >= 0");
@@ -847,6 +918,7 @@ int dtx_get_ds(dtx_ctx* ctx, int chunk, int subspace, float* out, int64_t count)
     if (!ctx || !out) return DTX_ERR_ARG;
     if (!ctx->ran || chunk < 0 || chunk >= ctx->nchunks || subspace < 0 || subspace >= ctx->run_S)
         return fail(ctx, DTX_ERR_STATE, "dtx_get_ds: no run / bad index");
+    if (ctx->last_fused) return fail(ctx, DTX_ERR_STATE, "dtx_get_ds: the last run was fused (dtx_set_fused): no dense DS exists");
     const ChunkDesc& cd = ctx->h_chunks[chunk];
     if (count < cd.T) return fail(ctx, DTX_ERR_CAPACITY, "dtx_get_ds: buffer smaller than T");
     DTX_CUDA(cudaSetDevice(ctx->device));
@@ -881,6 +953,7 @@ int dtx_get_stalta(dtx_ctx* ctx, int chunk, int subspace, int W, float* out, int
     if (!ctx || !out) return DTX_ERR_ARG;
     if (!ctx->ran || chunk < 0 || chunk >= ctx->nchunks || subspace < 0 || subspace >= ctx->run_S || W < 1)
         return fail(ctx, DTX_ERR_STATE, "dtx_get_stalta: no run / bad index");
+    if (ctx->last_fused) return fail(ctx, DTX_ERR_STATE, "dtx_get_stalta: the last run was fused (dtx_set_fused): no dense DS exists");
     const ChunkDesc& cd = ctx->h_chunks[chunk];
     if (count < cd.T) return fail(ctx, DTX_ERR_CAPACITY, "dtx_get_stalta: buffer smaller than T");
     DTX_CUDA(cudaSetDevice(ctx->device));

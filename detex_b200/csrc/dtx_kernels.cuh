@@ -73,6 +73,27 @@ struct BasisLayout {
     Seg seg[MAX_SEGS];
 };
 
+// Histogram bin of np.histogram(x, bins=np.linspace(lo, hi, nb + 1)) from a float32 pre-binning: the
+// exact float64 edge comparison is only needed when the value sits within 1e-3 of a bin edge (float32
+// rounding of (x - lo) * nb / (hi - lo) is ~1e-5 of a bin).  Near edge e = round(t) the value lies
+// strictly between edges e-1 and e+1, so the bin is e or e-1 by ONE float64 comparison against
+// lo + e*step -- no float64 division.  -1 = outside [lo, hi] (or NaN).  Used by K3 and by K1's fused
+// epilogue, so both produce the same counts.
+__device__ __forceinline__ int hist_bin_fast(float x, float flo, float finv, double lo, double hi, double step,
+                                             int nb) {
+    const float t = (x - flo) * finv;
+    const float fl = floorf(t);
+    const float fr = t - fl;
+    if (fr > 1e-3f && fr < 0.999f && t > 0.f && t < static_cast<float>(nb)) return static_cast<int>(fl);
+    const float r = rintf(t);
+    if (!(r >= 0.f) || r > static_cast<float>(nb)) return -1;   // outside by more than half a bin
+    const int e = static_cast<int>(r);
+    const double xd = static_cast<double>(x);
+    if (e == 0) return xd >= lo ? 0 : -1;
+    if (e == nb) return xd <= hi ? nb - 1 : -1;
+    return xd >= lo + e * step ? e : e - 1;
+}
+
 // ------------------------------------------------------------------ launchers
 // k0_prep.cu
 // d_zeroE (may be null): per chunk, set to 1 when a window's energy is zero within round-off; such
@@ -81,7 +102,7 @@ struct BasisLayout {
 void launch_k0(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nchunks, int Nc, int n,
                int max_Lpad, int max_ntiles, double* d_sum, unsigned* d_maxbits, float* d_scale,
                __half* d_xsplit, float* d_mu, float* d_invE, int x8_policy, float k4_limit,
-               unsigned* d_k4bits, int* d_chunk_mode, int* d_zeroE, cudaStream_t st);
+               unsigned* d_k4bits, int* d_chunk_mode, int* d_zeroE, int* d_chunk_bad, cudaStream_t st);
 // DS[s][t] = +inf for every subspace row at the lags whose window energy is zero (invE = +inf), for
 // the chunks k0_norm flagged.  nrows = DS rows per chunk.  DS64 may be null.
 void launch_zero_energy_fix(const ChunkDesc* d_chunks, int nchunks, int max_ntiles, int nrows, const float* d_invE,
@@ -98,6 +119,14 @@ void launch_sum_pieces(const ChunkDesc* d_chunks, int nchunks, int max_Tpad, con
 void launch_basis_row_stats(const double* d_U, int R, int n, double* d_out, cudaStream_t st);
 void launch_basis_image(const double* d_U, const int* d_slot_row, const BasisLayout& lay,
                         uint8_t* d_Aimg, int x8, cudaStream_t st);
+
+// one candidate trigger (K3 / K1's fused epilogue -> launch_lta -> host)
+struct Candidate {
+    int row;     // chunk * S + subspace
+    int t;       // lag index
+    float ds;    // detection statistic
+    float lta;   // denominator of DS_STALTA: |ds| / lta = STA / LTA at t (filled by launch_lta)
+};
 
 // k1_project.cu : tcgen05 Hankel projection + normalisation -> DS
 struct K1Args {
@@ -118,6 +147,22 @@ struct K1Args {
     int num_sms;
     int nq;        // MMA N: 256 (tiles of 2048 lags) or 128 (tiles of 1024 lags)
     int mode;      // 0 = detection statistic, 1 = signed correlation coefficient (CCX)
+    // fused epilogue (MODE 2): the per-row reductions of K3 run on the statistic while it is still in
+    // registers and DS is never written.  Same outputs as launch_k3.
+    int fused;                       // 1 = MODE 2
+    const float* thr;                // [S] thresholds (INFINITY = none)
+    unsigned* rowmax_bits;           // [rows] float bits, zeroed before the launch (DS >= 0: uint order == float order)
+    int* rowflags;                   // [rows], zeroed before the launch; bit 1 = zero-energy windows counted as 0
+    unsigned long long* hist;        // [S][HIST_MAX_BINS]
+    double hist_lo, hist_hi;
+    int nbins;
+    Candidate* cand;
+    int cand_cap;
+    int* ncand;
+    double* fas;                     // [S][5] or null
+    int row_base;                    // rows of this batch start here (accumulation over batches)
+    const int* chunk_bad;            // [chunks] 1 = non-finite samples: every row of the chunk is NaN
+    int S;                           // subspaces (rows per chunk)
     int hi_only;   // 1 = ONE MMA per K step (fp16 hi * hi only, 11-bit operands): a screening series whose
                    // error is bounded by ~2^-10 of the normalised value; CCX uses it to LOCATE the maximum,
                    // which is then re-scored in float64 (k4_ccx.cu)
@@ -130,13 +175,15 @@ void launch_direct(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, in
                    const double* d_U, const int* d_rank_off, int S, int n, int Nc, int maxT,
                    const double* d_sum, float* d_DS, double* d_DS64, cudaStream_t st);
 
+// fused mode (K1 MODE 2): LTA windows of the candidates from the float64 closed form, NaN rows of bad chunks
+void launch_lta_direct(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, const double* d_sum, const double* d_U,
+                       const int* d_rank_off, int n, int Nc, int S, Candidate* d_cand, const int* d_ncand,
+                       const int* d_ncand_before, int cand_cap, int row_base, int W, int Wsta, double* d_acc2,
+                       cudaStream_t st);
+void launch_fused_bad_rows(const int* d_chunk_bad, int nchunks, int S, int row_base, unsigned* d_rowmax_bits,
+                           int* d_rowflags, cudaStream_t st);
+
 // k3_post.cu : per (chunk, subspace) row -> max, histogram, candidates
-struct Candidate {
-    int row;     // chunk * S + subspace
-    int t;       // lag index
-    float ds;    // detection statistic
-    float lta;   // denominator of DS_STALTA: |ds| / lta = STA / LTA at t (filled by launch_lta)
-};
 // row_base: candidate rows and the rowmax / rowflags entries of this batch start at row_base
 // (= chunks of earlier batches * S when results accumulate over the batches of a station)
 void launch_k3(const float* DS, const ChunkDesc* d_chunks, int nchunks, int S, const float* d_thr,

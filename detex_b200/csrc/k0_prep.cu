@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(256)
 k0_split(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
          const double* __restrict__ sum, const unsigned* __restrict__ maxbits,
          float* __restrict__ scale_out, __half* __restrict__ xsplit, int Nc, int x8_policy,
-         float k4_limit, const unsigned* __restrict__ k4bits, int* __restrict__ chunk_mode) {
+         float k4_limit, const unsigned* __restrict__ k4bits, int* __restrict__ chunk_mode,
+         int* __restrict__ chunk_bad) {
     const ChunkDesc cd = chunks[blockIdx.y];
     // precision mode of this chunk ("8-bit cross terms"): off, forced, or chosen from the
     // worst window kurtosis K4 = sum (x - chunk mean)^4 / ||w - window mean||^4 that k0_norm found
@@ -76,7 +77,12 @@ k0_split(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
     if (blockIdx.x == 0 && threadIdx.x == 0) chunk_mode[blockIdx.y] = x8 ? 1 : 0;
     const double mean = sum[blockIdx.y] / static_cast<double>(cd.L);
     const int ex = scale_exp(__uint_as_float(maxbits[blockIdx.y]), mean);
-    if (blockIdx.x == 0 && threadIdx.x == 0) scale_out[blockIdx.y] = exp2f(static_cast<float>(-ex));
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scale_out[blockIdx.y] = exp2f(static_cast<float>(-ex));
+        // a NaN / inf sample makes the chunk's sum non-finite: every statistic of the chunk is NaN in the
+        // reference (FFT of the whole chunk) and every row is dropped here (K3: has_nan; fused: this flag)
+        if (chunk_bad) chunk_bad[blockIdx.y] = isfinite(mean) ? 0 : 1;
+    }
     const T* x = raw + cd.raw_off;
     __half* out = xsplit + cd.sig_off;
     const long long total = static_cast<long long>(Nc) * cd.Lpad;
@@ -255,7 +261,7 @@ k0_norm(const T* __restrict__ raw, const ChunkDesc* __restrict__ chunks,
 void launch_k0(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nchunks, int Nc, int n,
                int max_Lpad, int max_ntiles, double* d_sum, unsigned* d_maxbits, float* d_scale,
                __half* d_xsplit, float* d_mu, float* d_invE, int x8_policy, float k4_limit,
-               unsigned* d_k4bits, int* d_chunk_mode, int* d_zeroE, cudaStream_t st) {
+               unsigned* d_k4bits, int* d_chunk_mode, int* d_zeroE, int* d_chunk_bad, cudaStream_t st) {
     cudaMemsetAsync(d_sum, 0, sizeof(double) * nchunks, st);
     if (d_zeroE) cudaMemsetAsync(d_zeroE, 0, sizeof(int) * nchunks, st);
     cudaMemsetAsync(d_maxbits, 0, sizeof(unsigned) * nchunks, st);
@@ -273,13 +279,13 @@ void launch_k0(const void* raw, int dtype_f32, const ChunkDesc* d_chunks, int nc
         k0_stats<float><<<g1, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits);
         k0_norm<float><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n, k4, d_maxbits, d_zeroE, ratio_mode);
         k0_split<float><<<g2, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits, d_scale, d_xsplit, Nc, x8_policy,
-                                            k4_limit, d_k4bits, d_chunk_mode);
+                                            k4_limit, d_k4bits, d_chunk_mode, d_chunk_bad);
     } else {
         const double* r = static_cast<const double*>(raw);
         k0_stats<double><<<g1, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits);
         k0_norm<double><<<g3, 256, 0, st>>>(r, d_chunks, d_sum, d_mu, d_invE, Nc, n, k4, d_maxbits, d_zeroE, ratio_mode);
         k0_split<double><<<g2, 256, 0, st>>>(r, d_chunks, d_sum, d_maxbits, d_scale, d_xsplit, Nc, x8_policy,
-                                             k4_limit, d_k4bits, d_chunk_mode);
+                                             k4_limit, d_k4bits, d_chunk_mode, d_chunk_bad);
     }
 }
 

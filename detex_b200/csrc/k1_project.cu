@@ -67,6 +67,15 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * SIG_BUF_BYTES + 2 * NORM_B
 // UBLKCP in an ELECT loop, ~128 cycles per MMA, i.e. the issuer paces the tensor pipe).  Same-box
 // A/B (experiments/gpu_round1k.sh, profiles/r01_issue_ab.md): converged is +0.8 % with 3 MMAs per
 // K step and +2.2 % with the 8-bit cross terms, where the pipe is not saturated.
+// Drain warps add each TMEM partial sum to their register accumulators with packed fp32x2 additions
+// (FADD2: 64 instead of 128 instructions per drain; same round-to-nearest results).  1 = on.
+#ifndef DTX_FADD2
+#define DTX_FADD2 1
+#endif
+// Software-pipelined drain (needs DTX_FADD2): 1 = on.
+#ifndef DTX_DRAIN_PIPE
+#define DTX_DRAIN_PIPE 0
+#endif
 // A-operand collector reuse between the hi*hi and hi*lo MMAs of a K step (1 = on).
 #ifndef DTX_COLLECTOR_A
 #define DTX_COLLECTOR_A 1
@@ -342,7 +351,17 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
     const int kl = lane >> 1;                    // basis-vector slot of this thread's row
     const uint32_t taddr0 = tmem + (static_cast<uint32_t>(lq * 32) << 16) + colhalf * NCOL;
     Ring ac(2), nm(2);
+#if DTX_FADD2
+    unsigned long long sums2[NCOL / 2];
+#define SUM_AT(idx) f32x2_get(sums2[(idx) >> 1], (idx) & 1)
+#else
     float sums[NCOL];
+#define SUM_AT(idx) sums[idx]
+#endif
+    const double f_step = MODE == 2 ? (P.a.hist_hi - P.a.hist_lo) / P.a.nbins : 0.0;
+    const float f_flo = static_cast<float>(P.a.hist_lo);
+    const float f_finv = MODE == 2 ? static_cast<float>(P.a.nbins / (P.a.hist_hi - P.a.hist_lo)) : 0.f;
+    const float f_toff = -f_flo * f_finv;
     for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
         const int4 it = P.a.items[item];
         const ChunkDesc cd = P.a.chunks[it.x];
@@ -354,12 +373,38 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
         const float* sie = smu + TILE_T;
         {
             const int b = it.z;
+#if DTX_FADD2
+#pragma unroll
+            for (int i = 0; i < NCOL / 2; ++i) sums2[i] = 0ull;
+#else
 #pragma unroll
             for (int i = 0; i < NCOL; ++i) sums[i] = 0.f;
+#endif
             for (int dr = 0; dr < ndrains; ++dr) {
                 mbar_wait(&S.accfull[ac.idx], ac.phase);
                 tc_fence_after();
                 const uint32_t ta = taddr0 + ac.idx * 256;
+#if DTX_DRAIN_PIPE
+                // two 32-column loads in flight: the additions of one overlap the TMEM read of the next
+                uint32_t va[32], vb[32];
+                tmem_ld_x32(ta, va);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < NCOL / 32; ++i) {
+                    uint32_t(&v)[32] = (i & 1) ? vb : va;
+                    uint32_t(&vn)[32] = (i & 1) ? va : vb;
+                    if (i + 1 < NCOL / 32) tmem_ld_x32(ta + (i + 1) * 32, vn);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        sums2[i * 16 + j] = f32x2_add(sums2[i * 16 + j], f32x2_pack(v[2 * j], v[2 * j + 1]));
+                    if (i + 1 < NCOL / 32) tmem_wait_ld();
+                    if (i == NCOL / 32 - 2) {     // the last load has landed: the accumulator is free
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&S.accempty[ac.idx]);
+                    }
+                }
+#else
 #pragma unroll
                 for (int i = 0; i < NCOL / 32; ++i) {
                     uint32_t v[32];
@@ -370,9 +415,16 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&S.accempty[ac.idx]);
                     }
+#if DTX_FADD2
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        sums2[i * 16 + j] = f32x2_add(sums2[i * 16 + j], f32x2_pack(v[2 * j], v[2 * j + 1]));
+#else
 #pragma unroll
                     for (int j = 0; j < 32; ++j) sums[i * 32 + j] += __uint_as_float(v[j]);
+#endif
                 }
+#endif
                 ac.advance();
             }
             // ---------------------------------------------------- K2 epilogue
@@ -391,6 +443,20 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
             BlockInfo hb[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) hb[k] = P.a.binfo[b * VEC_PER_BLOCK + lq + 4 * k];
+            // MODE 2 (fused K3): per-role running maximum, histogram run, FAS partial sums of this item
+            float f_thr[4], f_max[4], f_s1[4], f_s2[4], f_s3[4], f_s4[4];
+            int f_cur[4], f_cnt[4], f_n[4];
+            unsigned f_zero = 0;
+            const bool f_skip = MODE == 2 && P.a.chunk_bad[it.x] != 0;   // non-finite samples: rows are NaN, nothing counted
+            if (MODE == 2) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool on = hb[k].nrows != 0 && hb[k].out_row >= 0;
+                    f_thr[k] = on ? P.a.thr[hb[k].out_row] : INFINITY;
+                    f_max[k] = 0.f; f_cur[k] = -1; f_cnt[k] = 0; f_n[k] = 0;
+                    f_s1[k] = f_s2[k] = f_s3[k] = f_s4[k] = 0.f;
+                }
+            }
 #pragma unroll
             for (int c = 0; c < NCOL / EPI_QC; ++c) {
 #pragma unroll
@@ -400,8 +466,8 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int j = 4 * j4 + jj;
-                        const float cc = fmaf(sums[c * EPI_QC + j], sc, mm[jj] * nsumU);
-                        wr[8 * j] = MODE == 0 ? cc * cc : cc;
+                        const float cc = fmaf(SUM_AT(c * EPI_QC + j), sc, mm[jj] * nsumU);
+                        wr[8 * j] = MODE != 1 ? cc * cc : cc;
                     }
                 }
                 named_bar_sync(1 + colhalf, 128);
@@ -423,12 +489,109 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
                         else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
                     }
                     acc.x *= ie.x; acc.y *= ie.y; acc.z *= ie.z; acc.w *= ie.w;
-                    float* dst = dsbase + static_cast<long long>(hb[k].out_row) * cd.Tpad + c * EPI_LAGS;
-                    // (pieces of a rank > 16 subspace have rows of their own: launch_sum_pieces adds them
-                    // up in a fixed order afterwards, so DS does not depend on CTA timing)
-                    store_ds_row(dst, acc);
+                    if (MODE == 2) {
+                        // the statistic of 4 consecutive lags of one subspace, never written: maximum,
+                        // histogram (run-length: noise sits in one bin), candidates, FAS sums -- exactly
+                        // what k3_fast_kernel does with the stored row
+                        if (!f_skip) {
+                            const int t0 = it.y * TT + 8 * NCOL * colhalf + c * EPI_LAGS + lane * 4;
+                            const float vv[4] = {acc.x, acc.y, acc.z, acc.w};
+                            const float iv[4] = {ie.x, ie.y, ie.z, ie.w};
+                            // four values at once, branch free (the quad path of k3_fast_kernel): all four core
+                            // lags, finite energy, well inside the bin of the current run, below the threshold
+                            const float curf = static_cast<float>(f_cur[k]);
+                            const float q0 = fmaf(acc.x, f_finv, f_toff), q1 = fmaf(acc.y, f_finv, f_toff),
+                                        q2 = fmaf(acc.z, f_finv, f_toff), q3 = fmaf(acc.w, f_finv, f_toff);
+                            const float g0 = floorf(q0), g1 = floorf(q1), g2 = floorf(q2), g3 = floorf(q3);
+                            const bool inside = fabsf(q0 - g0 - 0.5f) < 0.499f && fabsf(q1 - g1 - 0.5f) < 0.499f &&
+                                                fabsf(q2 - g2 - 0.5f) < 0.499f && fabsf(q3 - g3 - 0.5f) < 0.499f;
+                            const bool same = f_cur[k] >= 0 && g0 == curf && g1 == curf && g2 == curf && g3 == curf;
+                            const float m4 = fmaxf(fmaxf(acc.x, acc.y), fmaxf(acc.z, acc.w));
+                            const float e4 = fmaxf(fmaxf(ie.x, ie.y), fmaxf(ie.z, ie.w));
+                            if (inside && same && m4 < f_thr[k] && e4 < INFINITY && t0 >= cd.t_lo && t0 + 3 < cd.t_hi &&
+                                !P.a.fas) {
+                                f_cnt[k] += 4;
+                                f_max[k] = fmaxf(f_max[k], m4);
+                            } else
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int t = t0 + e;
+                                if (t < cd.t_lo || t >= cd.t_hi) continue;
+                                float v = vv[e];
+                                if (isinf(iv[e])) {      // zero-energy window: the reference's inf, zeroed (detect.py:275-281)
+                                    v = 0.f;
+                                    f_zero |= 1u << k;
+                                }
+                                f_max[k] = fmaxf(f_max[k], v);
+                                const int bin = hist_bin_fast(v, f_flo, f_finv, P.a.hist_lo, P.a.hist_hi, f_step, P.a.nbins);
+                                if (bin == f_cur[k]) ++f_cnt[k];
+                                else {
+                                    if (f_cnt[k] > 0 && f_cur[k] >= 0)
+                                        atomicAdd(&P.a.hist[static_cast<long long>(hb[k].out_row) * HIST_MAX_BINS + f_cur[k]],
+                                                  static_cast<unsigned long long>(f_cnt[k]));
+                                    f_cur[k] = bin;
+                                    f_cnt[k] = 1;
+                                }
+                                if (v >= f_thr[k]) {
+                                    const int q = atomicAdd(P.a.ncand, 1);
+                                    if (q < P.a.cand_cap) {
+                                        Candidate cnd;
+                                        cnd.row = P.a.row_base + it.x * P.a.S + hb[k].out_row;
+                                        cnd.t = t; cnd.ds = v; cnd.lta = 0.f;
+                                        P.a.cand[q] = cnd;
+                                    }
+                                }
+                                if (P.a.fas) {
+                                    f_s1[k] += v;
+                                    f_s2[k] = fmaf(v, v, f_s2[k]);
+                                    f_s3[k] += logf(fmaxf(v, 1e-30f));
+                                    f_s4[k] += log1pf(-fminf(v, 0.99999994f));
+                                    ++f_n[k];
+                                }
+                            }
+                        }
+                    } else {
+                        float* dst = dsbase + static_cast<long long>(hb[k].out_row) * cd.Tpad + c * EPI_LAGS;
+                        // (pieces of a rank > 16 subspace have rows of their own: launch_sum_pieces adds them
+                        // up in a fixed order afterwards, so DS does not depend on CTA timing)
+                        store_ds_row(dst, acc);
+                    }
                 }
                 named_bar_sync(1 + colhalf, 128);
+            }
+            if (MODE == 2 && !f_skip) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (hb[k].nrows == 0 || hb[k].out_row < 0) continue;   // warp-uniform
+                    const int orow = hb[k].out_row;
+                    const int row = P.a.row_base + it.x * P.a.S + orow;
+                    float m = f_max[k];
+                    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    if (lane == 0 && m > 0.f) atomicMax(&P.a.rowmax_bits[row], __float_as_uint(m));
+                    if (__any_sync(0xffffffffu, (f_zero >> k) & 1u) && lane == 0) atomicOr(&P.a.rowflags[row], 2);
+                    // histogram runs: one atomic per distinct bin of the warp
+                    const int cur = f_cnt[k] > 0 ? f_cur[k] : -1;
+                    const unsigned grp = __match_any_sync(0xffffffffu, cur);
+                    const int tot = __reduce_add_sync(grp, f_cnt[k]);
+                    if (cur >= 0 && lane == __ffs(grp) - 1)
+                        atomicAdd(&P.a.hist[static_cast<long long>(orow) * HIST_MAX_BINS + cur],
+                                  static_cast<unsigned long long>(tot));
+                    if (P.a.fas) {
+                        double d1 = f_s1[k], d2 = f_s2[k], d3 = f_s3[k], d4 = f_s4[k], dn = f_n[k];
+                        for (int o = 16; o > 0; o >>= 1) {
+                            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                            d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+                            d3 += __shfl_xor_sync(0xffffffffu, d3, o);
+                            d4 += __shfl_xor_sync(0xffffffffu, d4, o);
+                            dn += __shfl_xor_sync(0xffffffffu, dn, o);
+                        }
+                        if (lane == 0) {
+                            double* f = P.a.fas + orow * 5;
+                            atomicAdd(f, dn); atomicAdd(f + 1, d1); atomicAdd(f + 2, d2);
+                            atomicAdd(f + 3, d3); atomicAdd(f + 4, d4);
+                        }
+                    }
+                }
             }
         }
         __syncwarp();
@@ -608,9 +771,11 @@ void launch_k1(const K1Args& a, const BasisLayout& lay, cudaStream_t st) {
     if (grid < 1) return;
     if (a.nq == 128) {
         if (a.mode == 1) launch_k1_t<128, 1>(P, grid, st);
+        else if (a.fused) launch_k1_t<128, 2>(P, grid, st);
         else launch_k1_t<128, 0>(P, grid, st);
     } else {
         if (a.mode == 1) launch_k1_t<256, 1>(P, grid, st);
+        else if (a.fused) launch_k1_t<256, 2>(P, grid, st);
         else launch_k1_t<256, 0>(P, grid, st);
     }
 }

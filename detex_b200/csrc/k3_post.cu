@@ -36,27 +36,6 @@ __device__ __forceinline__ int hist_bin(float xf, double lo, double hi, double s
     return i;
 }
 
-// Float32 pre-binning: the exact float64 edge comparison is only needed when the value sits
-// within 1e-3 of a bin edge (float32 rounding of (x - lo) * 400 is ~1e-5 of a bin).  Near edge
-// e = round(t) the value lies strictly between edges e-1 and e+1, so the bin is e or e-1 by ONE
-// float64 comparison against the same `lo + e*step` hist_bin uses -- no float64 division.  (Noise
-// DS of a rank-1 subspace is below 1e-3 of a bin 12 % of the time; with the generic fallback
-// nearly every warp took the division path.)
-__device__ __forceinline__ int hist_bin_fast(float x, float flo, float finv, double lo, double hi, double step,
-                                             int nb) {
-    const float t = (x - flo) * finv;
-    const float fl = floorf(t);
-    const float fr = t - fl;
-    if (fr > 1e-3f && fr < 0.999f && t > 0.f && t < static_cast<float>(nb)) return static_cast<int>(fl);
-    const float r = rintf(t);
-    if (!(r >= 0.f) || r > static_cast<float>(nb)) return -1;   // outside by more than half a bin
-    const int e = static_cast<int>(r);
-    const double xd = static_cast<double>(x);
-    if (e == 0) return xd >= lo ? 0 : -1;
-    if (e == nb) return xd <= hi ? nb - 1 : -1;
-    return xd >= lo + e * step ? e : e - 1;
-}
-
 constexpr int K3_THREADS = 256;
 
 __global__ void __launch_bounds__(K3_THREADS)

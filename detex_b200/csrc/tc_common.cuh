@@ -193,6 +193,23 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+// Packed fp32 pair arithmetic (sm_100: SASS FADD2): two round-to-nearest additions per instruction.
+__device__ __forceinline__ unsigned long long f32x2_pack(uint32_t lo, uint32_t hi) {
+    unsigned long long p;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "r"(lo), "r"(hi));
+    return p;
+}
+__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float f32x2_get(unsigned long long p, int hi) {
+    uint32_t a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(p));
+    return __uint_as_float(hi ? b : a);
+}
+
 // ------------------------------------------------ shared-memory descriptor
 // K-major, no swizzle ("interleave") canonical layout, in 16-byte units:
 //   ((8 rows, n groups), 2 k-cores) : ((1, SBO), LBO)

@@ -181,6 +181,11 @@ class Engine(object):
         """triggerSTATime in samples (detect.py:282-288): 0 = the reference default STA = |DS|."""
         self._check(self._L.dtx_set_trigger_sta(self._h, int(sta_window)))
 
+    def set_fused(self, on=True):
+        """Fused mode: later detect_run calls never write the dense statistic (no get_ds / get_stalta);
+        maxima, histograms, candidates and FAS sums come out of the projection kernel itself."""
+        self._check(self._L.dtx_set_fused(self._h, int(bool(on))))
+
     def set_x8_tolerance(self, eps):
         """Adaptive engine ("tcgen05_auto"): admitted rms error of a normalised projection."""
         self._check(self._L.dtx_set_x8_tolerance(self._h, float(eps)))

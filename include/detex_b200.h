@@ -130,7 +130,7 @@ int dtx_get_chunk(dtx_ctx* ctx, int chunk, double* out, int64_t count, int64_t* 
  * per subspace, candidate compaction against the thresholds, LTA of |DS| over
  * `lta_window` samples at the candidates, and (want_fas) the beta-fit sufficient
  * statistics of fas._initFAS (fas.py:74-84).
- * kblk: 64-tap chunks accumulated in TMEM between drains (0 = default 2). */
+ * kblk: 64-tap chunks accumulated in TMEM between drains (0 = default 3). */
 int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_lo, double hist_hi,
                    int lta_window, int want_fas, int keep_ds64);
 
@@ -146,6 +146,17 @@ int dtx_detect_run(dtx_ctx* ctx, int set_id, int engine, int kblk, double hist_l
  * / dtx_est_mags keep addressing the chunks of the LAST run by their index inside that run. */
 int dtx_accumulate_begin(dtx_ctx* ctx, int64_t total_chunks);
 int dtx_accumulate_end(dtx_ctx* ctx);
+
+/* Fused mode ---------------------------------------------------------------------------------
+ * on != 0: later dtx_detect_run calls with a tensor-core engine (and keep_ds64 == 0, ranks <= 16) never
+ * write the dense detection statistic: MaxDS, flags, histograms, candidates and FAS sums come out of
+ * the projection kernel's own read-out (the reductions of _corDat detect.py:177-190 on values still in
+ * registers), and the LTA windows of the few candidates are re-evaluated from the float64 closed form.
+ * Same MaxDS / histograms / candidate set, bit for bit; the candidates' `lta` differs from the
+ * unfused run's by float rounding (~1e-6 relative).  No DS buffer (18 GB per 48-chunk batch of
+ * configs[3]) is needed, so a whole station fits one batch; dtx_get_ds / dtx_get_stalta report
+ * DTX_ERR_STATE after a fused run. */
+int dtx_set_fused(dtx_ctx* ctx, int on);
 
 /* DTX_ENGINE_TCGEN05_AUTO: admitted rms error of a normalised projection (u.w)/(|u||w|) under the
  * random-rounding model (default 2e-6: the 8-bit terms then add 2 sqrt(DS) eps <= 4e-6 per model
