@@ -638,6 +638,28 @@ def gpu_arm(args):
                                     "sample": "1 chunk x 3 subspaces of rank 1, 2, 3 (same cost per value as 2 "
                                               "rank-3 subspaces), one process: the reference has one subspace to "
                                               "parallelise over here (%.1f s)" % r[1]}
+        # the function-level drop-ins called once per (chunk, subspace) / per pair,
+        # the way the reference's own loops would call them: latency paths, measured so that nobody has to guess
+        from detex_b200 import construct as dconstruct
+        from detex_b200 import detect as ddetect
+        chunk_h = data[0].cpu().numpy()
+        pair = synth.event_families(3003, 1, 2, CCX_NS, NC, max_shift=100)
+        ddetect._MPXDS(chunk_h, 0, U3, None, NC, None, engine=eng)
+        dconstruct._CCX2(None, None, pair[0], pair[1], "ENZ", "ENZ", engine=eng)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ddetect._MPXDS(chunk_h, 0, U3, None, NC, None, engine=eng)
+        t_mpx = (time.perf_counter() - t0) / 5
+        t0 = time.perf_counter()
+        for _ in range(20):
+            dconstruct._CCX2(None, None, pair[0], pair[1], "ENZ", "ENZ", engine=eng)
+        t_ccx = (time.perf_counter() - t0) / 20
+        cfg1["dropin_latency"] = {
+            "_MPXDS_ms_per_call": 1e3 * t_mpx, "_MPXDS_ts_per_s": T_PER_CHUNK / t_mpx,
+            "_CCX2_ms_per_pair": 1e3 * t_ccx,
+            "note": "detect._MPXDS(one 3720 s chunk, one rank-3 subspace) and construct._CCX2(one pair, n = 3000) through "
+                    "the reference's per-call signatures: basis upload + 8.9 MB H2D + K0/K1/K3 + 1.5 MB D2H per call; the "
+                    "batched seams above are what the throughput numbers use"}
         line["cfg1"] = cfg1
 
     # ===================================================================== configs[4]: FAS sweep

@@ -339,6 +339,79 @@ __device__ __forceinline__ void store_ds_row(float* dst, float4 v) {
 #endif
 }
 
+// Fused read-out, per-value path (MODE 2).  Kept OUT of line on purpose: the read-out loop is unrolled 8 x 4
+// times (register-resident accumulators), and with this body inlined at every site the kernel grew to 31 k
+// SASS instructions -- the drain warps then streamed ~400 KB of code per work item through the instruction
+// cache and the fused mode ran 9-14 % slower than writing DS (profiles/r02_fused_epilogue.md).
+struct FusedState {
+    float mx;
+    int cur, cnt, zero;
+    float s1, s2, s3, s4;
+    int n;
+};
+__device__ __noinline__ FusedState fused_values(FusedState st, float4 acc, float4 ie, int t0, int t_lo, int t_hi,
+                                                float thr, int out_row, int row, const K1Args* a, float flo,
+                                                float finv, double step) {
+    {
+        // four values at once, branch free (the quad path of k3_fast_kernel): all four core lags, finite
+        // energy, well inside the bin of the current run, below the threshold
+        const float toff = -flo * finv;
+        const float curf = static_cast<float>(st.cur);
+        const float q0 = fmaf(acc.x, finv, toff), q1 = fmaf(acc.y, finv, toff), q2 = fmaf(acc.z, finv, toff),
+                    q3 = fmaf(acc.w, finv, toff);
+        const float g0 = floorf(q0), g1 = floorf(q1), g2 = floorf(q2), g3 = floorf(q3);
+        const bool inside = fabsf(q0 - g0 - 0.5f) < 0.499f && fabsf(q1 - g1 - 0.5f) < 0.499f &&
+                            fabsf(q2 - g2 - 0.5f) < 0.499f && fabsf(q3 - g3 - 0.5f) < 0.499f;
+        const bool same = st.cur >= 0 && g0 == curf && g1 == curf && g2 == curf && g3 == curf;
+        const float m4 = fmaxf(fmaxf(acc.x, acc.y), fmaxf(acc.z, acc.w));
+        const float e4 = fmaxf(fmaxf(ie.x, ie.y), fmaxf(ie.z, ie.w));
+        if (inside && same && m4 < thr && e4 < INFINITY && t0 >= t_lo && t0 + 3 < t_hi && !a->fas) {
+            st.cnt += 4;
+            st.mx = fmaxf(st.mx, m4);
+            return st;
+        }
+    }
+    const float vv[4] = {acc.x, acc.y, acc.z, acc.w};
+    const float iv[4] = {ie.x, ie.y, ie.z, ie.w};
+#pragma unroll 1
+    for (int e = 0; e < 4; ++e) {
+        const int t = t0 + e;
+        if (t < t_lo || t >= t_hi) continue;
+        float v = vv[e];
+        if (isinf(iv[e])) {      // zero-energy window: the reference's inf, zeroed (detect.py:275-281)
+            v = 0.f;
+            st.zero = 1;
+        }
+        st.mx = fmaxf(st.mx, v);
+        const int bin = hist_bin_fast(v, flo, finv, a->hist_lo, a->hist_hi, step, a->nbins);
+        if (bin == st.cur) ++st.cnt;
+        else {
+            if (st.cnt > 0 && st.cur >= 0)
+                atomicAdd(&a->hist[static_cast<long long>(out_row) * HIST_MAX_BINS + st.cur],
+                          static_cast<unsigned long long>(st.cnt));
+            st.cur = bin;
+            st.cnt = 1;
+        }
+        if (v >= thr) {
+            const int q = atomicAdd(a->ncand, 1);
+            if (q < a->cand_cap) {
+                Candidate cnd;
+                cnd.row = row;
+                cnd.t = t; cnd.ds = v; cnd.lta = 0.f;
+                a->cand[q] = cnd;
+            }
+        }
+        if (a->fas) {
+            st.s1 += v;
+            st.s2 = fmaf(v, v, st.s2);
+            st.s3 += logf(fmaxf(v, 1e-30f));
+            st.s4 += log1pf(-fminf(v, 0.99999994f));
+            ++st.n;
+        }
+    }
+    return st;
+}
+
 template <int NQ, int MODE>
 __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uint32_t tmem, int warp,
                                            int lane) {
@@ -495,59 +568,13 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
                         // what k3_fast_kernel does with the stored row
                         if (!f_skip) {
                             const int t0 = it.y * TT + 8 * NCOL * colhalf + c * EPI_LAGS + lane * 4;
-                            const float vv[4] = {acc.x, acc.y, acc.z, acc.w};
-                            const float iv[4] = {ie.x, ie.y, ie.z, ie.w};
-                            // four values at once, branch free (the quad path of k3_fast_kernel): all four core
-                            // lags, finite energy, well inside the bin of the current run, below the threshold
-                            const float curf = static_cast<float>(f_cur[k]);
-                            const float q0 = fmaf(acc.x, f_finv, f_toff), q1 = fmaf(acc.y, f_finv, f_toff),
-                                        q2 = fmaf(acc.z, f_finv, f_toff), q3 = fmaf(acc.w, f_finv, f_toff);
-                            const float g0 = floorf(q0), g1 = floorf(q1), g2 = floorf(q2), g3 = floorf(q3);
-                            const bool inside = fabsf(q0 - g0 - 0.5f) < 0.499f && fabsf(q1 - g1 - 0.5f) < 0.499f &&
-                                                fabsf(q2 - g2 - 0.5f) < 0.499f && fabsf(q3 - g3 - 0.5f) < 0.499f;
-                            const bool same = f_cur[k] >= 0 && g0 == curf && g1 == curf && g2 == curf && g3 == curf;
-                            const float m4 = fmaxf(fmaxf(acc.x, acc.y), fmaxf(acc.z, acc.w));
-                            const float e4 = fmaxf(fmaxf(ie.x, ie.y), fmaxf(ie.z, ie.w));
-                            if (inside && same && m4 < f_thr[k] && e4 < INFINITY && t0 >= cd.t_lo && t0 + 3 < cd.t_hi &&
-                                !P.a.fas) {
-                                f_cnt[k] += 4;
-                                f_max[k] = fmaxf(f_max[k], m4);
-                            } else
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int t = t0 + e;
-                                if (t < cd.t_lo || t >= cd.t_hi) continue;
-                                float v = vv[e];
-                                if (isinf(iv[e])) {      // zero-energy window: the reference's inf, zeroed (detect.py:275-281)
-                                    v = 0.f;
-                                    f_zero |= 1u << k;
-                                }
-                                f_max[k] = fmaxf(f_max[k], v);
-                                const int bin = hist_bin_fast(v, f_flo, f_finv, P.a.hist_lo, P.a.hist_hi, f_step, P.a.nbins);
-                                if (bin == f_cur[k]) ++f_cnt[k];
-                                else {
-                                    if (f_cnt[k] > 0 && f_cur[k] >= 0)
-                                        atomicAdd(&P.a.hist[static_cast<long long>(hb[k].out_row) * HIST_MAX_BINS + f_cur[k]],
-                                                  static_cast<unsigned long long>(f_cnt[k]));
-                                    f_cur[k] = bin;
-                                    f_cnt[k] = 1;
-                                }
-                                if (v >= f_thr[k]) {
-                                    const int q = atomicAdd(P.a.ncand, 1);
-                                    if (q < P.a.cand_cap) {
-                                        Candidate cnd;
-                                        cnd.row = P.a.row_base + it.x * P.a.S + hb[k].out_row;
-                                        cnd.t = t; cnd.ds = v; cnd.lta = 0.f;
-                                        P.a.cand[q] = cnd;
-                                    }
-                                }
-                                if (P.a.fas) {
-                                    f_s1[k] += v;
-                                    f_s2[k] = fmaf(v, v, f_s2[k]);
-                                    f_s3[k] += logf(fmaxf(v, 1e-30f));
-                                    f_s4[k] += log1pf(-fminf(v, 0.99999994f));
-                                    ++f_n[k];
-                                }
+                            {
+                                FusedState stt{f_max[k], f_cur[k], f_cnt[k], 0, f_s1[k], f_s2[k], f_s3[k], f_s4[k], f_n[k]};
+                                stt = fused_values(stt, acc, ie, t0, cd.t_lo, cd.t_hi, f_thr[k], hb[k].out_row,
+                                                   P.a.row_base + it.x * P.a.S + hb[k].out_row, &P.a, f_flo, f_finv, f_step);
+                                f_max[k] = stt.mx; f_cur[k] = stt.cur; f_cnt[k] = stt.cnt;
+                                f_zero |= static_cast<unsigned>(stt.zero) << k;
+                                f_s1[k] = stt.s1; f_s2[k] = stt.s2; f_s3[k] = stt.s3; f_s4[k] = stt.s4; f_n[k] = stt.n;
                             }
                         }
                     } else {

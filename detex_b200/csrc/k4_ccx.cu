@@ -18,6 +18,16 @@
 
 #include "dtx_kernels.cuh"
 
+// unroll factors of the re-scoring loops (experiment knobs, profiles/r02_ccx_rescoring.md)
+#ifndef DTX_CCX_UNROLL3
+#define DTX_CCX_UNROLL3 3
+#endif
+#ifndef DTX_CCX_UNROLL4
+#define DTX_CCX_UNROLL4 4
+#endif
+#define DTX_PRAGMA_(x) _Pragma(#x)
+#define DTX_UNROLL(n) DTX_PRAGMA_(unroll n)
+
 namespace dtx {
 namespace {
 
@@ -535,6 +545,7 @@ ccx_scan_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
 // warps -- 16 warps per CTA -- is SLOWER, 48 ms against 37 ms per 8.4 M pairs, and so are 12 independent
 // partial sums per warp, 40 ms: the kernel is bound by the float64 FMA count, not by latency.)
 constexpr int POST_PARTS = 1;
+
 constexpr int POST_SIGS = 8;     // signals per CTA at most
 constexpr int POST_WARPS = POST_SIGS * POST_PARTS;
 
@@ -564,7 +575,7 @@ __device__ __forceinline__ void sm_dot3(const double* __restrict__ s1, const dou
         }
         if (ilo < ihi) {
             double w0 = x2[ilo - 1], w1 = x2[ilo];
-#pragma unroll 3
+DTX_UNROLL(DTX_CCX_UNROLL3)
             for (int j = ilo; j < ihi; ++j) {
                 const double w2 = x2[j + 1];
                 const double v = x1[j];
@@ -613,21 +624,52 @@ __device__ __forceinline__ double sm_dot1(const double* __restrict__ s1, const d
     return a0;
 }
 
+// Two lags in one pass over the template row (bounds-checked loads: of the variants measured --
+// four lags per pass, one check-free pass per lag, check-free two-lag pass with edge loops -- this one is
+// the fastest, profiles/r02_ccx_rescoring.md).
+__device__ __forceinline__ void sm_dot2(const double* __restrict__ s1, const double* __restrict__ s2, int ns, int Nc,
+                                        int m, int kap0, int kap1, int lane, double& r0, double& r1) {
+    double a0 = 0.0, a1 = 0.0;
+    const int j0 = lane * m, j1 = min(ns, j0 + m);
+    for (int c = 0; c < Nc; ++c) {
+        const double* x1 = s1 + c * ns;
+        const double* x2 = s2 + c * ns;
+DTX_UNROLL(DTX_CCX_UNROLL4)
+        for (int j = j0; j < j1; ++j) {
+            const double v = x1[j];
+            a0 = fma(v, sm_at(x2, j + kap0, ns), a0);
+            a1 = fma(v, sm_at(x2, j + kap1, ns), a1);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    r0 = a0;
+    r1 = a1;
+}
+
 // Several lags within the band (rare path, kept out of the main loop's register allocation): their
-// float64 values, the first largest wins (np.nanargmax), NaN values are skipped.  Returns the
-// winning lag or -1 (every value NaN).
+// float64 values, two lags per pass; the first largest wins (np.nanargmax), NaN values are skipped.
+// Returns the winning lag or -1 (every value NaN).
 __device__ __noinline__ int sm_best_of(const double* s1, const double* s2, int ns, int Nc, int m, int4 kc, int koff,
                                        int lane, double sum1, double std1, double dn, const double* wac,
                                        const double* wbc) {
     double bestv = 0.0;
     int bestk = -1;
-    const int ks[4] = {kc.x, kc.y, kc.z, kc.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int k = ks[q];
-        if (k < 0) break;
-        const double v = (sm_dot1(s1, s2, ns, Nc, m, k + koff, lane) - sum1 * wac[k]) / (dn * wbc[k] * std1);
+    auto take = [&](int k, double a) {
+        const double v = (a - sum1 * wac[k]) / (dn * wbc[k] * std1);
         if (!isnan(v) && (bestk < 0 || v > bestv)) { bestv = v; bestk = k; }
+    };
+    double a0, a1;
+    sm_dot2(s1, s2, ns, Nc, m, kc.x + koff, kc.y + koff, lane, a0, a1);
+    take(kc.x, a0);
+    take(kc.y, a1);
+    if (kc.z >= 0) {
+        const int k3 = kc.w >= 0 ? kc.w : kc.z;
+        sm_dot2(s1, s2, ns, Nc, m, kc.z + koff, k3 + koff, lane, a0, a1);
+        take(kc.z, a0);
+        if (kc.w >= 0) take(kc.w, a1);
     }
     return bestk;
 }

@@ -52,7 +52,8 @@ def make(verbose=False):
         r = subprocess.run([sys.executable, "-m", "pip", "install", "--no-index", "--no-build-isolation",
                             "--no-deps", "--target", DST, cp], capture_output=True, text=True)
         if r.returncode != 0 or not os.path.isdir(os.path.join(DST, "detex")):
-            how = "copy (pip: %s)" % (r.stderr.strip().splitlines() or ["failed"])[-1][:120]
+            why = [l.strip() for l in r.stderr.splitlines() if "Invalid" in l or "Error" in l or "error:" in l]
+            how = "copy (pip install failed: %s)" % (why[0] if why else "see oracle/make_ref.py")[:160]
             shutil.rmtree(os.path.join(DST, "detex"), ignore_errors=True)
             shutil.copytree(pkg, os.path.join(DST, "detex"), ignore=shutil.ignore_patterns("__pycache__"))
     assert _same_tree(pkg, os.path.join(DST, "detex")), "oracle/_ref/detex differs from the reference"
