@@ -368,8 +368,13 @@ static int set_bases_device(dtx_ctx* ctx, BasisSet& bs, int set_id, const std::f
         members[b].push_back(pi);
     }
     lay.nblocks = static_cast<int>(used.size());
-    std::vector<int> slot_row(static_cast<size_t>(lay.nblocks) * VEC_PER_BLOCK, -1);
-    std::vector<BlockInfo> binfo(static_cast<size_t>(lay.nblocks) * VEC_PER_BLOCK);
+    // one all-zero padding block behind an odd number of blocks: CTA pairs (cta_group::2) take blocks two at a time
+    const int nblk_pad = lay.nblocks + (lay.nblocks & 1);
+    std::vector<int> slot_row(static_cast<size_t>(nblk_pad) * VEC_PER_BLOCK, -1);
+    std::vector<BlockInfo> binfo(static_cast<size_t>(nblk_pad) * VEC_PER_BLOCK);
+    for (size_t i = static_cast<size_t>(lay.nblocks) * VEC_PER_BLOCK; i < binfo.size(); ++i) {
+        binfo[i].sumU = 0.f; binfo[i].out_row = -1; binfo[i].nrows = 0; binfo[i].seg_end = static_cast<int>(i % VEC_PER_BLOCK) + 1;
+    }
     double umax = 0.0;
     for (int k = 0; k < R; ++k) umax = std::max(umax, stats[static_cast<size_t>(k) * 4 + 1]);
     int eu = 0;
@@ -409,7 +414,7 @@ static int set_bases_device(dtx_ctx* ctx, BasisSet& bs, int set_id, const std::f
     DTX_CUDA(bs.d_thr.reserve(S));
     DTX_CUDA(bs.d_hist.reserve(static_cast<size_t>(S) * HIST_MAX_BINS));
     DTX_CUDA(bs.d_fas.reserve(static_cast<size_t>(S) * 5));
-    const size_t img_bytes = static_cast<size_t>(lay.nblocks) * lay.nchunks * 32768;
+    const size_t img_bytes = static_cast<size_t>(nblk_pad) * lay.nchunks * 32768;
     DTX_CUDA(bs.d_Aimg.reserve(img_bytes));
     // synchronous copies: the caller's arrays need not outlive this call
     DTX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -426,7 +431,11 @@ static int set_bases_device(dtx_ctx* ctx, BasisSet& bs, int set_id, const std::f
     DTX_CUDA(cudaMemcpy(bs.d_thr.p, thr.data(), sizeof(float) * S, cudaMemcpyHostToDevice));
     DTX_CUDA(cudaMemset(bs.d_hist.p, 0, sizeof(unsigned long long) * S * HIST_MAX_BINS));
     DTX_CUDA(cudaMemset(bs.d_fas.p, 0, sizeof(double) * S * 5));
-    launch_basis_image(bs.d_U.p, bs.d_slot_row.p, lay, bs.d_Aimg.p, 0, ctx->stream);
+    {
+        BasisLayout lp = lay;
+        lp.nblocks = nblk_pad;
+        launch_basis_image(bs.d_U.p, bs.d_slot_row.p, lp, bs.d_Aimg.p, 0, ctx->stream);
+    }
     bs.have_img8 = false;
     ctx->launches += 1;
     DTX_CUDA(cudaGetLastError());
@@ -613,9 +622,15 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         if (std::atoi(g) > 0) group = std::atoi(g);
     if (const char* g = std::getenv("DTX_K1_SUPER"))
         if (std::atoi(g) > 0) super = std::atoi(g);
-    const int wave = ctx->num_sms;
+    // CTA pairs (cta_group::2, DTX_K1_CG2=1): detection only, 2048-lag tiles; one item per cluster and block PAIR
+    int cg2 = 0;
+    if (const char* g = std::getenv("DTX_K1_CG2")) cg2 = std::atoi(g) != 0;
+    cg2 = cg2 && mode != 1 && nq == 256 && engine != DTX_ENGINE_FP64 && ctx->num_sms >= 2;
+    const int bstep = cg2 ? 2 : 1;
+    if (cg2) super = std::max(2, super & ~1);
+    const int wave = cg2 ? ctx->num_sms / 2 : ctx->num_sms;
     // the list only depends on the batch's shape: reuse the device copy when it has not changed
-    std::vector<int> sig_key{nq, lay.nblocks, group, nchunks, super, wave};
+    std::vector<int> sig_key{nq, lay.nblocks, group, nchunks, super, wave, cg2};
     for (int i = 0; i < nchunks; ++i) {
         sig_key.push_back(ctx->h_chunks[i].T);
         sig_key.push_back(ctx->h_chunks[i].blk_hi);
@@ -635,7 +650,7 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         }
         for (int sb = 0; sb < max_blk; sb += super)
             for (size_t w0 = 0; w0 < tl.size(); w0 += (super > 1 ? wave : tl.size()))
-                for (int b = sb; b < std::min(sb + super, max_blk); ++b) {
+                for (int b = sb; b < std::min(sb + super, max_blk); b += bstep) {
                     const size_t w1 = super > 1 ? std::min(tl.size(), w0 + wave) : tl.size();
                     for (size_t k = w0; k < w1; ++k) {
                         const ChunkDesc& cd = ctx->h_chunks[tl[k].first];
@@ -692,8 +707,10 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     const int k0_policy = mode == 1 ? X8_RATIO : x8;
     const float k4_limit = static_cast<float>(std::pow(ctx->x8_eps / X8_C, 4.0) / bs.nu4);
     if (x8 && !bs.have_img8) {
-        DTX_CUDA(bs.d_Aimg8.reserve(static_cast<size_t>(lay.nblocks) * lay.nchunks * 32768));
-        launch_basis_image(bs.d_U.p, bs.d_slot_row.p, lay, bs.d_Aimg8.p, 1, st);
+        BasisLayout lp = lay;
+        lp.nblocks = lay.nblocks + (lay.nblocks & 1);
+        DTX_CUDA(bs.d_Aimg8.reserve(static_cast<size_t>(lp.nblocks) * lay.nchunks * 32768));
+        launch_basis_image(bs.d_U.p, bs.d_slot_row.p, lp, bs.d_Aimg8.p, 1, st);
         bs.have_img8 = true;
         ctx->launches += 1;
     }
@@ -715,6 +732,7 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         a.binfo = bs.d_binfo.p; a.DS = ctx->d_DS.p; a.nitems = ctx->n_items;
         a.kblk = kblk; a.num_sms = ctx->num_sms; a.nq = nq; a.mode = mode;
         a.hi_only = hi_only;
+        a.cg2 = cg2;
         a.fused = fused ? 1 : 0;
         a.thr = bs.d_thr.p; a.rowmax_bits = reinterpret_cast<unsigned*>(ctx->d_rowmax.p); a.rowflags = ctx->d_rowflags.p;
         a.hist = bs.d_hist.p; a.nbins = ctx->hist_bins; a.cand = ctx->d_cand.p; a.cand_cap = ctx->cand_cap;

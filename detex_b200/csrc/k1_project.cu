@@ -35,6 +35,8 @@
 // orders the items (chunk group, block, tile) so that at any time all 148 CTAs stream the SAME
 // 4.6 MB A block from L2 and a group's split signal stays L2-resident: DRAM traffic is then
 // about the algorithmic minimum (inputs once per group + the dense DS write).
+#include <algorithm>
+
 #include "dtx_kernels.cuh"
 #include "tc_common.cuh"
 
@@ -123,6 +125,7 @@ struct Smem {
     uint8_t* norm;
     uint8_t* epi;
     uint64_t *full, *empty, *sigfull, *sigempty, *accfull, *accempty, *normfull, *normempty;
+    uint64_t *pfull, *psigfull;   // CTA pairs: the peer's stage / signal span has landed (leader's copies are used)
 };
 
 // 64-tap stages accumulated in TMEM before accumulation `nacc` of a work item is drained.  The
@@ -166,9 +169,16 @@ __device__ __forceinline__ int item_x8(const K1Params& P, int chunk) {
 #endif
 
 // ------------------------------------------------ producer (warp 0, an elected lane issues)
-template <int NQ>
+// Work items of a CTA: every CTA its own (blockIdx.x, stride gridDim.x), or -- CTA pairs -- every cluster
+// its own, the two CTAs of the pair taking basis blocks it.z and it.z + 1 of the same (chunk, tile).
+template <bool CG2> __device__ __forceinline__ int item_first() { return CG2 ? cluster_id_x() : blockIdx.x; }
+template <bool CG2> __device__ __forceinline__ int item_step() { return CG2 ? cluster_nctaid_x() : gridDim.x; }
+
+template <int NQ, bool CG2>
 __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) {
     constexpr int TT = 8 * NQ;
+    constexpr int TSPAN = CG2 ? TT / 2 : TT;          // lags whose B rows this CTA supplies
+    const int brank = CG2 ? cluster_ctarank() : 0;
     Ring st(STAGES), sg(2), nm(2);
     const bool hi_only = P.a.hi_only != 0;
     const uint32_t a_bytes = hi_only ? TILE_BYTES : STAGE_BYTES;
@@ -178,7 +188,7 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
 #if DTX_A_HINT
     const uint64_t pol_a = l2_policy_evict_first();
 #endif
-    for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
+    for (int item = item_first<CG2>(); item < P.a.nitems; item += item_step<CG2>()) {
         const int4 it = P.a.items[item];
         const ChunkDesc cd = P.a.chunks[it.x];
         // window mean / inverse energy of this tile
@@ -192,14 +202,14 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
         }
         ISSUE_SYNC();
         nm.advance();
-        const __half* sig0 = P.a.xsplit + cd.sig_off + static_cast<long long>(it.y) * TT;
+        const __half* sig0 = P.a.xsplit + cd.sig_off + static_cast<long long>(it.y) * TT + brank * TSPAN;
         {
-            const int b = it.z;
+            const int b = it.z + brank;
             const uint8_t* ablk = (item_x8(P, it.x) ? P.a.Aimg8 : P.a.Aimg) +
                                   static_cast<size_t>(b) * P.nchunks * STAGE_BYTES;
             for (int g = 0; g < P.nseg; ++g) {
                 const Seg sgm = P.seg[g];
-                const uint32_t bytes = (TT + sgm.ntaps) * 2;
+                const uint32_t bytes = (TSPAN + sgm.ntaps) * 2;
                 mbar_wait(&S.sigempty[sg.idx], sg.phase ^ 1);
                 if (ISSUE_LANE) {
                     mbar_arrive_expect_tx(&S.sigfull[sg.idx], hi_only ? bytes : 2 * bytes);
@@ -230,32 +240,37 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
 }
 
 // ---------------------------------------------- MMA issuer (warp 1, an elected lane issues)
-template <int NQ>
+template <int NQ, bool CG2>
 __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint32_t tmem) {
-    const uint32_t idesc = idesc_f16_f32(128, NQ);
-    const uint32_t idesc8 = idesc_e4m3_e5m2_f32(128, NQ);
+    const uint32_t idesc = idesc_f16_f32(CG2 ? 256 : 128, NQ);
+    const uint32_t idesc8 = idesc_e4m3_e5m2_f32(CG2 ? 256 : 128, NQ);
     const uint64_t a_base = smem_desc_kmajor_noswz(0, A_LBO, A_SBO);
     const uint64_t b_base = smem_desc_kmajor_noswz(0, B_LBO, B_SBO);
     const uint32_t stage0 = smem_u32(S.stage), sig0 = smem_u32(S.sig);
     Ring st(STAGES), sg(2), ac(2);
     const bool hi_only = P.a.hi_only != 0;
-    int x8_next = blockIdx.x < P.a.nitems ? item_x8(P, P.a.items[blockIdx.x].x) : 0;
-    for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
+    int x8_next = item_first<CG2>() < P.a.nitems ? item_x8(P, P.a.items[item_first<CG2>()].x) : 0;
+    for (int item = item_first<CG2>(); item < P.a.nitems; item += item_step<CG2>()) {
         const bool x8 = x8_next != 0;
-        if (item + static_cast<int>(gridDim.x) < P.a.nitems)   // fetched while this item's MMAs issue
-            x8_next = item_x8(P, P.a.items[item + gridDim.x].x);
+        if (item + item_step<CG2>() < P.a.nitems)   // fetched while this item's MMAs issue
+            x8_next = item_x8(P, P.a.items[item + item_step<CG2>()].x);
         const int kblk = x8 ? P.a.kblk8 : P.a.kblk;
         {
             int cib = 0, done = 0, nacc = 0;
             for (int g = 0; g < P.nseg; ++g) {
                 const int nck = P.seg[g].ntaps / CHUNK_TAPS;
                 mbar_wait(&S.sigfull[sg.idx], sg.phase);
+                if (CG2) mbar_wait_cluster(&S.psigfull[sg.idx], sg.phase);   // the peer's half of the B rows
                 tc_fence_after();
                 const uint32_t sh = sig0 + sg.idx * SIG_BUF_BYTES;
                 const uint32_t sl = sh + SIG_HALFS * 2;
                 for (int kc = 0; kc < nck; ++kc) {
                     mbar_wait(&S.full[st.idx], st.phase);
-                    if (cib == 0) mbar_wait(&S.accempty[ac.idx], ac.phase ^ 1);
+                    if (CG2) mbar_wait_cluster(&S.pfull[st.idx], st.phase);      // the peer's A stage
+                    if (cib == 0) {
+                        if (CG2) mbar_wait_cluster(&S.accempty[ac.idx], ac.phase ^ 1);   // both CTAs' drain warps
+                        else mbar_wait(&S.accempty[ac.idx], ac.phase ^ 1);
+                    }
                     tc_fence_after();
                     const uint32_t d = tmem + ac.idx * 256;
                     const uint32_t ah = stage0 + st.idx * STAGE_BYTES;
@@ -263,7 +278,35 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
                     const uint32_t bo = kc * (CHUNK_TAPS * 2);
                     const bool last = (cib + 1 == acc_stages(nacc, kblk)) || (done + 1 == P.nchunks);
                     if (ISSUE_LANE) {
-                        if (hi_only) {
+                        if (CG2) {
+                            // one MMA of M = 256 for the pair: this CTA's and the peer's basis block against the
+                            // 2048-lag tile whose B rows the two CTAs hold half each
+                            if (x8) {
+#pragma unroll
+                                for (int kk = 0; kk < CHUNK_TAPS / 16; ++kk) {
+                                    const uint64_t dah = a_base | ((ah + kk * 256) >> 4);
+                                    const uint64_t dal = a_base | ((al + kk * 256) >> 4);
+                                    const uint64_t dbh = b_base | ((sh + bo + kk * 32) >> 4);
+                                    const uint64_t dbl = b_base | ((sl + bo + kk * 32) >> 4);
+                                    umma2_f16(d, dah, dbh, idesc, (cib | kk) ? 1u : 0u);
+                                    umma2_f8(d, dal, dbl, idesc8, 1u);
+                                }
+                            } else {
+#pragma unroll
+                                for (int kk = 0; kk < CHUNK_TAPS / 16; ++kk) {
+                                    const uint64_t dah = a_base | ((ah + kk * 256) >> 4);
+                                    const uint64_t dal = a_base | ((al + kk * 256) >> 4);
+                                    const uint64_t dbh = b_base | ((sh + bo + kk * 32) >> 4);
+                                    const uint64_t dbl = b_base | ((sl + bo + kk * 32) >> 4);
+                                    umma2_f16_a_fill(d, dah, dbh, idesc, (cib | kk) ? 1u : 0u);
+                                    umma2_f16_a_lastuse(d, dah, dbl, idesc, 1u);
+                                    umma2_f16(d, dal, dbh, idesc, 1u);
+                                }
+                            }
+                            umma2_commit_mc(&S.empty[st.idx], 0x3);
+                            if (last) umma2_commit_mc(&S.accfull[ac.idx], 0x3);
+                            if (kc == nck - 1) umma2_commit_mc(&S.sigempty[sg.idx], 0x3);
+                        } else if (hi_only) {
 #pragma unroll
                             for (int kk = 0; kk < CHUNK_TAPS / 16; ++kk) {
                                 const uint64_t dah = a_base | ((ah + kk * 256) >> 4);
@@ -301,9 +344,11 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
                                 umma_f16(d, dal, dbh, idesc, 1u);
                             }
                         }
-                        umma_commit(&S.empty[st.idx]);
-                        if (last) umma_commit(&S.accfull[ac.idx]);
-                        if (kc == nck - 1) umma_commit(&S.sigempty[sg.idx]);
+                        if (!CG2) {
+                            umma_commit(&S.empty[st.idx]);
+                            if (last) umma_commit(&S.accfull[ac.idx]);
+                            if (kc == nck - 1) umma_commit(&S.sigempty[sg.idx]);
+                        }
                     }
                     ISSUE_SYNC();
                     st.advance();
@@ -316,6 +361,27 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
                     }
                 }
                 sg.advance();
+            }
+        }
+    }
+}
+
+// --------------------------------------- CTA pairs: the peer CTA's forwarder (warp 2 of cluster rank 1)
+// Only the leader issues MMAs, so it has to learn when the PEER's signal spans and A stages have landed:
+// this warp follows the peer's own full barriers and arrives on the leader's copies.
+template <int NQ>
+__device__ __forceinline__ void forward_loop(const K1Params& P, const Smem& S) {
+    Ring st(STAGES), sg(2);
+    for (int item = item_first<true>(); item < P.a.nitems; item += item_step<true>()) {
+        for (int g = 0; g < P.nseg; ++g) {
+            mbar_wait(&S.sigfull[sg.idx], sg.phase);
+            mbar_arrive_leader(&S.psigfull[sg.idx]);
+            sg.advance();
+            const int nck = P.seg[g].ntaps / CHUNK_TAPS;
+            for (int kc = 0; kc < nck; ++kc) {
+                mbar_wait(&S.full[st.idx], st.phase);
+                mbar_arrive_leader(&S.pfull[st.idx]);
+                st.advance();
             }
         }
     }
@@ -412,9 +478,10 @@ __device__ __noinline__ FusedState fused_values(FusedState st, float4 acc, float
     return st;
 }
 
-template <int NQ, int MODE>
+template <int NQ, int MODE, bool CG2>
 __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uint32_t tmem, int warp,
                                            int lane) {
+    const int brank = CG2 ? cluster_ctarank() : 0;
     constexpr int TT = 8 * NQ;
     constexpr int NCOL = NQ / 2;                 // accumulator columns per thread
     const int dw = warp - FIRST_DRAIN_WARP;      // 0..7
@@ -435,7 +502,7 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
     const float f_flo = static_cast<float>(P.a.hist_lo);
     const float f_finv = MODE == 2 ? static_cast<float>(P.a.nbins / (P.a.hist_hi - P.a.hist_lo)) : 0.f;
     const float f_toff = -f_flo * f_finv;
-    for (int item = blockIdx.x; item < P.a.nitems; item += gridDim.x) {
+    for (int item = item_first<CG2>(); item < P.a.nitems; item += item_step<CG2>()) {
         const int4 it = P.a.items[item];
         const ChunkDesc cd = P.a.chunks[it.x];
         const int kblk = item_x8(P, it.x) ? P.a.kblk8 : P.a.kblk;
@@ -445,7 +512,7 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
         const float* smu = reinterpret_cast<const float*>(S.norm + nm.idx * NORM_BUF_BYTES);
         const float* sie = smu + TILE_T;
         {
-            const int b = it.z;
+            const int b = it.z + brank;
 #if DTX_FADD2
 #pragma unroll
             for (int i = 0; i < NCOL / 2; ++i) sums2[i] = 0ull;
@@ -486,7 +553,10 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
                     if (i == NCOL / 32 - 1) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&S.accempty[ac.idx]);
+                        if (lane == 0) {
+                            if (CG2) mbar_arrive_leader(&S.accempty[ac.idx]);   // the leader waits for both CTAs
+                            else mbar_arrive(&S.accempty[ac.idx]);
+                        }
                     }
 #if DTX_FADD2
 #pragma unroll
@@ -627,11 +697,11 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
     }
 }
 
-template <int NQ, int MODE>
+template <int NQ, int MODE, bool CG2>
 __global__ void __launch_bounds__(NTHREADS, 1) k1_kernel(const __grid_constant__ K1Params P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t full[STAGES], empty[STAGES];
-    __shared__ uint64_t sigfull[2], sigempty[2], accfull[2], accempty[2], normfull[2], normempty[2];
+    __shared__ uint64_t full[STAGES], empty[STAGES], pfull[STAGES];
+    __shared__ uint64_t sigfull[2], sigempty[2], accfull[2], accempty[2], normfull[2], normempty[2], psigfull[2];
     __shared__ uint32_t tmem_base_s;
     Smem S;
     S.stage = smem;
@@ -640,29 +710,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) k1_kernel(const __grid_constant__
     S.epi = S.norm + 2 * NORM_BUF_BYTES;
     S.full = full; S.empty = empty; S.sigfull = sigfull; S.sigempty = sigempty;
     S.accfull = accfull; S.accempty = accempty; S.normfull = normfull; S.normempty = normempty;
+    S.pfull = pfull; S.psigfull = psigfull;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
+            mbar_init(&pfull[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&sigfull[s], 1);
             mbar_init(&sigempty[s], 1);
             mbar_init(&accfull[s], 1);
-            mbar_init(&accempty[s], NDRAIN_WARPS);
+            mbar_init(&accempty[s], CG2 ? 2 * NDRAIN_WARPS : NDRAIN_WARPS);
+            mbar_init(&psigfull[s], 1);
             mbar_init(&normfull[s], 1);
             mbar_init(&normempty[s], NDRAIN_WARPS);
         }
         fence_barrier_init();
     }
     if (warp == 0) {
-        tmem_alloc(&tmem_base_s, 512);
-        tmem_relinquish();
+        if (CG2) {
+            tmem_alloc_cg2(&tmem_base_s, 512);
+            tmem_relinquish_cg2();
+        } else {
+            tmem_alloc(&tmem_base_s, 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG2) cluster_sync_all();   // both CTAs' barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
 
@@ -670,17 +749,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k1_kernel(const __grid_constant__
     if (warp < FIRST_DRAIN_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
         if (warp == 0 && ROLE_LANES(lane)) {
-            producer_loop<NQ>(P, S);
+            producer_loop<NQ, CG2>(P, S);
         } else if (warp == 1 && ROLE_LANES(lane)) {
-            mma_loop<NQ>(P, S, tmem);
+            if (!CG2 || cluster_ctarank() == 0) mma_loop<NQ, CG2>(P, S, tmem);   // pairs: only the leader issues
+        } else if (CG2 && warp == 2 && lane == 0) {
+            if (cluster_ctarank() == 1) forward_loop<NQ>(P, S);
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_DRAIN));
-        drain_loop<NQ, MODE>(P, S, tmem, warp, lane);
+        drain_loop<NQ, MODE, CG2>(P, S, tmem, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (CG2) cluster_sync_all();   // no CTA leaves while its peer may still signal it or read its shared memory
+    if (warp == 0) {
+        if (CG2) tmem_dealloc_cg2(tmem, 512);
+        else tmem_dealloc(tmem, 512);
+    }
 }
 
 // ---------------------------------------------------------------- basis image
@@ -736,8 +821,27 @@ basis_image_kernel(const double* __restrict__ U, const int* __restrict__ slot_ro
 
 template <int NQ, int MODE>
 void launch_k1_t(const K1Params& P, int grid, cudaStream_t st) {
-    cudaFuncSetAttribute(k1_kernel<NQ, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    k1_kernel<NQ, MODE><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+    if (P.a.cg2) {
+        // CTA pairs: clusters of 2 (same TPC), one work item per cluster
+        cudaFuncSetAttribute(k1_kernel<NQ, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaLaunchConfig_t cfg = {};
+        const int nclusters = std::max(1, std::min(P.a.nitems, P.a.num_sms / 2));
+        cfg.gridDim = dim3(2 * nclusters);
+        cfg.blockDim = dim3(NTHREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k1_kernel<NQ, MODE, true>, P);
+        return;
+    }
+    cudaFuncSetAttribute(k1_kernel<NQ, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    k1_kernel<NQ, MODE, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
 }
 
 }  // namespace

@@ -57,6 +57,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// the same with cluster-scope acquire: the arrivals come from the peer CTA of a pair
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
 
 // ------------------------------------------------------- bulk async copy
 // 1-D global -> shared bulk copy; completion is signalled on `bar` as
@@ -88,6 +101,68 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gm
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
         ::"r"(smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// ------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of a cluster (same TPC) execute one MMA of M = 256 together: each supplies 128 rows of A and
+// HALF of B's rows from its own shared memory and keeps its 128 rows of D in its own TMEM; the leader
+// (cluster rank 0) issues.  A shared::cluster address with bit 24 cleared is the leader's copy of a
+// barrier (the CUTLASS Sm100MmaPeerBitMask idiom).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctaid_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the LEADER CTA's copy of `bar` (works from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & 0xFEFFFFFFu)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+#define DTX_UMMA_CG2(NAME, KIND, COLL)                                                                      \
+    __device__ __forceinline__ void NAME(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, \
+                                         uint32_t accumulate) {                                             \
+        asm volatile(                                                                                       \
+            "{\n\t.reg .pred p;\n\t"                                                                        \
+            "setp.ne.b32 p, %4, 0;\n\t"                                                                     \
+            "tcgen05.mma.cta_group::2.kind::" KIND COLL " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),        \
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)                                           \
+            : "memory");                                                                                    \
+    }
+DTX_UMMA_CG2(umma2_f16, "f16", "")
+DTX_UMMA_CG2(umma2_f16_a_fill, "f16", ".collector::a::fill")
+DTX_UMMA_CG2(umma2_f16_a_lastuse, "f16", ".collector::a::lastuse")
+DTX_UMMA_CG2(umma2_f8, "f8f6f4", "")
+// all MMAs of the pair issued so far: arrive on `bar` in every CTA of `cta_mask` when they complete
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
         : "memory");
 }
 

@@ -67,12 +67,14 @@ def pack_condensed(cc, lag, sub, slot_rows, N):
     return cc[src, iu[1]], lag[src, iu[1]], sub[src, iu[1]]
 
 
-def ccx_sharded(eng, X, Nc, engine="tcgen05", out=None):
+def ccx_sharded(eng, X, Nc, engine="tcgen05", out=None, root=None):
     """The whole CCX matrix of one station over all ranks (BASELINE configs[2]): every
     rank computes its dealt rows with the results left in HBM, ONE all-gather of the equal-sized dense
-    blocks over NCCL / NVLink, then every rank packs the upper triangle into SciPy's condensed order
-    and copies it to the host.  Returns (cc, lag, subsamp) condensed; identical on every rank and to
-    the single-GPU result."""
+    blocks over NCCL / NVLink, then the upper triangle is packed into SciPy's condensed order and
+    copied to the host -- on every rank (root=None), or only on rank `root` (the one that runs
+    `linkage`, construct.py:152-157; the other ranks return None and the host memory system sees one
+    168 MB copy instead of `world` of them).  Returns (cc, lag, subsamp) condensed; identical on every
+    rank and to the single-GPU result."""
     world = _world()
     if world == 1:
         return eng.ccx_condensed(X, Nc, engine=engine, out=out)
@@ -96,7 +98,9 @@ def ccx_sharded(eng, X, Nc, engine="tcgen05", out=None):
     dist.all_gather_into_tensor(g_sub, d_sub)
     if dev.type == "cuda":
         torch.cuda.current_stream().synchronize()      # the engine may run on another stream
-    res = eng.ccx_pack(g_cc.data_ptr(), g_lag.data_ptr(), g_sub.data_ptr(), slot_rows, N, out=out)
+    res = None
+    if root is None or root == rank:
+        res = eng.ccx_pack(g_cc.data_ptr(), g_lag.data_ptr(), g_sub.data_ptr(), slot_rows, N, out=out)
     del g_cc, g_lag, g_sub
     return res
 

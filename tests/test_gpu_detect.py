@@ -306,3 +306,36 @@ def test_item_order_does_not_change_results(engine, monkeypatch):
             assert all(np.array_equal(a, b) for a, b in zip(out[0], ref[0]))
             assert np.array_equal(out[1], ref[1]) and np.array_equal(out[2], ref[2])
             assert np.array_equal(out[3], ref[3])
+
+
+def test_cta_pair_kernel_matches_default(engine):
+    """K1 with CTA pairs (`tcgen05.mma.cta_group::2`, M = 256: two basis blocks per MMA, the tile's B rows held
+    half by each CTA; opt-in through DTX_K1_CG2=1, see profiles/r02_cta_pairs.md): same statistic as the default
+    single-CTA kernel, incl. an odd number of basis blocks (zero padding block) and ragged chunks."""
+    import os
+    Nc, ns, Ls = 3, 300, 9000
+    ranks = [16, 1, 9, 7, 8, 8, 3, 2, 5, 11, 4, 16, 6]            # 5 basis blocks (odd)
+    chunks, bases, _ = synth.detection_case(27, 3, Ls, ns, Nc, ranks, planted=3)
+    chunks[1] = chunks[1][:(Ls - 411) * Nc]
+    engine.set_bases(19, bases, Nc, thresholds=[0.3] * len(ranks))
+    out = {}
+    for cg2 in ("0", "1"):
+        old = os.environ.get("DTX_K1_CG2")
+        os.environ["DTX_K1_CG2"] = cg2
+        try:
+            engine.hist(19, reset=True)
+            engine.load_chunks(chunks)
+            engine.detect_run(19, lta_window=50)
+            out[cg2] = ([engine.get_ds(ci, si).copy() for ci in range(3) for si in range(len(ranks))],
+                        np.sort(engine.candidates(), order=["row", "t"]), engine.hist(19, reset=True))
+        finally:
+            if old is None:
+                os.environ.pop("DTX_K1_CG2", None)
+            else:
+                os.environ["DTX_K1_CG2"] = old
+    for a, b in zip(out["0"][0], out["1"][0]):
+        assert np.abs(a - b).max() < 1e-6
+    assert np.array_equal(out["0"][1]["t"], out["1"][1]["t"]) and np.array_equal(out["0"][1]["row"], out["1"][1]["row"])
+    assert np.abs(out["0"][2] - out["1"][2]).sum() <= 4
+    for si, U in enumerate(bases):
+        assert np.abs(out["1"][0][si] - orc.mpx_ds_direct(chunks[0], U, Nc)).max() < TOL
