@@ -157,6 +157,10 @@ def _ccx_worker(rank, world, port, q):
     try:
         X = synth.event_families(77, 3, 6, 40, 3, max_shift=8)        # 18 events, n = 120
         res = parallel.ccx_sharded(OracleEngine(), X, 3)
+        only_root = parallel.ccx_sharded(OracleEngine(), X, 3, root=0)   # gather to the rank that clusters
+        assert (only_root is None) == (rank != 0)
+        if rank == 0:
+            assert all(np.array_equal(a, b) for a, b in zip(res, only_root))
         if rank == world - 1:
             q.put(res)
     finally:
