@@ -180,6 +180,7 @@ struct dtx_ctx {
     DevBuf<double> cx_wa, cx_wb, cx_es, cx_ed, cx_pad, cx_cc, cx_sub, cx_tcc, cx_tsub, cx_pcc, cx_psub;
     DevBuf<int> cx_lag, cx_tlag, cx_plag, cx_rows, cx_nflag, cx_slot;
     DevBuf<int4> cx_karg;
+    DevBuf<double> cx_xd;       // events de-multiplexed into float64 [N][Nc][ns] (ring re-scoring)
     PinBuf<int> cx_nflag_h;      // degenerate-pair count of the last CCX call, checked at the next synchronisation
     bool cx_flag_check = false;
     DevBuf<int2> cx_flag;
@@ -1426,6 +1427,11 @@ static int ccx_tcgen05(dtx_ctx* ctx, int dtype, const void* dX, int N, int n, in
     DTX_CUDA(ctx->cx_nflag.reserve(1));
     DTX_CUDA(ctx->cx_flag.reserve(flag_cap));
     DTX_CUDA(cudaMemsetAsync(ctx->cx_nflag.p, 0, sizeof(int), st));
+    // float64 de-multiplexed copy of the events: the ring re-scoring stages a waveform with one bulk copy
+    DTX_CUDA(ctx->cx_xd.reserve(static_cast<size_t>(N) * n));
+    launch_ccx_demux(dX, dtype == DTX_F32, N, n, Nc, ctx->cx_xd.p, st);
+    DTX_CUDA(cudaGetLastError());
+    ctx->launches += 1;
     std::vector<int64_t> offs, lens;
     std::vector<int> blk_hi;
     const int c_first = h_rows[0] + 1;   // signals c <= rows[0] have no template b < c
@@ -1453,7 +1459,7 @@ static int ccx_tcgen05(dtx_ctx* ctx, int dtype, const void* dX, int N, int n, in
         const float band0 = hi_only ? 2.2e-3f : 3e-5f;
         rc = project_run(ctx, bs, DTX_ENGINE_TCGEN05, hi_only ? bs.lay.nchunks : 2, 1, 0, blk_hi.data(), hi_only);
         if (rc != DTX_OK) return rc;
-        launch_ccx_post(ctx->d_DS.p, ctx->d_chunks.p, c0, nsig, dX, dtype == DTX_F32, N, n, Nc, ctx->cx_rows.p, nrows,
+        launch_ccx_post(ctx->d_DS.p, ctx->d_chunks.p, c0, nsig, dX, dtype == DTX_F32, ctx->cx_xd.p, N, n, Nc, ctx->cx_rows.p, nrows,
                         ctx->cx_wa.p, ctx->cx_wb.p, ctx->cx_es.p, ctx->cx_ed.p, dcc, dlag, dsub, ctx->cx_nflag.p,
                         ctx->cx_flag.p, flag_cap, ctx->cx_karg.p, ctx->d_k4bits.p, band0, st);
         DTX_CUDA(cudaGetLastError());

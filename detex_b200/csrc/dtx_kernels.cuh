@@ -214,11 +214,12 @@ void launch_ccx_templates(const void* d_X, int dtype_f32, int n, const int* d_ro
                           cudaStream_t st);
 void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int nsig, int P, int Lc, double* out,
                     cudaStream_t st);
+void launch_ccx_demux(const void* d_X, int dtype_f32, int N, int n, int Nc, double* d_Xd, cudaStream_t st);
 void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsig, const void* d_X, int dtype_f32,
-                     int N, int n, int Nc, const int* d_rows, int nrows, const double* wa, const double* wb,
-                     const double* es, const double* ed, double* d_cc, int* d_lag, double* d_sub, int* d_nflag,
-                     int2* d_flagged, int flag_cap, int4* d_karg, const unsigned* d_ratio_bits, float band0,
-                     cudaStream_t st);   // d_karg: [nsig][nrows] scratch; d_ratio_bits: per signal, from k0_norm
+                     const double* d_Xd, int N, int n, int Nc, const int* d_rows, int nrows, const double* wa,
+                     const double* wb, const double* es, const double* ed, double* d_cc, int* d_lag, double* d_sub,
+                     int* d_nflag, int2* d_flagged, int flag_cap, int4* d_karg, const unsigned* d_ratio_bits,
+                     float band0, cudaStream_t st);   // d_karg: [nsig][nrows] scratch; d_ratio_bits: per signal, from k0_norm
 // dense per-slot rows [nslots][N] -> SciPy condensed order (pair (b, c), b < c, at b*N - b(b+1)/2 + c-b-1);
 // d_slot_of_row[b] = slot holding event b's row
 void launch_ccx_pack(const double* d_cc, const int* d_lag, const double* d_sub, const int* d_slot_of_row, int N,

@@ -17,6 +17,7 @@
 #include <cstdlib>
 
 #include "dtx_kernels.cuh"
+#include "tc_common.cuh"
 
 // unroll factors of the re-scoring loops (experiment knobs, profiles/r02_ccx_rescoring.md)
 #ifndef DTX_CCX_UNROLL3
@@ -480,14 +481,32 @@ ccx_scan_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
     const ChunkDesc cd = chunks[ci];
     const float4* row4 = reinterpret_cast<const float4*>(DS + cd.ds_off + static_cast<long long>(r) * cd.Tpad);
     const int nq = (nl + 3) / 4;                         // rows are padded to a multiple of TILE_T floats
+    // rows of up to 1024 lags (one MODE-1 tile: every CCX of n <= 2048 per channel pair) are read ONCE, all
+    // eight 128-bit loads of a lane in flight together, and both passes run on registers
+    constexpr int SCAN_REG = 8;
+    const bool inreg = nq <= 32 * SCAN_REG;
+    float4 vr[SCAN_REG];
+    if (inreg) {
+#pragma unroll
+        for (int i = 0; i < SCAN_REG; ++i) {
+            const int q = lane + 32 * i;
+            vr[i] = q < nq ? __ldcs(row4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     float mx = -INFINITY, mn = INFINITY;
     int cnt = 0;
-    for (int q = lane; q < nq; q += 32) {
-        const float4 v4 = __ldcs(row4 + q);
+    auto stat4 = [&](const float4& v4, int q) {
         const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e)
             if (4 * q + e < nl && !isnan(v[e])) { mx = fmaxf(mx, v[e]); mn = fminf(mn, v[e]); ++cnt; }
+    };
+    if (inreg) {
+#pragma unroll
+        for (int i = 0; i < SCAN_REG; ++i)
+            if (lane + 32 * i < nq) stat4(vr[i], lane + 32 * i);
+    } else {
+        for (int q = lane; q < nq; q += 32) stat4(__ldcs(row4 + q), q);
     }
     for (int s = 16; s > 0; s >>= 1) {
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
@@ -505,16 +524,15 @@ ccx_scan_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
     bool slow = mx > lim || mn < -lim;
     if (!slow) {
         const float thr = mx - band;
-        for (int q0 = 0; q0 < nq && !slow; q0 += 32) {   // second read of the row: L1 / L2 hits
-            const int q = q0 + lane;
+        auto hits = [&](const float4& v4, int q) -> unsigned {
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
             unsigned m4 = 0;
-            if (q < nq) {
-                const float4 v4 = row4[q];
-                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (4 * q + e < nl && v[e] >= thr) m4 |= 1u << e;
-            }
+            for (int e = 0; e < 4; ++e)
+                if (4 * q + e < nl && v[e] >= thr) m4 |= 1u << e;
+            return m4;
+        };
+        auto collect = [&](unsigned m4, int q0) {         // warp-uniform: lags in ascending order
             unsigned any = __ballot_sync(0xffffffffu, m4 != 0);
             while (any && !slow) {
                 const int l = __ffs(any) - 1;
@@ -526,6 +544,20 @@ ccx_scan_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
                     if (nc < SCAN_MAXC) cand[nc++] = 4 * (q0 + l) + e;
                     else slow = true;
                 }
+            }
+        };
+        if (inreg) {
+#pragma unroll
+            for (int i = 0; i < SCAN_REG; ++i) {
+                if (32 * i < nq && !slow) {
+                    const int q = lane + 32 * i;
+                    collect(q < nq ? hits(vr[i], q) : 0u, 32 * i);
+                }
+            }
+        } else {
+            for (int q0 = 0; q0 < nq && !slow; q0 += 32) {   // second read of the row: L1 / L2 hits
+                const int q = q0 + lane;
+                collect(q < nq ? hits(row4[q], q) : 0u, q0);
             }
         }
     }
@@ -842,6 +874,258 @@ ccx_post_tiled_kernel(const int4* __restrict__ karg, int c0, int nsig,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Ring re-scoring (round 2, default).  The tiled kernel above synchronises the whole CTA twice per
+// template row, and every row takes as long as its slowest pair: with the one-MMA screening series about
+// half of the pairs carry 2-4 candidate lags, so nearly every row of 8 pairs waits for a slow one (ncu:
+// 2.7 barrier-stall cycles per issued instruction, shared-memory pipe 41 % busy).  Here
+//   * the events are de-multiplexed once per call into a float64 copy, so a waveform is ONE contiguous
+//     cp.async.bulk of n*8 bytes (no cooperative staging, no CTA barrier);
+//   * a producer warp keeps a ring of NB template rows full (mbarrier full / empty per slot; the row's
+//     candidate records and scalars are parked next to it), TC signals stay resident;
+//   * the consumer warps (11 by default) take (row, signal) tasks from a shared counter in row order -- a warp that drew a
+//     one-candidate pair simply takes the next task, up to NB - 1 rows ahead of the slowest warp;
+//   * a pair with several candidates is scored in ONE pass: the template sample is loaded once and every
+//     candidate rolls its own three-sample window of the signal (1 + C shared loads and 3C FMAs per tap;
+//     the two-pass scheme cost 3 + 2 loads for C = 2 and 6 + 2 for C = 4), which also yields the winner's
+//     neighbours for the cosine fit.
+// Sums are accumulated in the same order as sm_dot3, so results are bit-identical to the tiled kernel's.
+constexpr int RING_THREADS = 512;                 // at most; warp 0 = producer, the others consume (default 12 warps)
+constexpr int RING_TC_MAX = 16;                   // resident signals at most
+constexpr int RING_NB_MAX = 4;                    // ring slots at most
+
+struct RingRec {
+    int4 kc[RING_TC_MAX];
+    double std1, sum1;
+};
+
+// Three lags (k-1, k, k+1) of each of C candidate lags in one pass over the template row; bounds-checked
+// signal loads (zero outside [0, ns)), per-lane partition and summation order of sm_dot3.
+template <int C>
+__device__ __forceinline__ void sm_multi3(const double* __restrict__ s1, const double* __restrict__ s2, int ns, int Nc,
+                                          int m, const int (&kap)[C], int lane, double (&a)[C][3]) {
+#pragma unroll
+    for (int q = 0; q < C; ++q) a[q][0] = a[q][1] = a[q][2] = 0.0;
+    const int j0 = min(ns, lane * m), j1 = min(ns, j0 + m);
+    for (int c = 0; c < Nc; ++c) {
+        const double* x1 = s1 + c * ns;
+        const double* x2 = s2 + c * ns;
+        double w0[C], w1[C];
+#pragma unroll
+        for (int q = 0; q < C; ++q) {
+            w0[q] = sm_at(x2, j0 + kap[q] - 1, ns);
+            w1[q] = sm_at(x2, j0 + kap[q], ns);
+        }
+DTX_UNROLL(2)
+        for (int j = j0; j < j1; ++j) {
+            const double v = x1[j];
+#pragma unroll
+            for (int q = 0; q < C; ++q) {
+                const double w2 = sm_at(x2, j + kap[q] + 1, ns);
+                a[q][0] = fma(v, w0[q], a[q][0]);
+                a[q][1] = fma(v, w1[q], a[q][1]);
+                a[q][2] = fma(v, w2, a[q][2]);
+                w0[q] = w1[q];
+                w1[q] = w2;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < C; ++q)
+#pragma unroll
+        for (int e = 0; e < 3; ++e)
+            for (int o = 16; o > 0; o >>= 1) a[q][e] += __shfl_xor_sync(0xffffffffu, a[q][e], o);
+}
+
+// Winner among C candidates (first largest float64 value, NaN skipped: np.nanargmax) and its three sums.
+// Returns the winning lag or -1.
+template <int C>
+__device__ __noinline__ int sm_best3(const double* s1, const double* s2, int ns, int Nc, int m, int4 kc, int koff,
+                                     int lane, double sum1, double std1, double dn, const double* wac,
+                                     const double* wbc, double acc[3]) {
+    const int ks[4] = {kc.x, kc.y, kc.z, kc.w};
+    int kap[C];
+#pragma unroll
+    for (int q = 0; q < C; ++q) kap[q] = ks[q] + koff;
+    double a[C][3];
+    sm_multi3<C>(s1, s2, ns, Nc, m, kap, lane, a);
+    double bestv = 0.0;
+    int bestk = -1;
+#pragma unroll
+    for (int q = 0; q < C; ++q) {
+        const int k = ks[q];
+        const double v = (a[q][1] - sum1 * wac[k]) / (dn * wbc[k] * std1);
+        if (!isnan(v) && (bestk < 0 || v > bestv)) {
+            bestv = v; bestk = k;
+            acc[0] = a[q][0]; acc[1] = a[q][1]; acc[2] = a[q][2];
+        }
+    }
+    return bestk;
+}
+
+__global__ void __launch_bounds__(RING_THREADS, 1)
+ccx_post_ring_kernel(const int4* __restrict__ karg, int c0, int nsig, const double* __restrict__ Xd, int N, int n,
+                     int Nc, int trunc, int nl, const int* __restrict__ rows, int nrows, int TC, int NB, int RG,
+                     const double* __restrict__ wa, const double* __restrict__ wb,
+                     const double* __restrict__ evsum, const double* __restrict__ evstd,
+                     double* __restrict__ cc, int* __restrict__ lag, double* __restrict__ sub,
+                     int* __restrict__ nflag, int2* __restrict__ flagged, int flag_cap) {
+    extern __shared__ __align__(16) double sm[];   // [TC] signals, [NB] template rows; each [Nc][ns]
+    __shared__ __align__(8) uint64_t bar_full[RING_NB_MAX], bar_empty[RING_NB_MAX], bar_sig;
+    __shared__ RingRec rec[RING_NB_MAX];
+    __shared__ int next_task;
+    __shared__ volatile int issued;                      // rows whose load has been issued (see the consumer's wait)
+    const int ns = n / Nc;
+    const int m32 = ((ns + 31) / 32) | 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sig0 = blockIdx.y * TC;
+    const int nmine = min(TC, nsig - sig0);              // signals of this CTA
+    const int r0 = blockIdx.x * RG;
+    const int c_last = c0 + sig0 + nmine - 1;
+    if (r0 >= nrows || rows[r0] >= c_last) return;       // nothing with b < c in this tile (CTA-uniform)
+    // rows ascend: the rows of this tile that have a pair here are a prefix
+    int lo = r0, hi = min(nrows, r0 + RG);
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (rows[mid] < c_last) lo = mid + 1; else hi = mid;
+    }
+    const int nr = lo - r0;                               // >= 1
+    const uint32_t row_bytes = static_cast<uint32_t>(n) * 8u;
+    if (tid == 0) {
+        for (int i = 0; i < NB; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], nmine); }
+        mbar_init(&bar_sig, 1);
+        next_task = 0;
+        issued = 0;
+        fence_barrier_init();
+    }
+    __syncthreads();
+    double* srow = sm + static_cast<size_t>(TC) * n;
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bar_sig, row_bytes * nmine);
+            for (int s = 0; s < nmine; ++s)
+                bulk_g2s(sm + static_cast<size_t>(s) * n, Xd + static_cast<long long>(c0 + sig0 + s) * n, row_bytes,
+                         &bar_sig);
+        }
+        for (int i = 0; i < nr; ++i) {
+            const int slot = i % NB;
+            if (i >= NB) mbar_wait(&bar_empty[slot], ((i / NB) - 1) & 1);
+            const int r = r0 + i;
+            const int b = rows[r];
+            if (lane < nmine) {
+                const int ci = sig0 + lane;
+                rec[slot].kc[lane] = (b < c0 + ci) ? karg[static_cast<long long>(ci) * nrows + r]
+                                                   : make_int4(-2, -1, -1, -1);
+            }
+            if (lane == 0) { rec[slot].std1 = evstd[b]; rec[slot].sum1 = evsum[b]; }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&bar_full[slot], row_bytes);
+                bulk_g2s(srow + static_cast<size_t>(slot) * n, Xd + static_cast<long long>(b) * n, row_bytes,
+                         &bar_full[slot]);
+                __threadfence_block();
+                issued = i + 1;
+            }
+        }
+        return;
+    }
+    // ---------------------------------------------------------------------- consumers
+    const double dn = static_cast<double>(n);
+    const int koff = trunc + 1 - ns;
+    // deferred finalisation: lane (count % 32) keeps a finished pair's sums; every 32 pairs all lanes normalise,
+    // fit the cosine and store in parallel
+    double p_a0 = 0.0, p_a1 = 0.0, p_a2 = 0.0, p_sum = 0.0, p_std = 0.0;
+    long long p_o = -1;
+    int p_k = 0, p_r = 0, p_c = 0, npend = 0;
+    auto flush = [&]() {
+        if (p_o >= 0) {
+            const int k = p_k;
+            const double* wac = wa + static_cast<long long>(p_c) * nl;
+            const double* wbc = wb + static_cast<long long>(p_c) * nl;
+            const double v = (p_a1 - p_sum * wac[k]) / (dn * wbc[k] * p_std);
+            if (isnan(v) || v > 1.0 + CC_GUARD) {
+                const int q = atomicAdd(nflag, 1);
+                if (q < flag_cap) flagged[q] = make_int2(p_r, p_c);
+            } else {
+                double ss = 0.0;                          // maximum at either end of the lag range: 0 (construct.py:402)
+                if (k > 0 && k < nl - 1) {
+                    const double cb4 = (p_a0 - p_sum * wac[k - 1]) / (dn * wbc[k - 1] * p_std);
+                    const double caf = (p_a2 - p_sum * wac[k + 1]) / (dn * wbc[k + 1] * p_std);
+                    const double alpha = acos((cb4 + caf) / (2 * v));
+                    const double alsi = sin(alpha);
+                    const double tau = -(atan((cb4 - caf) / (2 * v * alsi)) / alpha);
+                    ss = (fabs(tau) > 0.5) ? static_cast<double>(k) : tau;   // reference quirk, construct.py:418-421
+                }
+                cc[p_o] = v;
+                lag[p_o] = (k + 1 + trunc) * Nc - n;
+                sub[p_o] = ss;
+            }
+            p_o = -1;
+        }
+        npend = 0;
+    };
+    mbar_wait(&bar_sig, 0);
+    const int ntask = nr * nmine;
+    for (;;) {
+        int id = 0;
+        if (lane == 0) id = atomicAdd(&next_task, 1);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id >= ntask) break;
+        const int i = id / nmine, s = id - i * nmine;
+        const int slot = i % NB;
+        // A parity wait is only meaningful once the barrier has reached this row's phase: with few tasks per row a
+        // warp can draw a task two uses of the slot ahead, where the parity test would alias to a finished phase.
+        while (issued <= i) __nanosleep(32);
+        mbar_wait(&bar_full[slot], (i / NB) & 1);
+        const int4 kc = rec[slot].kc[s];
+        if (kc.x >= 0) {                                  // else: b >= c, or left to ccx_post_kernel
+            const double std1 = rec[slot].std1, sum1 = rec[slot].sum1;
+            const int r = r0 + i, c = c0 + sig0 + s;
+            const double* s1 = srow + static_cast<size_t>(slot) * n;
+            const double* s2 = sm + static_cast<size_t>(s) * n;
+            double acc[3];
+            int k = kc.x;
+            if (kc.y >= 0) {
+                const double* wac = wa + static_cast<long long>(c) * nl;
+                const double* wbc = wb + static_cast<long long>(c) * nl;
+                if (kc.z < 0) k = sm_best3<2>(s1, s2, ns, Nc, m32, kc, koff, lane, sum1, std1, dn, wac, wbc, acc);
+                else if (kc.w < 0) k = sm_best3<3>(s1, s2, ns, Nc, m32, kc, koff, lane, sum1, std1, dn, wac, wbc, acc);
+                else k = sm_best3<4>(s1, s2, ns, Nc, m32, kc, koff, lane, sum1, std1, dn, wac, wbc, acc);
+            } else {
+                sm_dot3(s1, s2, ns, Nc, m32, k + koff, lane, acc);
+            }
+            if (k < 0) {                                  // every candidate NaN: let the float64 kernel decide
+                if (lane == 0) {
+                    const int q = atomicAdd(nflag, 1);
+                    if (q < flag_cap) flagged[q] = make_int2(r, c);
+                }
+            } else {
+                if (lane == npend) {
+                    p_a0 = acc[0]; p_a1 = acc[1]; p_a2 = acc[2];
+                    p_sum = sum1; p_std = std1; p_k = k; p_r = r; p_c = c;
+                    p_o = static_cast<long long>(r) * N + c;
+                }
+                if (++npend == 32) flush();
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[slot]);   // this task no longer reads the slot
+    }
+    flush();
+}
+
+// events de-multiplexed into float64 [N][Nc][ns] (one bulk copy per waveform in the ring kernel)
+template <typename T>
+__global__ void __launch_bounds__(256)
+ccx_demux_kernel(const T* __restrict__ X, int n, int Nc, double* __restrict__ Xd) {
+    const int ns = n / Nc;
+    const T* x = X + static_cast<long long>(blockIdx.x) * n;
+    double* d = Xd + static_cast<long long>(blockIdx.x) * n;
+    for (int i = threadIdx.x; i < n; i += 256) d[(i % Nc) * ns + i / Nc] = static_cast<double>(x[i]);
+}
+
 }  // namespace
 
 void launch_ccx_stats(const void* d_X, int dtype_f32, int N, int n, int Nc, double* wa, double* wb, double* es,
@@ -955,20 +1239,51 @@ void launch_ccx_pad(const void* d_X, int dtype_f32, int n, int Nc, int c0, int n
         ccx_pad_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(d_X), n, Nc, c0, P, Lc, out);
 }
 
+void launch_ccx_demux(const void* d_X, int dtype_f32, int N, int n, int Nc, double* d_Xd, cudaStream_t st) {
+    if (dtype_f32) ccx_demux_kernel<float><<<N, 256, 0, st>>>(static_cast<const float*>(d_X), n, Nc, d_Xd);
+    else ccx_demux_kernel<double><<<N, 256, 0, st>>>(static_cast<const double*>(d_X), n, Nc, d_Xd);
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
 void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsig, const void* d_X, int dtype_f32,
-                     int N, int n, int Nc, const int* d_rows, int nrows, const double* wa, const double* wb,
-                     const double* es, const double* ed, double* d_cc, int* d_lag, double* d_sub, int* d_nflag,
-                     int2* d_flagged, int flag_cap, int4* d_karg, const unsigned* d_ratio_bits, float band0,
-                     cudaStream_t st) {
+                     const double* d_Xd, int N, int n, int Nc, const int* d_rows, int nrows, const double* wa,
+                     const double* wb, const double* es, const double* ed, double* d_cc, int* d_lag, double* d_sub,
+                     int* d_nflag, int2* d_flagged, int flag_cap, int4* d_karg, const unsigned* d_ratio_bits,
+                     float band0, cudaStream_t st) {
     const int ns = n / Nc;
     const int trunc = n / (2 * Nc) - 1;
     const int nl = 2 * ns - 1 - 2 * trunc;
     const int rows = nrows;
-    // tiled variant: TC signals + 1 template row, float64, in shared memory
     const long long per_wave = static_cast<long long>(n) * 8;
-    const int TC = static_cast<int>(std::min<long long>(POST_SIGS, (220 * 1024 - 128) / per_wave - 1));
     const int4* karg = nullptr;
-    if (TC >= 1 && d_karg && !std::getenv("DTX_CCX_POST_UNTILED")) {
+    // ring variant (default): TC resident signals + a ring of NB template rows, float64, in shared memory
+    const int slots = static_cast<int>(std::min<long long>(RING_TC_MAX + RING_NB_MAX, (227 * 1024 - 2048 - 128) / per_wave));
+    const bool ring = d_Xd && d_karg && n % 2 == 0 && slots >= 3 && !env_int("DTX_CCX_POST_TILED", 0) &&
+                      !std::getenv("DTX_CCX_POST_UNTILED");
+    // tiled variant: TC signals + 1 template row, float64, in shared memory
+    const int TC = static_cast<int>(std::min<long long>(POST_SIGS, (220 * 1024 - 128) / per_wave - 1));
+    if (ring) {
+        const dim3 sg((rows + 7) / 8, nsig);
+        ccx_scan_kernel<<<sg, 256, 0, st>>>(DS, d_chunks, c0, N, nl, d_rows, nrows, es, ed, n, d_ratio_bits, band0, d_cc,
+                                            d_lag, d_sub, d_karg);
+        int NB = env_int("DTX_CCX_RING_NB", slots >= 8 ? 3 : 2);
+        NB = std::max(2, std::min(NB, std::min(RING_NB_MAX, slots - 1)));
+        int RTC = env_int("DTX_CCX_RING_TC", slots - NB);
+        RTC = std::max(1, std::min(RTC, std::min(RING_TC_MAX, slots - NB)));
+        const int RG = std::max(1, env_int("DTX_CCX_RING_RG", 64));
+        const size_t smem = static_cast<size_t>(RTC + NB) * per_wave + 128;
+        const dim3 tg((rows + RG - 1) / RG, (nsig + RTC - 1) / RTC);
+        cudaFuncSetAttribute(ccx_post_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        const int nthreads = 32 * std::max(2, std::min(RING_THREADS / 32, env_int("DTX_CCX_RING_WARPS", 12)));
+        ccx_post_ring_kernel<<<tg, nthreads, smem, st>>>(d_karg, c0, nsig, d_Xd, N, n, Nc, trunc, nl, d_rows, nrows,
+                                                             RTC, NB, RG, wa, wb, es, ed, d_cc, d_lag, d_sub, d_nflag,
+                                                             d_flagged, flag_cap);
+        karg = d_karg;   // ccx_post_kernel below: only the pairs the scan left for it
+    } else if (TC >= 1 && d_karg && !std::getenv("DTX_CCX_POST_UNTILED")) {
         const dim3 sg((rows + 7) / 8, nsig);
         ccx_scan_kernel<<<sg, 256, 0, st>>>(DS, d_chunks, c0, N, nl, d_rows, nrows, es, ed, n, d_ratio_bits, band0, d_cc,
                                             d_lag, d_sub, d_karg);
