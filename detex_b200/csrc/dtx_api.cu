@@ -629,9 +629,13 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     cg2 = cg2 && mode != 1 && nq == 256 && engine != DTX_ENGINE_FP64 && ctx->num_sms >= 2;
     const int bstep = cg2 ? 2 : 1;
     if (cg2) super = std::max(2, super & ~1);
+    // CCX screening series (mode 1, one MMA per K step, tiles of 1024 lags): chunks are taken in PAIRS that share
+    // the stream of the basis image (k1_project.cu, DUAL); DTX_K1_NODUAL=1 keeps one chunk per item
+    const bool dual = mode == 1 && hi_only && nq == 128 && !cg2 && engine != DTX_ENGINE_FP64 &&
+                      !(std::getenv("DTX_K1_NODUAL") && std::atoi(std::getenv("DTX_K1_NODUAL")) != 0);
     const int wave = cg2 ? ctx->num_sms / 2 : ctx->num_sms;
     // the list only depends on the batch's shape: reuse the device copy when it has not changed
-    std::vector<int> sig_key{nq, lay.nblocks, group, nchunks, super, wave, cg2};
+    std::vector<int> sig_key{nq, lay.nblocks, group, nchunks, super, wave, cg2, dual ? 1 : 0};
     for (int i = 0; i < nchunks; ++i) {
         sig_key.push_back(ctx->h_chunks[i].T);
         sig_key.push_back(ctx->h_chunks[i].blk_hi);
@@ -639,24 +643,27 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
     const bool items_cached = sig_key == ctx->items_key && ctx->d_items.p != nullptr;
     std::vector<int4> items;
     if (!items_cached) items.reserve(static_cast<size_t>(nitems) * 2 * lay.nblocks);
-    std::vector<std::pair<int, int>> tl;   // (chunk, tile) of the current group
+    struct TileRef { int chunk, tile, partner, blk_lo, blk_hi; };
+    std::vector<TileRef> tl;   // (chunk, tile) of the current group; with `dual`, (chunk pair, tile)
     for (int g0 = 0; g0 < nchunks && !items_cached; g0 += group) {
         const int g1 = std::min(nchunks, g0 + group);
         int max_blk = 0;
         tl.clear();
-        for (int i = g0; i < g1; ++i) {
-            max_blk = std::max(max_blk, ctx->h_chunks[i].blk_hi);
-            const int nt = (ctx->h_chunks[i].T + 8 * nq - 1) / (8 * nq);
-            for (int t = 0; t < nt; ++t) tl.emplace_back(i, t);
+        for (int i = g0; i < g1; i += dual ? 2 : 1) {
+            const int partner = (dual && i + 1 < g1) ? i + 1 : i;   // an odd last chunk pairs with itself
+            const ChunkDesc &c0 = ctx->h_chunks[i], &c1 = ctx->h_chunks[partner];
+            const int lo = std::min(c0.blk_lo, c1.blk_lo), hi = std::max(c0.blk_hi, c1.blk_hi);
+            max_blk = std::max(max_blk, hi);
+            const int nt = (std::max(c0.T, c1.T) + 8 * nq - 1) / (8 * nq);
+            for (int t = 0; t < nt; ++t) tl.push_back(TileRef{i, t, dual ? partner : 0, lo, hi});
         }
         for (int sb = 0; sb < max_blk; sb += super)
             for (size_t w0 = 0; w0 < tl.size(); w0 += (super > 1 ? wave : tl.size()))
                 for (int b = sb; b < std::min(sb + super, max_blk); b += bstep) {
                     const size_t w1 = super > 1 ? std::min(tl.size(), w0 + wave) : tl.size();
                     for (size_t k = w0; k < w1; ++k) {
-                        const ChunkDesc& cd = ctx->h_chunks[tl[k].first];
-                        if (b < cd.blk_lo || b >= cd.blk_hi) continue;
-                        items.push_back(make_int4(tl[k].first, tl[k].second, b, 0));
+                        if (b < tl[k].blk_lo || b >= tl[k].blk_hi) continue;
+                        items.push_back(make_int4(tl[k].chunk, tl[k].tile, b, tl[k].partner));
                     }
                 }
     }
@@ -731,8 +738,9 @@ static int project_run(dtx_ctx* ctx, BasisSet& bs, int engine, int kblk, int mod
         a.xsplit = ctx->d_xsplit.p; a.mu = ctx->d_mu.p; a.invE = ctx->d_invE.p;
         a.chunk_scale = ctx->d_scale.p; a.chunks = ctx->d_chunks.p; a.items = ctx->d_items.p;
         a.binfo = bs.d_binfo.p; a.DS = ctx->d_DS.p; a.nitems = ctx->n_items;
-        a.kblk = kblk; a.num_sms = ctx->num_sms; a.nq = nq; a.mode = mode;
+        a.kblk = kblk; a.num_sms = ctx->num_sms; a.nq = dual ? 256 : nq; a.mode = mode;
         a.hi_only = hi_only;
+        a.dual = dual ? 1 : 0;
         a.cg2 = cg2;
         a.fused = fused ? 1 : 0;
         a.thr = bs.d_thr.p; a.rowmax_bits = reinterpret_cast<unsigned*>(ctx->d_rowmax.p); a.rowflags = ctx->d_rowflags.p;

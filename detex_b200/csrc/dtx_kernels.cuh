@@ -165,6 +165,8 @@ struct K1Args {
     int S;                           // subspaces (rows per chunk)
     int cg2;       // 1 = CTA pairs (cta_group::2): items are (chunk, tile, EVEN basis block), the two CTAs of a
                    // cluster take blocks it.z and it.z + 1 and share the tile's B rows (N = 256 only)
+    int dual;      // 1 = CCX screening series on PAIRS of chunks (items (chunk, tile, block, partner chunk)): two
+                   //     N = 128 MMAs per K step share the A tile, the basis image is streamed once per pair
     int hi_only;   // 1 = ONE MMA per K step (fp16 hi * hi only, 11-bit operands): a screening series whose
                    // error is bounded by ~2^-10 of the normalised value; CCX uses it to LOCATE the maximum,
                    // which is then re-scored in float64 (k4_ccx.cu)

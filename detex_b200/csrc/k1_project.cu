@@ -177,10 +177,15 @@ __device__ __forceinline__ int item_x8(const K1Params& P, int chunk) {
 template <bool CG2> __device__ __forceinline__ int item_first() { return CG2 ? cluster_id_x() : blockIdx.x; }
 template <bool CG2> __device__ __forceinline__ int item_step() { return CG2 ? cluster_nctaid_x() : gridDim.x; }
 
-template <int NQ, bool CG2>
+// DUAL (CCX screening series, hi-only): an item is a PAIR of chunks (it.x, it.w) of at most 1024 lags each against
+// one basis block.  Each chunk supplies 128 B rows from its own span (the second one sits in the unused lo-plane
+// slot), two N = 128 MMAs per K step share the A tile, and the halves of the 256-column accumulator, of the norm
+// tile and of the read-out belong to the two chunks -- the basis image, whose stream out of L2 bounds the
+// one-chunk form of this mode (786 KB per item at n = 3000, 7 TB/s over the 148 SMs), is read once per pair.
+template <int NQ, bool CG2, bool DUAL>
 __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) {
     constexpr int TT = 8 * NQ;
-    constexpr int TSPAN = CG2 ? TT / 2 : TT;          // lags whose B rows this CTA supplies
+    constexpr int TSPAN = (CG2 || DUAL) ? TT / 2 : TT;   // lags whose B rows this CTA supplies (per chunk of a pair)
     const int brank = CG2 ? cluster_ctarank() : 0;
     Ring st(STAGES), sg(2), nm(2);
     const bool hi_only = P.a.hi_only != 0;
@@ -194,18 +199,30 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
     for (int item = item_first<CG2>(); item < P.a.nitems; item += item_step<CG2>()) {
         const int4 it = P.a.items[item];
         const ChunkDesc cd = P.a.chunks[it.x];
+        const ChunkDesc cd1 = P.a.chunks[DUAL ? it.w : it.x];
         // window mean / inverse energy of this tile
         mbar_wait(&S.normempty[nm.idx], nm.phase ^ 1);
         if (ISSUE_LANE) {
             mbar_arrive_expect_tx(&S.normfull[nm.idx], 2 * TT * 4);
-            SIG_G2S(S.norm + nm.idx * NORM_BUF_BYTES, P.a.mu + cd.norm_off + static_cast<long long>(it.y) * TT,
-                     TT * 4, &S.normfull[nm.idx]);
-            SIG_G2S(S.norm + nm.idx * NORM_BUF_BYTES + TILE_T * 4,
-                     P.a.invE + cd.norm_off + static_cast<long long>(it.y) * TT, TT * 4, &S.normfull[nm.idx]);
+            if (DUAL) {
+                uint8_t* nb = S.norm + nm.idx * NORM_BUF_BYTES;
+                const long long o0 = cd.norm_off + static_cast<long long>(it.y) * TSPAN;
+                const long long o1 = cd1.norm_off + static_cast<long long>(it.y) * TSPAN;
+                SIG_G2S(nb, P.a.mu + o0, TSPAN * 4, &S.normfull[nm.idx]);
+                SIG_G2S(nb + TSPAN * 4, P.a.mu + o1, TSPAN * 4, &S.normfull[nm.idx]);
+                SIG_G2S(nb + TILE_T * 4, P.a.invE + o0, TSPAN * 4, &S.normfull[nm.idx]);
+                SIG_G2S(nb + TILE_T * 4 + TSPAN * 4, P.a.invE + o1, TSPAN * 4, &S.normfull[nm.idx]);
+            } else {
+                SIG_G2S(S.norm + nm.idx * NORM_BUF_BYTES, P.a.mu + cd.norm_off + static_cast<long long>(it.y) * TT,
+                         TT * 4, &S.normfull[nm.idx]);
+                SIG_G2S(S.norm + nm.idx * NORM_BUF_BYTES + TILE_T * 4,
+                         P.a.invE + cd.norm_off + static_cast<long long>(it.y) * TT, TT * 4, &S.normfull[nm.idx]);
+            }
         }
         ISSUE_SYNC();
         nm.advance();
-        const __half* sig0 = P.a.xsplit + cd.sig_off + static_cast<long long>(it.y) * TT + brank * TSPAN;
+        const __half* sig0 = P.a.xsplit + cd.sig_off + static_cast<long long>(it.y) * (DUAL ? TSPAN : TT) + brank * TSPAN;
+        const __half* sig1 = P.a.xsplit + cd1.sig_off + static_cast<long long>(it.y) * TSPAN;   // DUAL only
         {
             const int b = it.z + brank;
             const uint8_t* ablk = (item_x8(P, it.x) ? P.a.Aimg8 : P.a.Aimg) +
@@ -215,10 +232,14 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
                 const uint32_t bytes = (TSPAN + sgm.ntaps) * 2;
                 mbar_wait(&S.sigempty[sg.idx], sg.phase ^ 1);
                 if (ISSUE_LANE) {
-                    mbar_arrive_expect_tx(&S.sigfull[sg.idx], hi_only ? bytes : 2 * bytes);
+                    mbar_arrive_expect_tx(&S.sigfull[sg.idx], (hi_only && !DUAL) ? bytes : 2 * bytes);
                     const __half* src = sig0 + static_cast<long long>(sgm.chan * 2) * cd.Lpad + sgm.tap0;
                     SIG_G2S(S.sig + sg.idx * SIG_BUF_BYTES, src, bytes, &S.sigfull[sg.idx]);
-                    if (!hi_only)
+                    if (DUAL)        // the second chunk's hi plane, in the lo-plane slot
+                        SIG_G2S(S.sig + sg.idx * SIG_BUF_BYTES + SIG_HALFS * 2,
+                                 sig1 + static_cast<long long>(sgm.chan * 2) * cd1.Lpad + sgm.tap0, bytes,
+                                 &S.sigfull[sg.idx]);
+                    else if (!hi_only)
                         SIG_G2S(S.sig + sg.idx * SIG_BUF_BYTES + SIG_HALFS * 2, src + cd.Lpad, bytes,
                                  &S.sigfull[sg.idx]);
                 }
@@ -243,9 +264,9 @@ __device__ __forceinline__ void producer_loop(const K1Params& P, const Smem& S) 
 }
 
 // ---------------------------------------------- MMA issuer (warp 1, an elected lane issues)
-template <int NQ, bool CG2>
+template <int NQ, bool CG2, bool DUAL>
 __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint32_t tmem) {
-    const uint32_t idesc = idesc_f16_f32(CG2 ? 256 : 128, NQ);
+    const uint32_t idesc = idesc_f16_f32(CG2 ? 256 : 128, DUAL ? NQ / 2 : NQ);
     const uint32_t idesc8 = idesc_e4m3_e5m2_f32(CG2 ? 256 : 128, NQ);
     const uint64_t a_base = smem_desc_kmajor_noswz(0, A_LBO, A_SBO);
     const uint64_t b_base = smem_desc_kmajor_noswz(0, B_LBO, B_SBO);
@@ -309,6 +330,16 @@ __device__ __forceinline__ void mma_loop(const K1Params& P, const Smem& S, uint3
                             umma2_commit_mc(&S.empty[st.idx], 0x3);
                             if (last) umma2_commit_mc(&S.accfull[ac.idx], 0x3);
                             if (kc == nck - 1) umma2_commit_mc(&S.sigempty[sg.idx], 0x3);
+                        } else if (DUAL) {
+                            // two chunks, one A tile: the second MMA takes it from the operand collector
+#pragma unroll
+                            for (int kk = 0; kk < CHUNK_TAPS / 16; ++kk) {
+                                const uint64_t dah = a_base | ((ah + kk * 256) >> 4);
+                                const uint64_t db0 = b_base | ((sh + bo + kk * 32) >> 4);
+                                const uint64_t db1 = b_base | ((sl + bo + kk * 32) >> 4);
+                                umma_f16_a_fill(d, dah, db0, idesc, (cib | kk) ? 1u : 0u);
+                                umma_f16_a_lastuse(d + NQ / 2, dah, db1, idesc, (cib | kk) ? 1u : 0u);
+                            }
                         } else if (hi_only) {
 #pragma unroll
                             for (int kk = 0; kk < CHUNK_TAPS / 16; ++kk) {
@@ -481,7 +512,7 @@ __device__ __noinline__ FusedState fused_values(FusedState st, float4 acc, float
     return st;
 }
 
-template <int NQ, int MODE, bool CG2>
+template <int NQ, int MODE, bool CG2, bool DUAL>
 __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uint32_t tmem, int warp,
                                            int lane) {
     const int brank = CG2 ? cluster_ctarank() : 0;
@@ -507,11 +538,12 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
     const float f_toff = -f_flo * f_finv;
     for (int item = item_first<CG2>(); item < P.a.nitems; item += item_step<CG2>()) {
         const int4 it = P.a.items[item];
-        const ChunkDesc cd = P.a.chunks[it.x];
+        const int mychunk = (DUAL && colhalf) ? it.w : it.x;   // DUAL: the column halves belong to two chunks
+        const ChunkDesc cd = P.a.chunks[mychunk];
         const int kblk = item_x8(P, it.x) ? P.a.kblk8 : P.a.kblk;
         int ndrains = 0;
         for (int rem = P.nchunks; rem > 0; ++ndrains) rem -= acc_stages(ndrains, kblk, P.nchunks);
-        const float sc = P.a.chunk_scale[it.x] * P.u_inv_scale;
+        const float sc = P.a.chunk_scale[mychunk] * P.u_inv_scale;
         const float* smu = reinterpret_cast<const float*>(S.norm + nm.idx * NORM_BUF_BYTES);
         const float* sie = smu + TILE_T;
         {
@@ -584,7 +616,8 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
             // mu tile is phase-major per 1024-lag group (k0_norm): this thread's 128 columns are contiguous
             const float* pmu = smu + (8 * NCOL * colhalf / 1024) * 1024 + p * 128 + (NCOL * colhalf) % 128;
             const float* pie4 = sie + 8 * NCOL * colhalf + lane * 4;
-            float* dsbase = P.a.DS + cd.ds_off + static_cast<long long>(it.y) * TT + 8 * NCOL * colhalf + lane * 4;
+            float* dsbase = DUAL ? P.a.DS + cd.ds_off + static_cast<long long>(it.y) * (TT / 2) + lane * 4
+                                 : P.a.DS + cd.ds_off + static_cast<long long>(it.y) * TT + 8 * NCOL * colhalf + lane * 4;
             // read-out role of this warp: the subspaces whose first slot is lq, lq+4, lq+8, lq+12
             BlockInfo hb[4];
 #pragma unroll
@@ -700,8 +733,9 @@ __device__ __forceinline__ void drain_loop(const K1Params& P, const Smem& S, uin
     }
 }
 
-template <int NQ, int MODE, bool CG2>
+template <int NQ, int MODE, bool CG2, bool DUAL = false>
 __global__ void __launch_bounds__(NTHREADS, 1) k1_kernel(const __grid_constant__ K1Params P) {
+    static_assert(!DUAL || (MODE == 1 && NQ == 256 && !CG2), "DUAL: CCX screening series only");
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full[STAGES], empty[STAGES], pfull[STAGES];
     __shared__ uint64_t sigfull[2], sigempty[2], accfull[2], accempty[2], normfull[2], normempty[2], psigfull[2];
@@ -752,15 +786,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k1_kernel(const __grid_constant__
     if (warp < FIRST_DRAIN_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
         if (warp == 0 && ROLE_LANES(lane)) {
-            producer_loop<NQ, CG2>(P, S);
+            producer_loop<NQ, CG2, DUAL>(P, S);
         } else if (warp == 1 && ROLE_LANES(lane)) {
-            if (!CG2 || cluster_ctarank() == 0) mma_loop<NQ, CG2>(P, S, tmem);   // pairs: only the leader issues
+            if (!CG2 || cluster_ctarank() == 0) mma_loop<NQ, CG2, DUAL>(P, S, tmem);   // pairs: only the leader issues
         } else if (CG2 && warp == 2 && lane == 0) {
             if (cluster_ctarank() == 1) forward_loop<NQ>(P, S);
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_DRAIN));
-        drain_loop<NQ, MODE, CG2>(P, S, tmem, warp, lane);
+        drain_loop<NQ, MODE, CG2, DUAL>(P, S, tmem, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -903,7 +937,10 @@ void launch_k1(const K1Args& a, const BasisLayout& lay, cudaStream_t st) {
     for (int i = 0; i < lay.nseg; ++i) P.seg[i] = lay.seg[i];
     const int grid = a.nitems < a.num_sms ? a.nitems : a.num_sms;
     if (grid < 1) return;
-    if (a.nq == 128) {
+    if (a.dual) {
+        cudaFuncSetAttribute(k1_kernel<256, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        k1_kernel<256, 1, false, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+    } else if (a.nq == 128) {
         if (a.mode == 1) launch_k1_t<128, 1>(P, grid, st);
         else if (a.fused) launch_k1_t<128, 2>(P, grid, st);
         else launch_k1_t<128, 0>(P, grid, st);
