@@ -27,6 +27,7 @@ EXPORTS = [
     "dtx_set_x8_tolerance", "dtx_get_chunk_modes", "dtx_set_trigger_sta", "dtx_preprocess_chunks_dec", "dtx_set_hist_bins",
     "dtx_accumulate_begin", "dtx_accumulate_end", "dtx_k1_ms_history", "dtx_ccx_device", "dtx_ccx_pack",
     "dtx_ccx_condensed", "dtx_set_ccx_batch", "dtx_host_alloc", "dtx_host_free", "dtx_set_core_lags", "dtx_set_ccx_passes", "dtx_set_fused",
+    "dtx_ccx_pack_rows", "dtx_host_register", "dtx_host_unregister",
 ]
 
 
@@ -100,6 +101,9 @@ def load():
     L.dtx_set_fused.argtypes = [p, C.c_int]
     L.dtx_host_alloc.argtypes = [C.POINTER(p), C.c_int64]
     L.dtx_host_free.argtypes = [p]
+    L.dtx_host_register.argtypes = [p, C.c_int64]
+    L.dtx_host_unregister.argtypes = [p]
+    L.dtx_ccx_pack_rows.argtypes = [p, p, p, p, p, C.c_int, C.c_int, p, p, p]
     for name in EXPORTS:
         if name not in ("dtx_destroy", "dtx_last_error"):
             getattr(L, name).restype = C.c_int

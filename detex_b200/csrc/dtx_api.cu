@@ -1601,6 +1601,34 @@ int dtx_ccx_pack(dtx_ctx* ctx, const double* d_cc, const int32_t* d_lag, const d
     return ccx_check_flags(ctx);
 }
 
+int dtx_ccx_pack_rows(dtx_ctx* ctx, const double* d_cc, const int32_t* d_lag, const double* d_sub,
+                      const int32_t* rows, int nrows, int N, double* cc, int32_t* lag, double* subsamp) {
+    if (!ctx) return DTX_ERR_ARG;
+    if (!d_cc || !d_lag || !d_sub || !rows || !cc || !lag || !subsamp || N < 2 || nrows < 0)
+        return fail(ctx, DTX_ERR_ARG, "dtx_ccx_pack_rows: bad arguments");
+    DTX_CUDA(cudaSetDevice(ctx->device));
+    for (int r = 0; r < nrows; ++r)
+        if (rows[r] < 0 || rows[r] >= N - 1) return fail(ctx, DTX_ERR_ARG, "dtx_ccx_pack_rows: row out of range");
+    // the outputs are written by the kernel itself: they must be visible to the device (page-locked + mapped)
+    void *p_cc = nullptr, *p_lag = nullptr, *p_sub = nullptr;
+    if (cudaHostGetDevicePointer(&p_cc, cc, 0) != cudaSuccess || cudaHostGetDevicePointer(&p_lag, lag, 0) != cudaSuccess ||
+        cudaHostGetDevicePointer(&p_sub, subsamp, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, DTX_ERR_ARG, "dtx_ccx_pack_rows: outputs must be page-locked (dtx_host_alloc / dtx_host_register)");
+    }
+    cudaStream_t st = ctx->stream;
+    if (nrows > 0) {
+        DTX_CUDA(ctx->cx_slot.reserve(nrows));
+        DTX_CUDA(cudaMemcpyAsync(ctx->cx_slot.p, rows, sizeof(int) * nrows, cudaMemcpyHostToDevice, st));
+        launch_ccx_pack_rows(d_cc, d_lag, d_sub, ctx->cx_slot.p, nrows, N, static_cast<double*>(p_cc),
+                             static_cast<int*>(p_lag), static_cast<double*>(p_sub), st);
+        DTX_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    DTX_CUDA(cudaStreamSynchronize(st));
+    return ccx_check_flags(ctx);
+}
+
 int dtx_ccx_condensed(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int engine, double* cc,
                       int32_t* lag, double* subsamp) {
     if (!ctx) return DTX_ERR_ARG;
@@ -1637,6 +1665,19 @@ int dtx_set_ccx_batch(dtx_ctx* ctx, int max_signals, int64_t ds_bytes) {
 int dtx_host_alloc(void** out, int64_t bytes) {
     if (!out || bytes < 1) return DTX_ERR_ARG;
     return cudaMallocHost(out, static_cast<size_t>(bytes)) == cudaSuccess ? DTX_OK : DTX_ERR_CUDA;
+}
+
+int dtx_host_register(void* p, int64_t bytes) {
+    if (!p || bytes < 1) return DTX_ERR_ARG;
+    const cudaError_t e = cudaHostRegister(p, static_cast<size_t>(bytes), cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) { cudaGetLastError(); return DTX_ERR_CUDA; }
+    return DTX_OK;
+}
+
+int dtx_host_unregister(void* p) {
+    if (!p) return DTX_OK;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return DTX_ERR_CUDA; }
+    return DTX_OK;
 }
 
 int dtx_host_free(void* p) {

@@ -224,6 +224,8 @@ void launch_ccx_post(const float* DS, const ChunkDesc* d_chunks, int c0, int nsi
                      float band0, cudaStream_t st);   // d_karg: [nsig][nrows] scratch; d_ratio_bits: per signal, from k0_norm
 // dense per-slot rows [nslots][N] -> SciPy condensed order (pair (b, c), b < c, at b*N - b(b+1)/2 + c-b-1);
 // d_slot_of_row[b] = slot holding event b's row
+void launch_ccx_pack_rows(const double* d_cc, const int* d_lag, const double* d_sub, const int* d_rows, int nrows, int N,
+                          double* o_cc, int* o_lag, double* o_sub, cudaStream_t st);
 void launch_ccx_pack(const double* d_cc, const int* d_lag, const double* d_sub, const int* d_slot_of_row, int N,
                      double* o_cc, int* o_lag, double* o_sub, cudaStream_t st);
 

@@ -497,9 +497,14 @@ ccx_scan_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
     int cnt = 0;
     auto stat4 = [&](const float4& v4, int q) {
         const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+        if (4 * q + 3 < nl) {                            // a whole quad: fmaxf / fminf skip NaN by themselves
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (4 * q + e < nl && !isnan(v[e])) { mx = fmaxf(mx, v[e]); mn = fminf(mn, v[e]); ++cnt; }
+            for (int e = 0; e < 4; ++e) { mx = fmaxf(mx, v[e]); mn = fminf(mn, v[e]); cnt += (v[e] == v[e]); }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (4 * q + e < nl && !isnan(v[e])) { mx = fmaxf(mx, v[e]); mn = fminf(mn, v[e]); ++cnt; }
+        }
     };
     if (inreg) {
 #pragma unroll
@@ -527,9 +532,11 @@ ccx_scan_kernel(const float* __restrict__ DS, const ChunkDesc* __restrict__ chun
         auto hits = [&](const float4& v4, int q) -> unsigned {
             const float v[4] = {v4.x, v4.y, v4.z, v4.w};
             unsigned m4 = 0;
+            if (fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])) >= thr) {   // rare: a handful of quads per row
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (4 * q + e < nl && v[e] >= thr) m4 |= 1u << e;
+                for (int e = 0; e < 4; ++e)
+                    if (4 * q + e < nl && v[e] >= thr) m4 |= 1u << e;
+            }
             return m4;
         };
         auto collect = [&](unsigned m4, int q0) {         // warp-uniform: lags in ascending order
@@ -1329,6 +1336,30 @@ ccx_pack_kernel(const double* __restrict__ cc, const int* __restrict__ lag, cons
     o_cc[dst] = cc[src];
     o_lag[dst] = lag[src];
     o_sub[dst] = sub[src];
+}
+
+// A rank's own template rows -> their places in the condensed arrays of the WHOLE matrix.  The output pointers may
+// be page-locked host memory mapped into the device (zero-copy stores over this GPU's own PCIe link; every row's
+// entries are contiguous, so a warp writes 256 / 128 contiguous bytes).  One block row per slot, threads over c > b.
+__global__ void __launch_bounds__(256)
+ccx_pack_rows_kernel(const double* __restrict__ cc, const int* __restrict__ lag, const double* __restrict__ sub,
+                     const int* __restrict__ rows, int N, double* __restrict__ o_cc, int* __restrict__ o_lag,
+                     double* __restrict__ o_sub) {
+    const int r = blockIdx.y;
+    const int b = rows[r];
+    const int c = b + 1 + blockIdx.x * 256 + threadIdx.x;
+    if (c >= N) return;
+    const long long src = static_cast<long long>(r) * N + c;
+    const long long dst = static_cast<long long>(b) * N - static_cast<long long>(b) * (b + 1) / 2 + (c - b - 1);
+    o_cc[dst] = cc[src];
+    o_lag[dst] = lag[src];
+    o_sub[dst] = sub[src];
+}
+
+void launch_ccx_pack_rows(const double* d_cc, const int* d_lag, const double* d_sub, const int* d_rows, int nrows, int N,
+                          double* o_cc, int* o_lag, double* o_sub, cudaStream_t st) {
+    const dim3 grid((N - 1 + 255) / 256, nrows);
+    ccx_pack_rows_kernel<<<grid, 256, 0, st>>>(d_cc, d_lag, d_sub, d_rows, N, o_cc, o_lag, o_sub);
 }
 
 void launch_ccx_pack(const double* d_cc, const int* d_lag, const double* d_sub, const int* d_slot_of_row, int N,

@@ -334,6 +334,24 @@ class Engine(object):
         buf = (C.c_char * max(1, nbytes)).from_address(ptr.value)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
+    def host_register(self, arr):
+        """Page-lock (and map for the device) the memory of a NumPy array the caller owns, e.g. a view of a
+        POSIX shared-memory segment; `host_unregister` before the memory goes away."""
+        if self._L.dtx_host_register(_ptr(arr), int(arr.nbytes)) != 0:
+            raise DtxError(1, "dtx_host_register failed")
+
+    def host_unregister(self, arr):
+        self._L.dtx_host_unregister(_ptr(arr))
+
+    def ccx_pack_rows(self, d_cc, d_lag, d_sub, rows, N, out):
+        """This GPU's dense device slots (slot r = event rows[r]) -> their places in the page-locked condensed
+        host arrays `out` = (cc, lag, subsamp) of the whole matrix (`pinned_empty` / `host_register`)."""
+        rows = np.ascontiguousarray(np.asarray(rows, dtype=np.int32))
+        cc, lag, sub = out
+        self._check(self._L.dtx_ccx_pack_rows(self._h, C.c_void_p(int(d_cc)), C.c_void_p(int(d_lag)),
+                                              C.c_void_p(int(d_sub)), _ptr(rows), len(rows), int(N), _ptr(cc), _ptr(lag),
+                                              _ptr(sub)))
+
     def ccx_condensed(self, X, Nc, engine="tcgen05", out=None):
         """All pairs b < c in SciPy's condensed order: (cc float64, lag int32, subsamp float64), each
         N (N-1)/2 long.  `out` = three preallocated (e.g. pinned) arrays to fill."""

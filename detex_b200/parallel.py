@@ -67,17 +67,68 @@ def pack_condensed(cc, lag, sub, slot_rows, N):
     return cc[src, iu[1]], lag[src, iu[1]], sub[src, iu[1]]
 
 
-def ccx_sharded(eng, X, Nc, engine="tcgen05", out=None, root=None):
+class CcxHostBuffer(object):
+    """Condensed (cc float64, lag int32, subsamp float64) arrays of ONE N-event pair matrix in host memory that
+    every rank of the box has mapped (a file under /dev/shm, unlinked as soon as all ranks hold it) and page-locked
+    for its GPU: `ccx_sharded(..., host=buf)` lets each GPU write the rows it computed straight to their places
+    over its own PCIe link -- no gather, no 20 B x N(N-1)/2 funnel through one link -- and every rank (the one that
+    runs `linkage`, construct.py:152-157, included) reads the whole matrix from `buf.cc / buf.lag / buf.sub`.
+    Create once per problem size (page-locking costs ~0.1 s per GB), reuse for every call, `close()` at the end."""
+
+    def __init__(self, eng, N, shm_dir="/dev/shm"):
+        import os
+        self.eng, self.N = eng, int(N)
+        npair = self.N * (self.N - 1) // 2
+        off_lag = 8 * npair
+        off_sub = off_lag + 8 * ((4 * npair + 7) // 8)
+        total = max(8, off_sub + 8 * npair)
+        world = _world()
+        self._registered = False
+        if world == 1:
+            self._base = eng.pinned_empty((total,), np.uint8) if hasattr(eng, "pinned_empty") else np.zeros(total, np.uint8)
+        else:
+            rank = dist.get_rank()
+            path = [None]
+            if rank == 0:
+                path[0] = os.path.join(shm_dir, "detex_b200_ccx_%d_%x" % (os.getpid(), id(self)))
+                self._base = np.memmap(path[0], dtype=np.uint8, mode="w+", shape=(total,))
+            dist.broadcast_object_list(path, src=0)
+            if rank != 0:
+                self._base = np.memmap(path[0], dtype=np.uint8, mode="r+", shape=(total,))
+            dist.barrier()
+            if rank == 0:
+                os.unlink(path[0])          # the mappings keep it alive; nothing to clean up after a crash
+            if hasattr(eng, "host_register"):
+                eng.host_register(self._base)
+                self._registered = True
+        self.cc = self._base[:8 * npair].view(np.float64)
+        self.lag = self._base[off_lag:off_lag + 4 * npair].view(np.int32)
+        self.sub = self._base[off_sub:off_sub + 8 * npair].view(np.float64)
+
+    def arrays(self):
+        return self.cc, self.lag, self.sub
+
+    def close(self):
+        if self._registered:
+            self.eng.host_unregister(self._base)
+            self._registered = False
+        self.cc = self.lag = self.sub = self._base = None
+
+
+def ccx_sharded(eng, X, Nc, engine="tcgen05", out=None, root=None, host=None):
     """The whole CCX matrix of one station over all ranks (BASELINE configs[2]): every
-    rank computes its dealt rows with the results left in HBM, ONE all-gather of the equal-sized dense
-    blocks over NCCL / NVLink, then the upper triangle is packed into SciPy's condensed order and
-    copied to the host -- on every rank (root=None), or only on rank `root` (the one that runs
-    `linkage`, construct.py:152-157; the other ranks return None and the host memory system sees one
-    168 MB copy instead of `world` of them).  Returns (cc, lag, subsamp) condensed; identical on every
-    rank and to the single-GPU result."""
+    rank computes its dealt rows with the results left in HBM.  Then either
+      * ONE all-gather of the equal-sized dense blocks over NCCL / NVLink, after which the upper triangle is
+        packed into SciPy's condensed order and copied to the host -- on every rank (root=None), or only on
+        rank `root` (the one that runs `linkage`, construct.py:152-157; the other ranks return None); or
+      * host = CcxHostBuffer: no collective at all -- each GPU writes its rows to their places in the shared,
+        page-locked condensed arrays over its own PCIe link (`dtx_ccx_pack_rows`), one barrier, and every
+        rank returns views of the same host memory.
+    On NCCL each rank uploads only its 1/world slice of X and the slices are all-gathered over NVLink.
+    Returns (cc, lag, subsamp) condensed; identical on every rank and to the single-GPU result."""
     world = _world()
     if world == 1:
-        return eng.ccx_condensed(X, Nc, engine=engine, out=out)
+        return eng.ccx_condensed(X, Nc, engine=engine, out=host.arrays() if host is not None else out)
     X = np.asarray(X)
     N = X.shape[0]
     rank = dist.get_rank()
@@ -88,8 +139,32 @@ def ccx_sharded(eng, X, Nc, engine="tcgen05", out=None, root=None):
     d_cc = torch.zeros((nmax, N), dtype=torch.float64, device=dev)
     d_lag = torch.zeros((nmax, N), dtype=torch.int32, device=dev)
     d_sub = torch.zeros((nmax, N), dtype=torch.float64, device=dev)
+    xg = None
+    if dev.type == "cuda" and X.dtype == np.float64:
+        # 1/world of the waveforms over this GPU's PCIe link, the rest over NVLink
+        per = (N + world - 1) // world
+        n = X.shape[1]
+        xg = torch.empty((world * per, n), dtype=torch.float64, device=dev)
+        part = torch.zeros((per, n), dtype=torch.float64, device=dev)
+        lo, hi = min(N, rank * per), min(N, (rank + 1) * per)
+        if hi > lo:
+            part[:hi - lo].copy_(torch.from_numpy(X[lo:hi]))
+        dist.all_gather_into_tensor(xg, part)
+        torch.cuda.current_stream().synchronize()      # the engine runs on its own stream
     if len(mine):
-        eng.ccx_device(X, Nc, mine, d_cc.data_ptr(), d_lag.data_ptr(), d_sub.data_ptr(), engine=engine)
+        if xg is not None:
+            eng.ccx_device(None, Nc, mine, d_cc.data_ptr(), d_lag.data_ptr(), d_sub.data_ptr(), engine=engine,
+                           x_device_ptr=xg.data_ptr(), shape=(N, X.shape[1]))
+        else:
+            eng.ccx_device(X, Nc, mine, d_cc.data_ptr(), d_lag.data_ptr(), d_sub.data_ptr(), engine=engine)
+    if host is not None:
+        eng.ccx_pack_rows(d_cc.data_ptr(), d_lag.data_ptr(), d_sub.data_ptr(), mine, N, host.arrays())   # synchronises
+        del xg
+        dist.barrier()
+        return host.arrays()
+    if dev.type == "cuda":
+        eng.sync()                                     # the engine may run on another stream than the collective
+    del xg
     g_cc = torch.empty((world * nmax, N), dtype=torch.float64, device=dev)
     g_lag = torch.empty((world * nmax, N), dtype=torch.int32, device=dev)
     g_sub = torch.empty((world * nmax, N), dtype=torch.float64, device=dev)

@@ -244,6 +244,14 @@ int dtx_ccx_device(dtx_ctx* ctx, const void* X, int x_on_device, int dtype, int 
  * the order `_flatNoNan(1.0000001 - DFcc)` feeds to linkage (construct.py:152-156). */
 int dtx_ccx_pack(dtx_ctx* ctx, const double* d_cc, const int32_t* d_lag, const double* d_sub,
                  const int32_t* slot_rows, int nslots, int N, double* cc, int32_t* lag, double* subsamp);
+/* (multi-GPU, no reference counterpart) The template rows ONE GPU computed with dtx_ccx_device (dense device slots
+ * r = 0 .. nrows-1 holding events rows[r]) written straight to their places in the host's condensed arrays of the
+ * whole matrix, over that GPU's own PCIe link.  cc / lag / subsamp must be page-locked memory the device can
+ * address (dtx_host_alloc, or dtx_host_register of POSIX shared memory mapped by every rank of a box): the 8 GPUs
+ * then fill one matrix in parallel -- createCluster's per-station CCX (construct.py:139-157) without funnelling
+ * N(N-1)/2 x 20 bytes through one link.  Synchronises the context's stream before returning. */
+int dtx_ccx_pack_rows(dtx_ctx* ctx, const double* d_cc, const int32_t* d_lag, const double* d_sub,
+                      const int32_t* rows, int nrows, int N, double* cc, int32_t* lag, double* subsamp);
 /* dtx_ccx_device over all rows + dtx_ccx_pack: host X in, condensed host cc / lag / subsamp out. */
 int dtx_ccx_condensed(dtx_ctx* ctx, const void* X, int dtype, int N, int n, int Nc, int engine, double* cc,
                       int32_t* lag, double* subsamp);
@@ -259,6 +267,10 @@ int dtx_set_ccx_batch(dtx_ctx* ctx, int max_signals, int64_t ds_bytes);
  * instead of through the driver's bounce buffer). */
 int dtx_host_alloc(void** out, int64_t bytes);
 int dtx_host_free(void* p);
+/* Page-lock (and map for the device) host memory the caller owns, e.g. a shared-memory segment several ranks have
+ * mapped; undo with dtx_host_unregister before the memory is released. */
+int dtx_host_register(void* p, int64_t bytes);
+int dtx_host_unregister(void* p);
 
 /* Zero-lag Pearson matrix of N equal-length waveforms (next row N3, validateClusters,
  * subspace.py:738-773: fast_normcorr of every pair of aligned, trimmed cluster members).

@@ -215,6 +215,16 @@ class OracleEngine(object):
         return parallel.pack_condensed(self._view(d_cc, (ns, N), np.float64), self._view(d_lag, (ns, N), np.int32),
                                        self._view(d_sub, (ns, N), np.float64), slot_rows, N)
 
+    def ccx_pack_rows(self, d_cc, d_lag, d_sub, rows, N, out):
+        cc, lag, sub = (self._view(d_cc, (len(rows), N), np.float64), self._view(d_lag, (len(rows), N), np.int32),
+                        self._view(d_sub, (len(rows), N), np.float64))
+        for r, b in enumerate(rows):
+            b = int(b)
+            o = b * N - b * (b + 1) // 2
+            out[0][o:o + N - 1 - b] = cc[r, b + 1:]
+            out[1][o:o + N - 1 - b] = lag[r, b + 1:]
+            out[2][o:o + N - 1 - b] = sub[r, b + 1:]
+
     def ccx_condensed(self, X, Nc, engine="tcgen05", out=None):
         cc, lag, sub = self.ccx(X, Nc, 0, len(X) - 1)
         iu = np.triu_indices(len(X), 1)

@@ -161,6 +161,13 @@ def _ccx_worker(rank, world, port, q):
         assert (only_root is None) == (rank != 0)
         if rank == 0:
             assert all(np.array_equal(a, b) for a, b in zip(res, only_root))
+        # no collective at all: every rank writes its rows into one shared host matrix (parallel.CcxHostBuffer)
+        buf = parallel.CcxHostBuffer(OracleEngine(), len(X))
+        shared = parallel.ccx_sharded(OracleEngine(), X, 3, host=buf)
+        assert all(np.array_equal(a, b) for a, b in zip(res, shared))
+        assert shared[0] is buf.cc and buf.lag.dtype == np.int32
+        dist.barrier()
+        buf.close()
         if rank == world - 1:
             q.put(res)
     finally:
