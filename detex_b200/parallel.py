@@ -90,9 +90,16 @@ class CcxHostBuffer(object):
             rank = dist.get_rank()
             path = [None]
             if rank == 0:
-                path[0] = os.path.join(shm_dir, "detex_b200_ccx_%d_%x" % (os.getpid(), id(self)))
-                self._base = np.memmap(path[0], dtype=np.uint8, mode="w+", shape=(total,))
+                try:        # a tmpfs smaller than the matrix would only fail later, with SIGBUS on first touch
+                    st = os.statvfs(shm_dir)
+                    if st.f_bavail * st.f_frsize > total + (64 << 20):
+                        path[0] = os.path.join(shm_dir, "detex_b200_ccx_%d_%x" % (os.getpid(), id(self)))
+                        self._base = np.memmap(path[0], dtype=np.uint8, mode="w+", shape=(total,))
+                except OSError:
+                    path[0] = None
             dist.broadcast_object_list(path, src=0)
+            if path[0] is None:             # every rank raises: callers fall back to the NCCL gather
+                raise RuntimeError("CcxHostBuffer: %s cannot hold %d bytes" % (shm_dir, total))
             if rank != 0:
                 self._base = np.memmap(path[0], dtype=np.uint8, mode="r+", shape=(total,))
             dist.barrier()

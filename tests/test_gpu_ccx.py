@@ -108,3 +108,35 @@ def test_validate_cluster_zero_lag_cc(engine):
     bad = subspace.validate_cluster(W, 0.5, engine=engine)
     exp = [i for i in range(4) if max(orc.fast_normcorr(W[i], W[j])[0] for j in range(i + 1, 5)) < 0.5]
     assert bad == exp and 2 in bad
+
+
+def test_pack_rows_fills_one_host_matrix_from_dealt_rows(engine):
+    """The multi-GPU result path on one GPU: the template rows dealt to 3 "ranks" are computed one rank at a time with
+    the results left in HBM (dtx_ccx_device) and written straight into ONE page-locked condensed host matrix
+    (dtx_ccx_pack_rows); the matrix equals dtx_ccx_condensed's and the oracle's."""
+    import torch
+    from detex_b200 import parallel
+    from detex_b200.engine import DtxError
+    X = synth.event_families(515, 3, 7, 100, 3, max_shift=12)          # 21 events, n = 300
+    N = len(X)
+    npair = N * (N - 1) // 2
+    out = (engine.pinned_empty((npair,), np.float64), engine.pinned_empty((npair,), np.int32),
+           engine.pinned_empty((npair,), np.float64))
+    out[0][:] = np.nan
+    out[1][:] = -99999
+    for rows in parallel.ccx_deal_rows(N, 3):
+        d_cc = torch.zeros((len(rows), N), dtype=torch.float64, device="cuda")
+        d_lag = torch.zeros((len(rows), N), dtype=torch.int32, device="cuda")
+        d_sub = torch.zeros((len(rows), N), dtype=torch.float64, device="cuda")
+        engine.ccx_device(X, 3, rows, d_cc.data_ptr(), d_lag.data_ptr(), d_sub.data_ptr(), engine="tcgen05")
+        engine.ccx_pack_rows(d_cc.data_ptr(), d_lag.data_ptr(), d_sub.data_ptr(), rows, N, out)
+    cc, lag, sub = engine.ccx_condensed(X, 3, engine="tcgen05")
+    assert np.array_equal(out[0], cc) and np.array_equal(out[1], lag) and np.array_equal(out[2], sub)
+    rcc, rlag, rsub = orc.make_cclags(X, 3)
+    iu = np.triu_indices(N, 1)
+    assert np.abs(out[0] - rcc[iu[0], iu[1] - 1]).max() < 1e-10
+    assert np.array_equal(out[1].astype(float), rlag[iu[0], iu[1] - 1])
+    # pageable outputs are refused (the kernel itself writes them), loudly
+    bad = (np.empty(npair), np.empty(npair, np.int32), np.empty(npair))
+    with pytest.raises(DtxError):
+        engine.ccx_pack_rows(d_cc.data_ptr(), d_lag.data_ptr(), d_sub.data_ptr(), rows, N, bad)
