@@ -140,3 +140,20 @@ def test_pack_rows_fills_one_host_matrix_from_dealt_rows(engine):
     bad = (np.empty(npair), np.empty(npair, np.int32), np.empty(npair))
     with pytest.raises(DtxError):
         engine.ccx_pack_rows(d_cc.data_ptr(), d_lag.data_ptr(), d_sub.data_ptr(), rows, N, bad)
+
+
+def test_long_events_take_the_fallback_paths(engine):
+    """The only workload the reference publishes a timing for (130 s x 100 Hz x 1 channel events):
+    n = 13 000 -> 13 001 lags (several 2048-lag tiles: no DUAL items) and 104 KB per float64 waveform (two do not
+    fit beside a ring in shared memory: tiled re-scoring with one resident signal).  Tensor engine = float64 engine
+    = oracle."""
+    X = synth.event_families(130, 2, 3, 13000, 1, max_shift=300)         # 6 events
+    cc, lag, sub = engine.ccx(X, 1, engine="tcgen05")
+    c64, l64, s64 = engine.ccx(X, 1, engine="fp64")
+    iu = np.triu_indices(len(X), 1)
+    assert np.array_equal(lag[iu], l64[iu])
+    assert np.abs(cc[iu] - c64[iu]).max() < 1e-12
+    assert np.nanmax(np.abs(sub[iu] - s64[iu])) < 1e-7
+    for b, c in ((0, 1), (1, 4), (3, 5)):
+        rcc, rlag, rsub = orc.ccx2(X[b], X[c], 1)
+        assert abs(cc[b, c] - rcc) < 1e-10 and lag[b, c] == rlag
