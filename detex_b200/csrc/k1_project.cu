@@ -139,8 +139,11 @@ struct Smem {
 // Only for long templates (>= 16 kblk stages): there the two long accumulations are a few percent of the taps;
 // for a short template they would be most of them and their doubled truncation bias the whole error
 // (ns = 300, kblk 3: max |DS - float64| 3.6e-6 with, 2e-6 without).
+#ifndef DTX_FIRST_LONG_FACTOR
+#define DTX_FIRST_LONG_FACTOR 2
+#endif
 __device__ __forceinline__ int acc_stages(int nacc, int kblk, int nstages) {
-    return (nacc < DTX_FIRST_LONG_ACCS && nstages >= 16 * kblk) ? 2 * kblk : kblk;
+    return (nacc < DTX_FIRST_LONG_ACCS && nstages >= 16 * kblk) ? DTX_FIRST_LONG_FACTOR * kblk : kblk;
 }
 
 // precision mode of a chunk: 1 = both cross terms in one 8-bit MMA (decided on the device by k0_split)
