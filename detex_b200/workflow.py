@@ -105,6 +105,69 @@ class ArrayFetcher(object):
                 yield traces, float(start)
 
 
+class StreamFetcher(object):
+    """Adapter: the reference's own `detex.getdata.DataFetcher` (getdata.py:244-609) -- or anything else whose
+    `getTemData` / `getConData` yield ObsPy Streams the way it does (getdata.py:351-453, 455-539) -- in front of
+    the array protocol of this module, so `createCluster` / `createSubSpace` / `SubSpace.getFAS / detex` take the
+    fetcher a Detex user already has.  Only duck-typed trace attributes are touched (`tr.data`,
+    `tr.stats.channel / sampling_rate / starttime.timestamp / npts`), no ObsPy import.
+
+    Per stream: traces sorted by channel name (`st.sort()`, construct.py:998) and cut to their common window
+    [latest start, earliest end] (construct.py:1019-1024) -- the one start time per entry the array protocol
+    carries; streams that are empty, have fewer traces than the first good one, or whose channels do not
+    overlap are skipped with a warning, as `_applyFilter` returns an empty Stream for them
+    (construct.py:1003-1022).  With `decimate` and channels that start at different samples the reference
+    decimates before it trims; here the trim comes first (edge samples of such a stream may differ)."""
+    method = 'stream'
+
+    def __init__(self, fetcher, conDatDuration=None, conBuff=None):
+        self.fetcher = fetcher
+        self.sr = None               # learnt from the first stream
+        self.channels = None
+        self.conDatDuration = conDatDuration if conDatDuration is not None else getattr(fetcher, 'conDatDuration', 3600)
+        self.conBuff = conBuff if conBuff is not None else getattr(fetcher, 'conBuff', 120)
+
+    def _arrays(self, st):
+        if st is None:
+            return None
+        trs = sorted(list(st), key=lambda tr: str(tr.stats.channel))
+        if len(trs) < 1 or (self.channels is not None and len(trs) != len(self.channels)):
+            log.warning('stream with %d traces skipped', len(trs))
+            return None
+        sr = float(trs[0].stats.sampling_rate)
+        if any(float(tr.stats.sampling_rate) != sr for tr in trs) or (self.sr is not None and sr != self.sr):
+            log.warning('stream with mixed sampling rates skipped')
+            return None
+        starts = [float(tr.stats.starttime.timestamp) for tr in trs]
+        ends = [b + (len(tr.data) - 1) / sr for tr, b in zip(trs, starts)]
+        t0, t1 = max(starts), min(ends)
+        if t0 > t1:
+            log.warning('channels do not overlap, stream skipped')
+            return None
+        npts = int(round((t1 - t0) * sr)) + 1
+        out = []
+        for tr, b in zip(trs, starts):
+            i0 = int(round((t0 - b) * sr))
+            out.append(np.asarray(tr.data[i0:i0 + npts], dtype=np.float64))
+        npts = min(len(x) for x in out)
+        if self.sr is None:
+            self.sr = sr
+            self.channels = [str(tr.stats.channel) for tr in trs]
+        return [x[:npts] for x in out], t0
+
+    def getTemData(self, temkey, stakey, tb4=None, taft=None, returnName=True, phases=None):
+        for st, name in self.fetcher.getTemData(temkey, stakey, tb4, taft, returnName=True, phases=phases):
+            got = self._arrays(st)
+            if got is not None:
+                yield got[0], got[1], name
+
+    def getConData(self, stakey, utcstart=None, utcend=None, randSamps=None):
+        for st in self.fetcher.getConData(stakey, utcstart=utcstart, utcend=utcend, randSamps=randSamps):
+            got = self._arrays(st)
+            if got is not None:
+                yield got
+
+
 def _filter_multiplex(traces_list, sr, filt, decimate, engine):
     """`_applyFilter` + `multiplex` (construct.py:990-1030, 928-987) of a batch on the device;
     returns the multiplexed float64 arrays."""
@@ -193,10 +256,16 @@ def createCluster(CCreq=0.5, fetch_arg=None, filt=[1, 10, 2, True], stationKey=N
                   trim=[10, 120], saveclust=True, fileName='clust.pkl', decimate=None, dtype='double',
                   eventsOnAllStations=False, enforceOrigin=False, fillZeros=False, phases=None,
                   engine=None, ccx_engine="tcgen05"):
-    """`detex.createCluster` (construct.py:25-171).  `fetch_arg` is an ArrayFetcher, the keys are
-    DataFrames (STATION/NETWORK/... and NAME/TIME/MAG/..., util.py:574-627)."""
-    if not isinstance(fetch_arg, ArrayFetcher):
-        _error('fetch_arg must be an ArrayFetcher (ObsPy data sources are out of scope)', TypeError)
+    """`detex.createCluster` (construct.py:25-171).  `fetch_arg` is an ArrayFetcher, a StreamFetcher, or a
+    reference-style DataFetcher (anything with getTemData / getConData yielding ObsPy Streams: wrapped in a
+    StreamFetcher); the keys are DataFrames (STATION/NETWORK/... and NAME/TIME/MAG/..., util.py:574-627)."""
+    if not isinstance(fetch_arg, (ArrayFetcher, StreamFetcher)):
+        if hasattr(fetch_arg, 'getTemData') and hasattr(fetch_arg, 'getConData'):
+            fetch_arg = StreamFetcher(fetch_arg)
+        else:
+            _error('fetch_arg must be an ArrayFetcher, a StreamFetcher or a DataFetcher-like object with '
+                   'getTemData / getConData (directory names and client strings are resolved by the reference\'s '
+                   'own DataFetcher)', TypeError)
     if enforceOrigin or fillZeros or phases is not None:
         raise NotImplementedError('enforceOrigin / fillZeros / phases act on ObsPy streams inside the '
                                   'DataFetcher; hand ArrayFetcher windows that already reflect them')
@@ -384,6 +453,8 @@ def createSubSpace(Pf=10 ** -12, clust=None, minEvents=2, dtype='double', conDat
     eng = engine or default_engine()
     temkey, stakey = cl.temkey, cl.stakey
     cfetcher = conDatFetcher if conDatFetcher is not None else cl.fetcher
+    if not isinstance(cfetcher, (ArrayFetcher, StreamFetcher)) and hasattr(cfetcher, 'getConData'):
+        cfetcher = StreamFetcher(cfetcher)        # the reference's DataFetcher (ObsPy Streams)
     TRDF = getattr(cl, '_TRDF', None)
     if TRDF is None:
         TRDF = _loadEvents(cl.fetcher, cl.filt, cl.trim, stakey, temkey, cl.decimate, dtype, eng)

@@ -269,3 +269,62 @@ def test_array_fetcher_generators():
     assert len(a) == 3 and a == b and set(a) <= set(starts)
     assert len([1 for _ in f.getConData(sk, randSamps=50)]) == 5            # asks for more than there is
     assert workflow._timestamp("2010-01-01T00-00-00") == workflow._timestamp("2010-01-01 00:00:00") == 1262304000.0
+
+
+# ------------------------------------------------------------------ the reference's fetcher protocol (ObsPy Streams)
+class _FakeDataFetcher(object):
+    """Yields what `detex.getdata.DataFetcher` yields (getdata.py:351-453, 455-539): ObsPy-Stream-like lists of
+    traces with `.data` and `.stats`; traces out of channel order, one channel starting 3 samples early and
+    another ending 5 samples late, as real archives deliver them."""
+
+    def __init__(self, case, sr):
+        self.case, self.sr = case, sr
+        self.conDatDuration, self.conBuff = 280, 20
+
+    def _stream(self, traces, start):
+        import types
+        rng = np.random.default_rng(int(start) % 1000)
+        chans = ["BHE", "BHN", "BHZ"]
+        out = []
+        for k, (c, x) in enumerate(zip(chans, traces)):
+            pre, post = (3, 0) if k == 1 else ((0, 5) if k == 2 else (0, 0))
+            data = np.concatenate([rng.normal(size=pre), x, rng.normal(size=post)])
+            st = types.SimpleNamespace(channel=c, sampling_rate=self.sr, npts=len(data), station="M17A",
+                                       starttime=types.SimpleNamespace(timestamp=start - pre / self.sr))
+            out.append(types.SimpleNamespace(data=data, stats=st))
+        return [out[2], out[0], out[1]]
+
+    def getTemData(self, temkey, stakey, tb4=None, taft=None, returnName=True, phases=None, **kw):
+        inner = workflow.ArrayFetcher(self.case["events"], self.case["continuous"], sr=self.sr)
+        for traces, start, name in inner.getTemData(temkey, stakey):
+            yield self._stream(traces, start), name
+        yield [], "empty-stream"                               # the reference logs and skips these
+
+    def getConData(self, stakey, utcstart=None, utcend=None, randSamps=None, **kw):
+        inner = workflow.ArrayFetcher(self.case["events"], self.case["continuous"], sr=self.sr, seed=5)
+        for traces, start in inner.getConData(stakey, utcstart=utcstart, utcend=utcend, randSamps=randSamps):
+            yield self._stream(traces, start)
+
+
+def test_stream_fetcher_adapter_equals_array_fetcher(tmp_path):
+    """`workflow.StreamFetcher` in front of a reference-style fetcher: sorted by channel, cut to the common window,
+    empty streams skipped -- the cluster tables equal those from the arrays themselves."""
+    case = synth.workflow_case(77)
+    eng = OracleEngine()
+    kw = dict(CCreq=CCREQ, filt=[1, 10, 2, True], stationKey=case["stakey"], templateKey=case["temkey"], trim=[2, 18],
+              saveclust=False, engine=eng)
+    ref = workflow.createCluster(fetch_arg=workflow.ArrayFetcher(case["events"], case["continuous"], sr=case["sr"]), **kw)
+    sf = workflow.StreamFetcher(_FakeDataFetcher(case, case["sr"]))
+    got = workflow.createCluster(fetch_arg=sf, **kw)
+    assert sf.sr == case["sr"] and sf.channels == ["BHE", "BHN", "BHZ"]
+    assert len(got) == len(ref)
+    for a, b in zip(ref.clusters, got.clusters):
+        assert a.station == b.station and a.clusts == b.clusts and a.singles == b.singles
+        assert np.array_equal(np.asarray(a.link), np.asarray(b.link))
+    # continuous data through the same adapter
+    chunks = list(sf.getConData(case["stakey"].iloc[:1]))
+    want = list(workflow.ArrayFetcher(case["events"], case["continuous"], sr=case["sr"], seed=5)
+                .getConData(case["stakey"].iloc[:1]))
+    assert len(chunks) == len(want) > 0
+    for (tr, t0), (wtr, w0) in zip(chunks, want):
+        assert t0 == w0 and all(np.array_equal(x, y) for x, y in zip(tr, wtr))
