@@ -319,6 +319,24 @@ class ClusterStream(object):
             self.clusters.append(Cluster(self, row.Station, temkey, evlist, row.Link, ccReq, filt, decimate,
                                          trim, row.CCs))
 
+    @classmethod
+    def from_reference(cls, obj, fetcher=None):
+        """A ClusterStream the REFERENCE built (`detex.createCluster`, or unpickled from its `clust.pkl` with Detex
+        importable) as one of ours.  The reference's constructor keeps all its arguments as attributes
+        (subspace.py:52-59: trdf, temkey, stakey, fetcher, eventList, filt, decimate, trim, fileName,
+        eventsOnAllStations, enforceOrigin) and its `trdf` carries the same Station / Link / CCs / Lags / Subsamp /
+        Events / Stats columns `createCluster` fills here (construct.py:139-168), so the dendrograms are re-cut
+        from the stored linkage at each station's stored `ccReq` (subspace.py:304-345) -- no waveform is touched.
+        `fetcher`: replacement for the pickled DataFetcher (default: the object's own, wrapped in a
+        StreamFetcher when first used)."""
+        f = fetcher if fetcher is not None else getattr(obj, 'fetcher', None)
+        new = cls(obj.trdf, obj.temkey, obj.stakey, f, obj.eventList, 1.0, obj.filt, obj.decimate, obj.trim,
+                  getattr(obj, 'filename', getattr(obj, 'fileName', 'clust.pkl')), obj.eventsOnAllStations,
+                  obj.enforceOrigin)
+        for c_new, c_old in zip(new.clusters, obj.clusters):
+            c_new.updateReqCC(float(c_old.ccReq))
+        return new
+
     def updateReqCC(self, reqCC):
         """subspace.py:108-147: a float for every station, or a {station: float} dict."""
         if isinstance(reqCC, (float, int)):
@@ -446,8 +464,12 @@ def createSubSpace(Pf=10 ** -12, clust=None, minEvents=2, dtype='double', conDat
     if isinstance(clust, str):
         with open(clust, 'rb') as f:
             cl = pickle.load(f)
+        if not isinstance(cl, ClusterStream):
+            cl = ClusterStream.from_reference(cl)    # a clust.pkl the reference wrote (Detex importable)
     elif isinstance(clust, ClusterStream):
         cl = clust
+    elif all(hasattr(clust, a) for a in ('trdf', 'clusters', 'temkey', 'stakey', 'eventList')):
+        cl = ClusterStream.from_reference(clust)     # the reference's own ClusterStream object
     else:
         _error('Invalid clust type, must be a path or ClusterStream instance.', ValueError)
     eng = engine or default_engine()
@@ -457,7 +479,10 @@ def createSubSpace(Pf=10 ** -12, clust=None, minEvents=2, dtype='double', conDat
         cfetcher = StreamFetcher(cfetcher)        # the reference's DataFetcher (ObsPy Streams)
     TRDF = getattr(cl, '_TRDF', None)
     if TRDF is None:
-        TRDF = _loadEvents(cl.fetcher, cl.filt, cl.trim, stakey, temkey, cl.decimate, dtype, eng)
+        lf = cl.fetcher
+        if not isinstance(lf, (ArrayFetcher, StreamFetcher)) and hasattr(lf, 'getTemData'):
+            lf = StreamFetcher(lf)
+        TRDF = _loadEvents(lf, cl.filt, cl.trim, stakey, temkey, cl.decimate, dtype, eng)
     origin = {r.NAME: _timestamp(r.TIME) for _, r in temkey.iterrows()}
     mags = {r.NAME: r.MAG for _, r in temkey.iterrows()}
     ssDict, singDic = {}, {}

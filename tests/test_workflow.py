@@ -328,3 +328,33 @@ def test_stream_fetcher_adapter_equals_array_fetcher(tmp_path):
     assert len(chunks) == len(want) > 0
     for (tr, t0), (wtr, w0) in zip(chunks, want):
         assert t0 == w0 and all(np.array_equal(x, y) for x, y in zip(tr, wtr))
+
+
+def test_reference_built_clusterstream_is_accepted(tmp_path):
+    """`createSubSpace(clust=<the reference's ClusterStream>)`: the reference keeps its constructor arguments as
+    attributes (subspace.py:52-59) and its Clusters carry `ccReq` (subspace.py:304-316); the object is re-cut from
+    the stored linkage.  The stand-in below has exactly those attributes and a reference-style fetcher."""
+    import types
+    case = synth.workflow_case(77)
+    eng = OracleEngine()
+    fetcher = workflow.ArrayFetcher(case["events"], case["continuous"], sr=case["sr"], conDatDuration=280, conBuff=20, seed=5)
+    ours = workflow.createCluster(CCreq=CCREQ, fetch_arg=fetcher, filt=[1, 10, 2, True], stationKey=case["stakey"],
+                                  templateKey=case["temkey"], trim=[2, 18], saveclust=False, engine=eng)
+    ours["TA.M18A"].updateReqCC(0.7)
+    ref_like = types.SimpleNamespace(
+        trdf=ours.trdf, temkey=ours.temkey, stakey=ours.stakey, fetcher=_FakeDataFetcher(case, case["sr"]),
+        eventList=ours.eventList, ccReq=None, filt=ours.filt, decimate=ours.decimate, trim=ours.trim,
+        fileName="clust.pkl", filename="clust.pkl", eventsOnAllStations=ours.eventsOnAllStations,
+        enforceOrigin=ours.enforceOrigin, stalist=list(ours.stalist),
+        clusters=[types.SimpleNamespace(ccReq=c.ccReq, station=c.station) for c in ours.clusters])
+    conv = workflow.ClusterStream.from_reference(ref_like)
+    for a, b in zip(ours.clusters, conv.clusters):
+        assert a.ccReq == b.ccReq and a.clusts == b.clusts and a.singles == b.singles
+    ss_ref = workflow.createSubSpace(Pf=1e-10, clust=ours, engine=eng)
+    ss_new = workflow.createSubSpace(Pf=1e-10, clust=ref_like, engine=eng)      # events re-read through the Stream fetcher
+    for sta in ("TA.M17A", "TA.M18A"):
+        a, b = ss_ref.subspaces[sta], ss_new.subspaces[sta]
+        assert list(a.Name) == list(b.Name) and [sorted(x) for x in a.Events] == [sorted(x) for x in b.Events]
+        for (_, ra), (_, rb) in zip(a.iterrows(), b.iterrows()):
+            for ev in ra.Events:
+                assert np.allclose(ra.AlignedTD[ev], rb.AlignedTD[ev], rtol=0, atol=1e-9)
