@@ -597,7 +597,7 @@ def gpu_arm(args):
         for _ in range(3):
             step_cfg1()
         nrep = 10
-        ms1, wall1, _, _ = timed(step_cfg1, nrep)
+        ms1, wall1, (c1_res, h1_res), _ = timed(step_cfg1, nrep)
         k1 = eng.k1_ms()
         ts1 = nday * T_PER_CHUNK * world
         step1 = max(ms1 / 1e3, wall1) / nrep
@@ -621,13 +621,21 @@ def gpu_arm(args):
         cfg1["roofline"]["frac"] = cfg1["roofline"]["achieved"] / cfg1["roofline"]["peak"]
         if hnp is not None:
             def step_cfg1_e2e():
-                eng.load_chunks([hnp[i] for i in range(nday)])
-                eng.detect_run(2, engine="tcgen05", kblk=args.kblk, lta_window=int(5 * SR))
+                # the day in three batches: the H2D of a batch overlaps the projection of the one before
+                # (same calls as the headline's end-to-end step)
+                eng.accumulate_begin(nday)
+                nb1 = max(1, (nday + 2) // 3)
+                for lo in range(0, nday, nb1):
+                    eng.load_chunks([hnp[i] for i in range(lo, min(nday, lo + nb1))])
+                    eng.detect_run(2, engine="tcgen05", kblk=args.kblk, lta_window=int(5 * SR))
                 eng.rowstats()
                 c = eng.candidates()
-                return c, eng.hist(2, reset=True)
+                h = eng.hist(2, reset=True)
+                eng.accumulate_end()
+                return c, h
             step_cfg1_e2e()
-            ms1e, wall1e, _, _ = timed(step_cfg1_e2e, nrep)
+            ms1e, wall1e, (c1_e, h1_e), _ = timed(step_cfg1_e2e, nrep)
+            assert len(c1_e) == len(c1_res) and np.array_equal(h1_e, h1_res), "cfg1: resident and host paths disagree"
             cfg1["e2e"] = {"value": ts1 / (max(ms1e / 1e3, wall1e) / nrep), "unit": UNIT,
                            "h2d_bytes_per_step": nday * L * 8, "d2h_bytes_per_step": nday * 8 + 400 * 8}
         if pool is not None:
@@ -746,6 +754,9 @@ def gpu_arm(args):
         Xp[:] = X
         out = (eng.pinned_empty((npair,), np.float64), eng.pinned_empty((npair,), np.int32),
                eng.pinned_empty((npair,), np.float64))
+
+        if args.ccx_ds_gib > 0:
+            eng.set_ccx_batch(512, args.ccx_ds_gib << 30)
 
         def step_ccx(root=None):
             return parallel.ccx_sharded(eng, Xp, NC, engine="tcgen05", out=out, root=root)
@@ -898,6 +909,8 @@ def main():
                     help="main = configs[3] headline, cfg1 = configs[1], fas = configs[4], ccx = configs[2]")
     ap.add_argument("--fas-chunks", type=int, default=1000, help="null segments of the FAS sweep (at 720 chunks)")
     ap.add_argument("--ccx-events", type=int, default=CCX_EVENTS)
+    ap.add_argument("--ccx-ds-gib", type=int, default=0,
+                    help="correlation-series buffer of one CCX signal batch in GiB (0 = library default 16)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -186,7 +186,7 @@ struct dtx_ctx {
     DevBuf<int2> cx_flag;
     int ccx_passes = 1;          // MMAs per K step of the CCX series: 1 = hi*hi screening (default), 3 = fp16x3
     int ccx_max_batch = 512;     // signals per K1 launch (dtx_set_ccx_batch lowers it for tests)
-    long long ccx_ds_bytes = 4LL << 30;   // DS budget of one CCX batch
+    long long ccx_ds_bytes = 16LL << 30;  // series buffer of one CCX batch (4096 events: 8 launches of 512 signals)
 };
 
 namespace {

@@ -313,7 +313,7 @@ class Engine(object):
                                     _ptr(sub)))
         return cc, lag, sub
 
-    def set_ccx_batch(self, max_signals=512, ds_bytes=4 << 30):
+    def set_ccx_batch(self, max_signals=512, ds_bytes=16 << 30):
         """Limits of one tensor-core CCX batch (tests lower them to force several batches)."""
         self._check(self._L.dtx_set_ccx_batch(self._h, int(max_signals), int(ds_bytes)))
 
