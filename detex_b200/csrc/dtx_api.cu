@@ -1427,8 +1427,22 @@ static int ccx_tcgen05(dtx_ctx* ctx, int dtype, const void* dX, int N, int n, in
     const long long Lm = static_cast<long long>(Lc) * Nc;
     // batch of signals bounded by the DS buffer (rows x Tpad floats per signal)
     const long long per_sig = static_cast<long long>(nrows) * ((nl + TILE_T - 1) / TILE_T * TILE_T) * 4;
-    const int batch = static_cast<int>(std::max<long long>(
+    int batch = static_cast<int>(std::max<long long>(
         1, std::min<long long>(ctx->ccx_max_batch, ctx->ccx_ds_bytes / std::max<long long>(1, per_sig))));
+    {
+        // the series buffer of a whole batch has to fit what is free on the device right now: halve the batch
+        // until it does (the default budget is 16 GiB) instead of failing the call
+        const long long tpad = (nl + TILE_T - 1) / TILE_T * TILE_T;
+        const long long rows_ds = std::max<long long>(nrows, bs.ds_rows);
+        const int nsig_max = std::max(1, N - (h_rows[0] + 1));
+        for (;;) {
+            const size_t elems = static_cast<size_t>(std::min(batch, nsig_max)) * rows_ds * tpad;
+            if (ctx->d_DS.reserve(elems) == cudaSuccess) break;
+            cudaGetLastError();
+            if (batch <= 8) return fail(ctx, DTX_ERR_CUDA, "dtx_ccx: out of device memory for the correlation series");
+            batch /= 2;
+        }
+    }
     const int flag_cap = 1 << 20;
     DTX_CUDA(ctx->cx_pad.reserve(static_cast<size_t>(batch) * Lm));
     DTX_CUDA(ctx->cx_karg.reserve(static_cast<size_t>(batch) * nrows));
