@@ -32,6 +32,7 @@ from . import construct, fas as _fas, preprocess, results, subspace as _subspace
 from .detect import HIST_BINS, SSDetex, default_engine
 
 log = logging.getLogger("detex_b200")
+from .util import readKey  # noqa: E402
 
 
 def _error(msg, e=Exception):
@@ -270,7 +271,9 @@ def createCluster(CCreq=0.5, fetch_arg=None, filt=[1, 10, 2, True], stationKey=N
         raise NotImplementedError('enforceOrigin / fillZeros / phases act on ObsPy streams inside the '
                                   'DataFetcher; hand ArrayFetcher windows that already reflect them')
     eng = engine or default_engine()
-    stakey, temkey = stationKey, templateKey
+    # paths or DataFrames, as the reference takes them (construct.py:104-106, util.readKey)
+    stakey = readKey('StationKey.csv' if stationKey is None else stationKey, 'station')
+    temkey = readKey('TemplateKey.csv' if templateKey is None else templateKey, 'template')
     _checkClusterInputs(filt, dtype, trim, decimate)
     fetcher = fetch_arg
     TRDF = _loadEvents(fetcher, filt, trim, stakey, temkey, decimate, dtype, eng)
@@ -592,6 +595,8 @@ class SubSpace(object):
         for col in ('TimeStamp', 'Station', 'Event'):
             if col not in pks.columns:
                 _error('%s is a required column of the pick file' % col)
+        if 'Phase' in pks.columns:
+            pks = readKey(pks, 'phases')          # subspace.py:1484: empty rows dropped, sorted
         fun = {'mean': np.mean, 'max': np.max, 'min': np.min, 'median': np.median}.get(function)
         if fun is None:
             _error('function %s not supported, options are: mean, median, min, max' % function)
