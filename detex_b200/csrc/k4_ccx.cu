@@ -898,6 +898,14 @@ ccx_post_tiled_kernel(const int4* __restrict__ karg, int c0, int nsig,
 //     the two-pass scheme cost 3 + 2 loads for C = 2 and 6 + 2 for C = 4), which also yields the winner's
 //     neighbours for the cosine fit.
 // Sums are accumulated in the same order as sm_dot3, so results are bit-identical to the tiled kernel's.
+// DTX_RING_TOOL_SYNC = 1 expresses the same producer / consumer protocol per THREAD -- every consumer lane arrives on
+// the slot's `empty` barrier itself, lane 0 of the producer parks the records it releases, the load gate is read with
+// atomics -- which is what compute-sanitizer's racecheck can follow: 0 hazards (profiles/r02_sanitizer.md).  The
+// default lets lane 0 arrive for its warp after a __syncwarp (32 x fewer shared-memory atomics per task: 83 ms
+// instead of 97 ms per 4096-event call); racecheck, which tracks barriers per thread, reports that form as hazards.
+#ifndef DTX_RING_TOOL_SYNC
+#define DTX_RING_TOOL_SYNC 0
+#endif
 constexpr int RING_THREADS = 512;                 // at most; warp 0 = producer, the others consume (default 12 warps)
 constexpr int RING_TC_MAX = 16;                   // resident signals at most
 constexpr int RING_NB_MAX = 4;                    // ring slots at most
@@ -982,7 +990,7 @@ ccx_post_ring_kernel(const int4* __restrict__ karg, int c0, int nsig, const doub
     __shared__ __align__(8) uint64_t bar_full[RING_NB_MAX], bar_empty[RING_NB_MAX], bar_sig;
     __shared__ RingRec rec[RING_NB_MAX];
     __shared__ int next_task;
-    __shared__ volatile int issued;                      // rows whose load has been issued (see the consumer's wait)
+    __shared__ int issued;                               // rows whose load has been issued (see the consumer's wait)
     const int ns = n / Nc;
     const int m32 = ((ns + 31) / 32) | 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1000,7 +1008,10 @@ ccx_post_ring_kernel(const int4* __restrict__ karg, int c0, int nsig, const doub
     const int nr = lo - r0;                               // >= 1
     const uint32_t row_bytes = static_cast<uint32_t>(n) * 8u;
     if (tid == 0) {
-        for (int i = 0; i < NB; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], nmine); }
+        for (int i = 0; i < NB; ++i) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], DTX_RING_TOOL_SYNC ? 32 * nmine : nmine);
+        }
         mbar_init(&bar_sig, 1);
         next_task = 0;
         issued = 0;
@@ -1021,11 +1032,21 @@ ccx_post_ring_kernel(const int4* __restrict__ karg, int c0, int nsig, const doub
             if (i >= NB) mbar_wait(&bar_empty[slot], ((i / NB) - 1) & 1);
             const int r = r0 + i;
             const int b = rows[r];
-            if (lane < nmine) {
-                const int ci = sig0 + lane;
-                rec[slot].kc[lane] = (b < c0 + ci) ? karg[static_cast<long long>(ci) * nrows + r]
-                                                   : make_int4(-2, -1, -1, -1);
+            // the lanes fetch the row's candidate records together
+            int4 kcl = make_int4(-2, -1, -1, -1);
+            if (lane < nmine && b < c0 + sig0 + lane) kcl = karg[static_cast<long long>(sig0 + lane) * nrows + r];
+#if DTX_RING_TOOL_SYNC
+            // lane 0 alone parks them and releases them with its own arrive
+#pragma unroll
+            for (int s = 0; s < RING_TC_MAX; ++s) {
+                int4 v;
+                v.x = __shfl_sync(0xffffffffu, kcl.x, s); v.y = __shfl_sync(0xffffffffu, kcl.y, s);
+                v.z = __shfl_sync(0xffffffffu, kcl.z, s); v.w = __shfl_sync(0xffffffffu, kcl.w, s);
+                if (lane == 0 && s < nmine) rec[slot].kc[s] = v;
             }
+#else
+            if (lane < nmine) rec[slot].kc[lane] = kcl;   // ordered before lane 0's arrive by the __syncwarp
+#endif
             if (lane == 0) { rec[slot].std1 = evstd[b]; rec[slot].sum1 = evsum[b]; }
             __syncwarp();
             if (lane == 0) {
@@ -1033,7 +1054,7 @@ ccx_post_ring_kernel(const int4* __restrict__ karg, int c0, int nsig, const doub
                 bulk_g2s(srow + static_cast<size_t>(slot) * n, Xd + static_cast<long long>(b) * n, row_bytes,
                          &bar_full[slot]);
                 __threadfence_block();
-                issued = i + 1;
+                atomicExch(&issued, i + 1);
             }
         }
         return;
@@ -1084,7 +1105,13 @@ ccx_post_ring_kernel(const int4* __restrict__ karg, int c0, int nsig, const doub
         const int slot = i % NB;
         // A parity wait is only meaningful once the barrier has reached this row's phase: with few tasks per row a
         // warp can draw a task two uses of the slot ahead, where the parity test would alias to a finished phase.
-        while (issued <= i) __nanosleep(32);
+#if DTX_RING_TOOL_SYNC
+        if (lane == 0)
+            while (atomicAdd(&issued, 0) <= i) __nanosleep(32);
+        __syncwarp();
+#else
+        while (*static_cast<volatile int*>(&issued) <= i) __nanosleep(32);
+#endif
         mbar_wait(&bar_full[slot], (i / NB) & 1);
         const int4 kc = rec[slot].kc[s];
         if (kc.x >= 0) {                                  // else: b >= c, or left to ccx_post_kernel
@@ -1117,8 +1144,12 @@ ccx_post_ring_kernel(const int4* __restrict__ karg, int c0, int nsig, const doub
                 if (++npend == 32) flush();
             }
         }
+#if DTX_RING_TOOL_SYNC
+        mbar_arrive(&bar_empty[slot]);                   // this lane no longer reads the slot
+#else
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_empty[slot]);   // this task no longer reads the slot
+        if (lane == 0) mbar_arrive(&bar_empty[slot]);   // this warp no longer reads the slot
+#endif
     }
     flush();
 }
