@@ -105,9 +105,19 @@ class CcxHostBuffer(object):
             dist.barrier()
             if rank == 0:
                 os.unlink(path[0])          # the mappings keep it alive; nothing to clean up after a crash
+            ok = 1
             if hasattr(eng, "host_register"):
-                eng.host_register(self._base)
-                self._registered = True
+                try:
+                    eng.host_register(self._base)
+                    self._registered = True
+                except Exception:
+                    ok = 0
+            # all ranks succeed or all give up (a rank that raised alone would leave the others in a barrier)
+            flag = torch.tensor([ok], dtype=torch.int32, device=_dev())
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag[0]) == 0:
+                self.close()
+                raise RuntimeError("CcxHostBuffer: page-locking the shared segment failed on a rank")
         self.cc = self._base[:8 * npair].view(np.float64)
         self.lag = self._base[off_lag:off_lag + 4 * npair].view(np.int32)
         self.sub = self._base[off_sub:off_sub + 8 * npair].view(np.float64)
@@ -116,7 +126,7 @@ class CcxHostBuffer(object):
         return self.cc, self.lag, self.sub
 
     def close(self):
-        if self._registered:
+        if getattr(self, "_registered", False):
             self.eng.host_unregister(self._base)
             self._registered = False
         self.cc = self.lag = self.sub = self._base = None
