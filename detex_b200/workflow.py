@@ -253,7 +253,8 @@ def _loadEvents(fetcher, filt, trim, stakey, temkey, decimate, dtype, engine, ba
     return TRDF
 
 
-def createCluster(CCreq=0.5, fetch_arg=None, filt=[1, 10, 2, True], stationKey=None, templateKey=None,
+def createCluster(CCreq=0.5, fetch_arg='EventWaveForms', filt=[1, 10, 2, True], stationKey='StationKey.csv',
+                  templateKey='TemplateKey.csv',
                   trim=[10, 120], saveclust=True, fileName='clust.pkl', decimate=None, dtype='double',
                   eventsOnAllStations=False, enforceOrigin=False, fillZeros=False, phases=None,
                   engine=None, ccx_engine="tcgen05"):
@@ -272,8 +273,8 @@ def createCluster(CCreq=0.5, fetch_arg=None, filt=[1, 10, 2, True], stationKey=N
                                   'DataFetcher; hand ArrayFetcher windows that already reflect them')
     eng = engine or default_engine()
     # paths or DataFrames, as the reference takes them (construct.py:104-106, util.readKey)
-    stakey = readKey('StationKey.csv' if stationKey is None else stationKey, 'station')
-    temkey = readKey('TemplateKey.csv' if templateKey is None else templateKey, 'template')
+    stakey = readKey(stationKey, 'station')
+    temkey = readKey(templateKey, 'template')
     _checkClusterInputs(filt, dtype, trim, decimate)
     fetcher = fetch_arg
     TRDF = _loadEvents(fetcher, filt, trim, stakey, temkey, decimate, dtype, eng)
@@ -461,7 +462,7 @@ def _ensureUnique(DFcc, seed=0):
     _error('cannot make Coeficients unique, killing program')
 
 
-def createSubSpace(Pf=10 ** -12, clust=None, minEvents=2, dtype='double', conDatFetcher=None, engine=None):
+def createSubSpace(Pf=10 ** -12, clust='clust.pkl', minEvents=2, dtype='double', conDatFetcher=None, engine=None):
     """`detex.createSubSpace` (construct.py:177-301): one row per (station, cluster) with the
     aligned waveforms, offsets and statistics the detector needs; singles per station."""
     if isinstance(clust, str):

@@ -358,3 +358,30 @@ def test_reference_built_clusterstream_is_accepted(tmp_path):
         for (_, ra), (_, rb) in zip(a.iterrows(), b.iterrows()):
             for ev in ra.Events:
                 assert np.allclose(ra.AlignedTD[ev], rb.AlignedTD[ev], rtol=0, atol=1e-9)
+
+
+def test_public_signatures_match_the_reference():
+    """Argument names (and the defaults the reference gives them) of the user-facing calls: a script written for
+    Detex passes the same keywords.  Extra keywords here: the engine handles and batch sizes."""
+    import inspect
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    ref_shim.load()
+    import detex.construct as rc
+    import detex.subspace as rs
+    pairs = [(rc.createCluster, workflow.createCluster), (rc.createSubSpace, workflow.createSubSpace),
+             (rs.SubSpace.SVD, workflow.SubSpace.SVD), (rs.SubSpace.getFAS, workflow.SubSpace.getFAS),
+             (rs.SubSpace.detex, workflow.SubSpace.detex), (rs.SubSpace.attachPickTimes, workflow.SubSpace.attachPickTimes),
+             (rs.SubSpace.setSinglesThresholds, workflow.SubSpace.setSinglesThresholds),
+             (rs.SubSpace.validateClusters, workflow.SubSpace.validateClusters),
+             (rs.Cluster.updateReqCC, workflow.Cluster.updateReqCC),
+             (rs.ClusterStream.updateReqCC, workflow.ClusterStream.updateReqCC)]
+    for ref, ours in pairs:
+        pa, pb = inspect.signature(ref).parameters, inspect.signature(ours).parameters
+        assert [k for k in pa if k not in pb] == [], ref.__qualname__
+        fixed = [k for k in pa if pa[k].kind is not inspect.Parameter.VAR_KEYWORD]
+        assert list(pb)[:len(fixed)] == fixed, ref.__qualname__                      # same order: positional calls work
+        for k in pa:
+            assert pa[k].default == pb[k].default or pa[k].default is inspect._empty, (ref.__qualname__, k)
+        assert set(pb) - set(pa) <= {"engine", "ccx_engine", "batch", "utcstart", "utcend"}
