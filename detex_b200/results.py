@@ -51,7 +51,7 @@ def _table_exists(con, name):
     return len(con.execute(q, (name,)).fetchall()) > 0
 
 
-def saveSQLite(DF, CorDB, Tablename):
+def saveSQLite(DF, CorDB, Tablename, silent=True):
     """`detex.util.saveSQLite` (util.py:870-893): create the table on first use, append after."""
     with sqlite3.connect(CorDB, detect_types=sqlite3.PARSE_DECLTYPES) as con:
         if not _table_exists(con, Tablename):
@@ -61,7 +61,7 @@ def saveSQLite(DF, CorDB, Tablename):
         con.executemany('INSERT INTO %s VALUES (%s)' % (Tablename, ','.join(['?'] * len(DF.columns))), rows)
 
 
-def loadSQLite(corDB, tableName, sql=None, convertNumeric=True):
+def loadSQLite(corDB, tableName, sql=None, readExcpetion=False, silent=True, convertNumeric=True):
     """`detex.util.loadSQLite` (util.py:896-931): None when the database / table is missing."""
     if sql is None:
         sql = 'SELECT %s FROM %s' % ('*', tableName)
@@ -387,9 +387,9 @@ class SSResults(object):
 
 
 def detResults(trigCon=0, trigParameter=0, associateReq=0, ss_associateBuffer=1, sg_associateBuffer=2.5,
-               requiredNumStations=4, veriBuffer=1, ssDB='SubSpace.db', templateKey=None, stationKey=None,
-               veriFile=None, includeAllVeriColumns=True, reduceDets=True, Pf=False, stations=None,
-               starttime=None, endtime=None, fetch=None, exceptionalThreshold=None):
+               requiredNumStations=4, veriBuffer=1, ssDB='SubSpace.db', templateKey='TemplateKey.csv',
+               stationKey='StationKey.csv', veriFile=None, includeAllVeriColumns=True, reduceDets=True, Pf=False,
+               stations=None, starttime=None, endtime=None, fetch='ContinuousWaveForms', exceptionalThreshold=None):
     """`detex.results.detResults` (results.py:22-173): load the detections a run left in `ssDB`, drop
     per-station duplicates, associate across stations, split off the auto-detections of the training
     events, verify against a catalogue.  The keys are DataFrames (or csv paths)."""
@@ -400,8 +400,9 @@ def detResults(trigCon=0, trigParameter=0, associateReq=0, ss_associateBuffer=1,
         raise Exception('trigCon must be 0 or 1')
     if associateReq != 0:
         raise Exception('associateReq values other than 0 not yet supported')     # results.py:120-122
-    temkey = pd.read_csv(templateKey) if isinstance(templateKey, str) else templateKey.copy()
-    stakey = pd.read_csv(stationKey) if isinstance(stationKey, str) else stationKey
+    from .util import readKey
+    temkey = readKey(templateKey, 'template').copy()                              # results.py:121-122
+    stakey = readKey(stationKey, 'station')
     from .workflow import _timestamp
     temkey['STMP'] = [_timestamp(t) for t in temkey['TIME']]                      # results.py:421
     ss_info, sg_info = loadSQLite(ssDB, 'ss_info'), loadSQLite(ssDB, 'sg_info')

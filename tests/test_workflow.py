@@ -377,6 +377,10 @@ def test_public_signatures_match_the_reference():
              (rs.SubSpace.validateClusters, workflow.SubSpace.validateClusters),
              (rs.Cluster.updateReqCC, workflow.Cluster.updateReqCC),
              (rs.ClusterStream.updateReqCC, workflow.ClusterStream.updateReqCC)]
+    import detex.results as rr
+    import detex.util as ru
+    pairs += [(rr.detResults, results.detResults), (ru.saveSQLite, results.saveSQLite),
+              (ru.loadSQLite, results.loadSQLite), (ru.readKey, workflow.readKey)]
     for ref, ours in pairs:
         pa, pb = inspect.signature(ref).parameters, inspect.signature(ours).parameters
         assert [k for k in pa if k not in pb] == [], ref.__qualname__
