@@ -53,3 +53,25 @@ def readKey(dfkey, key_type='template'):
         df['STATION'] = [str(x) for x in df['STATION']]
         df['NETWORK'] = [str(x) for x in df['NETWORK']]
     return df
+
+
+def loadClusters(filename='clust.pkl'):
+    """`detex.util.loadClusters` (util.py:934-950): the pickled ClusterStream -- one written here, or one the
+    reference wrote (Detex importable), which is converted (`ClusterStream.from_reference`)."""
+    from . import workflow
+    cl = pd.read_pickle(filename)
+    if isinstance(cl, workflow.ClusterStream):
+        return cl
+    if all(hasattr(cl, a) for a in ('trdf', 'clusters', 'temkey', 'stakey', 'eventList')):
+        return workflow.ClusterStream.from_reference(cl)
+    _error('%s is not a ClusterStream instance' % filename)
+
+
+def loadSubSpace(filename='subspace.pkl'):
+    """`detex.util.loadSubSpace` (util.py:953-969): a SubSpace written by `SubSpace.write` (it opens its own CUDA
+    context when first used)."""
+    from . import workflow
+    ss = pd.read_pickle(filename)
+    if not isinstance(ss, workflow.SubSpace):
+        _error('%s is not a SubSpaceStream instance' % filename)
+    return ss

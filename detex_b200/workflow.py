@@ -354,6 +354,10 @@ class ClusterStream(object):
         else:
             _error('reqCC must be a number or a dict')
 
+    def printAtr(self):
+        for cl in self.clusters:
+            cl.printAtr()
+
     def write(self):
         with open(self.filename, 'wb') as f:
             pickle.dump(self, f)
@@ -416,6 +420,15 @@ class Cluster(object):
 
     def __getitem__(self, index):
         return self.clusts[index]
+
+    def __iter__(self):                  # subspace.py:703-704
+        return iter(self.clusts)
+
+    def printAtr(self):                  # subspace.py:693-698
+        print('%s Cluster' % self.station)
+        print('%d Events cluster out of %d' % (self.clustcount, len(self.singles) + self.clustcount))
+        print('Total number of clusters = %d' % len(self.clusts))
+        print('Required Cross Correlation Coeficient = %.3f' % self.ccReq)
 
     def __len__(self):
         return len(self.clusts)
@@ -547,8 +560,47 @@ class SubSpace(object):
         self.ssStations = list(self.subspaces.keys())
         self.singStations = list(self.singles.keys())
         self.Stations = sorted(set(self.ssStations) | set(self.singStations))
-        self.engine = engine or default_engine()
+        self._engine = engine
         self.histSubSpaces = self.histSingles = None
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = default_engine()
+        return self._engine
+
+    def __getstate__(self):              # the CUDA context does not pickle: a loaded SubSpace opens its own
+        d = dict(self.__dict__)
+        d['_engine'] = None
+        return d
+
+    # ------------------------------------------------------------ containers / MISC (subspace.py:1998-2037)
+    def __getitem__(self, key):
+        if isinstance(key, (int, np.integer)):
+            return self.subspaces[self.ssStations[key]]
+        if isinstance(key, str):
+            parts = key.split('.')
+            if len(parts) == 2 and key in self.subspaces:
+                return self.subspaces[key]
+            if len(parts) == 1:
+                hits = [k for k in self.ssStations if k.split('.')[1] == key]
+                if hits:
+                    return self.subspaces[hits[0]]
+            _error('%s is not a station in this cluster object' % key)
+        _error('%s must either be a int or str of station name' % key)
+
+    def __len__(self):
+        return len(self.subspaces)
+
+    def write(self, filename='subspace.pkl'):
+        with open(filename, 'wb') as f:
+            pickle.dump(self, f)
+
+    def printOffsets(self):
+        for station in self.ssStations:
+            for _, row in self.subspaces[station].iterrows():
+                print('%s, %s, min=%3f, max=%3f, range=%3f' % (row.Station, row.Name, row.Offsets[0], row.Offsets[2],
+                                                            row.Offsets[2] - row.Offsets[0]))
 
     # ------------------------------------------------------------ validateClusters
     def validateClusters(self):

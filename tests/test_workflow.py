@@ -389,3 +389,32 @@ def test_public_signatures_match_the_reference():
         for k in pa:
             assert pa[k].default == pb[k].default or pa[k].default is inspect._empty, (ref.__qualname__, k)
         assert set(pb) - set(pa) <= {"engine", "ccx_engine", "batch", "utcstart", "utcend"}
+
+
+def test_containers_pickles_and_printouts(tmp_path, capsys):
+    """The non-plotting conveniences of the reference's containers (subspace.py:203-205, 693-707, 1998-2037) and the
+    loaders of util.py:934-969: indexing, iteration, printAtr / printOffsets, write + load round trips."""
+    from detex_b200 import util
+    case, cl, ss, db, found = _run(OracleEngine(), tmp_path)
+    c = cl["TA.M17A"]
+    assert [sorted(x) for x in c] == [sorted(x) for x in c.clusts] and len(c) == len(c.clusts)
+    cl.printAtr()
+    out = capsys.readouterr().out
+    assert "TA.M17A Cluster" in out and "Required Cross Correlation Coeficient = %.3f" % CCREQ in out
+    assert len(ss) == 2 and ss[0] is ss.subspaces[ss.ssStations[0]] and ss["M18A"] is ss["TA.M18A"]
+    with pytest.raises(Exception):
+        ss["XX.NOPE"]
+    ss.printOffsets()
+    out = capsys.readouterr().out
+    assert out.count("range=") == sum(len(v) for v in ss.subspaces.values())
+    # pickles: the ClusterStream written by createCluster and the SubSpace (without its engine handle)
+    cl2 = util.loadClusters(cl.filename)
+    assert isinstance(cl2, workflow.ClusterStream) and cl2["TA.M17A"].clusts == c.clusts
+    p = str(tmp_path / "subspace.pkl")
+    ss.write(p)
+    ss2 = util.loadSubSpace(p)
+    assert ss2._engine is None and list(ss2.subspaces["TA.M17A"].Name) == list(ss.subspaces["TA.M17A"].Name)
+    for (_, a), (_, b) in zip(ss.subspaces["TA.M17A"].iterrows(), ss2.subspaces["TA.M17A"].iterrows()):
+        assert a.Threshold == b.Threshold and all(np.array_equal(a.SVD[k], b.SVD[k]) for k in a.SVD)
+    with pytest.raises(Exception, match="not a SubSpaceStream"):
+        util.loadSubSpace(cl.filename)
