@@ -891,6 +891,10 @@ class SubSpace(object):
         singles over the continuous data and write ss_df / sg_df, *_info, *_hist, filt_params."""
         if multiprocess or trigCon != 0:
             _error('multiprocessing and trigcon other than 0 not supported')
+        if classifyEvents is not None or utcSaves is not None:
+            # detect.py:52-56, 63-72, 88-110: event classification never fills its `eventCorList` in the reference
+            # and utcSaves pickles raw debugging windows; neither is on the path -- refuse instead of ignoring
+            raise NotImplementedError('classifyEvents / utcSaves are not supported')
         if os.path.exists(subspaceDB) and delOldCorrs:
             os.remove(subspaceDB)
         out = {}
