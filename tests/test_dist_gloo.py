@@ -254,3 +254,40 @@ def test_time_segment_sharding_two_ranks_equals_one():
     assert len(a[0]) > 0 and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[3] == b[3]
     assert np.array_equal(a[2], b[2]) and a[4] == b[4]
     assert all(np.array_equal(a[5][k], b[5][k]) for k in a[5])
+
+
+def _hostbuf_fail_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        outcome = "created"
+        try:
+            parallel.CcxHostBuffer(OracleEngine(), 50, shm_dir="/nonexistent/shm")
+        except RuntimeError:
+            outcome = "refused"
+        dist.barrier()                      # nobody is stuck in a collective of the failed constructor
+        q.put((rank, outcome))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_host_buffer_is_refused_by_every_rank_when_the_segment_cannot_be_made():
+    """A tmpfs that cannot hold the matrix (here: a directory that does not exist) makes EVERY rank raise
+    RuntimeError -- callers fall back to the NCCL gather (bench.py does) -- instead of one rank raising and the
+    others waiting in a collective."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_hostbuf_fail_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [(0, "refused"), (1, "refused")]
